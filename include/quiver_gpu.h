@@ -1,0 +1,243 @@
+/*
+ * quiver_gpu.h — C ABI of libquivergpu.so, the B200 (sm_100a) implementation of
+ * Quiver's exact-search hot path.
+ *
+ * This is the drop-in boundary: the functions below are what a cgo package
+ * (pkg/gpu) binds so that a `gpu.Index` can satisfy
+ * `core.Index` (reference pkg/core/collection.go:78-87) / `hybrid.Index`
+ * (pkg/hybrid/types.go:196-214) and replace `hybrid.ExactIndex`
+ * (pkg/hybrid/exact.go:14-133) behind `HybridIndex.searchWithStrategy`
+ * (pkg/hybrid/hybrid_index.go:473-585).
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 (QG_OK) or a qg_status code,
+ *     and leaves a thread-local message readable through qg_last_error();
+ *   - rows are dense int64 row indices in upload order; string IDs stay in the
+ *     host language (the reference keeps them in Go maps, exact.go:16);
+ *   - the caller owns every in/out buffer; the library owns device memory
+ *     behind the opaque handles; no pointer is retained after a call returns;
+ *   - qg_search_*, qg_batch_distance*, qg_filter_eval are re-entrant (they
+ *     mirror the reference's shared RLock, exact.go:93); upload / tombstone /
+ *     facet-column / destroy calls need external exclusion (the reference's
+ *     exclusive Lock, exact.go:39,62);
+ *   - there is no CPU fallback: without a CUDA device every compute entry point
+ *     returns QG_ERR_CUDA.
+ */
+#ifndef QUIVER_GPU_H
+#define QUIVER_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QG_ABI_VERSION 1
+
+typedef enum qg_status {
+  QG_OK = 0,
+  QG_ERR_INVALID = 1,   /* bad argument (null pointer, negative size, ...)          */
+  QG_ERR_DIM = 2,       /* dimension mismatch  (exact.go:46,101)                    */
+  QG_ERR_K = 3,         /* k <= 0              (exact.go:104-106)                   */
+  QG_ERR_CUDA = 4,      /* CUDA runtime / driver failure, or no device              */
+  QG_ERR_OOM = 5,       /* device or pinned-host allocation failed                  */
+  QG_ERR_UNSUPPORTED = 6, /* predicate or option the device path does not implement */
+  QG_ERR_RANGE = 7      /* row index out of range                                   */
+} qg_status;
+
+/* Distance semantics: reference pkg/vectortypes/distances.go (line per metric). */
+typedef enum qg_metric {
+  QG_COSINE = 0, /* distances.go:12-40  1 - dot/(|a||b|), zero norm => 1, sim clamped */
+  QG_L2 = 1,     /* distances.go:43-55  sqrt(sum (a-b)^2), fp32 subtract, fp64 sum     */
+  QG_DOT = 2,    /* distances.go:77-90  1 - dot                                        */
+  QG_SQL2 = 3,   /* distances.go:60-72  sum (a-b)^2, sequential fp32                   */
+  QG_L1 = 4      /* distances.go:93-104 sum |a-b|, fp32 subtract, fp64 sum             */
+} qg_metric;
+
+/* Which reference arithmetic the returned float32 distances reproduce. */
+typedef enum qg_arith {
+  QG_ARITH_VECTORTYPES = 0, /* float64 accumulators, pkg/vectortypes/distances.go      */
+  QG_ARITH_HNSW_F32 = 1     /* sequential float32, pkg/hnsw/adapter.go:105-167
+                               (cosine / l2 / dot only)                                */
+} qg_arith;
+
+typedef struct qg_config {
+  int device;            /* CUDA device ordinal                                         */
+  int arith;             /* qg_arith                                                    */
+  int64_t reserve_rows;  /* capacity hint; 0 = grow on demand                           */
+  int select_margin;     /* extra fp32-scan candidates re-ranked exactly; 0 = default   */
+  int flags;             /* reserved, must be 0                                         */
+} qg_config;
+
+typedef struct qg_index qg_index;
+typedef struct qg_filter qg_filter;
+
+/* ---- library ----------------------------------------------------------------------- */
+int qg_abi_version(void);
+const char* qg_last_error(void);
+int qg_device_count(int* out_count);
+/* Name and SM count of a device (buffer may be NULL). */
+int qg_device_info(int device, char* name_buf, size_t name_len, int* out_sm_count,
+                   int* out_cc_major, int* out_cc_minor);
+
+/* ---- index lifecycle (replaces NewExactIndex / Insert / Delete / Size,
+ *      exact.go:29-70,136-141) ------------------------------------------------------- */
+int qg_index_create(qg_index** out, int dim, int metric, const qg_config* cfg /*nullable*/);
+int qg_index_destroy(qg_index* idx);
+/* Append n rows (row-major n x dim float32, host memory, pinned or pageable); rows are
+ * copied (exact.go:53-54). *first_row receives the index of the first appended row. */
+int qg_index_upload(qg_index* idx, const float* rows, int64_t n, int64_t* first_row /*nullable*/);
+/* Same, source already on this index's device. */
+int qg_index_upload_device(qg_index* idx, const void* d_rows, int64_t n, int64_t* first_row);
+/* Append n synthetic rows generated on the device by the counter-based generator shared
+ * with oracle/ (see oracle/synth.h): element (row, col) depends only on (kind, seed,
+ * global_row0 + row, col). kind: 0 uniform[0,1), 1 SIFT-like integers 0..217,
+ * 2 approx-normal (sum of 4 uniforms), 3 = kind 2 L2-normalised per row. */
+int qg_index_upload_synthetic(qg_index* idx, int kind, uint64_t seed, int64_t global_row0,
+                              int64_t n, int64_t* first_row);
+/* Mark rows deleted (Delete, exact.go:61-70). Already-deleted rows are a no-op. */
+int qg_index_tombstone(qg_index* idx, const int64_t* rows, int64_t n);
+int64_t qg_index_size(const qg_index* idx);  /* live rows                    */
+int64_t qg_index_rows(const qg_index* idx);  /* rows ever uploaded           */
+int qg_index_dim(const qg_index* idx);
+int qg_index_metric(const qg_index* idx);
+/* Copy stored vectors back (IncludeVectors, collection.go:766-770). */
+int qg_index_fetch(qg_index* idx, const int64_t* rows, int64_t n, float* out /* n x dim */);
+
+/* ---- facet / metadata columns and predicates ---------------------------------------
+ * One column per field. A row's value is described by:
+ *   kind  : qg_value_kind
+ *   num   : the float64 value when kind == QG_KIND_NUMBER
+ *   scode : order-preserving dictionary code of the value's Go "%v" text
+ *           (case-sensitive; core.valuesEqual / compareValues, collection.go:601-634);
+ *           -1 when kind is MISSING
+ *   fcode : dictionary code of the case-folded string (strings.EqualFold,
+ *           facets.go:73-77) for STRING rows, else -1
+ * Array-valued facets (facets.go:304-316) are out of the device path: mark them
+ * QG_KIND_OTHER; predicates that would need their elements return QG_ERR_UNSUPPORTED
+ * at compile time rather than a wrong mask. */
+typedef enum qg_value_kind {
+  QG_KIND_MISSING = 0, /* field absent from the row's metadata / facets */
+  QG_KIND_NULL = 1,    /* present, JSON null                            */
+  QG_KIND_STRING = 2,
+  QG_KIND_NUMBER = 3,
+  QG_KIND_BOOL = 4,    /* num = 0/1                                     */
+  QG_KIND_OTHER = 5,   /* array / map; flag bit 0x80 set = non-empty    */
+  QG_KIND_NOROW = 6    /* the row has no metadata / facet entry at all  */
+} qg_value_kind;
+
+int qg_facets_set_column(qg_index* idx, int field, const uint8_t* kind, const double* num,
+                         const int32_t* scode, const int32_t* fcode, int64_t n);
+
+/* A predicate is already lowered by the host-side compiler (quiver_b200/host) from the
+ * reference's filter objects into this normal form; the device evaluates
+ *   match(row) = AND_i pred_i(row)
+ * with each pred_i = OR over its clauses. */
+typedef enum qg_clause_op {
+  QG_OP_FALSE = 0,
+  QG_OP_TRUE = 1,
+  QG_OP_KIND_IN = 2,      /* kind bitmask test: (1<<kind) & ia                          */
+  QG_OP_NUM_EQ_TOL = 3,   /* kind NUMBER and |num - fa| <= fb    (collection.go:604)    */
+  QG_OP_NUM_EQ = 4,       /* kind NUMBER/BOOL per mask ia and num == fa (facets.go:81)  */
+  QG_OP_NUM_CMP = 5,      /* kind NUMBER and num (ia: 0 <,1 <=,2 >,3 >=) fa             */
+  QG_OP_NUM_RANGE = 6,    /* kind NUMBER and lo/hi bounds, ia bit0 has_lo, bit1 incl_lo,
+                             bit2 has_hi, bit3 incl_hi; fa = lo, fb = hi (facets.go:126) */
+  QG_OP_SCODE_EQ = 7,     /* kinds in mask ib and scode == ia                           */
+  QG_OP_SCODE_CMP = 8,    /* kinds in mask ib and scode (ic: 0 <,1 <=,2 >,3 >=) ia,
+                             where ia is a rank in the column's sorted dictionary       */
+  QG_OP_FCODE_EQ = 9,     /* kind STRING and fcode == ia                                */
+  QG_OP_SCODE_IN = 10,    /* kinds in mask ib and scode in set[ia .. ia+ic)             */
+  QG_OP_FCODE_IN = 11,    /* kind STRING and fcode in set[ia .. ia+ic)                  */
+  QG_OP_NUM_IN_TOL = 12,  /* kind NUMBER and any |num - fset[ia+j]| <= fb, j < ic       */
+  QG_OP_NUM_IN = 13,      /* kinds in mask ib and num == fset[ia+j] for some j < ic     */
+  QG_OP_NUM_BITS_EQ = 14  /* kind NUMBER and bit pattern of num == bits(fa)             */
+} qg_clause_op;
+
+typedef struct qg_clause {
+  int32_t op;      /* qg_clause_op */
+  int32_t field;   /* column index */
+  int32_t negate;  /* 1 = logical NOT of the clause result */
+  int32_t ia, ib, ic;
+  double fa, fb;
+} qg_clause;
+
+typedef struct qg_pred {
+  int32_t first_clause; /* index into the clause array            */
+  int32_t n_clauses;    /* OR of these; 0 clauses = false         */
+  int32_t negate;       /* 1 = NOT(OR(...))                       */
+  int32_t require_row;  /* 1 = rows of kind NOROW never match     */
+} qg_pred;
+
+int qg_filter_compile(qg_index* idx, const qg_pred* preds, int n_preds, const qg_clause* clauses,
+                      int n_clauses, const int32_t* iset, int n_iset, const double* fset,
+                      int n_fset, qg_filter** out);
+/* Evaluate over all uploaded rows; tombstoned rows are NOT removed from this mask (the
+ * search ANDs the live mask itself). mask_out (nullable) receives ceil(rows/64) words,
+ * bit r%64 of word r/64 = row r matches. */
+int qg_filter_eval(qg_index* idx, qg_filter* f, uint64_t* mask_out, int64_t* out_matches);
+int qg_filter_destroy(qg_filter* f);
+
+/* ---- search (replaces ExactIndex.Search exact.go:92-133, the exact branch of
+ *      searchWithStrategy hybrid_index.go:515-570 and BatchSearch :677-811) ----------
+ * For each of q queries: the k nearest live rows that pass `filter` (nullable), ascending
+ * by (distance, row). out_dist / out_row are q x k, unused tail entries are +inf / -1;
+ * out_count[i] = number of results of query i = min(k, matching live rows).
+ * When `negatives` (q x dim, nullable) is given, out_negdist[i*k+j] = distance between
+ * result row j and negatives[i] in the index metric (hybrid_index.go:536-546); the
+ * caller applies `d - w*d_neg` and the (score, ID) order, which needs the string IDs.
+ * Error order follows exact.go:96-106: an empty index returns 0 results and QG_OK even
+ * when k <= 0; then the dimension is checked by the caller-supplied `dim`; then k. */
+int qg_search_batch(qg_index* idx, const float* queries, int q, int dim, int k,
+                    qg_filter* filter, const float* negatives, float* out_dist,
+                    float* out_negdist, int64_t* out_row, int* out_count);
+
+/* Same with every buffer resident on the index's device and the work enqueued on
+ * `stream` (a cudaStream_t passed as void*; NULL = the legacy default stream). Returns
+ * after enqueueing; results are valid once the stream has been synchronised. */
+int qg_search_batch_device(qg_index* idx, const void* d_queries, int q, int dim, int k,
+                           qg_filter* filter, const void* d_negatives, void* d_out_dist,
+                           void* d_out_negdist, void* d_out_row, void* d_out_count,
+                           void* stream);
+
+/* ---- row-sharded search across GPUs (no reference counterpart) -----------
+ * Per-shard top-k as packed 64-bit keys: high 32 bits = order-preserving image of the
+ * exact float32 distance, low 32 bits = global row (row_base + local row). Missing
+ * entries are all-ones. The keys of all shards are exchanged by the host layer (NCCL
+ * all-gather) and merged by qg_merge_shard_keys_device. */
+int qg_search_shard_keys_device(qg_index* idx, const void* d_queries, int q, int dim, int k,
+                                qg_filter* filter, int64_t row_base, void* d_out_keys /* q x k u64 */,
+                                void* stream);
+/* d_keys_gathered: world x q x k u64 (rank-major). Writes q x k distances / int64 global
+ * rows / counts. `device` = device the buffers live on. */
+int qg_merge_shard_keys_device(int device, const void* d_keys_gathered, int world, int q, int k,
+                               void* d_out_dist, void* d_out_row, void* d_out_count,
+                               void* stream);
+
+/* ---- neighbour-distance batches for HNSW (replaces the per-pair computeDistance call
+ *      in searchLayer, pkg/hnsw/hnsw.go:536-563 / :547) ------------------------------
+ * out[i] = distance(query, row rows[i]) in the index metric and arithmetic;
+ * rows[i] == 0xFFFFFFFF yields +inf. */
+int qg_batch_distance(qg_index* idx, const float* query, int dim, const uint32_t* rows, int n,
+                      float* out);
+/* b queries at once, each with m candidate rows (row-major b x m, 0xFFFFFFFF = skip). */
+int qg_batch_distance_multi(qg_index* idx, const float* queries, int b, int dim,
+                            const uint32_t* rows, int m, float* out);
+
+/* ---- introspection for benchmarks and tests -----------------------------------------*/
+typedef struct qg_scan_stats {
+  int64_t rows_scanned;     /* rows whose vector bytes the last scan read            */
+  int64_t bytes_algorithmic;/* rows_scanned*dim*4 + side columns read                */
+  int32_t kernel_launches;  /* kernels launched by the last search call              */
+  int32_t queries_per_pass; /* queries served by one pass over the corpus            */
+  int32_t passes;           /* corpus passes of the last call                        */
+  int32_t escalations;      /* selections repeated with a larger candidate set       */
+  int32_t path;             /* 0 none, 1 flat scan, 2 gather scan, 3 tensor-core     */
+  int32_t reserved;
+} qg_scan_stats;
+int qg_last_scan_stats(const qg_index* idx, qg_scan_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUIVER_GPU_H */

@@ -1,0 +1,1175 @@
+// api.cu — the C ABI of libquivergpu.so (include/quiver_gpu.h): index lifecycle, upload through
+// pinned staging buffers, facet columns / filters, search orchestration.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/quiver_gpu.h"
+#include "common.cuh"
+#include "exact.cuh"
+#include "finalize.cuh"
+#include "misc.cuh"
+#include "scan.cuh"
+
+namespace qg {
+
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+int fail(int code, const std::string& msg) {
+  g_error = msg;
+  return code;
+}
+
+// ---- per-device one-time state ----------------------------------------------------------------
+struct DeviceState {
+  bool attrs_done = false;
+  int sm_count = 0;
+};
+static std::mutex g_dev_mu;
+static DeviceState g_dev[64];
+
+static int ensure_device(int device) {
+  if (device < 0 || device >= 64) return fail(QG_ERR_INVALID, "device ordinal out of range");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(QG_ERR_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") +
+                                 cudaGetErrorString(e));
+  if (device >= n) return fail(QG_ERR_INVALID, "device ordinal >= device count");
+  QG_CUDA_OK(cudaSetDevice(device));
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  DeviceState& ds = g_dev[device];
+  if (!ds.attrs_done) {
+    cudaDeviceProp prop;
+    QG_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+      return fail(QG_ERR_CUDA, std::string("libquivergpu is built for sm_100a only; device is ") + prop.name);
+    ds.sm_count = prop.multiProcessorCount;
+    if (int rc = scan_set_attributes()) return rc;
+    if (int rc = finalize_set_attributes()) return rc;
+    ds.attrs_done = true;
+  }
+  return 0;
+}
+
+// ---- growable device buffer ---------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t need) {
+    if (need <= bytes) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    size_t want = std::max(need, (size_t)256);
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return fail(QG_ERR_OOM, std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e));
+    }
+    bytes = want;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+};
+
+struct PinBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t need) {
+    if (need <= bytes) return 0;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    bytes = 0;
+    size_t want = std::max(need, (size_t)4096);
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return fail(QG_ERR_OOM, std::string("cudaHostAlloc(") + std::to_string(want) + "): " + cudaGetErrorString(e));
+    }
+    bytes = want;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    bytes = 0;
+  }
+};
+
+// Per-call scratch: acquired from the index's pool so concurrent searches never share one.
+struct Workspace {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;  // recorded when an async (device-API) call finished using this workspace
+  bool busy_async = false;
+  DevBuf qpad, negpad, partial, mask, counters;
+  DevBuf d_q, d_neg, d_dist, d_negdist, d_row, d_count, d_rows32, d_rows64, d_fetch;
+  PinBuf h_in, h_out;
+  ExhaustiveWork ex;
+  void destroy() {
+    qpad.release(); negpad.release(); partial.release(); mask.release(); counters.release();
+    d_q.release(); d_neg.release(); d_dist.release(); d_negdist.release(); d_row.release(); d_count.release();
+    d_rows32.release(); d_rows64.release(); d_fetch.release();
+    h_in.release(); h_out.release();
+    exhaustive_free(ex);
+    if (done) cudaEventDestroy(done);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+struct FacetColumn {
+  bool set = false;
+  long long n = 0;
+  DevBuf kind, num, scode, fcode;
+};
+
+}  // namespace qg
+
+using namespace qg;
+
+struct qg_filter {
+  qg_index* owner = nullptr;
+  std::vector<qg_pred> preds;
+  std::vector<qg_clause> clauses;
+  std::vector<int32_t> iset;
+  std::vector<double> fset;
+  DevBuf d_preds, d_clauses, d_iset, d_fset;
+  // cache (guarded by mu)
+  std::mutex mu;
+  long long raw_rows = -1;
+  uint64_t raw_facet_epoch = ~0ull;
+  DevBuf raw_mask;
+  long long raw_matches = 0;
+  uint64_t comb_live_epoch = ~0ull;
+  DevBuf comb_mask, gather_list;
+  long long comb_matches = 0;
+  bool gather_valid = false;
+};
+
+struct qg_index {
+  int device = 0;
+  int dim = 0, dp = 0;
+  int metric = 0, arith = 0;
+  int margin = 16;
+  int sm_count = 148;
+  long long cap = 0, n_rows = 0, n_live = 0;
+  float* vec = nullptr;
+  float* inv_norm = nullptr;
+  uint32_t* live = nullptr;
+  float* max_norm2 = nullptr;  // device scalar
+  uint64_t live_epoch = 0, facet_epoch = 0;
+  std::vector<FacetColumn> cols;
+  DevBuf col_table;  // FacetColDev[]
+  bool col_table_dirty = true;
+  std::mutex ws_mu;
+  std::vector<std::unique_ptr<Workspace>> ws_free;
+  std::vector<std::unique_ptr<Workspace>> ws_async;  // in flight on caller streams
+  PinBuf stage[2];
+  cudaStream_t up_stream = nullptr;
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+  qg_scan_stats stats{};
+};
+
+namespace qg {
+
+static int scan_mode_of(int metric) {
+  switch (metric) {
+    case METRIC_L2:
+    case METRIC_SQL2: return MODE_L2;
+    case METRIC_L1: return MODE_L1;
+    default: return MODE_DOT;
+  }
+}
+
+static Workspace* ws_acquire(qg_index* idx) {
+  std::lock_guard<std::mutex> lk(idx->ws_mu);
+  // recycle async workspaces whose work has completed
+  for (size_t i = 0; i < idx->ws_async.size();) {
+    if (cudaEventQuery(idx->ws_async[i]->done) == cudaSuccess) {
+      idx->ws_async[i]->busy_async = false;
+      idx->ws_free.push_back(std::move(idx->ws_async[i]));
+      idx->ws_async.erase(idx->ws_async.begin() + i);
+    } else {
+      ++i;
+    }
+  }
+  if (!idx->ws_free.empty()) {
+    Workspace* w = idx->ws_free.back().release();
+    idx->ws_free.pop_back();
+    return w;
+  }
+  Workspace* w = new Workspace();
+  if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&w->done, cudaEventDisableTiming) != cudaSuccess) {
+    w->destroy();
+    delete w;
+    return nullptr;
+  }
+  return w;
+}
+
+static void ws_release(qg_index* idx, Workspace* w) {
+  std::lock_guard<std::mutex> lk(idx->ws_mu);
+  idx->ws_free.emplace_back(w);
+}
+
+static void ws_release_async(qg_index* idx, Workspace* w, cudaStream_t st) {
+  cudaEventRecord(w->done, st);
+  w->busy_async = true;
+  std::lock_guard<std::mutex> lk(idx->ws_mu);
+  idx->ws_async.emplace_back(w);
+}
+
+static int grow(qg_index* idx, long long need_rows) {
+  if (need_rows <= idx->cap) return 0;
+  long long ncap = std::max<long long>(idx->cap * 2, 1024);
+  ncap = std::max(ncap, need_rows);
+  ncap = (ncap + 1023) & ~1023ll;  // whole mask words, 16-byte aligned columns
+  float* nvec = nullptr;
+  float* ninv = nullptr;
+  uint32_t* nlive = nullptr;
+  cudaError_t e = cudaMalloc(&nvec, (size_t)ncap * idx->dp * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&ninv, (size_t)ncap * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&nlive, (size_t)(ncap / 32) * sizeof(uint32_t));
+  if (e != cudaSuccess) {
+    if (nvec) cudaFree(nvec);
+    if (ninv) cudaFree(ninv);
+    if (nlive) cudaFree(nlive);
+    return fail(QG_ERR_OOM, std::string("device allocation for ") + std::to_string(ncap) +
+                                " rows failed: " + cudaGetErrorString(e));
+  }
+  QG_CUDA_OK(cudaMemsetAsync(nlive, 0, (size_t)(ncap / 32) * sizeof(uint32_t), idx->up_stream));
+  if (idx->n_rows > 0) {
+    QG_CUDA_OK(cudaMemcpyAsync(nvec, idx->vec, (size_t)idx->n_rows * idx->dp * sizeof(float),
+                               cudaMemcpyDeviceToDevice, idx->up_stream));
+    QG_CUDA_OK(cudaMemcpyAsync(ninv, idx->inv_norm, (size_t)idx->n_rows * sizeof(float), cudaMemcpyDeviceToDevice,
+                               idx->up_stream));
+    QG_CUDA_OK(cudaMemcpyAsync(nlive, idx->live, (size_t)((idx->n_rows + 31) / 32) * sizeof(uint32_t),
+                               cudaMemcpyDeviceToDevice, idx->up_stream));
+  }
+  QG_CUDA_OK(cudaStreamSynchronize(idx->up_stream));
+  if (idx->vec) cudaFree(idx->vec);
+  if (idx->inv_norm) cudaFree(idx->inv_norm);
+  if (idx->live) cudaFree(idx->live);
+  idx->vec = nvec;
+  idx->inv_norm = ninv;
+  idx->live = nlive;
+  idx->cap = ncap;
+  return 0;
+}
+
+// Post-copy bookkeeping shared by the three upload flavours.
+static int finish_append(qg_index* idx, long long n, int64_t* first_row) {
+  const long long row0 = idx->n_rows;
+  if (idx->metric == METRIC_COSINE || idx->metric == METRIC_DOT) {
+    if (int rc = launch_row_norms(idx->vec, row0, n, idx->dp, idx->dim, idx->inv_norm, idx->max_norm2,
+                                  idx->up_stream))
+      return rc;
+  }
+  if (int rc = launch_set_live(idx->live, row0, n, idx->up_stream)) return rc;
+  QG_CUDA_OK(cudaStreamSynchronize(idx->up_stream));
+  idx->n_rows += n;
+  idx->n_live += n;
+  idx->live_epoch++;
+  if (first_row) *first_row = row0;
+  return 0;
+}
+
+static int check_index(const qg_index* idx) {
+  if (!idx) return fail(QG_ERR_INVALID, "index handle is null");
+  QG_CUDA_OK(cudaSetDevice(idx->device));
+  return 0;
+}
+
+}  // namespace qg
+
+// ================================================================================================
+extern "C" {
+
+int qg_abi_version(void) { return QG_ABI_VERSION; }
+const char* qg_last_error(void) { return g_error.c_str(); }
+
+int qg_device_count(int* out_count) {
+  if (!out_count) return fail(QG_ERR_INVALID, "out_count is null");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *out_count = 0;
+    return fail(QG_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+  }
+  *out_count = n;
+  return 0;
+}
+
+int qg_device_info(int device, char* name_buf, size_t name_len, int* out_sm_count, int* out_cc_major,
+                   int* out_cc_minor) {
+  cudaDeviceProp prop;
+  QG_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (name_buf && name_len) {
+    std::strncpy(name_buf, prop.name, name_len - 1);
+    name_buf[name_len - 1] = 0;
+  }
+  if (out_sm_count) *out_sm_count = prop.multiProcessorCount;
+  if (out_cc_major) *out_cc_major = prop.major;
+  if (out_cc_minor) *out_cc_minor = prop.minor;
+  return 0;
+}
+
+int qg_index_create(qg_index** out, int dim, int metric, const qg_config* cfg) {
+  if (!out) return fail(QG_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (dim <= 0) return fail(QG_ERR_DIM, "dimension must be positive");
+  if (metric < 0 || metric > 4) return fail(QG_ERR_INVALID, "unknown metric");
+  const int device = cfg ? cfg->device : 0;
+  if (cfg && cfg->flags != 0) return fail(QG_ERR_INVALID, "qg_config.flags must be 0");
+  if (int rc = ensure_device(device)) return rc;
+  std::unique_ptr<qg_index> idx(new qg_index());
+  idx->device = device;
+  idx->dim = dim;
+  idx->dp = (dim + 3) & ~3;
+  idx->metric = metric;
+  idx->arith = cfg ? cfg->arith : 0;
+  if (idx->arith != ARITH_VECTORTYPES && idx->arith != ARITH_HNSW_F32) return fail(QG_ERR_INVALID, "unknown arith");
+  if (idx->arith == ARITH_HNSW_F32 && (metric == METRIC_SQL2 || metric == METRIC_L1))
+    return fail(QG_ERR_INVALID, "hnsw float32 arithmetic exists for cosine / l2 / dot only");
+  idx->margin = (cfg && cfg->select_margin > 0) ? cfg->select_margin : 16;
+  {
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    idx->sm_count = g_dev[device].sm_count;
+  }
+  QG_CUDA_OK(cudaStreamCreateWithFlags(&idx->up_stream, cudaStreamNonBlocking));
+  QG_CUDA_OK(cudaEventCreateWithFlags(&idx->stage_ev[0], cudaEventDisableTiming));
+  QG_CUDA_OK(cudaEventCreateWithFlags(&idx->stage_ev[1], cudaEventDisableTiming));
+  QG_CUDA_OK(cudaMalloc(&idx->max_norm2, sizeof(float)));
+  QG_CUDA_OK(cudaMemset(idx->max_norm2, 0, sizeof(float)));
+  if (cfg && cfg->reserve_rows > 0) {
+    if (int rc = grow(idx.get(), cfg->reserve_rows)) return rc;
+  }
+  *out = idx.release();
+  return 0;
+}
+
+int qg_index_destroy(qg_index* idx) {
+  if (!idx) return 0;
+  cudaSetDevice(idx->device);
+  cudaDeviceSynchronize();
+  for (auto& w : idx->ws_free) w->destroy();
+  for (auto& w : idx->ws_async) w->destroy();
+  for (auto& c : idx->cols) {
+    c.kind.release(); c.num.release(); c.scode.release(); c.fcode.release();
+  }
+  idx->col_table.release();
+  idx->stage[0].release();
+  idx->stage[1].release();
+  if (idx->vec) cudaFree(idx->vec);
+  if (idx->inv_norm) cudaFree(idx->inv_norm);
+  if (idx->live) cudaFree(idx->live);
+  if (idx->max_norm2) cudaFree(idx->max_norm2);
+  if (idx->stage_ev[0]) cudaEventDestroy(idx->stage_ev[0]);
+  if (idx->stage_ev[1]) cudaEventDestroy(idx->stage_ev[1]);
+  if (idx->up_stream) cudaStreamDestroy(idx->up_stream);
+  delete idx;
+  return 0;
+}
+
+int qg_index_upload(qg_index* idx, const float* rows, int64_t n, int64_t* first_row) {
+  if (int rc = check_index(idx)) return rc;
+  if (n < 0 || (n > 0 && !rows)) return fail(QG_ERR_INVALID, "rows is null or n < 0");
+  if (idx->n_rows + n > 0xFFFFFFFEll) return fail(QG_ERR_RANGE, "an index holds at most 2^32-2 rows");
+  if (n == 0) {
+    if (first_row) *first_row = idx->n_rows;
+    return 0;
+  }
+  if (int rc = grow(idx, idx->n_rows + n)) return rc;
+  const int d = idx->dim, dp = idx->dp;
+  float* dst0 = idx->vec + (size_t)idx->n_rows * dp;
+  if (dp != d) QG_CUDA_OK(cudaMemsetAsync(dst0, 0, (size_t)n * dp * sizeof(float), idx->up_stream));
+  // pinned double-buffered staging: host memcpy of chunk i+1 overlaps the H2D DMA of chunk i
+  const size_t row_bytes = (size_t)d * sizeof(float);
+  const long long chunk_rows = std::max<long long>(1, (long long)((32u << 20) / row_bytes));
+  for (int b = 0; b < 2; ++b)
+    if (int rc = idx->stage[b].ensure((size_t)std::min<long long>(chunk_rows, n) * row_bytes)) return rc;
+  int buf = 0;
+  for (long long off = 0; off < n; off += chunk_rows, buf ^= 1) {
+    const long long m = std::min(chunk_rows, n - off);
+    QG_CUDA_OK(cudaEventSynchronize(idx->stage_ev[buf]));  // previous DMA out of this buffer is done
+    std::memcpy(idx->stage[buf].p, rows + (size_t)off * d, (size_t)m * row_bytes);
+    if (dp == d) {
+      QG_CUDA_OK(cudaMemcpyAsync(dst0 + (size_t)off * dp, idx->stage[buf].p, (size_t)m * row_bytes,
+                                 cudaMemcpyHostToDevice, idx->up_stream));
+    } else {
+      QG_CUDA_OK(cudaMemcpy2DAsync(dst0 + (size_t)off * dp, (size_t)dp * sizeof(float), idx->stage[buf].p, row_bytes,
+                                   row_bytes, (size_t)m, cudaMemcpyHostToDevice, idx->up_stream));
+    }
+    QG_CUDA_OK(cudaEventRecord(idx->stage_ev[buf], idx->up_stream));
+  }
+  return finish_append(idx, n, first_row);
+}
+
+int qg_index_upload_device(qg_index* idx, const void* d_rows, int64_t n, int64_t* first_row) {
+  if (int rc = check_index(idx)) return rc;
+  if (n < 0 || (n > 0 && !d_rows)) return fail(QG_ERR_INVALID, "d_rows is null or n < 0");
+  if (idx->n_rows + n > 0xFFFFFFFEll) return fail(QG_ERR_RANGE, "an index holds at most 2^32-2 rows");
+  if (n == 0) {
+    if (first_row) *first_row = idx->n_rows;
+    return 0;
+  }
+  if (int rc = grow(idx, idx->n_rows + n)) return rc;
+  const int d = idx->dim, dp = idx->dp;
+  float* dst0 = idx->vec + (size_t)idx->n_rows * dp;
+  if (dp == d) {
+    QG_CUDA_OK(cudaMemcpyAsync(dst0, d_rows, (size_t)n * d * sizeof(float), cudaMemcpyDeviceToDevice, idx->up_stream));
+  } else {
+    QG_CUDA_OK(cudaMemsetAsync(dst0, 0, (size_t)n * dp * sizeof(float), idx->up_stream));
+    QG_CUDA_OK(cudaMemcpy2DAsync(dst0, (size_t)dp * sizeof(float), d_rows, (size_t)d * sizeof(float),
+                                 (size_t)d * sizeof(float), (size_t)n, cudaMemcpyDeviceToDevice, idx->up_stream));
+  }
+  return finish_append(idx, n, first_row);
+}
+
+int qg_index_upload_synthetic(qg_index* idx, int kind, uint64_t seed, int64_t global_row0, int64_t n,
+                              int64_t* first_row) {
+  if (int rc = check_index(idx)) return rc;
+  if (n < 0) return fail(QG_ERR_INVALID, "n < 0");
+  if (idx->n_rows + n > 0xFFFFFFFEll) return fail(QG_ERR_RANGE, "an index holds at most 2^32-2 rows");
+  if (n == 0) {
+    if (first_row) *first_row = idx->n_rows;
+    return 0;
+  }
+  if (int rc = grow(idx, idx->n_rows + n)) return rc;
+  if (int rc = launch_synth_fill(idx->vec, idx->n_rows, n, idx->dp, idx->dim, kind, seed, global_row0,
+                                 idx->up_stream))
+    return rc;
+  return finish_append(idx, n, first_row);
+}
+
+int qg_index_tombstone(qg_index* idx, const int64_t* rows, int64_t n) {
+  if (int rc = check_index(idx)) return rc;
+  if (n < 0 || (n > 0 && !rows)) return fail(QG_ERR_INVALID, "rows is null or n < 0");
+  if (n == 0) return 0;
+  for (int64_t i = 0; i < n; ++i)
+    if (rows[i] < 0 || rows[i] >= idx->n_rows) return fail(QG_ERR_RANGE, "tombstone: row index out of range");
+  DevBuf d_rows, d_cnt;
+  if (int rc = d_rows.ensure((size_t)n * 8)) return rc;
+  if (int rc = d_cnt.ensure(8)) {
+    d_rows.release();
+    return rc;
+  }
+  int rc = 0;
+  unsigned long long cleared = 0;
+  do {
+    cudaError_t e = cudaMemcpyAsync(d_rows.p, rows, (size_t)n * 8, cudaMemcpyHostToDevice, idx->up_stream);
+    if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, cudaGetErrorString(e)); break; }
+    rc = launch_tombstone(idx->live, (const long long*)d_rows.p, n, idx->n_rows, (unsigned long long*)d_cnt.p,
+                          idx->up_stream);
+    if (rc) break;
+    e = cudaMemcpyAsync(&cleared, d_cnt.p, 8, cudaMemcpyDeviceToHost, idx->up_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(idx->up_stream);
+    if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, cudaGetErrorString(e)); break; }
+  } while (0);
+  d_rows.release();
+  d_cnt.release();
+  if (rc) return rc;
+  idx->n_live -= (long long)cleared;
+  idx->live_epoch++;
+  return 0;
+}
+
+int64_t qg_index_size(const qg_index* idx) { return idx ? idx->n_live : 0; }
+int64_t qg_index_rows(const qg_index* idx) { return idx ? idx->n_rows : 0; }
+int qg_index_dim(const qg_index* idx) { return idx ? idx->dim : 0; }
+int qg_index_metric(const qg_index* idx) { return idx ? idx->metric : -1; }
+
+int qg_index_fetch(qg_index* idx, const int64_t* rows, int64_t n, float* out) {
+  if (int rc = check_index(idx)) return rc;
+  if (n < 0 || (n > 0 && (!rows || !out))) return fail(QG_ERR_INVALID, "fetch: null buffer or n < 0");
+  if (n == 0) return 0;
+  for (int64_t i = 0; i < n; ++i)
+    if (rows[i] < 0 || rows[i] >= idx->n_rows) return fail(QG_ERR_RANGE, "fetch: row index out of range");
+  Workspace* w = ws_acquire(idx);
+  if (!w) return fail(QG_ERR_CUDA, "could not create a stream");
+  int rc = 0;
+  do {
+    if ((rc = w->d_rows64.ensure((size_t)n * 8))) break;
+    if ((rc = w->d_fetch.ensure((size_t)n * idx->dim * 4))) break;
+    cudaError_t e = cudaMemcpyAsync(w->d_rows64.p, rows, (size_t)n * 8, cudaMemcpyHostToDevice, w->stream);
+    if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, cudaGetErrorString(e)); break; }
+    if ((rc = launch_fetch_rows(idx->vec, idx->dp, idx->dim, idx->n_rows, (const long long*)w->d_rows64.p, n,
+                                (float*)w->d_fetch.p, w->stream)))
+      break;
+    e = cudaMemcpyAsync(out, w->d_fetch.p, (size_t)n * idx->dim * 4, cudaMemcpyDeviceToHost, w->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
+    if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, cudaGetErrorString(e)); break; }
+  } while (0);
+  ws_release(idx, w);
+  return rc;
+}
+
+// ---- facet columns and filters ----------------------------------------------------------------------
+int qg_facets_set_column(qg_index* idx, int field, const uint8_t* kind, const double* num, const int32_t* scode,
+                         const int32_t* fcode, int64_t n) {
+  if (int rc = check_index(idx)) return rc;
+  if (field < 0 || field >= 4096) return fail(QG_ERR_INVALID, "field index out of range");
+  if (n < 0 || n > idx->n_rows) return fail(QG_ERR_RANGE, "column longer than the index");
+  if (n > 0 && (!kind || !num || !scode || !fcode)) return fail(QG_ERR_INVALID, "null column buffer");
+  if ((size_t)field >= idx->cols.size()) idx->cols.resize(field + 1);
+  FacetColumn& c = idx->cols[field];
+  const size_t cap = (size_t)std::max<long long>(idx->cap, 1);
+  if (int rc = c.kind.ensure(cap)) return rc;
+  if (int rc = c.num.ensure(cap * 8)) return rc;
+  if (int rc = c.scode.ensure(cap * 4)) return rc;
+  if (int rc = c.fcode.ensure(cap * 4)) return rc;
+  // rows beyond n have no metadata entry
+  QG_CUDA_OK(cudaMemsetAsync(c.kind.p, QG_KIND_NOROW, c.kind.bytes, idx->up_stream));
+  if (n > 0) {
+    QG_CUDA_OK(cudaMemcpyAsync(c.kind.p, kind, (size_t)n, cudaMemcpyHostToDevice, idx->up_stream));
+    QG_CUDA_OK(cudaMemcpyAsync(c.num.p, num, (size_t)n * 8, cudaMemcpyHostToDevice, idx->up_stream));
+    QG_CUDA_OK(cudaMemcpyAsync(c.scode.p, scode, (size_t)n * 4, cudaMemcpyHostToDevice, idx->up_stream));
+    QG_CUDA_OK(cudaMemcpyAsync(c.fcode.p, fcode, (size_t)n * 4, cudaMemcpyHostToDevice, idx->up_stream));
+  }
+  QG_CUDA_OK(cudaStreamSynchronize(idx->up_stream));
+  c.set = true;
+  c.n = n;
+  idx->facet_epoch++;
+  idx->col_table_dirty = true;
+  return 0;
+}
+
+int qg_filter_compile(qg_index* idx, const qg_pred* preds, int n_preds, const qg_clause* clauses, int n_clauses,
+                      const int32_t* iset, int n_iset, const double* fset, int n_fset, qg_filter** out) {
+  if (int rc = check_index(idx)) return rc;
+  if (!out) return fail(QG_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (n_preds < 0 || n_clauses < 0 || n_iset < 0 || n_fset < 0) return fail(QG_ERR_INVALID, "negative count");
+  if ((n_preds && !preds) || (n_clauses && !clauses) || (n_iset && !iset) || (n_fset && !fset))
+    return fail(QG_ERR_INVALID, "null program buffer");
+  for (int i = 0; i < n_preds; ++i) {
+    if (preds[i].first_clause < 0 || preds[i].n_clauses < 0 || preds[i].first_clause + preds[i].n_clauses > n_clauses)
+      return fail(QG_ERR_INVALID, "predicate clause range out of bounds");
+  }
+  for (int i = 0; i < n_clauses; ++i) {
+    const qg_clause& c = clauses[i];
+    if (c.op < QG_OP_FALSE || c.op > QG_OP_NUM_BITS_EQ) return fail(QG_ERR_UNSUPPORTED, "unknown clause op");
+    if (c.op >= QG_OP_KIND_IN) {
+      if (c.field < 0 || c.field >= 4096) return fail(QG_ERR_INVALID, "clause field out of range");
+    }
+    if (c.op == QG_OP_SCODE_IN || c.op == QG_OP_FCODE_IN) {
+      if (c.ia < 0 || c.ic < 0 || c.ia + c.ic > n_iset) return fail(QG_ERR_INVALID, "clause int-set out of bounds");
+    }
+    if (c.op == QG_OP_NUM_IN_TOL || c.op == QG_OP_NUM_IN) {
+      if (c.ia < 0 || c.ic < 0 || c.ia + c.ic > n_fset) return fail(QG_ERR_INVALID, "clause float-set out of bounds");
+    }
+  }
+  std::unique_ptr<qg_filter> f(new qg_filter());
+  f->owner = idx;
+  f->preds.assign(preds, preds + n_preds);
+  f->clauses.assign(clauses, clauses + n_clauses);
+  f->iset.assign(iset, iset + n_iset);
+  f->fset.assign(fset, fset + n_fset);
+  if (int rc = f->d_preds.ensure(std::max<size_t>(1, n_preds) * sizeof(qg_pred))) return rc;
+  if (int rc = f->d_clauses.ensure(std::max<size_t>(1, n_clauses) * sizeof(qg_clause))) return rc;
+  if (int rc = f->d_iset.ensure(std::max<size_t>(1, n_iset) * 4)) return rc;
+  if (int rc = f->d_fset.ensure(std::max<size_t>(1, n_fset) * 8)) return rc;
+  if (n_preds) QG_CUDA_OK(cudaMemcpy(f->d_preds.p, preds, n_preds * sizeof(qg_pred), cudaMemcpyHostToDevice));
+  if (n_clauses)
+    QG_CUDA_OK(cudaMemcpy(f->d_clauses.p, clauses, n_clauses * sizeof(qg_clause), cudaMemcpyHostToDevice));
+  if (n_iset) QG_CUDA_OK(cudaMemcpy(f->d_iset.p, iset, (size_t)n_iset * 4, cudaMemcpyHostToDevice));
+  if (n_fset) QG_CUDA_OK(cudaMemcpy(f->d_fset.p, fset, (size_t)n_fset * 8, cudaMemcpyHostToDevice));
+  *out = f.release();
+  return 0;
+}
+
+int qg_filter_destroy(qg_filter* f) {
+  if (!f) return 0;
+  if (f->owner) cudaSetDevice(f->owner->device);
+  f->d_preds.release(); f->d_clauses.release(); f->d_iset.release(); f->d_fset.release();
+  f->raw_mask.release(); f->comb_mask.release(); f->gather_list.release();
+  delete f;
+  return 0;
+}
+
+}  // extern "C"
+
+namespace qg {
+
+// Make every column referenced by the filter exist and cover all rows; refresh the pointer table.
+static int prepare_columns(qg_index* idx, const qg_filter* f) {
+  int max_field = -1;
+  for (const qg_clause& c : f->clauses)
+    if (c.op >= QG_OP_KIND_IN) max_field = std::max(max_field, c.field);
+  if (max_field >= (int)idx->cols.size()) {
+    idx->cols.resize(max_field + 1);
+    idx->col_table_dirty = true;
+  }
+  const size_t cap = (size_t)std::max<long long>(idx->cap, 1);
+  for (const qg_clause& c : f->clauses) {
+    if (c.op < QG_OP_KIND_IN) continue;
+    FacetColumn& col = idx->cols[c.field];
+    if (!col.set || col.kind.bytes < cap) {
+      // unknown field, or rows were appended after the column was set: those rows have no value
+      DevBuf nk, nn, ns, nf;
+      if (int rc = nk.ensure(cap)) return rc;
+      if (int rc = nn.ensure(cap * 8)) return rc;
+      if (int rc = ns.ensure(cap * 4)) return rc;
+      if (int rc = nf.ensure(cap * 4)) return rc;
+      QG_CUDA_OK(cudaMemset(nk.p, col.set ? QG_KIND_NOROW : QG_KIND_MISSING, nk.bytes));
+      QG_CUDA_OK(cudaMemset(nn.p, 0, nn.bytes));
+      QG_CUDA_OK(cudaMemset(ns.p, 0xff, ns.bytes));
+      QG_CUDA_OK(cudaMemset(nf.p, 0xff, nf.bytes));
+      if (col.set && col.n > 0) {
+        QG_CUDA_OK(cudaMemcpy(nk.p, col.kind.p, (size_t)col.n, cudaMemcpyDeviceToDevice));
+        QG_CUDA_OK(cudaMemcpy(nn.p, col.num.p, (size_t)col.n * 8, cudaMemcpyDeviceToDevice));
+        QG_CUDA_OK(cudaMemcpy(ns.p, col.scode.p, (size_t)col.n * 4, cudaMemcpyDeviceToDevice));
+        QG_CUDA_OK(cudaMemcpy(nf.p, col.fcode.p, (size_t)col.n * 4, cudaMemcpyDeviceToDevice));
+      }
+      col.kind.release(); col.num.release(); col.scode.release(); col.fcode.release();
+      col.kind = nk; col.num = nn; col.scode = ns; col.fcode = nf;
+      col.set = true;
+      idx->col_table_dirty = true;
+    }
+  }
+  if (idx->col_table_dirty) {
+    std::vector<FacetColDev> tab(std::max<size_t>(1, idx->cols.size()));
+    for (size_t i = 0; i < idx->cols.size(); ++i) {
+      tab[i].kind = (const uint8_t*)idx->cols[i].kind.p;
+      tab[i].num = (const double*)idx->cols[i].num.p;
+      tab[i].scode = (const int32_t*)idx->cols[i].scode.p;
+      tab[i].fcode = (const int32_t*)idx->cols[i].fcode.p;
+    }
+    if (int rc = idx->col_table.ensure(tab.size() * sizeof(FacetColDev))) return rc;
+    QG_CUDA_OK(cudaMemcpy(idx->col_table.p, tab.data(), tab.size() * sizeof(FacetColDev), cudaMemcpyHostToDevice));
+    idx->col_table_dirty = false;
+  }
+  return 0;
+}
+
+// Evaluate (or reuse) the raw predicate mask, then the mask combined with the live bits and, when
+// the selectivity is low, the compacted row list for the gather scan.
+static int filter_refresh(qg_index* idx, qg_filter* f, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(f->mu);
+  const long long n = idx->n_rows;
+  const size_t words = (size_t)((n + 31) / 32) + 1;
+  DevBuf cnt;
+  if (f->raw_rows != n || f->raw_facet_epoch != idx->facet_epoch) {
+    if (int rc = prepare_columns(idx, f)) return rc;
+    if (int rc = f->raw_mask.ensure(words * 4)) return rc;
+    if (int rc = cnt.ensure(8)) return rc;
+    FilterProgDev prog{(const qg_pred*)f->d_preds.p, (int)f->preds.size(), (const qg_clause*)f->d_clauses.p,
+                       (const int32_t*)f->d_iset.p, (const double*)f->d_fset.p};
+    int rc = launch_filter_eval((const FacetColDev*)idx->col_table.p, prog, n, (uint32_t*)f->raw_mask.p,
+                                (unsigned long long*)cnt.p, st);
+    unsigned long long m = 0;
+    if (!rc) {
+      cudaError_t e = cudaMemcpyAsync(&m, cnt.p, 8, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) rc = fail(QG_ERR_CUDA, cudaGetErrorString(e));
+    }
+    if (rc) {
+      cnt.release();
+      return rc;
+    }
+    f->raw_matches = (long long)m;
+    f->raw_rows = n;
+    f->raw_facet_epoch = idx->facet_epoch;
+    f->comb_live_epoch = ~0ull;
+  }
+  if (f->comb_live_epoch != idx->live_epoch) {
+    int rc = 0;
+    unsigned long long m = 0;
+    do {
+      if ((rc = f->comb_mask.ensure(words * 4))) break;
+      if ((rc = cnt.ensure(8))) break;
+      if ((rc = launch_mask_and((const uint32_t*)f->raw_mask.p, idx->live, n, (uint32_t*)f->comb_mask.p,
+                                (unsigned long long*)cnt.p, st)))
+        break;
+      cudaError_t e = cudaMemcpyAsync(&m, cnt.p, 8, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, cudaGetErrorString(e)); break; }
+      f->comb_matches = (long long)m;
+      f->gather_valid = false;
+      // gather list when at most a quarter of the rows pass: the scan then reads only those rows
+      if (f->comb_matches > 0 && f->comb_matches * 4 <= n) {
+        if ((rc = f->gather_list.ensure((size_t)f->comb_matches * 4 + 64))) break;
+        if ((rc = launch_mask_compact((const uint32_t*)f->comb_mask.p, n, (uint32_t*)f->gather_list.p,
+                                      (unsigned long long*)cnt.p, st)))
+          break;
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, cudaGetErrorString(e)); break; }
+        f->gather_valid = true;
+      }
+      f->comb_live_epoch = idx->live_epoch;
+    } while (0);
+    if (rc) {
+      cnt.release();
+      return rc;
+    }
+  }
+  cnt.release();
+  return 0;
+}
+
+__global__ void fill_empty_kernel(float* dist, float* negdist, long long* row, int* count, uint64_t* keys,
+                                  long long n, int nq) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (dist) dist[i] = __int_as_float(0x7f800000);
+    if (negdist) negdist[i] = __int_as_float(0x7f800000);
+    if (row) row[i] = -1;
+    if (keys) keys[i] = KEY_NONE;
+    if (count && i < nq) count[i] = 0;
+  }
+}
+
+struct SearchArgs {
+  const float* d_queries;  // [q x dim] contiguous, device
+  int q, k;
+  qg_filter* filter;
+  const float* d_neg;  // [q x dim] or nullptr
+  float* d_dist;
+  float* d_negdist;
+  long long* d_row;
+  int* d_count;
+  uint64_t* d_keys;  // shard mode
+  long long row_base;
+};
+
+// Enqueue the whole search on `st` using workspace `w`. Validation already done.
+static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cudaStream_t st) {
+  const int q = a.q, k = a.k, d = idx->dim, dp = idx->dp;
+  qg_scan_stats stats{};
+  const uint32_t* mask = nullptr;
+  const uint32_t* gather = nullptr;
+  long long n_pass = idx->n_live;
+  long long n_items = idx->n_rows;
+  if (a.filter) {
+    if (int rc = filter_refresh(idx, a.filter, st)) return rc;
+    mask = (const uint32_t*)a.filter->comb_mask.p;
+    n_pass = a.filter->comb_matches;
+    if (a.filter->gather_valid) {
+      gather = (const uint32_t*)a.filter->gather_list.p;
+      n_items = n_pass;
+    }
+  } else if (idx->n_live < idx->n_rows) {
+    mask = idx->live;
+  }
+
+  const long long out_n = (long long)q * k;
+  if (n_pass == 0) {
+    fill_empty_kernel<<<64, 256, 0, st>>>(a.d_dist, a.d_negdist, a.d_row, a.d_count, a.d_keys,
+                                          std::max<long long>(out_n, q), q);
+    QG_CUDA_OK(cudaGetLastError());
+    idx->stats = stats;
+    return 0;
+  }
+
+  // padded queries / negatives
+  const float* qpad = a.d_queries;
+  const float* negpad = a.d_neg;
+  if (dp != d) {
+    if (int rc = w->qpad.ensure((size_t)q * dp * 4)) return rc;
+    QG_CUDA_OK(cudaMemsetAsync(w->qpad.p, 0, (size_t)q * dp * 4, st));
+    QG_CUDA_OK(cudaMemcpy2DAsync(w->qpad.p, (size_t)dp * 4, a.d_queries, (size_t)d * 4, (size_t)d * 4, (size_t)q,
+                                 cudaMemcpyDeviceToDevice, st));
+    qpad = (const float*)w->qpad.p;
+    if (a.d_neg) {
+      if (int rc = w->negpad.ensure((size_t)q * dp * 4)) return rc;
+      QG_CUDA_OK(cudaMemsetAsync(w->negpad.p, 0, (size_t)q * dp * 4, st));
+      QG_CUDA_OK(cudaMemcpy2DAsync(w->negpad.p, (size_t)dp * 4, a.d_neg, (size_t)d * 4, (size_t)d * 4, (size_t)q,
+                                   cudaMemcpyDeviceToDevice, st));
+      negpad = (const float*)w->negpad.p;
+    }
+  }
+
+  const long long keff = std::min<long long>(k, n_pass);
+  int kp = 32;
+  while (kp < keff + idx->margin && kp < 2048) kp <<= 1;
+
+  if (kp > 1024) {
+    // exhaustive path, one query at a time (the reference's own algorithm, exact.go:114-129)
+    for (int i = 0; i < q; ++i) {
+      if (int rc = exhaustive_search(w->ex, idx->vec, idx->n_rows, dp, d, mask, qpad + (size_t)i * dp,
+                                     negpad ? negpad + (size_t)i * dp : nullptr, idx->metric, idx->arith, k,
+                                     a.d_dist ? a.d_dist + (size_t)i * k : nullptr,
+                                     a.d_negdist ? a.d_negdist + (size_t)i * k : nullptr,
+                                     a.d_row ? a.d_row + (size_t)i * k : nullptr, a.d_count ? a.d_count + i : nullptr,
+                                     a.d_keys ? a.d_keys + (size_t)i * k : nullptr, a.row_base, st))
+        return rc;
+      stats.kernel_launches += 3;
+    }
+    stats.path = 0;
+    stats.passes = q;
+    stats.queries_per_pass = 1;
+    stats.rows_scanned = idx->n_rows;
+    stats.bytes_algorithmic = n_pass * (long long)d * 4;
+    idx->stats = stats;
+    return 0;
+  }
+
+  const int mode = scan_mode_of(idx->metric);
+  const bool fast = scan_fast_supported(dp) && mode != MODE_L1;
+  int tile_rows, nw = SCAN_NW, stages = 4, max_qb;
+  if (fast) {
+    tile_rows = scan_fast_tile_rows(dp);
+    max_qb = scan_fast_max_qb(dp);
+  } else {
+    const int row_bytes = dp * 4;
+    tile_rows = std::max(1, std::min(32, 4096 / row_bytes));
+    const size_t tile_bytes = (size_t)tile_rows * row_bytes;
+    // ring budget ~160 KB: shrink stages, then warps, for very wide rows
+    while (nw > 1 && (size_t)nw * 2 * tile_bytes > 160 * 1024) nw >>= 1;
+    stages = (int)std::min<size_t>(4, (160 * 1024) / ((size_t)nw * tile_bytes));
+    if (stages < 2) return fail(QG_ERR_UNSUPPORTED, "dimension too large for the scan kernels (max 16384)");
+    max_qb = 8;
+    while (max_qb > 1 && (size_t)max_qb * dp * 4 > 32 * 1024) max_qb >>= 1;
+  }
+  // pools must fit next to the ring
+  {
+    const size_t ring = fast ? (size_t)0 : (size_t)nw * stages * tile_rows * dp * 4;
+    const size_t ring_fast = fast ? (size_t)scan_fast_ring_bytes(dp) : 0;
+    const size_t avail = 225 * 1024 - (fast ? ring_fast : ring) - (fast ? 0 : (size_t)max_qb * dp * 4);
+    while (max_qb > 1 && (size_t)max_qb * pool_slots(kp) * 8 > avail) max_qb >>= 1;
+  }
+  int qb = 1;
+  while (qb < max_qb && qb < q) qb <<= 1;
+
+  const long long n_tiles = (n_items + tile_rows - 1) / tile_rows;
+  int nb = (int)std::min<long long>(idx->sm_count, (n_tiles + nw - 1) / nw);
+  nb = std::max(nb, 1);
+
+  // finalize in chunks so the partial buffer stays bounded
+  int qchunk = std::max(qb, std::min(q, std::max(8, 16384 / kp)));
+  qchunk = (qchunk / qb) * qb;
+  if (int rc = w->partial.ensure((size_t)qchunk * nb * kp * 8)) return rc;
+
+  ScanParams sp{};
+  sp.vec = idx->vec;
+  sp.inv_norm = idx->metric == METRIC_COSINE ? idx->inv_norm : nullptr;
+  sp.mask = mask;
+  sp.gather = gather;
+  sp.n_items = n_items;
+  sp.kp = kp;
+  sp.cosine = idx->metric == METRIC_COSINE;
+  sp.dp = dp;
+  sp.tile_rows = tile_rows;
+  sp.stages = stages;
+
+  FinalizeParams fp{};
+  fp.nb = nb;
+  fp.kp = kp;
+  fp.vec = idx->vec;
+  fp.dp = dp;
+  fp.d = d;
+  fp.metric = idx->metric;
+  fp.arith = idx->arith;
+  fp.mode = mode;
+  fp.cosine = sp.cosine;
+  fp.k = k;
+  fp.gamma = (float)((d + 16) * 5.9604645e-8);
+  fp.max_norm2 = idx->max_norm2;
+  fp.row_base = a.row_base;
+
+  for (int q0 = 0; q0 < q; q0 += qchunk) {
+    const int qn = std::min(qchunk, q - q0);
+    for (int p0 = 0; p0 < qn; p0 += qb) {
+      sp.queries = qpad + (size_t)(q0 + p0) * dp;
+      sp.nq = std::min(qb, qn - p0);
+      sp.partial = (uint64_t*)w->partial.p + (size_t)p0 * nb * kp;
+      int rc = fast ? launch_scan_fast(dp, qb, mode, sp, nb, st) : launch_scan_generic(qb, mode, sp, nb, nw, st);
+      if (rc) return rc;
+      stats.kernel_launches++;
+      stats.passes++;
+    }
+    fp.partial = (const uint64_t*)w->partial.p;
+    fp.queries = qpad + (size_t)q0 * dp;
+    fp.negatives = negpad ? negpad + (size_t)q0 * dp : nullptr;
+    fp.out_dist = a.d_dist ? a.d_dist + (size_t)q0 * k : nullptr;
+    fp.out_negdist = a.d_negdist ? a.d_negdist + (size_t)q0 * k : nullptr;
+    fp.out_row = a.d_row ? a.d_row + (size_t)q0 * k : nullptr;
+    fp.out_count = a.d_count ? a.d_count + q0 : nullptr;
+    fp.out_keys = a.d_keys ? a.d_keys + (size_t)q0 * k : nullptr;
+    if (int rc = launch_finalize(fp, qn, st)) return rc;
+    stats.kernel_launches++;
+  }
+  stats.path = gather ? 2 : 1;
+  stats.queries_per_pass = qb;
+  stats.rows_scanned = n_items;
+  stats.bytes_algorithmic = n_items * (long long)d * 4 + (mask && !gather ? idx->n_rows / 8 : 0) +
+                            (sp.inv_norm ? n_items * 4 : 0) + (gather ? n_items * 4 : 0);
+  idx->stats = stats;
+  return 0;
+}
+
+// Common argument checks in the reference's order (exact.go:96-106). Returns 1 when the index is
+// empty (zero results, no error), 0 to proceed, <0 never; errors are returned via *err.
+static int validate_search(qg_index* idx, int q, int dim, int k, int* err) {
+  *err = 0;
+  if (q < 0) {
+    *err = fail(QG_ERR_INVALID, "negative query count");
+    return 0;
+  }
+  if (idx->n_live == 0) return 1;
+  if (dim != idx->dim) {
+    *err = fail(QG_ERR_DIM, "query dimension mismatch: expected " + std::to_string(idx->dim) + ", got " +
+                                std::to_string(dim));
+    return 0;
+  }
+  if (k <= 0) {
+    *err = fail(QG_ERR_K, "k must be positive");
+    return 0;
+  }
+  return 0;
+}
+
+}  // namespace qg
+
+extern "C" {
+
+int qg_filter_eval(qg_index* idx, qg_filter* f, uint64_t* mask_out, int64_t* out_matches) {
+  if (int rc = check_index(idx)) return rc;
+  if (!f || f->owner != idx) return fail(QG_ERR_INVALID, "filter does not belong to this index");
+  Workspace* w = ws_acquire(idx);
+  if (!w) return fail(QG_ERR_CUDA, "could not create a stream");
+  int rc = filter_refresh(idx, f, w->stream);
+  if (!rc && mask_out) {
+    const size_t words64 = (size_t)((idx->n_rows + 63) / 64);
+    const size_t bytes32 = (size_t)((idx->n_rows + 31) / 32) * 4;
+    std::memset(mask_out, 0, words64 * 8);
+    cudaError_t e = cudaMemcpy(mask_out, f->raw_mask.p, bytes32, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(QG_ERR_CUDA, cudaGetErrorString(e));
+  }
+  if (!rc && out_matches) *out_matches = f->raw_matches;
+  ws_release(idx, w);
+  return rc;
+}
+
+int qg_search_batch_device(qg_index* idx, const void* d_queries, int q, int dim, int k, qg_filter* filter,
+                           const void* d_negatives, void* d_out_dist, void* d_out_negdist, void* d_out_row,
+                           void* d_out_count, void* stream) {
+  if (int rc = check_index(idx)) return rc;
+  int err = 0;
+  const int empty = validate_search(idx, q, dim, k, &err);
+  if (err) return err;
+  if (q == 0) return 0;
+  if (filter && filter->owner != idx) return fail(QG_ERR_INVALID, "filter does not belong to this index");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (empty) {
+    if (k > 0) {
+      fill_empty_kernel<<<64, 256, 0, st>>>((float*)d_out_dist, (float*)d_out_negdist, (long long*)d_out_row,
+                                            (int*)d_out_count, nullptr, std::max<long long>((long long)q * k, q), q);
+    } else {
+      fill_empty_kernel<<<1, 256, 0, st>>>(nullptr, nullptr, nullptr, (int*)d_out_count, nullptr, q, q);
+    }
+    QG_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  if (!d_queries || !d_out_dist || !d_out_row || !d_out_count) return fail(QG_ERR_INVALID, "null device buffer");
+  if (d_negatives && !d_out_negdist) return fail(QG_ERR_INVALID, "negatives given without out_negdist");
+  Workspace* w = ws_acquire(idx);
+  if (!w) return fail(QG_ERR_CUDA, "could not create a stream");
+  SearchArgs a{(const float*)d_queries, q, k, filter, (const float*)d_negatives, (float*)d_out_dist,
+               d_negatives ? (float*)d_out_negdist : nullptr, (long long*)d_out_row, (int*)d_out_count, nullptr, 0};
+  const int rc = search_enqueue(idx, w, a, st);
+  ws_release_async(idx, w, st);
+  return rc;
+}
+
+int qg_search_shard_keys_device(qg_index* idx, const void* d_queries, int q, int dim, int k, qg_filter* filter,
+                                int64_t row_base, void* d_out_keys, void* stream) {
+  if (int rc = check_index(idx)) return rc;
+  if (q < 0) return fail(QG_ERR_INVALID, "negative query count");
+  if (k <= 0) return fail(QG_ERR_K, "k must be positive");
+  if (dim != idx->dim)
+    return fail(QG_ERR_DIM, "query dimension mismatch: expected " + std::to_string(idx->dim) + ", got " +
+                                std::to_string(dim));
+  if (q == 0) return 0;
+  if (!d_queries || !d_out_keys) return fail(QG_ERR_INVALID, "null device buffer");
+  if (filter && filter->owner != idx) return fail(QG_ERR_INVALID, "filter does not belong to this index");
+  if (row_base < 0 || row_base + idx->n_rows > 0xFFFFFFFFll)
+    return fail(QG_ERR_RANGE, "global rows must fit 32 bits in the packed shard keys");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (idx->n_live == 0) {
+    fill_empty_kernel<<<64, 256, 0, st>>>(nullptr, nullptr, nullptr, nullptr, (uint64_t*)d_out_keys,
+                                          (long long)q * k, q);
+    QG_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  Workspace* w = ws_acquire(idx);
+  if (!w) return fail(QG_ERR_CUDA, "could not create a stream");
+  int rc = w->d_count.ensure((size_t)q * 4);
+  if (!rc) {
+    SearchArgs a{(const float*)d_queries, q, k, filter, nullptr, nullptr, nullptr, nullptr, (int*)w->d_count.p,
+                 (uint64_t*)d_out_keys, row_base};
+    rc = search_enqueue(idx, w, a, st);
+  }
+  ws_release_async(idx, w, st);
+  return rc;
+}
+
+int qg_merge_shard_keys_device(int device, const void* d_keys_gathered, int world, int q, int k, void* d_out_dist,
+                               void* d_out_row, void* d_out_count, void* stream) {
+  if (world <= 0 || q < 0 || k <= 0) return fail(QG_ERR_INVALID, "merge: bad sizes");
+  if (!d_keys_gathered || !d_out_dist || !d_out_row || !d_out_count) return fail(QG_ERR_INVALID, "null device buffer");
+  QG_CUDA_OK(cudaSetDevice(device));
+  return launch_merge_shards((const uint64_t*)d_keys_gathered, world, q, k, (float*)d_out_dist,
+                             (long long*)d_out_row, (int*)d_out_count, (cudaStream_t)stream);
+}
+
+int qg_search_batch(qg_index* idx, const float* queries, int q, int dim, int k, qg_filter* filter,
+                    const float* negatives, float* out_dist, float* out_negdist, int64_t* out_row, int* out_count) {
+  if (int rc = check_index(idx)) return rc;
+  int err = 0;
+  const int empty = validate_search(idx, q, dim, k, &err);
+  if (err) return err;
+  if (q == 0) return 0;
+  if (!out_count) return fail(QG_ERR_INVALID, "out_count is null");
+  if (empty) {
+    for (int i = 0; i < q; ++i) out_count[i] = 0;
+    if (k > 0) {
+      for (long long i = 0; i < (long long)q * k; ++i) {
+        if (out_dist) out_dist[i] = INFINITY;
+        if (out_row) out_row[i] = -1;
+        if (out_negdist) out_negdist[i] = INFINITY;
+      }
+    }
+    return 0;
+  }
+  if (!queries || !out_dist || !out_row) return fail(QG_ERR_INVALID, "null buffer");
+  if (negatives && !out_negdist) return fail(QG_ERR_INVALID, "negatives given without out_negdist");
+  if (filter && filter->owner != idx) return fail(QG_ERR_INVALID, "filter does not belong to this index");
+  Workspace* w = ws_acquire(idx);
+  if (!w) return fail(QG_ERR_CUDA, "could not create a stream");
+  const size_t qbytes = (size_t)q * dim * 4;
+  const size_t obytes = (size_t)q * k;
+  int rc = 0;
+  do {
+    if ((rc = w->h_in.ensure(qbytes * (negatives ? 2 : 1)))) break;
+    if ((rc = w->h_out.ensure(obytes * (4 + 4 + 8) + (size_t)q * 4))) break;
+    if ((rc = w->d_q.ensure(qbytes))) break;
+    if (negatives && (rc = w->d_neg.ensure(qbytes))) break;
+    if ((rc = w->d_dist.ensure(obytes * 4))) break;
+    if ((rc = w->d_negdist.ensure(obytes * 4))) break;
+    if ((rc = w->d_row.ensure(obytes * 8))) break;
+    if ((rc = w->d_count.ensure((size_t)q * 4))) break;
+    cudaStream_t st = w->stream;
+    std::memcpy(w->h_in.p, queries, qbytes);
+    cudaError_t e = cudaMemcpyAsync(w->d_q.p, w->h_in.p, qbytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && negatives) {
+      std::memcpy((char*)w->h_in.p + qbytes, negatives, qbytes);
+      e = cudaMemcpyAsync(w->d_neg.p, (char*)w->h_in.p + qbytes, qbytes, cudaMemcpyHostToDevice, st);
+    }
+    if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, cudaGetErrorString(e)); break; }
+    SearchArgs a{(const float*)w->d_q.p, q, k, filter, negatives ? (const float*)w->d_neg.p : nullptr,
+                 (float*)w->d_dist.p, negatives ? (float*)w->d_negdist.p : nullptr, (long long*)w->d_row.p,
+                 (int*)w->d_count.p, nullptr, 0};
+    if ((rc = search_enqueue(idx, w, a, st))) break;
+    char* ho = (char*)w->h_out.p;
+    float* h_dist = (float*)ho;
+    float* h_neg = (float*)(ho + obytes * 4);
+    long long* h_row = (long long*)(ho + obytes * 8);
+    int* h_cnt = (int*)(ho + obytes * 16);
+    e = cudaMemcpyAsync(h_dist, w->d_dist.p, obytes * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && negatives) e = cudaMemcpyAsync(h_neg, w->d_negdist.p, obytes * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_row, w->d_row.p, obytes * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_cnt, w->d_count.p, (size_t)q * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, std::string("search: ") + cudaGetErrorString(e)); break; }
+    // queries the flat scan could not certify: redo with the exhaustive path
+    int escalations = 0;
+    for (int i = 0; i < q && !rc; ++i) {
+      if (h_cnt[i] >= 0) continue;
+      ++escalations;
+      const uint32_t* mask = filter ? (const uint32_t*)filter->comb_mask.p
+                                    : (idx->n_live < idx->n_rows ? idx->live : nullptr);
+      const float* qpad = (const float*)w->d_q.p;
+      const float* npad = negatives ? (const float*)w->d_neg.p : nullptr;
+      if (idx->dp != idx->dim) {
+        qpad = (const float*)w->qpad.p;
+        npad = negatives ? (const float*)w->negpad.p : nullptr;
+      }
+      rc = exhaustive_search(w->ex, idx->vec, idx->n_rows, idx->dp, idx->dim, mask, qpad + (size_t)i * idx->dp,
+                             npad ? npad + (size_t)i * idx->dp : nullptr, idx->metric, idx->arith, k,
+                             (float*)w->d_dist.p + (size_t)i * k,
+                             negatives ? (float*)w->d_negdist.p + (size_t)i * k : nullptr,
+                             (long long*)w->d_row.p + (size_t)i * k, (int*)w->d_count.p + i, nullptr, 0, st);
+      if (rc) break;
+      e = cudaMemcpyAsync(h_dist + (size_t)i * k, (float*)w->d_dist.p + (size_t)i * k, (size_t)k * 4,
+                          cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess && negatives)
+        e = cudaMemcpyAsync(h_neg + (size_t)i * k, (float*)w->d_negdist.p + (size_t)i * k, (size_t)k * 4,
+                            cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(h_row + (size_t)i * k, (long long*)w->d_row.p + (size_t)i * k, (size_t)k * 8,
+                            cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(h_cnt + i, (int*)w->d_count.p + i, 4, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) rc = fail(QG_ERR_CUDA, std::string("exhaustive search: ") + cudaGetErrorString(e));
+    }
+    if (rc) break;
+    idx->stats.escalations = escalations;
+    std::memcpy(out_dist, h_dist, obytes * 4);
+    if (negatives) std::memcpy(out_negdist, h_neg, obytes * 4);
+    std::memcpy(out_row, h_row, obytes * 8);
+    std::memcpy(out_count, h_cnt, (size_t)q * 4);
+  } while (0);
+  ws_release(idx, w);
+  return rc;
+}
+
+int qg_batch_distance_multi(qg_index* idx, const float* queries, int b, int dim, const uint32_t* rows, int m,
+                            float* out) {
+  if (int rc = check_index(idx)) return rc;
+  if (b < 0 || m < 0) return fail(QG_ERR_INVALID, "negative batch size");
+  if (dim != idx->dim)
+    return fail(QG_ERR_DIM, "query dimension mismatch: expected " + std::to_string(idx->dim) + ", got " +
+                                std::to_string(dim));
+  if (b == 0 || m == 0) return 0;
+  if (!queries || !rows || !out) return fail(QG_ERR_INVALID, "null buffer");
+  Workspace* w = ws_acquire(idx);
+  if (!w) return fail(QG_ERR_CUDA, "could not create a stream");
+  const size_t qbytes = (size_t)b * dim * 4, rbytes = (size_t)b * m * 4;
+  int rc = 0;
+  do {
+    if ((rc = w->h_in.ensure(qbytes + rbytes))) break;
+    if ((rc = w->h_out.ensure(rbytes))) break;
+    if ((rc = w->d_q.ensure(qbytes))) break;
+    if ((rc = w->d_rows32.ensure(rbytes))) break;
+    if ((rc = w->d_dist.ensure(rbytes))) break;
+    cudaStream_t st = w->stream;
+    std::memcpy(w->h_in.p, queries, qbytes);
+    std::memcpy((char*)w->h_in.p + qbytes, rows, rbytes);
+    cudaError_t e = cudaMemcpyAsync(w->d_q.p, w->h_in.p, qbytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(w->d_rows32.p, (char*)w->h_in.p + qbytes, rbytes, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, cudaGetErrorString(e)); break; }
+    // unpadded queries are fine here: the pair kernel reads only the first `dim` elements
+    if ((rc = launch_batch_distance(idx->vec, idx->dp, idx->dim, idx->n_rows, idx->metric, idx->arith,
+                                    (const float*)w->d_q.p, dim, b, (const uint32_t*)w->d_rows32.p, m,
+                                    (float*)w->d_dist.p, st)))
+      break;
+    e = cudaMemcpyAsync(w->h_out.p, w->d_dist.p, rbytes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, cudaGetErrorString(e)); break; }
+    std::memcpy(out, w->h_out.p, rbytes);
+  } while (0);
+  ws_release(idx, w);
+  return rc;
+}
+
+int qg_batch_distance(qg_index* idx, const float* query, int dim, const uint32_t* rows, int n, float* out) {
+  return qg_batch_distance_multi(idx, query, 1, dim, rows, n, out);
+}
+
+int qg_last_scan_stats(const qg_index* idx, qg_scan_stats* out) {
+  if (!idx || !out) return fail(QG_ERR_INVALID, "null argument");
+  *out = idx->stats;
+  return 0;
+}
+
+}  // extern "C"

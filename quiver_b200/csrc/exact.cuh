@@ -1,0 +1,132 @@
+// exact.cuh — warp-cooperative distance in the REFERENCE's arithmetic and operation order.
+//
+// The distances Quiver returns are float64-accumulated sums rounded once to float32
+// (reference pkg/vectortypes/distances.go:12-104) or, after a reload, sequential float32
+// sums (pkg/hnsw/adapter.go:105-167). Floating-point addition is not associative, so to
+// return the SAME float32 a candidate's terms are produced in parallel (each term is exact:
+// the product of two float32 values fits a float64 mantissa, so an FMA contraction cannot
+// change it) and then summed by ONE lane in index order, like the Go loop. Only the
+// handful of candidates that survive the fp32 scan pay this.
+#pragma once
+#include "common.cuh"
+
+namespace qg {
+
+enum { METRIC_COSINE = 0, METRIC_L2 = 1, METRIC_DOT = 2, METRIC_SQL2 = 3, METRIC_L1 = 4 };
+enum { ARITH_VECTORTYPES = 0, ARITH_HNSW_F32 = 1 };
+
+constexpr int EXACT_CHUNK = 128;                                     // elements per staging chunk
+constexpr int EXACT_SCRATCH_BYTES = 3 * EXACT_CHUNK * sizeof(double);  // per warp
+
+// All 32 lanes of a warp call this with the same arguments; the result is returned on every
+// lane. `a` is the first argument of the reference's distFunc (the query), `b` the stored row.
+// `scratch` is EXACT_SCRATCH_BYTES of shared memory private to the warp.
+__device__ __forceinline__ float exact_distance_warp(int metric, int arith, const float* __restrict__ a,
+                                                     const float* __restrict__ b, int d, double* scratch) {
+  const int lane = threadIdx.x & 31;
+  if (arith == ARITH_HNSW_F32 && (metric == METRIC_COSINE || metric == METRIC_L2 || metric == METRIC_DOT)) {
+    // pkg/hnsw/adapter.go:105-167 — everything float32, sequential, no fused multiply-add.
+    float* t0 = reinterpret_cast<float*>(scratch);
+    float* t1 = t0 + EXACT_CHUNK;
+    float* t2 = t1 + EXACT_CHUNK;
+    float s = 0.f;  // lane 0: dot or sum; lane 1: normA; lane 2: normB
+    for (int base = 0; base < d; base += EXACT_CHUNK) {
+      const int n = min(EXACT_CHUNK, d - base);
+      for (int i = lane; i < n; i += 32) {
+        const float x = a[base + i], y = b[base + i];
+        if (metric == METRIC_L2) {
+          const float df = __fsub_rn(x, y);
+          t0[i] = __fmul_rn(df, df);
+        } else {
+          t0[i] = __fmul_rn(x, y);
+          if (metric == METRIC_COSINE) {
+            t1[i] = __fmul_rn(x, x);
+            t2[i] = __fmul_rn(y, y);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane < 3) {
+        const float* t = lane == 0 ? t0 : (lane == 1 ? t1 : t2);
+        if (lane == 0 || metric == METRIC_COSINE) {
+          for (int i = 0; i < n; ++i) s = __fadd_rn(s, t[i]);
+        }
+      }
+      __syncwarp();
+    }
+    const float s0 = __shfl_sync(0xffffffffu, s, 0);
+    const float s1 = __shfl_sync(0xffffffffu, s, 1);
+    const float s2 = __shfl_sync(0xffffffffu, s, 2);
+    if (metric == METRIC_L2) return (float)sqrt((double)s0);  // adapter.go:150
+    if (metric == METRIC_DOT) return __fsub_rn(1.0f, s0);      // adapter.go:165
+    if (s1 == 0.f || s2 == 0.f) return 1.0f;                   // adapter.go:121-123
+    const float sa = (float)sqrt((double)s1), sb = (float)sqrt((double)s2);
+    float sim = __fdiv_rn(s0, __fmul_rn(sa, sb));              // adapter.go:127
+    if (sim > 1.0f) sim = 1.0f;
+    else if (sim < -1.0f) sim = -1.0f;
+    return __fsub_rn(1.0f, sim);
+  }
+
+  if (metric == METRIC_SQL2) {
+    // distances.go:60-72 — float32 subtraction, float32 square, sequential float32 sum.
+    float* t0 = reinterpret_cast<float*>(scratch);
+    float s = 0.f;
+    for (int base = 0; base < d; base += EXACT_CHUNK) {
+      const int n = min(EXACT_CHUNK, d - base);
+      for (int i = lane; i < n; i += 32) {
+        const float df = __fsub_rn(a[base + i], b[base + i]);
+        t0[i] = __fmul_rn(df, df);
+      }
+      __syncwarp();
+      if (lane == 0)
+        for (int i = 0; i < n; ++i) s = __fadd_rn(s, t0[i]);
+      __syncwarp();
+    }
+    return __shfl_sync(0xffffffffu, s, 0);
+  }
+
+  // float64 accumulators (distances.go:17-22, 48-52, 82-85, 99-101).
+  double* t0 = scratch;
+  double* t1 = t0 + EXACT_CHUNK;
+  double* t2 = t1 + EXACT_CHUNK;
+  double s = 0.0;  // lane 0: dot / sum; lane 1: magnitudeA; lane 2: magnitudeB
+  for (int base = 0; base < d; base += EXACT_CHUNK) {
+    const int n = min(EXACT_CHUNK, d - base);
+    for (int i = lane; i < n; i += 32) {
+      const float x = a[base + i], y = b[base + i];
+      if (metric == METRIC_L2) {
+        const double df = (double)__fsub_rn(x, y);  // float32 subtraction first, distances.go:50
+        t0[i] = df * df;
+      } else if (metric == METRIC_L1) {
+        t0[i] = fabs((double)__fsub_rn(x, y));  // distances.go:100
+      } else {
+        t0[i] = (double)x * (double)y;
+        if (metric == METRIC_COSINE) {
+          t1[i] = (double)x * (double)x;
+          t2[i] = (double)y * (double)y;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane < 3) {
+      const double* t = lane == 0 ? t0 : (lane == 1 ? t1 : t2);
+      if (lane == 0 || metric == METRIC_COSINE) {
+        for (int i = 0; i < n; ++i) s = __dadd_rn(s, t[i]);
+      }
+    }
+    __syncwarp();
+  }
+  const double s0 = __shfl_sync(0xffffffffu, s, 0);
+  const double s1 = __shfl_sync(0xffffffffu, s, 1);
+  const double s2 = __shfl_sync(0xffffffffu, s, 2);
+  if (metric == METRIC_L2) return (float)sqrt(s0);            // distances.go:54
+  if (metric == METRIC_L1) return (float)s0;                  // distances.go:103
+  if (metric == METRIC_DOT) return (float)(1.0 - s0);         // distances.go:89
+  if (s1 == 0.0 || s2 == 0.0) return 1.0f;                    // distances.go:25-27
+  double sim = s0 / (sqrt(s1) * sqrt(s2));                    // distances.go:30
+  if (sim > 1.0) sim = 1.0;
+  else if (sim < -1.0) sim = -1.0;
+  return (float)(1.0 - sim);                                  // distances.go:39
+}
+
+}  // namespace qg

@@ -1,0 +1,2 @@
+#include "scan_fast_inst.cuh"
+QG_DEFINE_SCAN_FAST(1536)
