@@ -18,7 +18,11 @@ CU_HDRS   := $(wildcard $(CSRC)/*.cuh) include/quiver_gpu.h
 HOST_SRCS := $(wildcard quiver_b200/host/*.cpp)
 HOST_HDRS := $(wildcard quiver_b200/host/*.hpp) include/quiver_gpu.h include/quiver_host.h
 
+ifeq ($(strip $(HOST_SRCS)),)
+all: lib oracle
+else
 all: lib host oracle
+endif
 
 lib: $(LIBDIR)/libquivergpu.so
 host: $(LIBDIR)/libquiverhost.so
