@@ -1,0 +1,383 @@
+#!/usr/bin/env python3
+"""bench.py — exact k-NN QPS on the reference's headline configuration, through the C ABI.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--queries Q] [--k 10]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...        # the reference algorithm on the host cores
+
+Workload (BASELINE.json configs[1]): flat L2 exact search, 1M x 128 fp32 SIFT-shaped synthetic
+corpus (oracle/synth.h kind 1, seed 42), k = 10, one step = one batch of Q queries.
+  value   queries/s with the query batch already resident in HBM (device API, CUDA events)
+  e2e     queries/s through qg_search_batch with HOST buffers (pinned staging, H2D + D2H inside)
+  N > 1   the corpus is row-sharded across the ranks (contiguous blocks), every rank scans its
+          shard for the replicated query batch, the per-shard top-k keys are exchanged with one
+          NCCL all-gather and merged on every rank (strong scaling: the corpus is fixed).
+The oracle (oracle/) is used only as the checker and for the cpu_baseline / --impl reference legs.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "exact k-NN QPS (k=10, 1M x 128 L2)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--rows", type=int, default=1_000_000)
+    ap.add_argument("--dim", type=int, default=128)
+    ap.add_argument("--queries", type=int, default=1, help="queries per step (batch)")
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--metric", default="l2", choices=["l2", "cosine", "dot"])
+    ap.add_argument("--kind", type=int, default=1, help="synthetic kind (oracle/synth.h)")
+    ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-check", action="store_true")
+    return ap.parse_args()
+
+
+METRIC_ID = {"cosine": 0, "l2": 1, "dot": 2}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def make_queries(oracle, args, nq):
+    # queries come from the same generator, a different seed (query seed 9999)
+    return oracle.synth(args.kind, 9999, 0, nq, args.dim, threads=min(8, host_cores()))
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_qps(oracle, args, corpus, steps, warmup, budget_s):
+    """The reference algorithm (oracle port of exact.go:92-133 under BatchSearch's goroutine-per-query
+    model, hybrid_index.go:703-795) on all host cores. One step = one batch of `cores` queries."""
+    cores = host_cores()
+    mid = METRIC_ID[args.metric]
+    q1 = make_queries(oracle, args, 1)
+    t0 = time.perf_counter()
+    oracle.exact_search_batch(corpus, q1, args.k, mid, threads=1)
+    t_single = time.perf_counter() - t0
+    per_step = cores
+    total_steps = steps + warmup
+    # bound the whole run: CPU work ~= budget_s
+    max_q = max(1, int(budget_s / max(t_single, 1e-6)))
+    if per_step * total_steps > max_q:
+        per_step = max(1, max_q // total_steps)
+    threads = min(cores, per_step)
+    qs = make_queries(oracle, args, per_step)
+    for _ in range(warmup):
+        oracle.exact_search_batch(corpus, qs, args.k, mid, threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle.exact_search_batch(corpus, qs, args.k, mid, threads=threads)
+    dt = time.perf_counter() - t0
+    qps = per_step * steps / dt
+    return {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
+            "sample": f"{steps} steps x {per_step} queries over the full {args.rows}x{args.dim} corpus, "
+                      f"one query per thread on {threads} of {cores} host cores (full scan + full sort per query, "
+                      f"exact.go:114-129); single query {t_single*1e3:.1f} ms"}, dt / steps * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    corpus = oracle.synth(args.kind, args.seed, 0, args.rows, args.dim, threads=min(16, host_cores()))
+    steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
+    base, ms = cpu_reference_qps(oracle, args, corpus, steps, warmup, budget_s=60.0)
+    line = {"metric": METRIC, "value": base["value"], "unit": "queries/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"flat {args.metric} exact search {args.rows}x{args.dim} fp32, k={args.k}, "
+                                   "reference algorithm (C restatement of the Go path; no Go toolchain in the image)",
+                       "rows": args.rows, "dim": args.dim, "k": args.k},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_native(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from quiver_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != max(1, args.gpus) and world > 1:
+        args.gpus = world
+    capi.load()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import oracle  # checker + cpu_baseline only
+    oracle.build()
+
+    mid = METRIC_ID[args.metric]
+    Q, k, d = args.queries, args.k, args.dim
+    # row shard of this rank (contiguous block)
+    per = (args.rows + world - 1) // world
+    row0 = min(args.rows, rank * per)
+    nloc = max(0, min(args.rows, row0 + per) - row0)
+    idx = capi.Index(d, mid, device=local_rank, reserve_rows=max(nloc, 1))
+    idx.upload_synthetic(args.kind, args.seed, row0, nloc)
+
+    q_host = make_queries(oracle, args, Q)
+    q_pin = torch.from_numpy(q_host).pin_memory()
+    dq = q_pin.to(dev)
+    st = torch.cuda.current_stream().cuda_stream
+    d_dist = torch.empty((Q, k), dtype=torch.float32, device=dev)
+    d_row = torch.empty((Q, k), dtype=torch.int64, device=dev)
+    d_cnt = torch.empty((Q,), dtype=torch.int32, device=dev)
+    if world > 1:
+        d_keys = torch.empty((Q, k), dtype=torch.int64, device=dev)  # packed u64 keys
+        d_all = torch.empty((world, Q, k), dtype=torch.int64, device=dev)
+
+    def step_device():
+        if world == 1:
+            idx.search_device(dq.data_ptr(), Q, k, d_dist.data_ptr(), d_row.data_ptr(), d_cnt.data_ptr(), stream=st)
+        else:
+            idx.search_shard_keys_device(dq.data_ptr(), Q, k, row0, d_keys.data_ptr(), stream=st)
+            dist.all_gather_into_tensor(d_all, d_keys)
+            capi.merge_shard_keys_device(local_rank, d_all.data_ptr(), world, Q, k, d_dist.data_ptr(),
+                                         d_row.data_ptr(), d_cnt.data_ptr(), stream=st)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- parity gate before any timing is reported ------------------------------------------------
+    step_device()
+    torch.cuda.synchronize()
+    checked = None
+    host_corpus = None
+    if not args.no_check and rank == 0:
+        nchk = min(Q, 2)
+        # full oracle check when the corpus fits comfortably in host memory, else a 200k-row prefix
+        sub_rows = args.rows if args.rows * d <= 300_000_000 else 200_000
+        if sub_rows == args.rows:
+            corpus_chk = oracle.synth(args.kind, args.seed, 0, sub_rows, d, threads=min(16, host_cores()))
+            host_corpus = corpus_chk
+            got_d, got_r = d_dist.cpu().numpy(), d_row.cpu().numpy()
+            for i in range(nchk):
+                od, orow = oracle.exact_search(corpus_chk, q_host[i], k, mid)
+                assert np.array_equal(got_r[i, :len(orow)], orow), (i, got_r[i], orow)
+                assert np.array_equal(got_d[i, :len(od)].view(np.uint32), od.view(np.uint32))
+            checked = f"{nchk} queries bit-identical to the oracle over all {sub_rows} rows"
+        else:
+            # full-size property: distances of the returned rows equal the oracle's pairwise arithmetic,
+            # ascending, and no row of a 200k-row prefix beats the k-th result
+            corpus_chk = oracle.synth(args.kind, args.seed, 0, sub_rows, d, threads=min(16, host_cores()))
+            got_d, got_r = d_dist.cpu().numpy(), d_row.cpu().numpy()
+            for i in range(nchk):
+                rows_i = got_r[i]
+                vecs = np.stack([oracle.synth(args.kind, args.seed, int(r), 1, d, threads=1)[0] for r in rows_i])
+                want = np.array([oracle.distance(mid, q_host[i], v) for v in vecs], dtype=np.float32)
+                assert np.array_equal(want.view(np.uint32), got_d[i].view(np.uint32)), (want, got_d[i])
+                assert np.all(np.diff(got_d[i]) >= 0)
+                od, orow = oracle.exact_search(corpus_chk, q_host[i], k, mid)
+                inside = rows_i < sub_rows
+                assert od[0] >= got_d[i][0] and set(orow[od < got_d[i][-1]]).issubset(set(rows_i[inside]))
+            checked = (f"{nchk} queries: returned distances bit-identical to the oracle's pairwise arithmetic, "
+                       f"ascending, and consistent with the oracle's exact top-{k} over a {sub_rows}-row prefix")
+
+    # ---- value: device-resident, CUDA events on the launching stream ----------------------------------
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    barrier()
+    idx.read_profile()
+    idx.set_profiling(True)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    idx.set_profiling(False)
+    prof = idx.read_profile()
+    stats = idx.stats()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    qps = Q / (ms_step * 1e-3)
+
+    # ---- e2e: host buffers through the C ABI call a Go caller would make ----------------------------------
+    e2e_steps = max(10, min(args.steps, 100))
+    if world == 1:
+        def step_e2e():
+            return idx.search(q_host, k)
+    else:
+        h_keys = torch.empty((Q, k), dtype=torch.int64).pin_memory()
+
+        def step_e2e():
+            dq.copy_(q_pin, non_blocking=True)
+            step_device()
+            out = (d_dist.cpu(), d_row.cpu(), d_cnt.cpu())
+            return out
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_qps = Q * e2e_steps / float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the scan), timed live by events inside the timed region ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    scan_launch_ms = prof["scan_ms"] / max(1, prof["scan_launches"])
+    bytes_per_launch = stats["bytes_algorithmic"]  # rows_scanned*dim*4 (+ side columns read); one corpus pass
+    achieved = bytes_per_launch / (scan_launch_ms * 1e-3) / 1e9 if scan_launch_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "scan_fast_kernel", "launch_ms": scan_launch_ms,
+                "bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
+                "frac_of_nominal_8TBs": achieved / 8000.0,
+                "scan_share_of_step": prof["scan_ms"] / (ms_step * args.steps) if ms_step > 0 else None,
+                "finalize_launch_ms": prof["finalize_ms"] / max(1, prof["finalize_launches"])}
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        roofline["traffic"] = tr.get("scan_fast_kernel_bytes_per_launch")
+    except Exception:
+        pass
+
+    cpu_base = None
+    if not args.no_cpu_baseline:
+        corpus = host_corpus if host_corpus is not None else \
+            oracle.synth(args.kind, args.seed, 0, args.rows, d, threads=min(16, host_cores()))
+        cpu_base, _ = cpu_reference_qps(oracle, args, corpus, steps=2, warmup=1, budget_s=args.cpu_seconds)
+
+    launches_per_step = stats["kernel_launches"] + (1 if world > 1 else 0)
+    line = {
+        "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32 scan + f64 re-rank", "data": "synthetic",
+        "config": {"workload": f"flat {args.metric} exact search {args.rows}x{d} fp32 (SIFT-shaped synthetic, "
+                               f"oracle/synth.h kind {args.kind} seed {args.seed}), query batch {Q}, k={k}",
+                   "rows": args.rows, "dim": d, "k": k, "queries_per_step": Q,
+                   "parallelism": "single GPU" if world == 1 else f"row-sharded x{world}, NCCL all-gather of per-shard top-k",
+                   "l2_policy": f"inputs larger than L2: every step streams the {args.rows*d*4/1e6:.0f} MB corpus "
+                                f"({nloc*d*4/1e6:.0f} MB per GPU)",
+                   "parity_check": checked},
+        "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": Q * d * 4,
+                "d2h_bytes_per_step": Q * k * 12 + Q * 4, "steps": e2e_steps,
+                "api": "qg_search_batch (host buffers, pinned staging)" if world == 1 else
+                       "pinned H2D + shard search + all-gather + merge + D2H"},
+        "gpu_launches": launches_per_step * args.steps,
+        "kernels_per_step": {"scan": stats["passes"], "finalize": stats["kernel_launches"] - stats["passes"],
+                             "merge": 1 if world > 1 else 0},
+        "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_base,
+        "host_cores": host_cores(), "device": capi.device_info(local_rank)["name"],
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -237,6 +237,18 @@ typedef struct qg_scan_stats {
 } qg_scan_stats;
 int qg_last_scan_stats(const qg_index* idx, qg_scan_stats* out);
 
+/* Per-kernel device time, for roofline reporting: while profiling is on, every scan / merge
+ * launch of qg_search_*_device is bracketed by CUDA events on the caller's stream.
+ * qg_index_read_profile waits for the recorded events, returns the sums and clears them. */
+typedef struct qg_profile {
+  double scan_ms;            /* sum over scan-kernel launches                       */
+  double finalize_ms;        /* sum over merge / re-rank launches                   */
+  int64_t scan_launches;
+  int64_t finalize_launches;
+} qg_profile;
+int qg_index_set_profiling(qg_index* idx, int on);
+int qg_index_read_profile(qg_index* idx, qg_profile* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,11 @@ class qg_scan_stats(C.Structure):
                 ("path", C.c_int32), ("reserved", C.c_int32)]
 
 
+class qg_profile(C.Structure):
+    _fields_ = [("scan_ms", C.c_double), ("finalize_ms", C.c_double), ("scan_launches", C.c_int64),
+                ("finalize_launches", C.c_int64)]
+
+
 # every symbol include/quiver_gpu.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = [
     "qg_abi_version", "qg_last_error", "qg_device_count", "qg_device_info", "qg_index_create",
@@ -57,7 +62,8 @@ EXPORTED_SYMBOLS = [
     "qg_index_tombstone", "qg_index_size", "qg_index_rows", "qg_index_dim", "qg_index_metric",
     "qg_index_fetch", "qg_facets_set_column", "qg_filter_compile", "qg_filter_eval", "qg_filter_destroy",
     "qg_search_batch", "qg_search_batch_device", "qg_search_shard_keys_device", "qg_merge_shard_keys_device",
-    "qg_batch_distance", "qg_batch_distance_multi", "qg_last_scan_stats",
+    "qg_batch_distance", "qg_batch_distance_multi", "qg_last_scan_stats", "qg_index_set_profiling",
+    "qg_index_read_profile",
 ]
 
 _lib = None
@@ -100,6 +106,8 @@ def load() -> C.CDLL:
     lib.qg_batch_distance.argtypes = [vp, vp, i32, vp, i32, vp]
     lib.qg_batch_distance_multi.argtypes = [vp, vp, i32, i32, vp, i32, vp]
     lib.qg_last_scan_stats.argtypes = [vp, C.POINTER(qg_scan_stats)]
+    lib.qg_index_set_profiling.argtypes = [vp, i32]
+    lib.qg_index_read_profile.argtypes = [vp, C.POINTER(qg_profile)]
     _lib = lib
     return lib
 
@@ -279,6 +287,14 @@ class Index:
         _check(self._lib.qg_batch_distance_multi(self.handle, _ptr(queries), queries.shape[0], queries.shape[1],
                                                  _ptr(rows), rows.shape[1], _ptr(out)))
         return out
+
+    def set_profiling(self, on: bool) -> None:
+        _check(self._lib.qg_index_set_profiling(self.handle, 1 if on else 0))
+
+    def read_profile(self) -> dict:
+        pr = qg_profile()
+        _check(self._lib.qg_index_read_profile(self.handle, C.byref(pr)))
+        return {f: getattr(pr, f) for f, _ in pr._fields_}
 
     def stats(self) -> dict:
         s = qg_scan_stats()

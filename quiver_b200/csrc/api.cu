@@ -110,6 +110,27 @@ struct Workspace {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;  // recorded when an async (device-API) call finished using this workspace
   bool busy_async = false;
+  cudaStream_t last_stream = nullptr;  // caller stream of the async call that parked this workspace
+  // profiling: event pairs (begin, end); kind 0 = scan, 1 = finalize
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<int> prof_kind;
+  size_t prof_used = 0;  // events in use (2 per bracket)
+  int prof_begin(int kind, cudaStream_t st) {
+    if (prof_used + 2 > prof_ev.size()) {
+      cudaEvent_t a = nullptr, b = nullptr;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return -1;
+      prof_ev.push_back(a);
+      prof_ev.push_back(b);
+      prof_kind.push_back(kind);
+    }
+    prof_kind[prof_used / 2] = kind;
+    cudaEventRecord(prof_ev[prof_used], st);
+    return 0;
+  }
+  void prof_end(cudaStream_t st) {
+    cudaEventRecord(prof_ev[prof_used + 1], st);
+    prof_used += 2;
+  }
   DevBuf qpad, negpad, partial, mask, counters;
   DevBuf d_q, d_neg, d_dist, d_negdist, d_row, d_count, d_rows32, d_rows64, d_fetch;
   PinBuf h_in, h_out;
@@ -120,6 +141,8 @@ struct Workspace {
     d_rows32.release(); d_rows64.release(); d_fetch.release();
     h_in.release(); h_out.release();
     exhaustive_free(ex);
+    for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
+    prof_ev.clear();
     if (done) cudaEventDestroy(done);
     if (stream) cudaStreamDestroy(stream);
   }
@@ -176,6 +199,7 @@ struct qg_index {
   cudaStream_t up_stream = nullptr;
   cudaEvent_t stage_ev[2] = {nullptr, nullptr};
   qg_scan_stats stats{};
+  bool profiling = false;
 };
 
 namespace qg {
@@ -189,8 +213,20 @@ static int scan_mode_of(int metric) {
   }
 }
 
-static Workspace* ws_acquire(qg_index* idx) {
+// `st_hint`: a workspace parked by an earlier async call on the SAME stream can be reused at once —
+// the new work is ordered behind the old one on that stream.
+static Workspace* ws_acquire(qg_index* idx, cudaStream_t st_hint = nullptr, bool have_hint = false) {
   std::lock_guard<std::mutex> lk(idx->ws_mu);
+  if (have_hint) {
+    for (size_t i = 0; i < idx->ws_async.size(); ++i) {
+      if (idx->ws_async[i]->last_stream == st_hint) {
+        Workspace* w = idx->ws_async[i].release();
+        idx->ws_async.erase(idx->ws_async.begin() + i);
+        w->busy_async = false;
+        return w;
+      }
+    }
+  }
   // recycle async workspaces whose work has completed
   for (size_t i = 0; i < idx->ws_async.size();) {
     if (cudaEventQuery(idx->ws_async[i]->done) == cudaSuccess) {
@@ -224,6 +260,7 @@ static void ws_release(qg_index* idx, Workspace* w) {
 static void ws_release_async(qg_index* idx, Workspace* w, cudaStream_t st) {
   cudaEventRecord(w->done, st);
   w->busy_async = true;
+  w->last_stream = st;
   std::lock_guard<std::mutex> lk(idx->ws_mu);
   idx->ws_async.emplace_back(w);
 }
@@ -881,7 +918,9 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
       sp.queries = qpad + (size_t)(q0 + p0) * dp;
       sp.nq = std::min(qb, qn - p0);
       sp.partial = (uint64_t*)w->partial.p + (size_t)p0 * nb * kp;
+      const bool prof = idx->profiling && w->prof_begin(0, st) == 0;
       int rc = fast ? launch_scan_fast(dp, qb, mode, sp, nb, st) : launch_scan_generic(qb, mode, sp, nb, nw, st);
+      if (prof) w->prof_end(st);
       if (rc) return rc;
       stats.kernel_launches++;
       stats.passes++;
@@ -894,7 +933,10 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
     fp.out_row = a.d_row ? a.d_row + (size_t)q0 * k : nullptr;
     fp.out_count = a.d_count ? a.d_count + q0 : nullptr;
     fp.out_keys = a.d_keys ? a.d_keys + (size_t)q0 * k : nullptr;
-    if (int rc = launch_finalize(fp, qn, st)) return rc;
+    const bool prof = idx->profiling && w->prof_begin(1, st) == 0;
+    const int frc = launch_finalize(fp, qn, st);
+    if (prof) w->prof_end(st);
+    if (frc) return frc;
     stats.kernel_launches++;
   }
   stats.path = gather ? 2 : 1;
@@ -971,7 +1013,7 @@ int qg_search_batch_device(qg_index* idx, const void* d_queries, int q, int dim,
   }
   if (!d_queries || !d_out_dist || !d_out_row || !d_out_count) return fail(QG_ERR_INVALID, "null device buffer");
   if (d_negatives && !d_out_negdist) return fail(QG_ERR_INVALID, "negatives given without out_negdist");
-  Workspace* w = ws_acquire(idx);
+  Workspace* w = ws_acquire(idx, st, true);
   if (!w) return fail(QG_ERR_CUDA, "could not create a stream");
   SearchArgs a{(const float*)d_queries, q, k, filter, (const float*)d_negatives, (float*)d_out_dist,
                d_negatives ? (float*)d_out_negdist : nullptr, (long long*)d_out_row, (int*)d_out_count, nullptr, 0};
@@ -1000,7 +1042,7 @@ int qg_search_shard_keys_device(qg_index* idx, const void* d_queries, int q, int
     QG_CUDA_OK(cudaGetLastError());
     return 0;
   }
-  Workspace* w = ws_acquire(idx);
+  Workspace* w = ws_acquire(idx, st, true);
   if (!w) return fail(QG_ERR_CUDA, "could not create a stream");
   int rc = w->d_count.ensure((size_t)q * 4);
   if (!rc) {
@@ -1164,6 +1206,40 @@ int qg_batch_distance_multi(qg_index* idx, const float* queries, int b, int dim,
 
 int qg_batch_distance(qg_index* idx, const float* query, int dim, const uint32_t* rows, int n, float* out) {
   return qg_batch_distance_multi(idx, query, 1, dim, rows, n, out);
+}
+
+int qg_index_set_profiling(qg_index* idx, int on) {
+  if (!idx) return fail(QG_ERR_INVALID, "index handle is null");
+  idx->profiling = on != 0;
+  return 0;
+}
+
+int qg_index_read_profile(qg_index* idx, qg_profile* out) {
+  if (int rc = check_index(idx)) return rc;
+  if (!out) return fail(QG_ERR_INVALID, "out is null");
+  *out = qg_profile{};
+  std::lock_guard<std::mutex> lk(idx->ws_mu);
+  auto drain = [&](Workspace* w) -> int {
+    for (size_t i = 0; i + 1 < w->prof_used; i += 2) {
+      float ms = 0.f;
+      QG_CUDA_OK(cudaEventSynchronize(w->prof_ev[i + 1]));
+      QG_CUDA_OK(cudaEventElapsedTime(&ms, w->prof_ev[i], w->prof_ev[i + 1]));
+      if (w->prof_kind[i / 2] == 0) {
+        out->scan_ms += ms;
+        out->scan_launches++;
+      } else {
+        out->finalize_ms += ms;
+        out->finalize_launches++;
+      }
+    }
+    w->prof_used = 0;
+    return 0;
+  };
+  for (auto& w : idx->ws_free)
+    if (int rc = drain(w.get())) return rc;
+  for (auto& w : idx->ws_async)
+    if (int rc = drain(w.get())) return rc;
+  return 0;
 }
 
 int qg_last_scan_stats(const qg_index* idx, qg_scan_stats* out) {

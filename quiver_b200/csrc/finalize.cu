@@ -17,12 +17,13 @@
 
 namespace qg {
 
-constexpr int FIN_THREADS = 256;
+constexpr int FIN_THREADS = 1024;
 constexpr int FIN_WARPS = FIN_THREADS / 32;
 
+__host__ __device__ constexpr int fin_slots(int kp) { return kp <= 512 ? 2048 : 4096; }
+
 __host__ __device__ inline size_t finalize_smem(int kp) {
-  const int slots = pool_slots(kp);
-  return (size_t)slots * 8 * 2 + (size_t)FIN_WARPS * EXACT_SCRATCH_BYTES + 64;
+  return (size_t)fin_slots(kp) * 8 * 2 + (size_t)FIN_WARPS * EXACT_SCRATCH_BYTES + 64;
 }
 
 // Largest fp32 scan score a row with exact (reference-arithmetic) distance <= E can have.
@@ -50,14 +51,44 @@ __device__ __forceinline__ float score_upper_bound(int metric, int mode, int cos
   return tf;
 }
 
+// Best kp keys of the nb sorted lists into pool[0..*cnt) (sorted). Keys are read in rank-major
+// rounds of one key per thread, the next round's key already in flight while the current one is
+// filtered. pool has `slots` >= kp + FIN_THREADS entries. All threads of the block call.
+__device__ __forceinline__ void generic_select(const uint64_t* part, int total, int nb, int kp, uint64_t* pool,
+                                               int slots, int* s_cnt, float* s_tau) {
+  const int tid = threadIdx.x;
+  const int highwater = slots - FIN_THREADS;
+  auto load_key = [&](int i) -> uint64_t {
+    return i < total ? __ldcg(part + (size_t)(i % nb) * kp + (i / nb)) : KEY_NONE;
+  };
+  uint64_t next_key = load_key(tid);
+  __syncthreads();
+  if (tid == 0) {
+    *s_cnt = 0;
+    *s_tau = __int_as_float(0x7f800000);
+  }
+  __syncthreads();
+  PoolRef pr{pool, s_cnt, s_tau};
+  for (int base = 0; base < total; base += FIN_THREADS) {
+    const uint64_t key = next_key;
+    next_key = load_key(base + FIN_THREADS + tid);
+    const bool pass = (key != KEY_NONE) && (key_score(key) <= *s_tau);
+    warp_append(pr, pass, key);
+    __syncthreads();
+    if (*s_cnt >= highwater || (base == 0 && *s_cnt > kp)) block_prune(pr, kp);
+  }
+  block_prune(pr, kp);
+}
+
+// One CTA (1024 threads) per query. The nb*kp scan keys are read in rank-major rounds of one key
+// per thread, the next round's key already in flight while the current one is filtered, so the
+// whole selection costs a handful of L2 round trips instead of one per round.
 __global__ void __launch_bounds__(FIN_THREADS, 1) finalize_kernel(const FinalizeParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int q = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kp = p.kp, nb = p.nb, k = p.k;
-  const int slots = pool_slots(kp);
-  const int highwater = slots - FIN_THREADS;
-
+  const int slots = fin_slots(kp);
   uint64_t* pool = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* ex = pool + slots;
   double* scratch = reinterpret_cast<double*>(ex + slots) + (size_t)warp * (EXACT_SCRATCH_BYTES / 8);
@@ -69,14 +100,13 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) finalize_kernel(const Finalize
 
   const uint64_t* part = p.partial + (size_t)q * nb * kp;
   const float* qv = p.queries + (size_t)q * p.dp;
-
+  const int total = nb * kp;
+  // rank-major order: index i -> list i % nb, rank i / nb (so the threshold tightens early)
   if (tid == 0) {
-    s_cnt = 0;
-    s_tau = __int_as_float(0x7f800000);
     s_extra = 0;
     s_bad = 0;
   }
-  if (warp == 0) {  // |q|^2 for the dot-product bound
+  if (warp == 1) {  // |q|^2 for the dot-product bound
     double s = 0.0;
     for (int i = lane; i < p.d; i += 32) s += (double)qv[i] * (double)qv[i];
     for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -84,24 +114,12 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) finalize_kernel(const Finalize
   }
   __syncthreads();
 
-  PoolRef pr{pool, &s_cnt, &s_tau};
-
-  // ---- 1. best kp scan keys among nb*kp, rank-major so the threshold tightens early -------
-  const int total = nb * kp;
-  for (int base = 0; base < total; base += FIN_THREADS) {
-    const int idx = base + tid;
-    uint64_t key = KEY_NONE;
-    if (idx < total) key = part[(size_t)(idx % nb) * kp + (idx / nb)];
-    const bool pass = (key != KEY_NONE) && (key_score(key) <= s_tau);
-    warp_append(pr, pass, key);
-    __syncthreads();
-    if (s_cnt >= highwater) block_prune(pr, kp);
-  }
-  block_prune(pr, kp);
+  // ---- 1. best kp scan keys among nb*kp ----------------------------------------------------------
+  generic_select(part, total, nb, kp, pool, slots, &s_cnt, &s_tau);
   const int ncand = s_cnt;
   const uint64_t last_key = ncand > 0 ? pool[ncand - 1] : 0ull;
 
-  // ---- 2. exact re-rank --------------------------------------------------------------------
+  // ---- 2. exact re-rank ----------------------------------------------------------------------------
   for (int c = warp; c < ncand; c += FIN_WARPS) {
     const uint32_t row = key_row(pool[c]);
     const float dist = exact_distance_warp(p.metric, p.arith, qv, p.vec + (size_t)row * p.dp, p.d, scratch);
@@ -115,23 +133,23 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) finalize_kernel(const Finalize
     block_bitonic_sort(ex, n2);
   }
 
-  // ---- 3. certificate and widening ------------------------------------------------------------
+  // ---- 3. certificate and widening -----------------------------------------------------------------
   if (ncand >= k && ncand > 0) {
     const float E = key_score(ex[k - 1]);
     const float T = score_upper_bound(p.metric, p.mode, p.cosine, E, (double)p.gamma, s_qn2,
                                       (double)(p.max_norm2 ? *p.max_norm2 : 0.f));
-    for (int base = 0; base < total; base += FIN_THREADS) {
-      const int idx = base + tid;
-      if (idx < total) {
-        const int b = idx % nb, j = idx / nb;
-        const uint64_t key = part[(size_t)b * kp + j];
-        if (key != KEY_NONE) {
-          const bool within = key_score(key) <= T;
-          if (within && key > last_key) {
-            const int pos = atomicAdd(&s_extra, 1);
-            if (ncand + pos < slots) pool[ncand + pos] = key;
-          }
-          if (within && j == kp - 1) s_bad = 1;  // a full list may have dropped rows <= T
+    // every list is sorted: a list can only hold something <= T if its rank-0 key is <= T, and its
+    // last key decides whether the scan CTA may have dropped such rows.
+    for (int b = tid; b < nb; b += FIN_THREADS) {
+      const uint64_t* lst = part + (size_t)b * kp;
+      const uint64_t lastk = __ldcg(lst + kp - 1);
+      if (lastk != KEY_NONE && key_score(lastk) <= T) s_bad = 1;  // a full list may have dropped rows <= T
+      for (int j = 0; j < kp; ++j) {
+        const uint64_t key = __ldcg(lst + j);
+        if (key == KEY_NONE || key_score(key) > T) break;
+        if (key > last_key) {
+          const int pos = atomicAdd(&s_extra, 1);
+          if (ncand + pos < slots) pool[ncand + pos] = key;
         }
       }
     }
@@ -156,11 +174,221 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) finalize_kernel(const Finalize
   } else {
     // fewer candidates than k: nothing may have been dropped anywhere
     for (int b = tid; b < nb; b += FIN_THREADS)
-      if (part[(size_t)b * kp + kp - 1] != KEY_NONE) s_bad = 1;
+      if (__ldcg(part + (size_t)b * kp + kp - 1) != KEY_NONE) s_bad = 1;
   }
   __syncthreads();
 
-  // ---- 4. results ------------------------------------------------------------------------------
+  // ---- 4. results ----------------------------------------------------------------------------------
+  const int kk = nex < k ? nex : k;
+  const bool bad = s_bad != 0;
+  if (p.out_keys != nullptr) {
+    for (int j = tid; j < k; j += FIN_THREADS) {
+      uint64_t o = KEY_NONE;
+      if (j < kk && !bad) o = (ex[j] & 0xFFFFFFFF00000000ull) | (uint64_t)(uint32_t)(p.row_base + key_row(ex[j]));
+      p.out_keys[(size_t)q * k + j] = o;
+    }
+    if (tid == 0 && p.out_count) p.out_count[q] = bad ? -1 : kk;
+    return;
+  }
+  for (int j = tid; j < k; j += FIN_THREADS) {
+    const bool ok = j < kk;
+    p.out_dist[(size_t)q * k + j] = ok ? key_score(ex[j]) : __int_as_float(0x7f800000);
+    p.out_row[(size_t)q * k + j] = ok ? (long long)key_row(ex[j]) + p.row_base : -1ll;
+  }
+  if (p.out_negdist != nullptr) {
+    const float* nv = p.negatives + (size_t)q * p.dp;
+    for (int j = warp; j < k; j += FIN_WARPS) {
+      float nd = __int_as_float(0x7f800000);
+      if (j < kk) {
+        // hybrid_index.go:544  negDistance: idx.distFunc(vector, negExample)
+        nd = exact_distance_warp(p.metric, p.arith, p.vec + (size_t)key_row(ex[j]) * p.dp, nv, p.d, scratch);
+      }
+      if (lane == 0) p.out_negdist[(size_t)q * k + j] = nd;
+    }
+  }
+  if (tid == 0) p.out_count[q] = bad ? -1 : kk;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Low-latency variant for kp <= 128 (k <= 112): every thread keeps its share of the nb*kp scan
+// keys in registers (one L2 round trip), the threshold, the selection and both sorts are done by
+// all-pairs rank counting (a handful of barriers instead of ~100 bitonic steps), and the
+// certificate re-uses the register-resident keys.
+// ------------------------------------------------------------------------------------------------
+constexpr int FF_MAXR = 19;        // keys per thread: 148 lists * 128 keys / 1024 threads
+constexpr int FF_SAMPLE = 256;     // keys used to derive the selection threshold
+constexpr int FF_CAP = 1024;       // candidate capacity
+
+__host__ __device__ inline size_t finalize_fast_smem() {
+  return (size_t)FF_SAMPLE * 8 + (size_t)FF_CAP * 4 + (size_t)FF_CAP * 8 * 3 +
+         (size_t)FIN_WARPS * EXACT_SCRATCH_BYTES + 64;
+}
+
+// dst[rank of src[i]] = src[i] for n <= FF_CAP distinct keys; all FIN_THREADS threads call.
+__device__ __forceinline__ void block_rank_sort(const uint64_t* src, int n, uint64_t* dst, int* rank) {
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n; i += FIN_THREADS) rank[i] = 0;
+  __syncthreads();
+  if (n > 0) {
+    const int nparts = FIN_THREADS / n > 0 ? FIN_THREADS / n : 1;
+    const int chunk = (n + nparts - 1) / nparts;
+    const int a = tid % n, part = tid / n;
+    if (part < nparts) {
+      const uint64_t mine = src[a];
+      const int lo = part * chunk, hi = min(n, lo + chunk);
+      int c = 0;
+      for (int j = lo; j < hi; ++j) c += src[j] < mine;
+      if (c) atomicAdd(&rank[a], c);
+    }
+  }
+  __syncthreads();
+  if (tid < n) dst[rank[tid]] = src[tid];
+  __syncthreads();
+}
+
+template <int FF_R>
+__global__ void __launch_bounds__(FIN_THREADS, 1) finalize_fast_kernel(const FinalizeParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kp = p.kp, nb = p.nb, k = p.k;
+
+  uint64_t* samp = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* cand = samp + FF_SAMPLE;
+  uint64_t* sel = cand + FF_CAP;
+  uint64_t* ex = sel + FF_CAP;
+  int* rank = reinterpret_cast<int*>(ex + FF_CAP);
+  double* scratch = reinterpret_cast<double*>(rank + FF_CAP) + (size_t)warp * (EXACT_SCRATCH_BYTES / 8);
+  __shared__ int s_ncand, s_extra, s_bad, s_gcnt;
+  __shared__ float s_gtau;
+  __shared__ unsigned long long s_taukey;
+  __shared__ double s_qn2;
+
+  const uint64_t* part = p.partial + (size_t)q * nb * kp;
+  const float* qv = p.queries + (size_t)q * p.dp;
+  const int total = nb * kp;
+
+  // ---- 0. all keys into registers, rank-major (index i -> list i % nb, rank i / nb) -------------
+  uint64_t keys[FF_R];
+#pragma unroll
+  for (int r = 0; r < FF_R; ++r) {
+    const int i = r * FIN_THREADS + tid;
+    keys[r] = i < total ? __ldcg(part + (size_t)(i % nb) * kp + (i / nb)) : KEY_NONE;
+  }
+  if (tid == 0) {
+    s_ncand = 0;
+    s_extra = 0;
+    s_bad = 0;
+    s_taukey = KEY_NONE;
+  }
+  if (warp == 1) {  // |q|^2 for the dot-product bound
+    double s = 0.0;
+    for (int i = lane; i < p.d; i += 32) s += (double)qv[i] * (double)qv[i];
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) s_qn2 = s;
+  }
+  if (tid < FF_SAMPLE) {
+    samp[tid] = keys[0];
+    rank[tid] = 0;
+  }
+  __syncthreads();
+
+  // ---- 1. threshold: the kp-th smallest of the first 256 keys bounds the global kp-th -------------
+  if (total >= FF_SAMPLE) {
+    const int a = tid & (FF_SAMPLE - 1), part_i = tid >> 8;  // 4 parts of 64 comparisons
+    const uint64_t mine = samp[a];
+    int c = 0;
+    for (int j = part_i * 64; j < part_i * 64 + 64; ++j) c += samp[j] < mine;
+    if (c) atomicAdd(&rank[a], c);
+    __syncthreads();
+    if (tid < FF_SAMPLE && rank[tid] == kp - 1 && samp[tid] != KEY_NONE) s_taukey = samp[tid];
+    __syncthreads();
+  }
+  const uint64_t taukey = s_taukey;
+
+  // ---- 2. candidates = keys <= threshold ---------------------------------------------------------
+#pragma unroll
+  for (int r = 0; r < FF_R; ++r) {
+    if (keys[r] != KEY_NONE && keys[r] <= taukey) {
+      const int pos = atomicAdd(&s_ncand, 1);
+      if (pos < FF_CAP) cand[pos] = keys[r];
+    }
+  }
+  __syncthreads();
+  int ncand = s_ncand;
+  int nsel;
+  if (ncand > FF_CAP) {
+    // very uneven lists (the sample held fewer than kp keys): general pool selection instead.
+    // cand and sel are contiguous: 2 * FF_CAP slots.
+    generic_select(part, total, nb, kp, cand, 2 * FF_CAP, &s_gcnt, &s_gtau);
+    nsel = s_gcnt;
+    __syncthreads();
+    uint64_t tmp = tid < nsel ? cand[tid] : 0ull;
+    __syncthreads();
+    if (tid < nsel) sel[tid] = tmp;
+    __syncthreads();
+  } else {
+    // ---- 3. sort candidates by scan key, keep the best kp --------------------------------------------
+    block_rank_sort(cand, ncand, sel, rank);
+    nsel = ncand < kp ? ncand : kp;
+  }
+  const uint64_t last_key = nsel > 0 ? sel[nsel - 1] : 0ull;
+
+  // ---- 4. exact re-rank --------------------------------------------------------------------------------
+  for (int c = warp; c < nsel; c += FIN_WARPS) {
+    const uint32_t row = key_row(sel[c]);
+    const float dist = exact_distance_warp(p.metric, p.arith, qv, p.vec + (size_t)row * p.dp, p.d, scratch);
+    if (lane == 0) cand[c] = make_key(dist, row);
+  }
+  __syncthreads();
+  int nex = nsel;
+  block_rank_sort(cand, nex, ex, rank);
+
+  // ---- 5. certificate and widening --------------------------------------------------------------------
+  if (nsel >= k && nsel > 0) {
+    const float E = key_score(ex[k - 1]);
+    const float T = score_upper_bound(p.metric, p.mode, p.cosine, E, (double)p.gamma, s_qn2,
+                                      (double)(p.max_norm2 ? *p.max_norm2 : 0.f));
+#pragma unroll
+    for (int r = 0; r < FF_R; ++r) {
+      const uint64_t key = keys[r];
+      if (key != KEY_NONE && key_score(key) <= T) {
+        const int i = r * FIN_THREADS + tid;
+        if (i / nb == kp - 1) s_bad = 1;  // a full list may have dropped rows with score <= T
+        if (key > last_key) {
+          const int pos = atomicAdd(&s_extra, 1);
+          if (nsel + pos < FF_CAP) sel[nsel + pos] = key;
+        }
+      }
+    }
+    __syncthreads();
+    int extra = s_extra;
+    if (nsel + extra > FF_CAP) {
+      extra = FF_CAP - nsel;
+      if (tid == 0) s_bad = 1;
+    }
+    if (extra > 0) {
+      for (int c = tid; c < nsel; c += FIN_THREADS) cand[c] = ex[c];
+      for (int c = warp; c < extra; c += FIN_WARPS) {
+        const uint32_t row = key_row(sel[nsel + c]);
+        const float dist = exact_distance_warp(p.metric, p.arith, qv, p.vec + (size_t)row * p.dp, p.d, scratch);
+        if (lane == 0) cand[nsel + c] = make_key(dist, row);
+      }
+      __syncthreads();
+      nex = nsel + extra;
+      block_rank_sort(cand, nex, ex, rank);
+    }
+  } else {
+    // fewer candidates than k: nothing may have been dropped anywhere
+#pragma unroll
+    for (int r = 0; r < FF_R; ++r) {
+      const int i = r * FIN_THREADS + tid;
+      if (keys[r] != KEY_NONE && i / nb == kp - 1) s_bad = 1;
+    }
+  }
+  __syncthreads();
+
+  // ---- 6. results -------------------------------------------------------------------------------------
   const int kk = nex < k ? nex : k;
   const bool bad = s_bad != 0;
   if (p.out_keys != nullptr) {
@@ -194,12 +422,26 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) finalize_kernel(const Finalize
 int finalize_set_attributes() {
   QG_CUDA_OK(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)finalize_smem(1024)));
+  QG_CUDA_OK(cudaFuncSetAttribute(finalize_fast_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)finalize_fast_smem()));
+  QG_CUDA_OK(cudaFuncSetAttribute(finalize_fast_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)finalize_fast_smem()));
+  QG_CUDA_OK(cudaFuncSetAttribute(finalize_fast_kernel<FF_MAXR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)finalize_fast_smem()));
   return 0;
 }
 
 int launch_finalize(const FinalizeParams& p, int nq, cudaStream_t st) {
   if (nq <= 0) return 0;
-  finalize_kernel<<<nq, FIN_THREADS, finalize_smem(p.kp), st>>>(p);
+  const long long per_thread = ((long long)p.nb * p.kp + FIN_THREADS - 1) / FIN_THREADS;
+  if (p.kp <= 128 && per_thread <= 5)
+    finalize_fast_kernel<5><<<nq, FIN_THREADS, finalize_fast_smem(), st>>>(p);
+  else if (p.kp <= 128 && per_thread <= 10)
+    finalize_fast_kernel<10><<<nq, FIN_THREADS, finalize_fast_smem(), st>>>(p);
+  else if (p.kp <= 128 && per_thread <= FF_MAXR)
+    finalize_fast_kernel<FF_MAXR><<<nq, FIN_THREADS, finalize_fast_smem(), st>>>(p);
+  else
+    finalize_kernel<<<nq, FIN_THREADS, finalize_smem(p.kp), st>>>(p);
   QG_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -41,6 +41,9 @@ struct ScanParams {
 };
 
 constexpr int SCAN_NW = 8;  // warps per CTA of the fast kernels
+#ifndef QG_SCAN_TILE_TARGET
+#define QG_SCAN_TILE_TARGET 8192  // bytes per bulk copy (tile) the geometry aims for
+#endif
 
 template <int D>
 struct ScanGeom {
@@ -53,11 +56,19 @@ struct ScanGeom {
   // passes (= accumulators per lane per query) chosen so that a tile is about 4 KB
   static constexpr int RB_RAW = 4096 / (ROW_BYTES * RPP);
   static constexpr int RB = RB_RAW >= 8 ? 8 : (RB_RAW >= 4 ? 4 : (RB_RAW >= 2 ? 2 : 1));
-  static constexpr int RT = RPP * RB;  // rows per tile
+  static constexpr int RS = RPP * RB;  // rows per sub-batch (one butterfly + one filter step)
+  // sub-batches per tile; a tile never exceeds 32 rows (one gather copy per lane, and the pool
+  // head-room of select.cuh assumes at most 32 appends per warp per query between flag checks)
+  static constexpr int NSUB_CAP = 32 / RS;
+  static constexpr int NSUB_RAW0 = QG_SCAN_TILE_TARGET / (RS * ROW_BYTES);
+  static constexpr int NSUB_RAW = NSUB_RAW0 < NSUB_CAP ? NSUB_RAW0 : NSUB_CAP;
+  static constexpr int NSUB = NSUB_RAW >= 4 ? 4 : (NSUB_RAW >= 2 ? 2 : 1);
+  static constexpr int RT = RS * NSUB;  // rows per tile = one bulk copy
   static constexpr int TILE_BYTES = RT * ROW_BYTES;
-  static constexpr int STAGES = TILE_BYTES <= 4096 ? 4 : (TILE_BYTES <= 6144 ? 3 : 2);
+  static constexpr int STAGES = TILE_BYTES <= 4096 ? 4 : (TILE_BYTES <= 8192 ? 3 : 2);
   static constexpr int REP = G / RB;  // lanes holding the same reduced row
   static_assert(RB <= G, "butterfly needs RB <= G");
+  static_assert(RT <= 32, "a tile holds at most 32 rows");
 };
 
 // Reduce RB per-row accumulators over the G lanes of a row group. On return a[0] holds the
@@ -189,7 +200,7 @@ template <int D, int QB, int MODE>
 __global__ void __launch_bounds__(SCAN_NW * 32, 1) scan_fast_kernel(const ScanParams p) {
   using Gm = ScanGeom<D>;
   constexpr int C = Gm::C, G = Gm::G, CPL = Gm::CPL, RPP = Gm::RPP, RB = Gm::RB, RT = Gm::RT;
-  constexpr int S = Gm::STAGES, TILE_BYTES = Gm::TILE_BYTES;
+  constexpr int S = Gm::STAGES, TILE_BYTES = Gm::TILE_BYTES, RS = Gm::RS, NSUB = Gm::NSUB;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -292,14 +303,20 @@ __global__ void __launch_bounds__(SCAN_NW * 32, 1) scan_fast_kernel(const ScanPa
     const int stage = (int)(it % S);
     const uint32_t parity = (uint32_t)((it / S) & 1);
     const long long item0 = t * RT;
-    const long long my_item = item0 + my_row_in_tile;
-    bool valid = my_unique && (my_item < n_items);
-    uint32_t my_row = 0;
-    float rinv = 1.f;
-    if (valid) {
-      my_row = gather ? __ldg(p.gather + my_item) : (uint32_t)my_item;
-      if (p.mask != nullptr && !gather) valid = (__ldg(p.mask + (my_row >> 5)) >> (my_row & 31)) & 1u;
-      if (MODE == MODE_DOT && p.inv_norm != nullptr) rinv = __ldg(p.inv_norm + my_row);
+    bool valid[NSUB];
+    uint32_t my_row[NSUB];
+    float rinv[NSUB];
+#pragma unroll
+    for (int sb = 0; sb < NSUB; ++sb) {
+      const long long my_item = item0 + sb * RS + my_row_in_tile;
+      valid[sb] = my_unique && (my_item < n_items);
+      my_row[sb] = 0;
+      rinv[sb] = 1.f;
+      if (valid[sb]) {
+        my_row[sb] = gather ? __ldg(p.gather + my_item) : (uint32_t)my_item;
+        if (p.mask != nullptr && !gather) valid[sb] = (__ldg(p.mask + (my_row[sb] >> 5)) >> (my_row[sb] & 31)) & 1u;
+        if (MODE == MODE_DOT && p.inv_norm != nullptr) rinv[sb] = __ldg(p.inv_norm + my_row[sb]);
+      }
     }
 
     float tau_r[QB];
@@ -307,33 +324,37 @@ __global__ void __launch_bounds__(SCAN_NW * 32, 1) scan_fast_kernel(const ScanPa
     for (int qi = 0; qi < QB; ++qi) tau_r[qi] = *reinterpret_cast<volatile float*>(&tau[qi]);
 
     mbar_wait(&mybar[stage], parity);
-    const float4* tb = reinterpret_cast<const float4*>(ring + (size_t)stage * TILE_BYTES);
-
-    float acc[QB][RB];
-#pragma unroll
-    for (int qi = 0; qi < QB; ++qi)
-#pragma unroll
-      for (int pr = 0; pr < RB; ++pr) acc[qi][pr] = 0.f;
+    const float4* tile = reinterpret_cast<const float4*>(ring + (size_t)stage * TILE_BYTES);
 
 #pragma unroll
-    for (int pr = 0; pr < RB; ++pr) {
+    for (int sb = 0; sb < NSUB; ++sb) {
+      const float4* tb = tile + sb * RS * C;
+      float acc[QB][RB];
 #pragma unroll
-      for (int c = 0; c < CPL; ++c) {
-        const float4 x = tb[(pr * RPP + grp) * C + c * G + gl];
+      for (int qi = 0; qi < QB; ++qi)
 #pragma unroll
-        for (int qi = 0; qi < QB; ++qi) acc[qi][pr] = accum4<MODE>(acc[qi][pr], x, qreg[qi][c]);
+        for (int pr = 0; pr < RB; ++pr) acc[qi][pr] = 0.f;
+
+#pragma unroll
+      for (int pr = 0; pr < RB; ++pr) {
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+          const float4 x = tb[(pr * RPP + grp) * C + c * G + gl];
+#pragma unroll
+          for (int qi = 0; qi < QB; ++qi) acc[qi][pr] = accum4<MODE>(acc[qi][pr], x, qreg[qi][c]);
+        }
       }
-    }
 
 #pragma unroll
-    for (int qi = 0; qi < QB; ++qi) {
-      float v = butterfly_reduce<RB, G>(acc[qi], lane);
-      if (qi < p.nq) {  // warp-uniform
-        float score = v;
-        if (MODE == MODE_DOT) score = 1.0f - v * (rinv * rnq[qi]);
-        const bool pass = valid && (score <= tau_r[qi]);
-        const int after = warp_append(ps.ref(qi), pass, make_key(score, my_row));
-        if (after >= highwater && lane == 0) st_volatile_s32(&ctl->prune_flag, 1);
+      for (int qi = 0; qi < QB; ++qi) {
+        float v = butterfly_reduce<RB, G>(acc[qi], lane);
+        if (qi < p.nq) {  // warp-uniform
+          float score = v;
+          if (MODE == MODE_DOT) score = 1.0f - v * (rinv[sb] * rnq[qi]);
+          const bool pass = valid[sb] && (score <= tau_r[qi]);
+          const int after = warp_append(ps.ref(qi), pass, make_key(score, my_row[sb]));
+          if (after >= highwater && lane == 0) st_volatile_s32(&ctl->prune_flag, 1);
+        }
       }
     }
     __syncwarp();
