@@ -9,3 +9,4 @@ from .cref import (  # noqa: F401
     COSINE, L2, DOT, SQL2, L1, ARITH_VECTORTYPES, ARITH_HNSW_F32,
     distance, distances, exact_search, exact_search_batch, synth, build, lib_path,
 )
+from . import filters, gotypes, rerank  # noqa: F401,E402
