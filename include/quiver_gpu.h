@@ -232,7 +232,7 @@ typedef struct qg_scan_stats {
   int32_t queries_per_pass; /* queries served by one pass over the corpus            */
   int32_t passes;           /* corpus passes of the last call                        */
   int32_t escalations;      /* selections repeated with a larger candidate set       */
-  int32_t path;             /* 0 none, 1 flat scan, 2 gather scan, 3 tensor-core     */
+  int32_t path;             /* 0 exhaustive, 1 flat scan, 2 gather scan, 3 tensor-core */
   int32_t reserved;
 } qg_scan_stats;
 int qg_last_scan_stats(const qg_index* idx, qg_scan_stats* out);
@@ -248,6 +248,13 @@ typedef struct qg_profile {
 } qg_profile;
 int qg_index_set_profiling(qg_index* idx, int on);
 int qg_index_read_profile(qg_index* idx, qg_profile* out);
+
+/* Development aid: run one tensor-core pass (sample -> threshold -> scan) for nq <= 256 host
+ * queries and copy back the per-query admission thresholds, candidate counts and the raw
+ * candidate keys (nq x *cap_out; high 32 bits = order-preserving image of the tf32 scan score,
+ * low 32 bits = row). Nothing is re-ranked. */
+int qg_debug_tc_pass(qg_index* idx, const float* queries, int nq, int k, float* tau_out, int* cnt_out,
+                     uint64_t* cand_out, int* cap_out);
 
 #ifdef __cplusplus
 }

@@ -63,7 +63,7 @@ EXPORTED_SYMBOLS = [
     "qg_index_fetch", "qg_facets_set_column", "qg_filter_compile", "qg_filter_eval", "qg_filter_destroy",
     "qg_search_batch", "qg_search_batch_device", "qg_search_shard_keys_device", "qg_merge_shard_keys_device",
     "qg_batch_distance", "qg_batch_distance_multi", "qg_last_scan_stats", "qg_index_set_profiling",
-    "qg_index_read_profile",
+    "qg_index_read_profile", "qg_debug_tc_pass",
 ]
 
 _lib = None
@@ -108,6 +108,7 @@ def load() -> C.CDLL:
     lib.qg_last_scan_stats.argtypes = [vp, C.POINTER(qg_scan_stats)]
     lib.qg_index_set_profiling.argtypes = [vp, i32]
     lib.qg_index_read_profile.argtypes = [vp, C.POINTER(qg_profile)]
+    lib.qg_debug_tc_pass.argtypes = [vp, vp, i32, i32, vp, vp, vp, C.POINTER(i32)]
     _lib = lib
     return lib
 
@@ -287,6 +288,18 @@ class Index:
         _check(self._lib.qg_batch_distance_multi(self.handle, _ptr(queries), queries.shape[0], queries.shape[1],
                                                  _ptr(rows), rows.shape[1], _ptr(out)))
         return out
+
+    def debug_tc_pass(self, queries: np.ndarray, k: int):
+        """One tensor-core pass without the re-rank: (tau [q], count [q], keys [q, cap] uint64)."""
+        queries = np.ascontiguousarray(queries, dtype=np.float32)
+        q = queries.shape[0]
+        tau = np.zeros(q, dtype=np.float32)
+        cnt = np.zeros(q, dtype=np.int32)
+        cand = np.zeros((q, 2048), dtype=np.uint64)
+        cap = C.c_int(0)
+        _check(self._lib.qg_debug_tc_pass(self.handle, _ptr(queries), q, k, _ptr(tau), _ptr(cnt), _ptr(cand),
+                                          C.byref(cap)))
+        return tau, cnt, cand[:, :cap.value]
 
     def set_profiling(self, on: bool) -> None:
         _check(self._lib.qg_index_set_profiling(self.handle, 1 if on else 0))

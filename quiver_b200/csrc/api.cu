@@ -2,6 +2,7 @@
 // pinned staging buffers, facet columns / filters, search orchestration.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -14,6 +15,7 @@
 #include "finalize.cuh"
 #include "misc.cuh"
 #include "scan.cuh"
+#include "tc_scan.cuh"
 
 namespace qg {
 
@@ -51,6 +53,7 @@ static int ensure_device(int device) {
     ds.sm_count = prop.multiProcessorCount;
     if (int rc = scan_set_attributes()) return rc;
     if (int rc = finalize_set_attributes()) return rc;
+    if (int rc = tc_set_attributes()) return rc;
     ds.attrs_done = true;
   }
   return 0;
@@ -132,11 +135,13 @@ struct Workspace {
     prof_used += 2;
   }
   DevBuf qpad, negpad, partial, mask, counters;
+  DevBuf tc_sample, tc_tau, tc_cand, tc_cnt;
   DevBuf d_q, d_neg, d_dist, d_negdist, d_row, d_count, d_rows32, d_rows64, d_fetch;
   PinBuf h_in, h_out;
   ExhaustiveWork ex;
   void destroy() {
     qpad.release(); negpad.release(); partial.release(); mask.release(); counters.release();
+    tc_sample.release(); tc_tau.release(); tc_cand.release(); tc_cnt.release();
     d_q.release(); d_neg.release(); d_dist.release(); d_negdist.release(); d_row.release(); d_count.release();
     d_rows32.release(); d_rows64.release(); d_fetch.release();
     h_in.release(); h_out.release();
@@ -186,6 +191,7 @@ struct qg_index {
   long long cap = 0, n_rows = 0, n_live = 0;
   float* vec = nullptr;
   float* inv_norm = nullptr;
+  float* norm2 = nullptr;
   uint32_t* live = nullptr;
   float* max_norm2 = nullptr;  // device scalar
   uint64_t live_epoch = 0, facet_epoch = 0;
@@ -200,6 +206,8 @@ struct qg_index {
   cudaEvent_t stage_ev[2] = {nullptr, nullptr};
   qg_scan_stats stats{};
   bool profiling = false;
+  int tc_min_q = 8;             // query batches at least this large use the tensor-core regime
+  long long tc_min_rows = 32768;
 };
 
 namespace qg {
@@ -272,13 +280,16 @@ static int grow(qg_index* idx, long long need_rows) {
   ncap = (ncap + 1023) & ~1023ll;  // whole mask words, 16-byte aligned columns
   float* nvec = nullptr;
   float* ninv = nullptr;
+  float* nn2 = nullptr;
   uint32_t* nlive = nullptr;
   cudaError_t e = cudaMalloc(&nvec, (size_t)ncap * idx->dp * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&ninv, (size_t)ncap * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&nn2, (size_t)ncap * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&nlive, (size_t)(ncap / 32) * sizeof(uint32_t));
   if (e != cudaSuccess) {
     if (nvec) cudaFree(nvec);
     if (ninv) cudaFree(ninv);
+    if (nn2) cudaFree(nn2);
     if (nlive) cudaFree(nlive);
     return fail(QG_ERR_OOM, std::string("device allocation for ") + std::to_string(ncap) +
                                 " rows failed: " + cudaGetErrorString(e));
@@ -289,15 +300,19 @@ static int grow(qg_index* idx, long long need_rows) {
                                cudaMemcpyDeviceToDevice, idx->up_stream));
     QG_CUDA_OK(cudaMemcpyAsync(ninv, idx->inv_norm, (size_t)idx->n_rows * sizeof(float), cudaMemcpyDeviceToDevice,
                                idx->up_stream));
+    QG_CUDA_OK(cudaMemcpyAsync(nn2, idx->norm2, (size_t)idx->n_rows * sizeof(float), cudaMemcpyDeviceToDevice,
+                               idx->up_stream));
     QG_CUDA_OK(cudaMemcpyAsync(nlive, idx->live, (size_t)((idx->n_rows + 31) / 32) * sizeof(uint32_t),
                                cudaMemcpyDeviceToDevice, idx->up_stream));
   }
   QG_CUDA_OK(cudaStreamSynchronize(idx->up_stream));
   if (idx->vec) cudaFree(idx->vec);
   if (idx->inv_norm) cudaFree(idx->inv_norm);
+  if (idx->norm2) cudaFree(idx->norm2);
   if (idx->live) cudaFree(idx->live);
   idx->vec = nvec;
   idx->inv_norm = ninv;
+  idx->norm2 = nn2;
   idx->live = nlive;
   idx->cap = ncap;
   return 0;
@@ -306,11 +321,9 @@ static int grow(qg_index* idx, long long need_rows) {
 // Post-copy bookkeeping shared by the three upload flavours.
 static int finish_append(qg_index* idx, long long n, int64_t* first_row) {
   const long long row0 = idx->n_rows;
-  if (idx->metric == METRIC_COSINE || idx->metric == METRIC_DOT) {
-    if (int rc = launch_row_norms(idx->vec, row0, n, idx->dp, idx->dim, idx->inv_norm, idx->max_norm2,
-                                  idx->up_stream))
-      return rc;
-  }
+  if (int rc = launch_row_norms(idx->vec, row0, n, idx->dp, idx->dim, idx->inv_norm, idx->norm2, idx->max_norm2,
+                                idx->up_stream))
+    return rc;
   if (int rc = launch_set_live(idx->live, row0, n, idx->up_stream)) return rc;
   QG_CUDA_OK(cudaStreamSynchronize(idx->up_stream));
   idx->n_rows += n;
@@ -378,6 +391,8 @@ int qg_index_create(qg_index** out, int dim, int metric, const qg_config* cfg) {
   if (idx->arith == ARITH_HNSW_F32 && (metric == METRIC_SQL2 || metric == METRIC_L1))
     return fail(QG_ERR_INVALID, "hnsw float32 arithmetic exists for cosine / l2 / dot only");
   idx->margin = (cfg && cfg->select_margin > 0) ? cfg->select_margin : 16;
+  if (const char* e = std::getenv("QG_TC_MIN_Q")) idx->tc_min_q = std::max(1, std::atoi(e));
+  if (const char* e = std::getenv("QG_TC_MIN_ROWS")) idx->tc_min_rows = std::max(128, std::atoi(e));
   {
     std::lock_guard<std::mutex> lk(g_dev_mu);
     idx->sm_count = g_dev[device].sm_count;
@@ -408,6 +423,7 @@ int qg_index_destroy(qg_index* idx) {
   idx->stage[1].release();
   if (idx->vec) cudaFree(idx->vec);
   if (idx->inv_norm) cudaFree(idx->inv_norm);
+  if (idx->norm2) cudaFree(idx->norm2);
   if (idx->live) cudaFree(idx->live);
   if (idx->max_norm2) cudaFree(idx->max_norm2);
   if (idx->stage_ev[0]) cudaEventDestroy(idx->stage_ev[0]);
@@ -850,6 +866,83 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
   }
 
   const int mode = scan_mode_of(idx->metric);
+
+  // ---- tensor-core regime: large query batches over a dense (possibly masked) corpus ----------------
+  TcPlan plan{};
+  if (q >= idx->tc_min_q && !gather && mode != MODE_L1 && kp <= 128 && n_items >= idx->tc_min_rows &&
+      tc_available() == 0 && tc_plan(dp, q, &plan) == 0) {
+    const long long n_tiles = (idx->n_rows + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
+    // sample so that about G rows per query fall under the TC_SAMPLE_RANK-th smallest sampled score
+    const long long G = std::max<long long>(256, 8ll * (k + 24));
+    long long n_sample = ((long long)TC_SAMPLE_RANK * idx->n_rows + G * TC_TILE_ROWS - 1) / (G * TC_TILE_ROWS);
+    n_sample = std::max<long long>(16, std::min<long long>(n_sample, std::min<long long>(n_tiles, 4096)));
+    if (int rc = w->tc_sample.ensure((size_t)plan.n_cols * n_sample * 2 * 4)) return rc;
+    if (int rc = w->tc_tau.ensure((size_t)TC_MAX_COLS * 4)) return rc;
+    if (int rc = w->tc_cand.ensure((size_t)plan.n_cols * TC_CAND_CAP * 8)) return rc;
+    if (int rc = w->tc_cnt.ensure((size_t)TC_MAX_COLS * 4)) return rc;
+    FinalizeCandParams cp{};
+    cp.cand = (const uint64_t*)w->tc_cand.p;
+    cp.cand_cnt = (const int*)w->tc_cnt.p;
+    cp.cap = TC_CAND_CAP;
+    cp.tau = (const float*)w->tc_tau.p;
+    cp.kp = kp;
+    cp.tc_gamma = 1.02 / 512.0 + (double)d / 4194304.0;
+    FinalizeParams& fb = cp.base;
+    fb.vec = idx->vec;
+    fb.dp = dp;
+    fb.d = d;
+    fb.metric = idx->metric;
+    fb.arith = idx->arith;
+    fb.mode = mode;
+    fb.cosine = idx->metric == METRIC_COSINE;
+    fb.k = k;
+    fb.gamma = (float)((d + 16) * 5.9604645e-8);
+    fb.max_norm2 = idx->max_norm2;
+    fb.row_base = a.row_base;
+    for (int p0 = 0; p0 < q; p0 += plan.n_cols) {
+      const int nq = std::min(plan.n_cols, q - p0);
+      TcArgs ta{};
+      ta.vec = idx->vec;
+      ta.n_rows = idx->n_rows;
+      ta.dp = dp;
+      ta.row_norm2 = idx->norm2;
+      ta.inv_norm = idx->metric == METRIC_COSINE ? idx->inv_norm : nullptr;
+      ta.mask = mask;
+      ta.queries = qpad + (size_t)p0 * dp;
+      ta.nq = nq;
+      ta.mode = mode;
+      ta.cosine = fb.cosine;
+      ta.sample = (uint32_t*)w->tc_sample.p;
+      ta.n_sample = (int)n_sample;
+      ta.tau = (float*)w->tc_tau.p;
+      ta.cand = (uint64_t*)w->tc_cand.p;
+      ta.cand_cnt = (int*)w->tc_cnt.p;
+      const bool prof = idx->profiling && w->prof_begin(0, st) == 0;
+      const int rc = launch_tc_pass(plan, ta, idx->sm_count, st, &stats.kernel_launches);
+      if (prof) w->prof_end(st);
+      if (rc) return rc;
+      stats.passes++;
+      fb.queries = qpad + (size_t)p0 * dp;
+      fb.negatives = negpad ? negpad + (size_t)p0 * dp : nullptr;
+      fb.out_dist = a.d_dist ? a.d_dist + (size_t)p0 * k : nullptr;
+      fb.out_negdist = a.d_negdist ? a.d_negdist + (size_t)p0 * k : nullptr;
+      fb.out_row = a.d_row ? a.d_row + (size_t)p0 * k : nullptr;
+      fb.out_count = a.d_count ? a.d_count + p0 : nullptr;
+      fb.out_keys = a.d_keys ? a.d_keys + (size_t)p0 * k : nullptr;
+      const bool prof2 = idx->profiling && w->prof_begin(1, st) == 0;
+      const int frc = launch_finalize_cand(cp, nq, st);
+      if (prof2) w->prof_end(st);
+      if (frc) return frc;
+      stats.kernel_launches++;
+    }
+    stats.path = 3;
+    stats.queries_per_pass = plan.n_cols;
+    stats.rows_scanned = idx->n_rows;
+    stats.bytes_algorithmic = idx->n_rows * (long long)d * 4 + idx->n_rows * 4 + (mask ? idx->n_rows / 8 : 0);
+    idx->stats = stats;
+    return 0;
+  }
+
   const bool fast = scan_fast_supported(dp) && mode != MODE_L1;
   int tile_rows, nw = SCAN_NW, stages = 4, max_qb;
   if (fast) {
@@ -1122,21 +1215,62 @@ int qg_search_batch(qg_index* idx, const float* queries, int q, int dim, int k, 
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_cnt, w->d_count.p, (size_t)q * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, std::string("search: ") + cudaGetErrorString(e)); break; }
-    // queries the flat scan could not certify: redo with the exhaustive path
     int escalations = 0;
+    // queries the tensor-core regime could not certify: redo one by one with the flat scan
+    if (idx->stats.path == 3) {
+      const qg_scan_stats first = idx->stats;
+      for (int i = 0; i < q && !rc; ++i) {
+        if (h_cnt[i] >= 0) continue;
+        ++escalations;
+        SearchArgs a1{(const float*)w->d_q.p + (size_t)i * dim, 1, k, filter,
+                      negatives ? (const float*)w->d_neg.p + (size_t)i * dim : nullptr,
+                      (float*)w->d_dist.p + (size_t)i * k,
+                      negatives ? (float*)w->d_negdist.p + (size_t)i * k : nullptr,
+                      (long long*)w->d_row.p + (size_t)i * k, (int*)w->d_count.p + i, nullptr, 0};
+        if ((rc = search_enqueue(idx, w, a1, st))) break;
+        e = cudaMemcpyAsync(h_dist + (size_t)i * k, (float*)w->d_dist.p + (size_t)i * k, (size_t)k * 4,
+                            cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && negatives)
+          e = cudaMemcpyAsync(h_neg + (size_t)i * k, (float*)w->d_negdist.p + (size_t)i * k, (size_t)k * 4,
+                              cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess)
+          e = cudaMemcpyAsync(h_row + (size_t)i * k, (long long*)w->d_row.p + (size_t)i * k, (size_t)k * 8,
+                              cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_cnt + i, (int*)w->d_count.p + i, 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = fail(QG_ERR_CUDA, std::string("flat re-scan: ") + cudaGetErrorString(e));
+      }
+      if (rc) break;
+      idx->stats = first;
+    }
+    // queries the flat scan could not certify either: redo with the exhaustive path
     for (int i = 0; i < q && !rc; ++i) {
       if (h_cnt[i] >= 0) continue;
       ++escalations;
       const uint32_t* mask = filter ? (const uint32_t*)filter->comb_mask.p
                                     : (idx->n_live < idx->n_rows ? idx->live : nullptr);
-      const float* qpad = (const float*)w->d_q.p;
-      const float* npad = negatives ? (const float*)w->d_neg.p : nullptr;
+      const float* qpad = (const float*)w->d_q.p + (size_t)i * idx->dp;
+      const float* npad = negatives ? (const float*)w->d_neg.p + (size_t)i * idx->dp : nullptr;
       if (idx->dp != idx->dim) {
+        // re-pad this one query (the padded batch may have been overwritten by a re-scan)
+        const size_t rowb = (size_t)idx->dp * 4, srcb = (size_t)idx->dim * 4;
+        if ((rc = w->qpad.ensure(rowb))) break;
+        e = cudaMemsetAsync(w->qpad.p, 0, rowb, st);
+        if (e == cudaSuccess)
+          e = cudaMemcpyAsync(w->qpad.p, (const float*)w->d_q.p + (size_t)i * idx->dim, srcb, cudaMemcpyDeviceToDevice, st);
         qpad = (const float*)w->qpad.p;
-        npad = negatives ? (const float*)w->negpad.p : nullptr;
+        if (e == cudaSuccess && negatives) {
+          if ((rc = w->negpad.ensure(rowb))) break;
+          e = cudaMemsetAsync(w->negpad.p, 0, rowb, st);
+          if (e == cudaSuccess)
+            e = cudaMemcpyAsync(w->negpad.p, (const float*)w->d_neg.p + (size_t)i * idx->dim, srcb,
+                                cudaMemcpyDeviceToDevice, st);
+          npad = (const float*)w->negpad.p;
+        }
+        if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, cudaGetErrorString(e)); break; }
       }
-      rc = exhaustive_search(w->ex, idx->vec, idx->n_rows, idx->dp, idx->dim, mask, qpad + (size_t)i * idx->dp,
-                             npad ? npad + (size_t)i * idx->dp : nullptr, idx->metric, idx->arith, k,
+      rc = exhaustive_search(w->ex, idx->vec, idx->n_rows, idx->dp, idx->dim, mask, qpad, npad, idx->metric,
+                             idx->arith, k,
                              (float*)w->d_dist.p + (size_t)i * k,
                              negatives ? (float*)w->d_negdist.p + (size_t)i * k : nullptr,
                              (long long*)w->d_row.p + (size_t)i * k, (int*)w->d_count.p + i, nullptr, 0, st);
@@ -1240,6 +1374,65 @@ int qg_index_read_profile(qg_index* idx, qg_profile* out) {
   for (auto& w : idx->ws_async)
     if (int rc = drain(w.get())) return rc;
   return 0;
+}
+
+int qg_debug_tc_pass(qg_index* idx, const float* queries, int nq, int k, float* tau_out, int* cnt_out,
+                     uint64_t* cand_out, int* cap_out) {
+  if (int rc = check_index(idx)) return rc;
+  if (!queries || nq <= 0 || nq > TC_MAX_COLS) return fail(QG_ERR_INVALID, "debug_tc_pass: 1..256 queries");
+  if (idx->n_rows == 0) return fail(QG_ERR_INVALID, "debug_tc_pass: empty index");
+  const int mode = scan_mode_of(idx->metric);
+  TcPlan plan{};
+  if (mode == MODE_L1 || tc_available() != 0 || tc_plan(idx->dp, nq, &plan) != 0)
+    return fail(QG_ERR_UNSUPPORTED, "tensor-core regime not available for this index");
+  Workspace* w = ws_acquire(idx);
+  if (!w) return fail(QG_ERR_CUDA, "could not create a stream");
+  int rc = 0;
+  do {
+    cudaStream_t st = w->stream;
+    const int dp = idx->dp, d = idx->dim;
+    if ((rc = w->qpad.ensure((size_t)nq * dp * 4))) break;
+    cudaError_t e = cudaMemsetAsync(w->qpad.p, 0, (size_t)nq * dp * 4, st);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2DAsync(w->qpad.p, (size_t)dp * 4, queries, (size_t)d * 4, (size_t)d * 4, (size_t)nq,
+                            cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, cudaGetErrorString(e)); break; }
+    const long long n_tiles = (idx->n_rows + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
+    const long long G = std::max<long long>(256, 8ll * (k + 24));
+    long long n_sample = ((long long)TC_SAMPLE_RANK * idx->n_rows + G * TC_TILE_ROWS - 1) / (G * TC_TILE_ROWS);
+    n_sample = std::max<long long>(16, std::min<long long>(n_sample, std::min<long long>(n_tiles, 4096)));
+    if ((rc = w->tc_sample.ensure((size_t)plan.n_cols * n_sample * 2 * 4))) break;
+    if ((rc = w->tc_tau.ensure((size_t)TC_MAX_COLS * 4))) break;
+    if ((rc = w->tc_cand.ensure((size_t)plan.n_cols * TC_CAND_CAP * 8))) break;
+    if ((rc = w->tc_cnt.ensure((size_t)TC_MAX_COLS * 4))) break;
+    TcArgs ta{};
+    ta.vec = idx->vec;
+    ta.n_rows = idx->n_rows;
+    ta.dp = dp;
+    ta.row_norm2 = idx->norm2;
+    ta.inv_norm = idx->metric == METRIC_COSINE ? idx->inv_norm : nullptr;
+    ta.mask = idx->n_live < idx->n_rows ? idx->live : nullptr;
+    ta.queries = (const float*)w->qpad.p;
+    ta.nq = nq;
+    ta.mode = mode;
+    ta.cosine = idx->metric == METRIC_COSINE;
+    ta.sample = (uint32_t*)w->tc_sample.p;
+    ta.n_sample = (int)n_sample;
+    ta.tau = (float*)w->tc_tau.p;
+    ta.cand = (uint64_t*)w->tc_cand.p;
+    ta.cand_cnt = (int*)w->tc_cnt.p;
+    int launches = 0;
+    if ((rc = launch_tc_pass(plan, ta, idx->sm_count, st, &launches))) break;
+    e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess && tau_out) e = cudaMemcpy(tau_out, w->tc_tau.p, (size_t)nq * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && cnt_out) e = cudaMemcpy(cnt_out, w->tc_cnt.p, (size_t)nq * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && cand_out)
+      e = cudaMemcpy(cand_out, w->tc_cand.p, (size_t)nq * TC_CAND_CAP * 8, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, std::string("debug_tc_pass: ") + cudaGetErrorString(e)); break; }
+    if (cap_out) *cap_out = TC_CAND_CAP;
+  } while (0);
+  ws_release(idx, w);
+  return rc;
 }
 
 int qg_last_scan_stats(const qg_index* idx, qg_scan_stats* out) {

@@ -419,7 +419,13 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) finalize_fast_kernel(const Fin
   if (tid == 0) p.out_count[q] = bad ? -1 : kk;
 }
 
+__global__ void finalize_cand_kernel(const FinalizeCandParams cp);
+__global__ void merge_shards_kernel(const uint64_t* __restrict__ keys, int world, int nq, int k, float* out_dist,
+                                    long long* out_row, int* out_count);
+
 int finalize_set_attributes() {
+  QG_CUDA_OK(cudaFuncSetAttribute(finalize_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  QG_CUDA_OK(cudaFuncSetAttribute(merge_shards_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   QG_CUDA_OK(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)finalize_smem(1024)));
   QG_CUDA_OK(cudaFuncSetAttribute(finalize_fast_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -442,6 +448,146 @@ int launch_finalize(const FinalizeParams& p, int nq, cudaStream_t st) {
     finalize_fast_kernel<FF_MAXR><<<nq, FIN_THREADS, finalize_fast_smem(), st>>>(p);
   else
     finalize_kernel<<<nq, FIN_THREADS, finalize_smem(p.kp), st>>>(p);
+  QG_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-core regime: candidates admitted by `score <= tau` (tc_scan.cu), one unordered list per
+// query. Sort by scan key, re-rank the best kp exactly, derive T (largest tf32 scan score a row of
+// the exact top-k can have), re-rank every further candidate with score <= T, and certify only if
+// T <= tau (so every such row was admitted) and the list did not overflow.
+// ------------------------------------------------------------------------------------------------
+constexpr int FC_THREADS = 256;
+constexpr int FC_WARPS = FC_THREADS / 32;
+
+__host__ __device__ inline size_t finalize_cand_smem(int cap) {
+  return (size_t)cap * 8 * 2 + (size_t)FC_WARPS * EXACT_SCRATCH_BYTES + 64;
+}
+
+// Largest tensor-core scan score of a row whose exact (reference-arithmetic) distance is <= E.
+// L2 scores are |x|^2 - 2 q.x (the |q|^2 term is dropped by the scan).
+__device__ __forceinline__ float tc_score_upper_bound(int metric, int mode, int cosine, float E, double g,
+                                                      double gamma_seq, double qn2, double max_norm2) {
+  const double qx = sqrt(qn2 * max_norm2);
+  double t;
+  if (mode == MODE_L2) {
+    double d2;
+    if (metric == METRIC_SQL2) {
+      d2 = (double)E * (1.0 + 2.0 * gamma_seq + 4e-7);
+    } else {
+      const double e = (double)E * (1.0 + 1.2e-7);
+      d2 = e * e * (1.0 + 3e-7);
+    }
+    t = d2 - qn2 + 2.0 * g * qx + 2.4e-7 * (max_norm2 + qn2 + 2.0 * qx) + 1e-30;
+  } else if (cosine) {
+    t = (double)E + g + 2e-6;
+  } else {
+    t = (double)E + g * qx + (fabs((double)E) + 1.0 + qx) * 4e-7;
+  }
+  float tf = (float)t;
+  if ((double)tf < t) tf = nextafterf(tf, __int_as_float(0x7f800000));
+  return tf;
+}
+
+__global__ void __launch_bounds__(FC_THREADS, 1) finalize_cand_kernel(const FinalizeCandParams cp) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const FinalizeParams& p = cp.base;
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cap = cp.cap, k = p.k;
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* ex = keys + cap;
+  double* scratch = reinterpret_cast<double*>(ex + cap) + (size_t)warp * (EXACT_SCRATCH_BYTES / 8);
+  __shared__ double s_qn2;
+
+  const int n_raw = cp.cand_cnt[q];
+  const bool overflow = n_raw > cap;
+  const int n = overflow ? cap : n_raw;
+  const float tau = cp.tau[q];
+  const bool all_admitted = tau == __int_as_float(0x7f800000);
+  const float* qv = p.queries + (size_t)q * p.dp;
+
+  if (warp == 0) {
+    double s = 0.0;
+    for (int i = lane; i < p.d; i += 32) s += (double)qv[i] * (double)qv[i];
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) s_qn2 = s;
+  }
+  const int n2 = next_pow2(n);
+  const uint64_t* src = cp.cand + (size_t)q * cap;
+  for (int i = tid; i < n2; i += FC_THREADS) keys[i] = i < n ? __ldcg(src + i) : KEY_NONE;
+  block_bitonic_sort(keys, n2);
+
+  // exact re-rank of the best kp candidates
+  int nsel = n < cp.kp ? n : cp.kp;
+  for (int c = warp; c < nsel; c += FC_WARPS) {
+    const uint32_t row = key_row(keys[c]);
+    const float dist = exact_distance_warp(p.metric, p.arith, qv, p.vec + (size_t)row * p.dp, p.d, scratch);
+    if (lane == 0) ex[c] = make_key(dist, row);
+  }
+  __syncthreads();
+  bool certified = !overflow;
+  int nex = nsel;
+  if (nsel >= k) {
+    {
+      const int m2 = next_pow2(nex);
+      for (int i = nex + tid; i < m2; i += FC_THREADS) ex[i] = KEY_NONE;
+      block_bitonic_sort(ex, m2);
+    }
+    const float E = key_score(ex[k - 1]);
+    const float T = tc_score_upper_bound(p.metric, p.mode, p.cosine, E, cp.tc_gamma, (double)p.gamma, s_qn2,
+                                         (double)(p.max_norm2 ? *p.max_norm2 : 0.f));
+    if (!(T <= tau) && !all_admitted) certified = false;
+    // keys are sorted by scan score: the candidates beyond nsel with score <= T are a prefix
+    int extra = 0;
+    while (nsel + extra < n && key_score(keys[nsel + extra]) <= T) ++extra;  // same walk on every thread
+    for (int c = warp; c < extra; c += FC_WARPS) {
+      const uint32_t row = key_row(keys[nsel + c]);
+      const float dist = exact_distance_warp(p.metric, p.arith, qv, p.vec + (size_t)row * p.dp, p.d, scratch);
+      if (lane == 0) ex[nsel + c] = make_key(dist, row);
+    }
+    __syncthreads();
+    nex = nsel + extra;
+  } else {
+    // fewer than k candidates: complete only if the scan admitted every row
+    if (!all_admitted) certified = false;
+  }
+  {
+    const int m2 = next_pow2(nex);
+    for (int i = nex + tid; i < m2; i += FC_THREADS) ex[i] = KEY_NONE;
+    block_bitonic_sort(ex, m2);
+  }
+
+  const int kk = nex < k ? nex : k;
+  if (p.out_keys != nullptr) {
+    for (int j = tid; j < k; j += FC_THREADS) {
+      uint64_t o = KEY_NONE;
+      if (j < kk && certified) o = (ex[j] & 0xFFFFFFFF00000000ull) | (uint64_t)(uint32_t)(p.row_base + key_row(ex[j]));
+      p.out_keys[(size_t)q * k + j] = o;
+    }
+    if (tid == 0 && p.out_count) p.out_count[q] = certified ? kk : -1;
+    return;
+  }
+  for (int j = tid; j < k; j += FC_THREADS) {
+    const bool ok = j < kk;
+    p.out_dist[(size_t)q * k + j] = ok ? key_score(ex[j]) : __int_as_float(0x7f800000);
+    p.out_row[(size_t)q * k + j] = ok ? (long long)key_row(ex[j]) + p.row_base : -1ll;
+  }
+  if (p.out_negdist != nullptr) {
+    const float* nv = p.negatives + (size_t)q * p.dp;
+    for (int j = warp; j < k; j += FC_WARPS) {
+      float nd = __int_as_float(0x7f800000);
+      if (j < kk) nd = exact_distance_warp(p.metric, p.arith, p.vec + (size_t)key_row(ex[j]) * p.dp, nv, p.d, scratch);
+      if (lane == 0) p.out_negdist[(size_t)q * k + j] = nd;
+    }
+  }
+  if (tid == 0) p.out_count[q] = certified ? kk : -1;
+}
+
+int launch_finalize_cand(const FinalizeCandParams& p, int nq, cudaStream_t st) {
+  if (nq <= 0) return 0;
+  finalize_cand_kernel<<<nq, FC_THREADS, finalize_cand_smem(p.cap), st>>>(p);
   QG_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -490,11 +636,6 @@ int launch_merge_shards(const uint64_t* keys, int world, int nq, int k, float* o
   while (n2 < total) n2 <<= 1;
   const size_t smem = (size_t)n2 * 8;
   if (smem > 200 * 1024) return fail(6, "merge_shards: world*k too large for one CTA");
-  static bool attr_done = false;
-  if (!attr_done) {
-    QG_CUDA_OK(cudaFuncSetAttribute(merge_shards_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = true;
-  }
   merge_shards_kernel<<<nq, 256, smem, st>>>(keys, world, nq, k, out_dist, out_row, out_count);
   QG_CUDA_OK(cudaGetLastError());
   return 0;

@@ -25,6 +25,20 @@ struct FinalizeParams {
 };
 
 int launch_finalize(const FinalizeParams& p, int nq, cudaStream_t st);
+
+// Tensor-core regime (tc_scan.cu): one unsorted candidate list per query (keys admitted by the
+// threshold tau), instead of per-CTA sorted lists.
+struct FinalizeCandParams {
+  const uint64_t* cand;     // [nq][cap] scan keys (score image << 32 | row), unordered
+  const int* cand_cnt;      // [nq] appended keys (may exceed cap = overflow)
+  int cap;
+  const float* tau;         // [nq] admission threshold the scan used (+inf = every row admitted)
+  int kp;                   // candidates re-ranked before the certificate (pow2 >= k + margin)
+  double tc_gamma;          // bound on |tf32 dot - exact dot| / (|q| |x|)
+  FinalizeParams base;      // vec, dp, d, queries, negatives, metric, arith, mode, cosine, k, gamma,
+                            // max_norm2, outputs, row_base (partial / nb unused)
+};
+int launch_finalize_cand(const FinalizeCandParams& p, int nq, cudaStream_t st);
 int finalize_set_attributes();
 
 int launch_merge_shards(const uint64_t* keys, int world, int nq, int k, float* out_dist, long long* out_row,

@@ -10,7 +10,7 @@ namespace qg {
 // re-derived exactly by finalize.cu.
 __global__ void __launch_bounds__(256) row_norms_kernel(const float* __restrict__ vec, long long row0, long long n,
                                                         int dp, int d, float* __restrict__ inv_norm,
-                                                        float* max_norm2) {
+                                                        float* __restrict__ norm2, float* max_norm2) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float local_max = 0.f;
   for (long long r = (long long)blockIdx.x * 8 + warp; r < n; r += (long long)gridDim.x * 8) {
@@ -19,7 +19,10 @@ __global__ void __launch_bounds__(256) row_norms_kernel(const float* __restrict_
     for (int i = lane; i < d; i += 32) s += (double)x[i] * (double)x[i];
     for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float sf = (float)s;
-    if (lane == 0) inv_norm[row0 + r] = s > 0.0 ? (float)(1.0 / sqrt(s)) : 0.f;
+    if (lane == 0) {
+      inv_norm[row0 + r] = s > 0.0 ? (float)(1.0 / sqrt(s)) : 0.f;
+      norm2[row0 + r] = sf;
+    }
     local_max = fmaxf(local_max, sf);
   }
   if (lane == 0 && local_max > 0.f) {
@@ -28,12 +31,12 @@ __global__ void __launch_bounds__(256) row_norms_kernel(const float* __restrict_
   }
 }
 
-int launch_row_norms(const float* vec, long long row0, long long n, int dp, int d, float* inv_norm, float* max_norm2,
-                     cudaStream_t st) {
+int launch_row_norms(const float* vec, long long row0, long long n, int dp, int d, float* inv_norm, float* norm2,
+                     float* max_norm2, cudaStream_t st) {
   if (n <= 0) return 0;
   long long blocks = (n + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  row_norms_kernel<<<(int)blocks, 256, 0, st>>>(vec, row0, n, dp, d, inv_norm, max_norm2);
+  row_norms_kernel<<<(int)blocks, 256, 0, st>>>(vec, row0, n, dp, d, inv_norm, norm2, max_norm2);
   QG_CUDA_OK(cudaGetLastError());
   return 0;
 }

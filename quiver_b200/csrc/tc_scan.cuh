@@ -1,0 +1,60 @@
+// tc_scan.cuh — tensor-core regime of the exact scan (large query batches).
+//
+// For Q >= ~8 queries the distance scan of hybrid.ExactIndex.Search / HybridIndex.BatchSearch
+// (reference pkg/hybrid/exact.go:114-129, hybrid_index.go:703-795: one goroutine per query, each
+// a full pass over the corpus) is a dense [rows x d] x [d x Q] contraction. tc_scan.cu runs it on
+// the 5th-generation tensor cores: TMA stages fp32 corpus tiles (128 rows x 32 floats, 128-byte
+// swizzle) in shared memory, one thread issues tcgen05.mma kind::tf32 with the accumulators in
+// TMEM, and the epilogue warps read them back with tcgen05.ld and keep only the rows whose score
+// is below a per-query threshold. The tf32 scores only SELECT candidates; returned distances are
+// recomputed in the reference's arithmetic and the selection is certified (finalize.cu).
+#pragma once
+#include "common.cuh"
+
+namespace qg {
+
+constexpr int TC_TILE_ROWS = 128;       // MMA M
+constexpr int TC_KBLOCK = 32;           // floats per 128-byte swizzle row
+constexpr int TC_STAGE_BYTES = TC_TILE_ROWS * TC_KBLOCK * 4;
+constexpr int TC_MAX_COLS = 256;        // MMA N (queries per pass)
+constexpr int TC_THREADS = 320;         // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int TC_SAMPLE_RANK = 8;       // order statistic of the sample used as threshold
+constexpr int TC_CAND_CAP = 2048;       // candidate capacity per query per pass
+
+struct TcPlan {
+  int n_cols;    // MMA N: queries per pass, multiple of 16
+  int kb;        // 32-float blocks per row
+  int stages;    // A ring depth
+  int smem;      // dynamic shared memory bytes
+};
+
+// Geometry for a padded dimension dp and nq queries; returns 0 when the tensor path fits.
+int tc_plan(int dp, int nq, TcPlan* out);
+
+struct TcArgs {
+  const float* vec;         // [n_rows x dp]
+  long long n_rows;
+  int dp;
+  const float* row_norm2;   // [n_rows] |x|^2 (L2 scores)
+  const float* inv_norm;    // [n_rows] 1/|x| (cosine), else nullptr
+  const uint32_t* mask;     // row-pass bits or nullptr
+  const float* queries;     // [nq x dp] device
+  int nq;
+  int mode;                 // MODE_L2 / MODE_DOT (scan.cuh)
+  int cosine;
+  // sample stage
+  uint32_t* sample;         // [n_cols][n_sample][2] ordered-float images
+  int n_sample;             // sampled tiles
+  float* tau;               // [n_cols] thresholds (written by the threshold kernel)
+  // main stage
+  uint64_t* cand;           // [n_cols][TC_CAND_CAP] scan keys
+  int* cand_cnt;            // [n_cols]
+};
+
+// Enqueue sample -> threshold -> main scan for one pass of args.nq <= plan.n_cols queries.
+int launch_tc_pass(const TcPlan& plan, const TcArgs& args, int sm_count, cudaStream_t st, int* launches);
+int tc_set_attributes();
+// 0 when the driver entry point for tensor maps is available.
+int tc_available();
+
+}  // namespace qg

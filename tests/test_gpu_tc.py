@@ -1,0 +1,120 @@
+"""Tensor-core regime (tc_scan.cu: TMA + tcgen05.mma kind::tf32 + TMEM) against the CPU oracle.
+The tf32 scores only select candidates; the returned lists must still be bit-identical to the
+oracle (exact re-rank + certificate), for every metric, ragged dimensions, masks and batch sizes."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(oracle, idx, corpus, queries, k, metric, which, live=None, arith=0, label=""):
+    dist, row, cnt, _ = idx.search(queries, k)
+    st = idx.stats()
+    for i in which:
+        od, orow = oracle.exact_search(corpus, queries[i], k, metric, arith, live)
+        n = len(od)
+        assert cnt[i] == n, f"{label} q{i}: count {cnt[i]} != {n} ({st})"
+        assert np.array_equal(row[i, :n], orow), f"{label} q{i}: rows {row[i, :n]} vs {orow} ({st})"
+        assert np.array_equal(dist[i, :n].view(np.uint32), od.view(np.uint32)), f"{label} q{i}: distances"
+    return st
+
+
+@pytest.mark.parametrize("metric", [1, 0, 2, 3])
+@pytest.mark.parametrize("nq", [8, 33, 256, 300])
+def test_tc_parity_batches(capi, oracle, metric, nq):
+    rng = np.random.default_rng(nq * 10 + metric)
+    n, d = 60000, 128
+    corpus = rng.random((n, d), dtype=np.float32)
+    queries = rng.random((nq, d), dtype=np.float32)
+    idx = capi.Index(d, metric)
+    idx.upload(corpus)
+    which = sorted(set([0, 1, nq // 2, nq - 1, min(nq - 1, 255), min(nq - 1, 256)]))
+    st = _check(oracle, idx, corpus, queries, 10, metric, which, label=f"m{metric}/Q{nq}")
+    assert st["path"] == 3, st
+    assert st["escalations"] <= max(1, nq // 50), st
+    idx.close()
+
+
+@pytest.mark.parametrize("d", [32, 96, 100, 260, 768])
+def test_tc_parity_dims(capi, oracle, d):
+    rng = np.random.default_rng(d)
+    n = 40000
+    corpus = rng.standard_normal((n, d)).astype(np.float32)
+    queries = rng.standard_normal((24, d)).astype(np.float32)
+    for metric in (1, 0):
+        idx = capi.Index(d, metric)
+        idx.upload(corpus)
+        st = _check(oracle, idx, corpus, queries, 10, metric, [0, 7, 23], label=f"d{d}/m{metric}")
+        assert st["path"] == 3, st
+        idx.close()
+
+
+def test_tc_k100_and_sift_like(capi, oracle):
+    n, d = 100000, 128
+    idx = capi.Index(d, 1)
+    idx.upload_synthetic(1, 42, 0, n)
+    corpus = oracle.synth(1, 42, 0, n, d)
+    queries = oracle.synth(1, 9999, 0, 64, d)
+    st = _check(oracle, idx, corpus, queries, 10, 1, [0, 31, 63], label="sift/k10")
+    assert st["path"] == 3
+    st = _check(oracle, idx, corpus, queries, 100, 1, [0, 63], label="sift/k100")
+    assert st["path"] == 3
+    idx.close()
+
+
+def test_tc_with_tombstones(capi, oracle):
+    rng = np.random.default_rng(5)
+    n, d = 50000, 96
+    corpus = rng.random((n, d), dtype=np.float32)
+    queries = rng.random((40, d), dtype=np.float32)
+    idx = capi.Index(d, 1)
+    idx.upload(corpus)
+    d0, r0, _, _ = idx.search(queries, 10)
+    dead = np.unique(np.concatenate([rng.choice(n, n // 3, replace=False), r0[:, :5].ravel()]))
+    idx.tombstone(dead)
+    live = np.ones(n, dtype=np.uint8)
+    live[dead] = 0
+    st = _check(oracle, idx, corpus, queries, 10, 1, [0, 19, 39], live=live, label="tombstones")
+    assert st["path"] == 3
+    idx.close()
+
+
+def test_tc_adversarial_order_falls_back_exactly(capi, oracle):
+    """Neighbours clustered in one stretch of rows and near-duplicate rows: the sample threshold is
+    a heuristic, so whatever it does the certified result must still equal the oracle's."""
+    rng = np.random.default_rng(6)
+    n, d = 40000, 64
+    corpus = rng.random((n, d), dtype=np.float32)
+    order = np.argsort(corpus[:, 0])
+    corpus = np.ascontiguousarray(corpus[order])
+    queries = rng.random((16, d), dtype=np.float32)
+    corpus[1000:1400] = queries[0] + 1e-3 * rng.standard_normal((400, d)).astype(np.float32)
+    for metric in (1, 0):
+        idx = capi.Index(d, metric)
+        idx.upload(corpus)
+        _check(oracle, idx, corpus, queries, 10, metric, [0, 1, 15], label=f"adversarial/m{metric}")
+        _check(oracle, idx, corpus, queries, 100, metric, [0, 15], label=f"adversarial/k100/m{metric}")
+        idx.close()
+
+
+def test_tc_device_api_matches_flat_path(capi):
+    """The same batch through the tensor-core regime and, forced query by query, the flat scan."""
+    import torch
+    n, d, nq, k = 80000, 128, 64, 10
+    idx = capi.Index(d, 1)
+    idx.upload_synthetic(0, 7, 0, n)
+    q = torch.rand((nq, d), device="cuda:0")
+    dist = torch.empty((nq, k), dtype=torch.float32, device="cuda:0")
+    row = torch.empty((nq, k), dtype=torch.int64, device="cuda:0")
+    cnt = torch.empty((nq,), dtype=torch.int32, device="cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    idx.search_device(q.data_ptr(), nq, k, dist.data_ptr(), row.data_ptr(), cnt.data_ptr(), stream=st)
+    torch.cuda.synchronize()
+    assert idx.stats()["path"] == 3
+    d1, r1, c1, _ = idx.search(q[:4].cpu().numpy(), k)  # 4 queries: flat scan
+    assert idx.stats()["path"] == 1
+    ok = cnt[:4].cpu().numpy() >= 0
+    assert ok.all()
+    assert np.array_equal(row[:4].cpu().numpy(), r1)
+    assert np.array_equal(dist[:4].cpu().numpy().view(np.uint32), d1.view(np.uint32))
+    idx.close()

@@ -32,21 +32,27 @@ def time_search(idx, dq, q, k, iters=20, warm=3):
 def main():
     out = []
     configs = [(1_000_000, 128, 1, 1), (1_000_000, 96, 1, 3), (200_000, 768, 0, 2), (4_000_000, 128, 1, 1)]
+    qs = (1, 2, 4, 8, 16, 64, 128, 256, 1024, 10000)
+    if len(sys.argv) > 1:
+        qs = tuple(int(x) for x in sys.argv[1].split(","))
+    if len(sys.argv) > 2:
+        configs = [configs[int(x)] for x in sys.argv[2].split(",")]
     for n, d, metric, kind in configs:
         idx = capi.Index(d, metric, reserve_rows=n)
         t0 = time.time()
         idx.upload_synthetic(kind, 42, 0, n)
         print(f"N={n} d={d} metric={metric} fill {time.time()-t0:.2f}s", flush=True)
-        for q in (1, 2, 4, 8, 16, 64):
+        for q in qs:
             for k in (10, 100):
                 dq = torch.rand((q, d), device="cuda:0")
                 if kind == 1:
                     dq = torch.floor(dq * 218)
-                ms, cnt = time_search(idx, dq, q, k)
+                ms, cnt = time_search(idx, dq, q, k, iters=20 if q <= 256 else 5)
                 st = idx.stats()
                 gbs = st["bytes_algorithmic"] * st["passes"] / (ms * 1e-3) / 1e9
+                tfl = 2.0 * q * n * d / (ms * 1e-3) / 1e12
                 rec = dict(n=n, d=d, metric=metric, q=q, k=k, ms=round(ms, 4), qps=round(q / ms * 1e3, 1),
-                           gbs=round(gbs, 1), passes=st["passes"], qb=st["queries_per_pass"],
+                           gbs=round(gbs, 1), tflops=round(tfl, 1), path=st["path"], passes=st["passes"], qb=st["queries_per_pass"],
                            launches=st["kernel_launches"], bad=int((cnt < 0).sum()))
                 print(json.dumps(rec), flush=True)
                 out.append(rec)
