@@ -2,6 +2,7 @@
 // pinned staging buffers, facet columns / filters, search orchestration.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -135,13 +136,13 @@ struct Workspace {
     prof_used += 2;
   }
   DevBuf qpad, negpad, partial, mask, counters;
-  DevBuf tc_sample, tc_tau, tc_cand, tc_cnt;
+  DevBuf tc_sample, tc_tau, tc_cand, tc_cnt, tc_bias;
   DevBuf d_q, d_neg, d_dist, d_negdist, d_row, d_count, d_rows32, d_rows64, d_fetch;
   PinBuf h_in, h_out;
   ExhaustiveWork ex;
   void destroy() {
     qpad.release(); negpad.release(); partial.release(); mask.release(); counters.release();
-    tc_sample.release(); tc_tau.release(); tc_cand.release(); tc_cnt.release();
+    tc_sample.release(); tc_tau.release(); tc_cand.release(); tc_cnt.release(); tc_bias.release();
     d_q.release(); d_neg.release(); d_dist.release(); d_negdist.release(); d_row.release(); d_count.release();
     d_rows32.release(); d_rows64.release(); d_fetch.release();
     h_in.release(); h_out.release();
@@ -191,7 +192,8 @@ struct qg_index {
   long long cap = 0, n_rows = 0, n_live = 0;
   float* vec = nullptr;
   float* inv_norm = nullptr;
-  float* norm2 = nullptr;
+  float* norm2 = nullptr;      // |x|^2, +inf beyond n_rows (tensor-core row term, L2)
+  float* unit_bias = nullptr;  // 1.0, +inf beyond n_rows (tensor-core row term, dot / cosine)
   uint32_t* live = nullptr;
   float* max_norm2 = nullptr;  // device scalar
   uint64_t live_epoch = 0, facet_epoch = 0;
@@ -211,6 +213,15 @@ struct qg_index {
 };
 
 namespace qg {
+
+// Number of corpus tiles the sample stage scores: chosen so that about G rows per query fall under
+// the TC_SAMPLE_RANK-th smallest sampled score (G ~ 256 for k = 10).
+static long long tc_sample_tiles(const TcPlan& plan, long long n_rows, int k) {
+  const long long n_tiles = (n_rows + plan.tile_rows - 1) / plan.tile_rows;
+  const long long G = std::max<long long>(256, 6ll * (k + 24));
+  long long n_sample = ((long long)TC_SAMPLE_RANK * n_rows + G * plan.tile_rows - 1) / (G * plan.tile_rows);
+  return std::max<long long>(16, std::min<long long>(n_sample, std::min<long long>(n_tiles, 8192)));
+}
 
 static int scan_mode_of(int metric) {
   switch (metric) {
@@ -281,26 +292,33 @@ static int grow(qg_index* idx, long long need_rows) {
   float* nvec = nullptr;
   float* ninv = nullptr;
   float* nn2 = nullptr;
+  float* nub = nullptr;
   uint32_t* nlive = nullptr;
   cudaError_t e = cudaMalloc(&nvec, (size_t)ncap * idx->dp * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&ninv, (size_t)ncap * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&nn2, (size_t)ncap * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&nub, (size_t)ncap * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&nlive, (size_t)(ncap / 32) * sizeof(uint32_t));
   if (e != cudaSuccess) {
     if (nvec) cudaFree(nvec);
     if (ninv) cudaFree(ninv);
     if (nn2) cudaFree(nn2);
+    if (nub) cudaFree(nub);
     if (nlive) cudaFree(nlive);
     return fail(QG_ERR_OOM, std::string("device allocation for ") + std::to_string(ncap) +
                                 " rows failed: " + cudaGetErrorString(e));
   }
   QG_CUDA_OK(cudaMemsetAsync(nlive, 0, (size_t)(ncap / 32) * sizeof(uint32_t), idx->up_stream));
+  if (int rc = launch_fill_f32(nn2, ncap, INFINITY, idx->up_stream)) return rc;
+  if (int rc = launch_fill_f32(nub, ncap, INFINITY, idx->up_stream)) return rc;
   if (idx->n_rows > 0) {
     QG_CUDA_OK(cudaMemcpyAsync(nvec, idx->vec, (size_t)idx->n_rows * idx->dp * sizeof(float),
                                cudaMemcpyDeviceToDevice, idx->up_stream));
     QG_CUDA_OK(cudaMemcpyAsync(ninv, idx->inv_norm, (size_t)idx->n_rows * sizeof(float), cudaMemcpyDeviceToDevice,
                                idx->up_stream));
     QG_CUDA_OK(cudaMemcpyAsync(nn2, idx->norm2, (size_t)idx->n_rows * sizeof(float), cudaMemcpyDeviceToDevice,
+                               idx->up_stream));
+    QG_CUDA_OK(cudaMemcpyAsync(nub, idx->unit_bias, (size_t)idx->n_rows * sizeof(float), cudaMemcpyDeviceToDevice,
                                idx->up_stream));
     QG_CUDA_OK(cudaMemcpyAsync(nlive, idx->live, (size_t)((idx->n_rows + 31) / 32) * sizeof(uint32_t),
                                cudaMemcpyDeviceToDevice, idx->up_stream));
@@ -309,10 +327,12 @@ static int grow(qg_index* idx, long long need_rows) {
   if (idx->vec) cudaFree(idx->vec);
   if (idx->inv_norm) cudaFree(idx->inv_norm);
   if (idx->norm2) cudaFree(idx->norm2);
+  if (idx->unit_bias) cudaFree(idx->unit_bias);
   if (idx->live) cudaFree(idx->live);
   idx->vec = nvec;
   idx->inv_norm = ninv;
   idx->norm2 = nn2;
+  idx->unit_bias = nub;
   idx->live = nlive;
   idx->cap = ncap;
   return 0;
@@ -321,8 +341,8 @@ static int grow(qg_index* idx, long long need_rows) {
 // Post-copy bookkeeping shared by the three upload flavours.
 static int finish_append(qg_index* idx, long long n, int64_t* first_row) {
   const long long row0 = idx->n_rows;
-  if (int rc = launch_row_norms(idx->vec, row0, n, idx->dp, idx->dim, idx->inv_norm, idx->norm2, idx->max_norm2,
-                                idx->up_stream))
+  if (int rc = launch_row_norms(idx->vec, row0, n, idx->dp, idx->dim, idx->inv_norm, idx->norm2, idx->unit_bias,
+                                idx->max_norm2, idx->up_stream))
     return rc;
   if (int rc = launch_set_live(idx->live, row0, n, idx->up_stream)) return rc;
   QG_CUDA_OK(cudaStreamSynchronize(idx->up_stream));
@@ -424,6 +444,7 @@ int qg_index_destroy(qg_index* idx) {
   if (idx->vec) cudaFree(idx->vec);
   if (idx->inv_norm) cudaFree(idx->inv_norm);
   if (idx->norm2) cudaFree(idx->norm2);
+  if (idx->unit_bias) cudaFree(idx->unit_bias);
   if (idx->live) cudaFree(idx->live);
   if (idx->max_norm2) cudaFree(idx->max_norm2);
   if (idx->stage_ev[0]) cudaEventDestroy(idx->stage_ev[0]);
@@ -871,15 +892,22 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
   TcPlan plan{};
   if (q >= idx->tc_min_q && !gather && mode != MODE_L1 && kp <= 128 && n_items >= idx->tc_min_rows &&
       tc_available() == 0 && tc_plan(dp, q, &plan) == 0) {
-    const long long n_tiles = (idx->n_rows + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
-    // sample so that about G rows per query fall under the TC_SAMPLE_RANK-th smallest sampled score
-    const long long G = std::max<long long>(256, 8ll * (k + 24));
-    long long n_sample = ((long long)TC_SAMPLE_RANK * idx->n_rows + G * TC_TILE_ROWS - 1) / (G * TC_TILE_ROWS);
-    n_sample = std::max<long long>(16, std::min<long long>(n_sample, std::min<long long>(n_tiles, 4096)));
-    if (int rc = w->tc_sample.ensure((size_t)plan.n_cols * n_sample * 2 * 4)) return rc;
+    const long long n_sample = tc_sample_tiles(plan, idx->n_rows, k);
+    if (int rc = w->tc_sample.ensure((size_t)plan.n_cols * n_sample * plan.sample_vals * 4)) return rc;
     if (int rc = w->tc_tau.ensure((size_t)TC_MAX_COLS * 4)) return rc;
     if (int rc = w->tc_cand.ensure((size_t)plan.n_cols * TC_CAND_CAP * 8)) return rc;
     if (int rc = w->tc_cnt.ensure((size_t)TC_MAX_COLS * 4)) return rc;
+    // TS variant: additive row term with the mask folded in (+inf = excluded)
+    const float* tc_bias = mode == MODE_L2 ? idx->norm2 : idx->unit_bias;
+    if (plan.variant == 1 && mask != nullptr) {
+      const long long n_pad = (idx->n_rows + 127) & ~127ll;
+      if (int rc = w->tc_bias.ensure((size_t)n_pad * 4)) return rc;
+      if (int rc = launch_tc_bias(mask, mode == MODE_L2 ? idx->norm2 : nullptr, idx->n_rows, n_pad,
+                                  (float*)w->tc_bias.p, st))
+        return rc;
+      stats.kernel_launches++;
+      tc_bias = (const float*)w->tc_bias.p;
+    }
     FinalizeCandParams cp{};
     cp.cand = (const uint64_t*)w->tc_cand.p;
     cp.cand_cnt = (const int*)w->tc_cnt.p;
@@ -908,6 +936,7 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
       ta.row_norm2 = idx->norm2;
       ta.inv_norm = idx->metric == METRIC_COSINE ? idx->inv_norm : nullptr;
       ta.mask = mask;
+      ta.bias = tc_bias;
       ta.queries = qpad + (size_t)p0 * dp;
       ta.nq = nq;
       ta.mode = mode;
@@ -1397,11 +1426,8 @@ int qg_debug_tc_pass(qg_index* idx, const float* queries, int nq, int k, float* 
       e = cudaMemcpy2DAsync(w->qpad.p, (size_t)dp * 4, queries, (size_t)d * 4, (size_t)d * 4, (size_t)nq,
                             cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, cudaGetErrorString(e)); break; }
-    const long long n_tiles = (idx->n_rows + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
-    const long long G = std::max<long long>(256, 8ll * (k + 24));
-    long long n_sample = ((long long)TC_SAMPLE_RANK * idx->n_rows + G * TC_TILE_ROWS - 1) / (G * TC_TILE_ROWS);
-    n_sample = std::max<long long>(16, std::min<long long>(n_sample, std::min<long long>(n_tiles, 4096)));
-    if ((rc = w->tc_sample.ensure((size_t)plan.n_cols * n_sample * 2 * 4))) break;
+    const long long n_sample = tc_sample_tiles(plan, idx->n_rows, k);
+    if ((rc = w->tc_sample.ensure((size_t)plan.n_cols * n_sample * plan.sample_vals * 4))) break;
     if ((rc = w->tc_tau.ensure((size_t)TC_MAX_COLS * 4))) break;
     if ((rc = w->tc_cand.ensure((size_t)plan.n_cols * TC_CAND_CAP * 8))) break;
     if ((rc = w->tc_cnt.ensure((size_t)TC_MAX_COLS * 4))) break;
@@ -1412,6 +1438,15 @@ int qg_debug_tc_pass(qg_index* idx, const float* queries, int nq, int k, float* 
     ta.row_norm2 = idx->norm2;
     ta.inv_norm = idx->metric == METRIC_COSINE ? idx->inv_norm : nullptr;
     ta.mask = idx->n_live < idx->n_rows ? idx->live : nullptr;
+    ta.bias = mode == MODE_L2 ? idx->norm2 : idx->unit_bias;
+    if (plan.variant == 1 && ta.mask != nullptr) {
+      const long long n_pad = (idx->n_rows + 127) & ~127ll;
+      if ((rc = w->tc_bias.ensure((size_t)n_pad * 4))) break;
+      if ((rc = launch_tc_bias(ta.mask, mode == MODE_L2 ? idx->norm2 : nullptr, idx->n_rows, n_pad,
+                               (float*)w->tc_bias.p, st)))
+        break;
+      ta.bias = (const float*)w->tc_bias.p;
+    }
     ta.queries = (const float*)w->qpad.p;
     ta.nq = nq;
     ta.mode = mode;
@@ -1422,8 +1457,20 @@ int qg_debug_tc_pass(qg_index* idx, const float* queries, int nq, int k, float* 
     ta.cand = (uint64_t*)w->tc_cand.p;
     ta.cand_cnt = (int*)w->tc_cnt.p;
     int launches = 0;
+    if ((rc = w->counters.ensure(64 * 8))) break;
+    cudaMemsetAsync(w->counters.p, 0, 64 * 8, st);
+    ta.dbg = (unsigned long long*)w->counters.p;
     if ((rc = launch_tc_pass(plan, ta, idx->sm_count, st, &launches))) break;
     e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess && std::getenv("QG_TC_TIMING")) {
+      unsigned long long h[64];
+      cudaMemcpy(h, w->counters.p, sizeof(h), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "tc timing (cycles, CTA 0): producer total %llu wait_xs %llu wait_empty %llu | mma total %llu "
+                      "wait_tmem_empty %llu wait_full %llu\n", h[0], h[1], h[2], h[3], h[4], h[5]);
+      for (int i = 0; i < 8; ++i)
+        fprintf(stderr, "  epilogue warp %d: total %llu wait_xs %llu wait_tmem_full %llu tmem_ld %llu\n", i + 2,
+                h[8 + i * 4], h[9 + i * 4], h[10 + i * 4], h[11 + i * 4]);
+    }
     if (e == cudaSuccess && tau_out) e = cudaMemcpy(tau_out, w->tc_tau.p, (size_t)nq * 4, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && cnt_out) e = cudaMemcpy(cnt_out, w->tc_cnt.p, (size_t)nq * 4, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && cand_out)

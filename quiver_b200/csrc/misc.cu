@@ -10,7 +10,8 @@ namespace qg {
 // re-derived exactly by finalize.cu.
 __global__ void __launch_bounds__(256) row_norms_kernel(const float* __restrict__ vec, long long row0, long long n,
                                                         int dp, int d, float* __restrict__ inv_norm,
-                                                        float* __restrict__ norm2, float* max_norm2) {
+                                                        float* __restrict__ norm2, float* __restrict__ unit_bias,
+                                                        float* max_norm2) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float local_max = 0.f;
   for (long long r = (long long)blockIdx.x * 8 + warp; r < n; r += (long long)gridDim.x * 8) {
@@ -22,6 +23,7 @@ __global__ void __launch_bounds__(256) row_norms_kernel(const float* __restrict_
     if (lane == 0) {
       inv_norm[row0 + r] = s > 0.0 ? (float)(1.0 / sqrt(s)) : 0.f;
       norm2[row0 + r] = sf;
+      unit_bias[row0 + r] = 1.0f;
     }
     local_max = fmaxf(local_max, sf);
   }
@@ -32,11 +34,25 @@ __global__ void __launch_bounds__(256) row_norms_kernel(const float* __restrict_
 }
 
 int launch_row_norms(const float* vec, long long row0, long long n, int dp, int d, float* inv_norm, float* norm2,
-                     float* max_norm2, cudaStream_t st) {
+                     float* unit_bias, float* max_norm2, cudaStream_t st) {
   if (n <= 0) return 0;
   long long blocks = (n + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  row_norms_kernel<<<(int)blocks, 256, 0, st>>>(vec, row0, n, dp, d, inv_norm, norm2, max_norm2);
+  row_norms_kernel<<<(int)blocks, 256, 0, st>>>(vec, row0, n, dp, d, inv_norm, norm2, unit_bias, max_norm2);
+  QG_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+__global__ void fill_f32_kernel(float* __restrict__ p, long long n, float v) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+
+int launch_fill_f32(float* p, long long n, float v, cudaStream_t st) {
+  if (n <= 0) return 0;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  fill_f32_kernel<<<(int)blocks, 256, 0, st>>>(p, n, v);
   QG_CUDA_OK(cudaGetLastError());
   return 0;
 }

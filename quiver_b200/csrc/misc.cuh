@@ -21,9 +21,11 @@ struct FilterProgDev {
   const double* fset;
 };
 
-// 1/|x| per row (0 for zero rows), |x|^2 per row and the running max |x|^2 (atomic, device scalar).
+// 1/|x| per row (0 for zero rows), |x|^2 per row, 1.0 into unit_bias, and the running max |x|^2
+// (atomic, device scalar).
 int launch_row_norms(const float* vec, long long row0, long long n, int dp, int d, float* inv_norm, float* norm2,
-                     float* max_norm2, cudaStream_t st);
+                     float* unit_bias, float* max_norm2, cudaStream_t st);
+int launch_fill_f32(float* p, long long n, float v, cudaStream_t st);
 // rows [row0, row0+n) of the index filled from the generator (kind 0..3).
 int launch_synth_fill(float* vec, long long row0, long long n, int dp, int d, int kind, uint64_t seed,
                       long long global_row0, cudaStream_t st);

@@ -25,6 +25,19 @@ namespace qg {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// One lane of a CONVERGED warp. The single-thread instructions (TMA, tcgen05.mma, tcgen05.commit) are
+// issued under this predicate from warp-uniform loops; wrapping a whole loop in `if (lane == 0)`
+// instead makes the warp divergent and ptxas then serialises every uniform-datapath instruction
+// behind an ELECT / BRA.U.ANY loop (measured: ~90 cycles per MMA issue).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -55,6 +68,28 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from tensor memory (the resident query block), B from shared memory.
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(
+          taddr),
+      "r"(__float_as_uint(r[0])), "r"(__float_as_uint(r[1])), "r"(__float_as_uint(r[2])), "r"(__float_as_uint(r[3])),
+      "r"(__float_as_uint(r[4])), "r"(__float_as_uint(r[5])), "r"(__float_as_uint(r[6])), "r"(__float_as_uint(r[7])),
+      "r"(__float_as_uint(r[8])), "r"(__float_as_uint(r[9])), "r"(__float_as_uint(r[10])),
+      "r"(__float_as_uint(r[11])), "r"(__float_as_uint(r[12])), "r"(__float_as_uint(r[13])),
+      "r"(__float_as_uint(r[14])), "r"(__float_as_uint(r[15]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -71,6 +106,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
 }
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&u)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -192,61 +236,64 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
+    // ===== TMA producer (converged warp, one elected lane issues) =====
+    if (elect_one()) {
       mbar_arrive_expect_tx(b_full, (uint32_t)(kb * n_cols * 128));
       for (int kbi = 0; kbi < kb; ++kbi) tma_load_2d(sB + (size_t)kbi * n_cols * 128, &tm_b, kbi * TC_KBLOCK, 0, b_full);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (long long w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const long long tile = tile_of(w);
-        for (int kbi = 0; kbi < kb; ++kbi) {
-          mbar_wait(&empty[stage], phase ^ 1u);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const long long tile = tile_of(w);
+      for (int kbi = 0; kbi < kb; ++kbi) {
+        mbar_wait(&empty[stage], phase ^ 1u);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&full[stage], TC_STAGE_BYTES);
           tma_load_2d(sA + (size_t)stage * TC_STAGE_BYTES, &tm_a, kbi * TC_KBLOCK, (int)(tile * TC_TILE_ROWS),
                       &full[stage]);
-          if (++stage == S) {
-            stage = 0;
-            phase ^= 1u;
-          }
+        }
+        __syncwarp();
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1u;
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      mbar_wait(b_full, 0);
+    // ===== MMA issuer (converged warp, one elected lane issues) =====
+    mbar_wait(b_full, 0);
+    tc_fence_after();
+    const uint64_t adesc0 = make_sdesc(smem_u32(sA));
+    const uint64_t bdesc0 = make_sdesc(smem_u32(sB));
+    int stage = 0;
+    uint32_t phase = 0;
+    long long it = 0;
+    for (long long w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+      const int acc = (int)(it & 1);
+      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
       tc_fence_after();
-      int stage = 0;
-      uint32_t phase = 0;
-      long long it = 0;
-      for (long long w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-        const int acc = (int)(it & 1);
-        const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * n_cols);
+      for (int kbi = 0; kbi < kb; ++kbi) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * n_cols);
-        for (int kbi = 0; kbi < kb; ++kbi) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + (size_t)stage * TC_STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(sB + (size_t)kbi * n_cols * 128);
+        if (elect_one()) {
+          const uint64_t adesc = adesc0 + (uint64_t)((uint32_t)stage * (TC_STAGE_BYTES >> 4));
+          const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)kbi * (uint32_t)((n_cols * 128) >> 4));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            umma_tf32(d_tmem, make_sdesc(a_addr + k * 32), make_sdesc(b_addr + k * 32), p.idesc,
-                      (uint32_t)((kbi | k) != 0));
-          }
+          for (int k = 0; k < 4; ++k)
+            umma_tf32(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (uint32_t)((kbi | k) != 0));
           umma_commit(&empty[stage]);  // frees the A stage once these MMAs have read it
-          if (++stage == S) {
-            stage = 0;
-            phase ^= 1u;
-          }
+          if (kbi == kb - 1) umma_commit(&tmem_full[acc]);
         }
-        umma_commit(&tmem_full[acc]);
+        __syncwarp();
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1u;
+        }
       }
     }
-    __syncwarp();
   } else {
     // ===== epilogue warps =====
     const int quarter = warp & 3;          // TMEM lanes [32*quarter, 32*quarter+32)
@@ -363,27 +410,449 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+
+// ================================================================================================
+// TS variant (dp <= 256): the QUERIES are the A operand, resident in tensor memory for the whole
+// pass (tcgen05.st once per CTA), and the corpus tile is the B operand streamed through shared
+// memory. D[query lane][corpus row column] — so every epilogue thread owns one query: its threshold
+// lives in a register, a tile's per-row terms are broadcast from shared memory, and all of shared
+// memory is left to the corpus ring (~190 KB in flight per SM, which the HBM pipe needs).
+//   TMEM columns: [0, nblk*kb*32) query blocks | then (blk*2 + acc) * 64 accumulators
+//   warps: 0 TMA (corpus tiles + the tile's per-row terms), 1 MMA + TMEM alloc, 2..9 epilogue
+// ================================================================================================
+constexpr int TS_KSTEP_BYTES = 128;               // one swizzle row: 32 floats
+constexpr int TS_THREADS = 320;
+constexpr int TS_XS = 8;                          // ring of per-tile row-term buffers
+// corpus rows per tile = MMA N: two resident query blocks leave 64 accumulator columns per buffer,
+// one block leaves 128 (512 TMEM columns = nblk * kb * 32 + nblk * 2 * rows)
+__host__ __device__ constexpr int ts_rows(int nblk) { return nblk == 2 ? 64 : 128; }
+
+struct TsKParams {
+  long long n_rows;
+  long long n_tiles;
+  int kb, stages, nq, nblk;
+  uint32_t idesc;
+  int cosine;
+  const float* bias;   // [rows padded to 128] additive row term: |x|^2 (L2) or 1 (dot); +inf = row excluded
+  const float* sc;     // [rows padded to 128] 1/|x| (cosine) or nullptr
+  const float* queries;
+  int dp;
+  uint32_t* sample;  // [n_cols][n_sample][2]
+  int n_sample;
+  const float* tau;
+  uint64_t* cand;
+  int* cand_cnt;
+  unsigned long long* dbg;  // optional per-role cycle counters of CTA 0 (development aid), else nullptr
+};
+
+struct TsSmem {
+  int off_ring, off_bias, off_sc, off_bars, off_tmem, total;
+};
+__host__ __device__ inline TsSmem ts_smem_layout(int stages, int kb, int rows) {
+  TsSmem s;
+  s.off_ring = 0;
+  s.off_bias = stages * kb * rows * TS_KSTEP_BYTES;  // one stage = one whole tile (kb k-blocks)
+  s.off_sc = s.off_bias + TS_XS * rows * 4;
+  s.off_bars = s.off_sc + TS_XS * rows * 4;
+  s.off_tmem = s.off_bars + (2 * stages + 4 + 2 * TS_XS + 1) * 8;
+  s.total = s.off_tmem + 16;
+  return s;
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+// KB > 0: compile-time number of 32-float blocks per row (MMA issue loop fully unrolled); KB == 0: p.kb.
+template <int MODE, bool SAMPLE, int NBLK, int KB>
+__global__ void __launch_bounds__(TS_THREADS, 1)
+    tc_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const TsKParams p) {
+  constexpr int ROWS = ts_rows(NBLK);
+  constexpr int KBLOCK_BYTES = ROWS * TS_KSTEP_BYTES;  // one 32-float block of a tile
+  extern __shared__ unsigned char smem_unaligned[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_unaligned) + 1023) &
+                                                         ~(uintptr_t)1023);
+  const int kb = KB > 0 ? KB : p.kb;
+  const int S = p.stages;
+  const TsSmem L = ts_smem_layout(S, kb, ROWS);
+  unsigned char* ring = smem + L.off_ring;
+  float* xs_bias = reinterpret_cast<float*>(smem + L.off_bias);
+  float* xs_sc = reinterpret_cast<float*>(smem + L.off_sc);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.off_bars);
+  uint64_t* empty = full + S;
+  uint64_t* tmem_full = empty + S;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* xs_full = tmem_empty + 2;
+  uint64_t* xs_empty = xs_full + TS_XS;
+  uint64_t* a_ready = xs_empty + TS_XS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.off_tmem);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int a_cols = kb * TC_KBLOCK;             // TMEM columns of one query block
+  const int tile_bytes = kb * KBLOCK_BYTES;      // one ring stage = one whole tile
+  const int d_off = NBLK * a_cols;               // first accumulator column
+  const long long n_work = SAMPLE ? (long long)p.n_sample : p.n_tiles;
+  auto tile_of = [&](long long w) -> long long { return SAMPLE ? (w * p.n_tiles) / p.n_sample : w; };
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_x);
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);
+    }
+    for (int i = 0; i < TS_XS; ++i) {
+      mbar_init(&xs_full[i], 1);
+      mbar_init(&xs_empty[i], 8);
+    }
+    mbar_init(a_ready, 8);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (converged warp, one elected lane issues): whole corpus tiles and the
+    //       tile's per-row terms =====
+    int stage = 0;
+    uint32_t phase = 0;
+    long long it = 0;
+    const bool with_sc = MODE != MODE_L2 && p.sc != nullptr;
+    const uint32_t xs_bytes = (uint32_t)(ROWS * 4 * (with_sc ? 2 : 1));
+    long long t_prod_xs = 0, t_prod_empty = 0;
+    const long long t_prod_begin = clock64();
+    for (long long w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+      const long long tile = tile_of(w);
+      const int xb = (int)(it % TS_XS);
+      const uint32_t xphase = (uint32_t)((it / TS_XS) & 1);
+      long long t0 = 0;
+      if (p.dbg) t0 = clock64();
+      mbar_wait(&xs_empty[xb], xphase ^ 1u);
+      if (p.dbg) t_prod_xs += clock64() - t0;
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&xs_full[xb], xs_bytes);
+        bulk_g2s(xs_bias + xb * ROWS, p.bias + tile * ROWS, ROWS * 4, &xs_full[xb]);
+        if (with_sc) bulk_g2s(xs_sc + xb * ROWS, p.sc + tile * ROWS, ROWS * 4, &xs_full[xb]);
+      }
+      __syncwarp();
+      if (p.dbg) t0 = clock64();
+      mbar_wait(&empty[stage], phase ^ 1u);
+      if (p.dbg) t_prod_empty += clock64() - t0;
+      if (elect_one()) {
+        unsigned char* dst = ring + (size_t)stage * tile_bytes;
+        mbar_arrive_expect_tx(&full[stage], (uint32_t)tile_bytes);
+        for (int kbi = 0; kbi < kb; ++kbi)
+          tma_load_2d(dst + (size_t)kbi * KBLOCK_BYTES, &tm_x, kbi * TC_KBLOCK, (int)(tile * ROWS), &full[stage]);
+      }
+      __syncwarp();
+      if (++stage == S) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+    if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0) {
+      p.dbg[0] = (unsigned long long)(clock64() - t_prod_begin);
+      p.dbg[1] = (unsigned long long)t_prod_xs;
+      p.dbg[2] = (unsigned long long)t_prod_empty;
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (converged warp, one elected lane issues) =====
+    long long t_mma_empty = 0, t_mma_full = 0;
+    const long long t_mma_begin = clock64();
+    mbar_wait(a_ready, 0);
+    tc_fence_after();
+    const uint64_t desc0 = make_sdesc(smem_u32(ring));
+    const uint32_t idesc = p.idesc;
+    int stage = 0;
+    uint32_t phase = 0;
+    long long it = 0;
+    for (long long w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+      const int acc = (int)(it & 1);
+      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+      long long t0 = 0;
+      if (p.dbg) t0 = clock64();
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+      if (p.dbg) t_mma_empty += clock64() - t0;
+      if (p.dbg) t0 = clock64();
+      mbar_wait(&full[stage], phase);
+      if (p.dbg) t_mma_full += clock64() - t0;
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t d0 = tmem_base + (uint32_t)(d_off + acc * ROWS);
+        const uint32_t d1 = d0 + 2 * ROWS;
+        const uint64_t bdesc = desc0 + (uint64_t)((uint32_t)stage * (uint32_t)(tile_bytes >> 4));
+        if (KB > 0) {
+#pragma unroll
+          for (int kbi = 0; kbi < (KB > 0 ? KB : 1); ++kbi) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t bd = bdesc + (uint64_t)(kbi * (KBLOCK_BYTES >> 4) + k * 2);
+              const uint32_t aa = tmem_base + (uint32_t)(kbi * TC_KBLOCK + k * 8);
+              umma_tf32_ts(d0, aa, bd, idesc, (kbi | k) != 0 ? 1u : 0u);
+              if (NBLK == 2) umma_tf32_ts(d1, aa + (uint32_t)(KB * TC_KBLOCK), bd, idesc, (kbi | k) != 0 ? 1u : 0u);
+            }
+          }
+        } else {
+          uint64_t bd0 = bdesc;
+          uint32_t a0 = tmem_base;
+          for (int kbi = 0; kbi < kb; ++kbi) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_tf32_ts(d0, a0 + k * 8, bd0 + (uint64_t)(k * 2), idesc, (kbi | k) != 0 ? 1u : 0u);
+              if (NBLK == 2) umma_tf32_ts(d1, a0 + a_cols + k * 8, bd0 + (uint64_t)(k * 2), idesc, (kbi | k) != 0 ? 1u : 0u);
+            }
+            bd0 += (uint64_t)(KBLOCK_BYTES >> 4);
+            a0 += TC_KBLOCK;
+          }
+        }
+        umma_commit(&empty[stage]);
+        umma_commit(&tmem_full[acc]);
+      }
+      __syncwarp();
+      if (++stage == S) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+    if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0) {
+      p.dbg[3] = (unsigned long long)(clock64() - t_mma_begin);
+      p.dbg[4] = (unsigned long long)t_mma_empty;
+      p.dbg[5] = (unsigned long long)t_mma_full;
+    }
+  } else {
+    // ===== epilogue warps: one query per thread, four 16-row chunks per warp and tile =====
+    const int quarter = warp & 3;
+    const int grp = (warp - 2) >> 2;                     // 0 or 1
+    const int blk = NBLK == 2 ? grp : 0;                 // query block of this warp
+    const int q = blk * 128 + quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    // NBLK == 2: chunks 0..3 of the 64-row tile; NBLK == 1: the two groups interleave the 8 chunks
+    auto chunk_of = [&](int ci) -> int { return NBLK == 2 ? ci : grp + 2 * ci; };
+
+    // ---- resident query block -> tensor memory (cosine: pre-scaled by 1/|q|) ----
+    if (NBLK == 2 || grp == 0) {
+      float rnq = 1.f;
+      if (MODE == MODE_DOT && p.cosine && q < p.nq) {
+        float s = 0.f;
+        const float* qv = p.queries + (size_t)q * p.dp;
+        for (int i = 0; i < p.dp; ++i) s = fmaf(qv[i], qv[i], s);
+        rnq = s > 0.f ? rsqrtf(s) : 0.f;
+      }
+      for (int c = 0; c < a_cols / 16; ++c) {
+        float v[16];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const int col = c * 16 + j4 * 4;
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (q < p.nq && col < p.dp) t = __ldg(reinterpret_cast<const float4*>(p.queries + (size_t)q * p.dp + col));
+          v[j4 * 4 + 0] = t.x * rnq;
+          v[j4 * 4 + 1] = t.y * rnq;
+          v[j4 * 4 + 2] = t.z * rnq;
+          v[j4 * 4 + 3] = t.w * rnq;
+        }
+        tmem_st16(tmem_base + lane_base + (uint32_t)(blk * a_cols + c * 16), v);
+      }
+      tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(a_ready);
+
+    float tau_me = -__int_as_float(0x7f800000);
+    if (!SAMPLE && q < p.nq) tau_me = __ldg(p.tau + q);
+    const bool has_sc = MODE != MODE_L2 && p.sc != nullptr;
+    const uint32_t bias_s = smem_u32(xs_bias), sc_s = smem_u32(xs_sc);
+    // a lane's hit is parked in registers and published one tile later, so the round trip of the
+    // global atomic that claims its slot never sits on the tile's critical path
+    uint64_t pend_key = 0, prev_key = 0;
+    int prev_pos = 0;
+    bool has_pend = false, prev_has = false;
+    long long t_epi_xs = 0, t_epi_full = 0;
+    const long long t_epi_begin = clock64();
+
+    long long it = 0;
+    for (long long w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+      const long long tile = tile_of(w);
+      const int acc = (int)(it & 1);
+      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+      const int xb = (int)(it % TS_XS);
+      const uint32_t xphase = (uint32_t)((it / TS_XS) & 1);
+      long long t0 = 0;
+      if (p.dbg) t0 = clock64();
+      mbar_wait(&xs_full[xb], xphase);
+      if (p.dbg) {
+        const long long t1 = clock64();
+        t_epi_xs += t1 - t0;
+        t0 = t1;
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      if (p.dbg) t_epi_full += clock64() - t0;
+      tc_fence_after();
+      const uint32_t d_addr = tmem_base + lane_base + (uint32_t)(d_off + (blk * 2 + acc) * ROWS);
+      // all of this warp's accumulator chunks are requested before the first one is consumed
+      uint32_t araw[4][16];
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) tmem_ld16_issue(d_addr + (uint32_t)(chunk_of(ci) * 16), araw[ci]);
+      tmem_ld_wait();
+      float tile_min = __int_as_float(0x7f800000);
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int c = chunk_of(ci);
+        float v[16];
+        const uint32_t boff = (uint32_t)((xb * ROWS + c * 16) * 4);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 bb = lds128(bias_s + boff + j4 * 16);
+          const float a0 = __uint_as_float(araw[ci][j4 * 4 + 0]), a1 = __uint_as_float(araw[ci][j4 * 4 + 1]);
+          const float a2 = __uint_as_float(araw[ci][j4 * 4 + 2]), a3 = __uint_as_float(araw[ci][j4 * 4 + 3]);
+          if (MODE == MODE_L2) {
+            v[j4 * 4 + 0] = fmaf(-2.f, a0, bb.x);
+            v[j4 * 4 + 1] = fmaf(-2.f, a1, bb.y);
+            v[j4 * 4 + 2] = fmaf(-2.f, a2, bb.z);
+            v[j4 * 4 + 3] = fmaf(-2.f, a3, bb.w);
+          } else {
+            float4 ss = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (has_sc) ss = lds128(sc_s + boff + j4 * 16);
+            v[j4 * 4 + 0] = fmaf(-a0, ss.x, bb.x);
+            v[j4 * 4 + 1] = fmaf(-a1, ss.y, bb.y);
+            v[j4 * 4 + 2] = fmaf(-a2, ss.z, bb.z);
+            v[j4 * 4 + 3] = fmaf(-a3, ss.w, bb.w);
+          }
+        }
+        const float m = fminf(fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])), fminf(fminf(v[4], v[5]), fminf(v[6], v[7]))),
+                              fminf(fminf(fminf(v[8], v[9]), fminf(v[10], v[11])),
+                                    fminf(fminf(v[12], v[13]), fminf(v[14], v[15]))));
+        if (SAMPLE) {
+          tile_min = fminf(tile_min, m);
+        } else {
+          const bool lane_hit = m <= tau_me;
+          if (__any_sync(0xffffffffu, lane_hit)) {
+            if (lane_hit) {  // usually a single lane: the others skip the 16 comparisons
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (v[j] <= tau_me) {
+                  if (has_pend) {  // second hit of this lane within one tile (rare): publish the first now
+                    const int pos = atomicAdd(p.cand_cnt + q, 1);
+                    if (pos < TC_CAND_CAP) p.cand[(size_t)q * TC_CAND_CAP + pos] = pend_key;
+                  }
+                  pend_key = make_key(v[j], (uint32_t)(tile * ROWS + c * 16 + j));
+                  has_pend = true;
+                }
+              }
+            }
+          }
+        }
+      }
+      if (!SAMPLE) {
+        if (prev_has && prev_pos < TC_CAND_CAP) p.cand[(size_t)q * TC_CAND_CAP + prev_pos] = prev_key;
+        prev_has = has_pend;
+        if (has_pend) {
+          prev_pos = atomicAdd(p.cand_cnt + q, 1);
+          prev_key = pend_key;
+          has_pend = false;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&tmem_empty[acc]);
+        mbar_arrive(&xs_empty[xb]);
+      }
+      if (SAMPLE && q < p.nq) {
+        // sample[q][w][g]: minimum score of this tile for this query, one slot per epilogue group
+        uint32_t* out = p.sample + ((size_t)q * p.n_sample + (size_t)w) * 2;
+        const uint32_t mn = tile_min == __int_as_float(0x7f800000) ? 0xFFFFFFFFu : f32_to_ordered(tile_min);
+        if (NBLK == 2) {
+          out[0] = mn;
+          out[1] = 0xFFFFFFFFu;
+        } else {
+          out[grp] = mn;
+        }
+      }
+    }
+    if (!SAMPLE && prev_has && prev_pos < TC_CAND_CAP) p.cand[(size_t)q * TC_CAND_CAP + prev_pos] = prev_key;
+    if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0) {
+      unsigned long long* o = p.dbg + 8 + (warp - 2) * 4;
+      o[0] = (unsigned long long)(clock64() - t_epi_begin);
+      o[1] = (unsigned long long)t_epi_xs;
+      o[2] = (unsigned long long)t_epi_full;
+      o[3] = 0;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 // Threshold per query: the TC_SAMPLE_RANK-th smallest sampled score (+inf when the sample holds
 // fewer valid scores). One warp per query; bitwise binary search over the ordered-float images.
 // Also clears the candidate counters of the pass.
-__global__ void __launch_bounds__(32) tc_tau_kernel(const uint32_t* __restrict__ sample, int n_sample, int rank,
+__global__ void __launch_bounds__(32) tc_tau_kernel(const uint32_t* __restrict__ sample, int n_vals, int rank,
                                                     float* __restrict__ tau, int* __restrict__ cand_cnt) {
   const int q = blockIdx.x, lane = threadIdx.x;
-  const uint32_t* vals = sample + (size_t)q * n_sample * 2;
-  const int n = n_sample * 2;
-  uint32_t prefix = 0;
-  for (int bit = 31; bit >= 0; --bit) {
-    const uint32_t probe = prefix | ((1u << bit) - 1u);  // largest value with this prefix and the bit clear
-    int c = 0;
-    for (int i = lane; i < n; i += 32) c += (vals[i] <= probe) && (vals[i] != 0xFFFFFFFFu);
-    c = __reduce_add_sync(0xffffffffu, c);
-    if (c < rank) prefix |= (1u << bit);
+  const uint32_t* vals = sample + (size_t)q * n_vals;
+  constexpr int R = TC_SAMPLE_RANK;
+  uint32_t best[R];  // this lane's R smallest values, ascending
+#pragma unroll
+  for (int r = 0; r < R; ++r) best[r] = 0xFFFFFFFFu;
+  for (int i = lane; i < n_vals; i += 32) {
+    uint32_t x = __ldg(vals + i);
+    if (x < best[R - 1]) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const uint32_t lo = min(best[r], x);
+        x = max(best[r], x);
+        best[r] = lo;
+      }
+    }
+  }
+  // warp merge: pop the global minimum `rank` times
+  uint32_t m = 0xFFFFFFFFu;
+  for (int t = 0; t < rank; ++t) {
+    m = __reduce_min_sync(0xffffffffu, best[0]);
+    const unsigned who = __ballot_sync(0xffffffffu, best[0] == m);
+    if (lane == __ffs(who) - 1) {
+#pragma unroll
+      for (int r = 0; r + 1 < R; ++r) best[r] = best[r + 1];
+      best[R - 1] = 0xFFFFFFFFu;
+    }
   }
   if (lane == 0) {
-    // prefix == 0xFFFFFFFF: fewer than `rank` valid samples -> admit everything
-    tau[q] = (prefix == 0xFFFFFFFFu) ? __int_as_float(0x7f800000) : ordered_to_f32(prefix);
+    // 0xFFFFFFFF: fewer than `rank` valid samples -> admit everything
+    tau[q] = (m == 0xFFFFFFFFu) ? __int_as_float(0x7f800000) : ordered_to_f32(m);
     cand_cnt[q] = 0;
   }
+}
+
+// Per-search row-term column for the TS variant when a mask (tombstones / filter) is active.
+__global__ void __launch_bounds__(256) tc_bias_kernel(const uint32_t* __restrict__ mask, const float* __restrict__ norm2,
+                                                      long long n_rows, long long n_pad, float* __restrict__ bias) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad;
+       i += (long long)gridDim.x * blockDim.x) {
+    bool ok = i < n_rows;
+    if (ok && mask != nullptr) ok = (__ldg(mask + (i >> 5)) >> (i & 31)) & 1u;
+    bias[i] = ok ? (norm2 ? __ldg(norm2 + i) : 1.0f) : __int_as_float(0x7f800000);
+  }
+}
+
+int launch_tc_bias(const uint32_t* mask, const float* norm2, long long n_rows, long long n_pad, float* bias,
+                   cudaStream_t st) {
+  if (n_pad <= 0) return 0;
+  long long blocks = (n_pad + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  tc_bias_kernel<<<(int)blocks, 256, 0, st>>>(mask, norm2, n_rows, n_pad, bias);
+  QG_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 // ---- host side --------------------------------------------------------------------------------------
@@ -418,27 +887,59 @@ static int encode_map(CUtensorMap* map, const float* base, long long rows, int d
   return 0;
 }
 
+static int encode_map_box(CUtensorMap* map, const float* base, long long rows, int dp, int box_rows) {
+  return encode_map(map, base, rows, dp, box_rows);
+}
+
 int tc_plan(int dp, int nq, TcPlan* out) {
   if (dp < 4 || dp % 4 != 0) return -1;
   const int kb = (dp + TC_KBLOCK - 1) / TC_KBLOCK;
   const int budget = 227 * 1024 - 1024;  // alignment slack
-  int n_cols = std::min(TC_MAX_COLS, ((nq + 15) / 16) * 16);
-  for (;;) {
-    if (n_cols < 16) return -1;
-    const TcSmem fixed = tc_smem_layout(n_cols, kb, 0);
-    const int left = budget - fixed.total;
-    int stages = left / (TC_STAGE_BYTES + 16);
-    // at least 64 KB of corpus loads in flight per SM (Little's law at ~6.5 TB/s over 148 SMs)
-    if (stages >= 4) {
-      stages = std::min(stages, 12);
-      out->n_cols = n_cols;
+  // TS variant: queries resident in tensor memory. 512 columns = nblk * kb * 32 (queries) +
+  // nblk * 2 * 64 (double-buffered accumulators).
+  if (kb <= 8) {
+    const int nblk = (kb <= 4 && nq > 128) ? 2 : 1;
+    const int rows = ts_rows(nblk);
+    int stages = (budget - ts_smem_layout(0, kb, rows).total) / (kb * rows * TS_KSTEP_BYTES + 16);
+    stages = std::min(stages, 12);
+    if (stages >= 2) {
+      out->variant = 1;
+      out->nblk = nblk;
+      out->n_cols = 128 * nblk;
       out->kb = kb;
       out->stages = stages;
-      out->smem = tc_smem_layout(n_cols, kb, stages).total + 1024;
+      out->tile_rows = rows;
+      out->sample_vals = 2;
+      out->smem = ts_smem_layout(stages, kb, rows).total + 1024;
       return 0;
     }
-    n_cols -= 16;
   }
+  // SS variant: queries in shared memory next to the corpus ring; fewer query columns leave more
+  // stages (bytes in flight), so pick the column count that maximises columns * min(1, stages / 11).
+  int best_cols = 0, best_stages = 0;
+  double best = 0.0;
+  for (int n_cols = 16; n_cols <= std::min(TC_MAX_COLS, ((nq + 15) / 16) * 16); n_cols += 16) {
+    const int left = budget - tc_smem_layout(n_cols, kb, 0).total;
+    int stages = left / (TC_STAGE_BYTES + 16);
+    if (stages < 4) break;
+    stages = std::min(stages, 12);
+    const double score = n_cols * std::min(1.0, stages / 11.0);
+    if (score > best) {
+      best = score;
+      best_cols = n_cols;
+      best_stages = stages;
+    }
+  }
+  if (best_cols == 0) return -1;
+  out->variant = 0;
+  out->nblk = 0;
+  out->n_cols = best_cols;
+  out->kb = kb;
+  out->stages = best_stages;
+  out->tile_rows = TC_TILE_ROWS;
+  out->sample_vals = 2;
+  out->smem = tc_smem_layout(best_cols, kb, best_stages).total + 1024;
+  return 0;
 }
 
 template <int MODE, bool SAMPLE>
@@ -448,7 +949,40 @@ static int set_attr_one() {
   return 0;
 }
 
+typedef void (*TsKernelFn)(const CUtensorMap, const TsKParams);
+
+template <int MODE, bool SAMPLE, int NBLK>
+static TsKernelFn ts_kernel_kb(int kb) {
+  switch (kb) {
+    case 1: return tc_ts_kernel<MODE, SAMPLE, NBLK, 1>;
+    case 2: return tc_ts_kernel<MODE, SAMPLE, NBLK, 2>;
+    case 3: return tc_ts_kernel<MODE, SAMPLE, NBLK, 3>;
+    case 4: return tc_ts_kernel<MODE, SAMPLE, NBLK, 4>;
+    default: return tc_ts_kernel<MODE, SAMPLE, NBLK, 0>;
+  }
+}
+
+static TsKernelFn ts_kernel(int mode, bool sample, int nblk, int kb) {
+  if (mode == MODE_L2) {
+    if (sample) return nblk == 2 ? ts_kernel_kb<MODE_L2, true, 2>(kb) : ts_kernel_kb<MODE_L2, true, 1>(kb);
+    return nblk == 2 ? ts_kernel_kb<MODE_L2, false, 2>(kb) : ts_kernel_kb<MODE_L2, false, 1>(kb);
+  }
+  if (sample) return nblk == 2 ? ts_kernel_kb<MODE_DOT, true, 2>(kb) : ts_kernel_kb<MODE_DOT, true, 1>(kb);
+  return nblk == 2 ? ts_kernel_kb<MODE_DOT, false, 2>(kb) : ts_kernel_kb<MODE_DOT, false, 1>(kb);
+}
+
+static int set_attr_ts() {
+  for (int mode : {MODE_L2, MODE_DOT})
+    for (int sample = 0; sample < 2; ++sample)
+      for (int nblk = 1; nblk <= 2; ++nblk)
+        for (int kb = 0; kb <= 4; ++kb)
+          QG_CUDA_OK(cudaFuncSetAttribute(ts_kernel(mode, sample != 0, nblk, kb == 0 ? 9 : kb),
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  return 0;
+}
+
 int tc_set_attributes() {
+  if (int e = set_attr_ts()) return e;
   if (int e = set_attr_one<MODE_L2, false>()) return e;
   if (int e = set_attr_one<MODE_L2, true>()) return e;
   if (int e = set_attr_one<MODE_DOT, false>()) return e;
@@ -456,7 +990,45 @@ int tc_set_attributes() {
   return 0;
 }
 
+static int launch_ts_pass(const TcPlan& plan, const TcArgs& a, int sm_count, cudaStream_t st, int* launches) {
+  const int rows = ts_rows(plan.nblk);
+  CUtensorMap tm_x;
+  if (int rc = encode_map_box(&tm_x, a.vec, a.n_rows, a.dp, rows)) return rc;
+  TsKParams p{};
+  p.n_rows = a.n_rows;
+  p.n_tiles = (a.n_rows + rows - 1) / rows;
+  p.kb = plan.kb;
+  p.stages = plan.stages;
+  p.nq = a.nq;
+  p.nblk = plan.nblk;
+  p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(rows >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  p.cosine = a.cosine;
+  p.bias = a.bias;
+  p.sc = a.cosine ? a.inv_norm : nullptr;
+  p.queries = a.queries;
+  p.dp = a.dp;
+  p.sample = a.sample;
+  p.n_sample = a.n_sample;
+  p.tau = a.tau;
+  p.cand = a.cand;
+  p.cand_cnt = a.cand_cnt;
+  p.dbg = nullptr;
+  if (a.bias == nullptr) return fail(1, "tensor-core TS pass needs the per-row bias column");
+  const int grid_s = (int)std::min<long long>(sm_count, a.n_sample);
+  const int grid_m = (int)std::min<long long>(sm_count, p.n_tiles);
+  ts_kernel(a.mode, true, plan.nblk, plan.kb)<<<grid_s, TS_THREADS, plan.smem, st>>>(tm_x, p);
+  QG_CUDA_OK(cudaGetLastError());
+  tc_tau_kernel<<<a.nq, 32, 0, st>>>(a.sample, a.n_sample * 2, TC_SAMPLE_RANK, a.tau, a.cand_cnt);
+  QG_CUDA_OK(cudaGetLastError());
+  p.dbg = a.dbg;
+  ts_kernel(a.mode, false, plan.nblk, plan.kb)<<<grid_m, TS_THREADS, plan.smem, st>>>(tm_x, p);
+  QG_CUDA_OK(cudaGetLastError());
+  if (launches) *launches += 3;
+  return 0;
+}
+
 int launch_tc_pass(const TcPlan& plan, const TcArgs& a, int sm_count, cudaStream_t st, int* launches) {
+  if (plan.variant == 1) return launch_ts_pass(plan, a, sm_count, st, launches);
   CUtensorMap tm_a, tm_b;
   if (int rc = encode_map(&tm_a, a.vec, a.n_rows, a.dp, TC_TILE_ROWS)) return rc;
   if (int rc = encode_map(&tm_b, a.queries, a.nq, a.dp, plan.n_cols)) return rc;
@@ -488,7 +1060,7 @@ int launch_tc_pass(const TcPlan& plan, const TcArgs& a, int sm_count, cudaStream
     tc_scan_kernel<MODE_DOT, true><<<grid_s, TC_THREADS, plan.smem, st>>>(tm_a, tm_b, p);
   }
   QG_CUDA_OK(cudaGetLastError());
-  tc_tau_kernel<<<a.nq, 32, 0, st>>>(a.sample, a.n_sample, TC_SAMPLE_RANK, a.tau, a.cand_cnt);
+  tc_tau_kernel<<<a.nq, 32, 0, st>>>(a.sample, a.n_sample * 2, TC_SAMPLE_RANK, a.tau, a.cand_cnt);
   QG_CUDA_OK(cudaGetLastError());
   if (a.mode == MODE_L2) {
     tc_scan_kernel<MODE_L2, false><<<grid_m, TC_THREADS, plan.smem, st>>>(tm_a, tm_b, p);

@@ -22,10 +22,14 @@ constexpr int TC_SAMPLE_RANK = 8;       // order statistic of the sample used as
 constexpr int TC_CAND_CAP = 2048;       // candidate capacity per query per pass
 
 struct TcPlan {
-  int n_cols;    // MMA N: queries per pass, multiple of 16
-  int kb;        // 32-float blocks per row
-  int stages;    // A ring depth
-  int smem;      // dynamic shared memory bytes
+  int variant;      // 1 = TS (queries resident in tensor memory, dp <= 256), 0 = SS (queries in shared memory)
+  int nblk;         // TS: resident blocks of 128 queries (1 or 2)
+  int n_cols;       // queries per pass
+  int kb;           // 32-float blocks per row
+  int stages;       // corpus ring depth
+  int tile_rows;    // corpus rows per tile (sample granularity)
+  int sample_vals;  // sampled scores kept per tile and query
+  int smem;         // dynamic shared memory bytes
 };
 
 // Geometry for a padded dimension dp and nq queries; returns 0 when the tensor path fits.
@@ -38,22 +42,28 @@ struct TcArgs {
   const float* row_norm2;   // [n_rows] |x|^2 (L2 scores)
   const float* inv_norm;    // [n_rows] 1/|x| (cosine), else nullptr
   const uint32_t* mask;     // row-pass bits or nullptr
+  const float* bias;        // TS variant: [rows padded to 64] |x|^2 (L2) or 1 (dot), +inf for rows that
+                            // may not match (mask already applied) and for the padding
   const float* queries;     // [nq x dp] device
   int nq;
   int mode;                 // MODE_L2 / MODE_DOT (scan.cuh)
   int cosine;
   // sample stage
-  uint32_t* sample;         // [n_cols][n_sample][2] ordered-float images
+  uint32_t* sample;         // [n_cols][n_sample][plan.sample_vals] ordered-float images
   int n_sample;             // sampled tiles
   float* tau;               // [n_cols] thresholds (written by the threshold kernel)
   // main stage
   uint64_t* cand;           // [n_cols][TC_CAND_CAP] scan keys
   int* cand_cnt;            // [n_cols]
+  unsigned long long* dbg;  // optional [64] per-role cycle counters of CTA 0 of the main scan, else nullptr
 };
 
 // Enqueue sample -> threshold -> main scan for one pass of args.nq <= plan.n_cols queries.
 int launch_tc_pass(const TcPlan& plan, const TcArgs& args, int sm_count, cudaStream_t st, int* launches);
 int tc_set_attributes();
+// bias[i] = row i passes (mask nullptr = all rows < n_rows) ? (norm2 ? norm2[i] : 1) : +inf, for i < n_pad.
+int launch_tc_bias(const uint32_t* mask, const float* norm2, long long n_rows, long long n_pad, float* bias,
+                   cudaStream_t st);
 // 0 when the driver entry point for tensor maps is available.
 int tc_available();
 
