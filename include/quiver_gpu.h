@@ -245,6 +245,8 @@ typedef struct qg_profile {
   double finalize_ms;        /* sum over merge / re-rank launches                   */
   int64_t scan_launches;
   int64_t finalize_launches;
+  double prep_ms;            /* tensor-core regime: sample + threshold kernels      */
+  int64_t prep_launches;
 } qg_profile;
 int qg_index_set_profiling(qg_index* idx, int on);
 int qg_index_read_profile(qg_index* idx, qg_profile* out);

@@ -52,7 +52,7 @@ class qg_scan_stats(C.Structure):
 
 class qg_profile(C.Structure):
     _fields_ = [("scan_ms", C.c_double), ("finalize_ms", C.c_double), ("scan_launches", C.c_int64),
-                ("finalize_launches", C.c_int64)]
+                ("finalize_launches", C.c_int64), ("prep_ms", C.c_double), ("prep_launches", C.c_int64)]
 
 
 # every symbol include/quiver_gpu.h declares (tests check the library exports all of them)

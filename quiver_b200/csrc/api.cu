@@ -946,9 +946,15 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
       ta.tau = (float*)w->tc_tau.p;
       ta.cand = (uint64_t*)w->tc_cand.p;
       ta.cand_cnt = (int*)w->tc_cnt.p;
-      const bool prof = idx->profiling && w->prof_begin(0, st) == 0;
-      const int rc = launch_tc_pass(plan, ta, idx->sm_count, st, &stats.kernel_launches);
-      if (prof) w->prof_end(st);
+      // profiling: kind 2 = sample + threshold kernels, kind 0 = main scan kernel
+      TcStageHook hook{[](void* ctx, int stage, int begin, cudaStream_t s) {
+                         Workspace* ws = static_cast<Workspace*>(ctx);
+                         if (begin) ws->prof_begin(stage == 0 ? 2 : 0, s);
+                         else ws->prof_end(s);
+                       },
+                       w};
+      const int rc = launch_tc_pass(plan, ta, idx->sm_count, st, &stats.kernel_launches,
+                                    idx->profiling ? &hook : nullptr);
       if (rc) return rc;
       stats.passes++;
       fb.queries = qpad + (size_t)p0 * dp;
@@ -1390,6 +1396,9 @@ int qg_index_read_profile(qg_index* idx, qg_profile* out) {
       if (w->prof_kind[i / 2] == 0) {
         out->scan_ms += ms;
         out->scan_launches++;
+      } else if (w->prof_kind[i / 2] == 2) {
+        out->prep_ms += ms;
+        out->prep_launches++;
       } else {
         out->finalize_ms += ms;
         out->finalize_launches++;

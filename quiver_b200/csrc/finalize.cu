@@ -424,7 +424,7 @@ __global__ void merge_shards_kernel(const uint64_t* __restrict__ keys, int world
                                     long long* out_row, int* out_count);
 
 int finalize_set_attributes() {
-  QG_CUDA_OK(cudaFuncSetAttribute(finalize_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  QG_CUDA_OK(cudaFuncSetAttribute(finalize_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
   QG_CUDA_OK(cudaFuncSetAttribute(merge_shards_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   QG_CUDA_OK(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)finalize_smem(1024)));
@@ -458,8 +458,9 @@ int launch_finalize(const FinalizeParams& p, int nq, cudaStream_t st) {
 // the exact top-k can have), re-rank every further candidate with score <= T, and certify only if
 // T <= tau (so every such row was admitted) and the list did not overflow.
 // ------------------------------------------------------------------------------------------------
-constexpr int FC_THREADS = 256;
+constexpr int FC_THREADS = 512;
 constexpr int FC_WARPS = FC_THREADS / 32;
+constexpr int FC_RANK_MAX = 1024;  // up to this many candidates are ordered by all-pairs rank counting
 
 __host__ __device__ inline size_t finalize_cand_smem(int cap) {
   return (size_t)cap * 8 * 2 + (size_t)FC_WARPS * EXACT_SCRATCH_BYTES + 64;
@@ -490,6 +491,26 @@ __device__ __forceinline__ float tc_score_upper_bound(int metric, int mode, int 
   return tf;
 }
 
+// dst[rank of src[i]] = src[i] for n distinct keys (n <= FC_RANK_MAX); returns through `my_rank` the
+// rank of the keys this thread owns (i = tid, tid + FC_THREADS). All threads of the block call.
+__device__ __forceinline__ void fc_rank_scatter(const uint64_t* src, int n, uint64_t* dst, int limit,
+                                                int (&my_rank)[FC_RANK_MAX / FC_THREADS]) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int s = 0; s < FC_RANK_MAX / FC_THREADS; ++s) {
+    const int i = tid + s * FC_THREADS;
+    int r = -1;
+    if (i < n) {
+      const uint64_t mine = src[i];
+      r = 0;
+      for (int j = 0; j < n; ++j) r += src[j] < mine;
+      if (r < limit) dst[r] = mine;
+    }
+    my_rank[s] = r;
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(FC_THREADS, 1) finalize_cand_kernel(const FinalizeCandParams cp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const FinalizeParams& p = cp.base;
@@ -500,6 +521,8 @@ __global__ void __launch_bounds__(FC_THREADS, 1) finalize_cand_kernel(const Fina
   uint64_t* ex = keys + cap;
   double* scratch = reinterpret_cast<double*>(ex + cap) + (size_t)warp * (EXACT_SCRATCH_BYTES / 8);
   __shared__ double s_qn2;
+  __shared__ int s_extra;
+  __shared__ float s_E;
 
   const int n_raw = cp.cand_cnt[q];
   const bool overflow = n_raw > cap;
@@ -514,36 +537,72 @@ __global__ void __launch_bounds__(FC_THREADS, 1) finalize_cand_kernel(const Fina
     for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) s_qn2 = s;
   }
-  const int n2 = next_pow2(n);
+  if (tid == 0) s_extra = 0;
   const uint64_t* src = cp.cand + (size_t)q * cap;
-  for (int i = tid; i < n2; i += FC_THREADS) keys[i] = i < n ? __ldcg(src + i) : KEY_NONE;
-  block_bitonic_sort(keys, n2);
+  const bool small = n <= FC_RANK_MAX;
+  int my_rank[FC_RANK_MAX / FC_THREADS];
+  const int nsel = n < cp.kp ? n : cp.kp;
+  uint64_t* sel;  // the best nsel scan keys, ascending
+  if (small) {
+    for (int i = tid; i < n; i += FC_THREADS) keys[i] = __ldcg(src + i);
+    __syncthreads();
+    sel = keys + FC_RANK_MAX;  // n <= FC_RANK_MAX <= cap / 2: the upper half of keys[] is free
+    fc_rank_scatter(keys, n, sel, nsel, my_rank);
+  } else {
+    const int n2 = next_pow2(n);
+    for (int i = tid; i < n2; i += FC_THREADS) keys[i] = i < n ? __ldcg(src + i) : KEY_NONE;
+    block_bitonic_sort(keys, n2);
+    sel = keys;
+  }
 
-  // exact re-rank of the best kp candidates
-  int nsel = n < cp.kp ? n : cp.kp;
+  // ---- exact re-rank of the best nsel candidates (one warp per candidate) ----
   for (int c = warp; c < nsel; c += FC_WARPS) {
-    const uint32_t row = key_row(keys[c]);
+    const uint32_t row = key_row(sel[c]);
     const float dist = exact_distance_warp(p.metric, p.arith, qv, p.vec + (size_t)row * p.dp, p.d, scratch);
     if (lane == 0) ex[c] = make_key(dist, row);
   }
   __syncthreads();
+
   bool certified = !overflow;
   int nex = nsel;
   if (nsel >= k) {
-    {
-      const int m2 = next_pow2(nex);
-      for (int i = nex + tid; i < m2; i += FC_THREADS) ex[i] = KEY_NONE;
-      block_bitonic_sort(ex, m2);
+    // E = k-th smallest exact distance among the re-ranked candidates
+    for (int i = tid; i < nsel; i += FC_THREADS) {
+      const uint64_t me = ex[i];
+      int r = 0;
+      for (int j = 0; j < nsel; ++j) r += ex[j] < me;
+      if (r == k - 1) s_E = key_score(me);
     }
-    const float E = key_score(ex[k - 1]);
-    const float T = tc_score_upper_bound(p.metric, p.mode, p.cosine, E, cp.tc_gamma, (double)p.gamma, s_qn2,
+    __syncthreads();
+    const float T = tc_score_upper_bound(p.metric, p.mode, p.cosine, s_E, cp.tc_gamma, (double)p.gamma, s_qn2,
                                          (double)(p.max_norm2 ? *p.max_norm2 : 0.f));
     if (!(T <= tau) && !all_admitted) certified = false;
-    // keys are sorted by scan score: the candidates beyond nsel with score <= T are a prefix
-    int extra = 0;
-    while (nsel + extra < n && key_score(keys[nsel + extra]) <= T) ++extra;  // same walk on every thread
+    // every further candidate whose scan score is <= T may still belong to the exact top-k
+    if (small) {
+#pragma unroll
+      for (int s = 0; s < FC_RANK_MAX / FC_THREADS; ++s) {
+        const int i = tid + s * FC_THREADS;
+        if (i < n && my_rank[s] >= nsel && key_score(keys[i]) <= T) {
+          const int pos = atomicAdd(&s_extra, 1);
+          if (nsel + pos < cap) ex[nsel + pos] = keys[i];  // scan key for now; replaced by the exact key below
+        }
+      }
+    } else {
+      for (int i = nsel + tid; i < n; i += FC_THREADS) {
+        if (key_score(keys[i]) <= T) {
+          const int pos = atomicAdd(&s_extra, 1);
+          if (nsel + pos < cap) ex[nsel + pos] = keys[i];
+        }
+      }
+    }
+    __syncthreads();
+    int extra = s_extra;
+    if (nsel + extra > cap) {
+      extra = cap - nsel;
+      certified = false;
+    }
     for (int c = warp; c < extra; c += FC_WARPS) {
-      const uint32_t row = key_row(keys[nsel + c]);
+      const uint32_t row = key_row(ex[nsel + c]);
       const float dist = exact_distance_warp(p.metric, p.arith, qv, p.vec + (size_t)row * p.dp, p.d, scratch);
       if (lane == 0) ex[nsel + c] = make_key(dist, row);
     }
@@ -553,17 +612,30 @@ __global__ void __launch_bounds__(FC_THREADS, 1) finalize_cand_kernel(const Fina
     // fewer than k candidates: complete only if the scan admitted every row
     if (!all_admitted) certified = false;
   }
-  {
+
+  // ---- order the exact keys and emit the first k ----
+  const int kk = nex < k ? nex : k;
+  uint64_t* outk = keys;  // final order (keys[] is no longer needed)
+  if (nex <= FC_RANK_MAX) {
+    __syncthreads();
+    for (int i = tid; i < nex; i += FC_THREADS) {
+      const uint64_t me = ex[i];
+      int r = 0;
+      for (int j = 0; j < nex; ++j) r += ex[j] < me;
+      if (r < k) outk[r] = me;
+    }
+    __syncthreads();
+  } else {
     const int m2 = next_pow2(nex);
     for (int i = nex + tid; i < m2; i += FC_THREADS) ex[i] = KEY_NONE;
     block_bitonic_sort(ex, m2);
+    outk = ex;
   }
 
-  const int kk = nex < k ? nex : k;
   if (p.out_keys != nullptr) {
     for (int j = tid; j < k; j += FC_THREADS) {
       uint64_t o = KEY_NONE;
-      if (j < kk && certified) o = (ex[j] & 0xFFFFFFFF00000000ull) | (uint64_t)(uint32_t)(p.row_base + key_row(ex[j]));
+      if (j < kk && certified) o = (outk[j] & 0xFFFFFFFF00000000ull) | (uint64_t)(uint32_t)(p.row_base + key_row(outk[j]));
       p.out_keys[(size_t)q * k + j] = o;
     }
     if (tid == 0 && p.out_count) p.out_count[q] = certified ? kk : -1;
@@ -571,14 +643,14 @@ __global__ void __launch_bounds__(FC_THREADS, 1) finalize_cand_kernel(const Fina
   }
   for (int j = tid; j < k; j += FC_THREADS) {
     const bool ok = j < kk;
-    p.out_dist[(size_t)q * k + j] = ok ? key_score(ex[j]) : __int_as_float(0x7f800000);
-    p.out_row[(size_t)q * k + j] = ok ? (long long)key_row(ex[j]) + p.row_base : -1ll;
+    p.out_dist[(size_t)q * k + j] = ok ? key_score(outk[j]) : __int_as_float(0x7f800000);
+    p.out_row[(size_t)q * k + j] = ok ? (long long)key_row(outk[j]) + p.row_base : -1ll;
   }
   if (p.out_negdist != nullptr) {
     const float* nv = p.negatives + (size_t)q * p.dp;
     for (int j = warp; j < k; j += FC_WARPS) {
       float nd = __int_as_float(0x7f800000);
-      if (j < kk) nd = exact_distance_warp(p.metric, p.arith, p.vec + (size_t)key_row(ex[j]) * p.dp, nv, p.d, scratch);
+      if (j < kk) nd = exact_distance_warp(p.metric, p.arith, p.vec + (size_t)key_row(outk[j]) * p.dp, nv, p.d, scratch);
       if (lane == 0) p.out_negdist[(size_t)q * k + j] = nd;
     }
   }
@@ -587,6 +659,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) finalize_cand_kernel(const Fina
 
 int launch_finalize_cand(const FinalizeCandParams& p, int nq, cudaStream_t st) {
   if (nq <= 0) return 0;
+  if (p.cap < 2 * FC_RANK_MAX) return fail(1, "finalize_cand: candidate capacity must be at least 2048");
   finalize_cand_kernel<<<nq, FC_THREADS, finalize_cand_smem(p.cap), st>>>(p);
   QG_CUDA_OK(cudaGetLastError());
   return 0;

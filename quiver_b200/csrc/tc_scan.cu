@@ -797,15 +797,37 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
 // Threshold per query: the TC_SAMPLE_RANK-th smallest sampled score (+inf when the sample holds
 // fewer valid scores). One warp per query; bitwise binary search over the ordered-float images.
 // Also clears the candidate counters of the pass.
-__global__ void __launch_bounds__(32) tc_tau_kernel(const uint32_t* __restrict__ sample, int n_vals, int rank,
-                                                    float* __restrict__ tau, int* __restrict__ cand_cnt) {
-  const int q = blockIdx.x, lane = threadIdx.x;
+// Pop the warp-wide minimum `rank` times from per-lane ascending lists best[0..R); returns the last
+// popped value (0xFFFFFFFF when the lists run dry).
+template <int R>
+__device__ __forceinline__ uint32_t warp_pop_rank(uint32_t (&best)[R], int rank, uint32_t* popped /*[rank], lane 0*/) {
+  const int lane = threadIdx.x & 31;
+  uint32_t m = 0xFFFFFFFFu;
+  for (int t = 0; t < rank; ++t) {
+    m = __reduce_min_sync(0xffffffffu, best[0]);
+    const unsigned who = __ballot_sync(0xffffffffu, best[0] == m);
+    if (lane == __ffs(who) - 1) {
+#pragma unroll
+      for (int r = 0; r + 1 < R; ++r) best[r] = best[r + 1];
+      best[R - 1] = 0xFFFFFFFFu;
+    }
+    if (popped != nullptr && lane == 0) popped[t] = m;
+  }
+  return m;
+}
+
+constexpr int TAU_THREADS = 128;
+
+__global__ void __launch_bounds__(TAU_THREADS) tc_tau_kernel(const uint32_t* __restrict__ sample, int n_vals, int rank,
+                                                             float* __restrict__ tau, int* __restrict__ cand_cnt) {
+  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t* vals = sample + (size_t)q * n_vals;
   constexpr int R = TC_SAMPLE_RANK;
+  __shared__ uint32_t s_part[TAU_THREADS / 32][R];
   uint32_t best[R];  // this lane's R smallest values, ascending
 #pragma unroll
   for (int r = 0; r < R; ++r) best[r] = 0xFFFFFFFFu;
-  for (int i = lane; i < n_vals; i += 32) {
+  for (int i = tid; i < n_vals; i += TAU_THREADS) {
     uint32_t x = __ldg(vals + i);
     if (x < best[R - 1]) {
 #pragma unroll
@@ -816,21 +838,17 @@ __global__ void __launch_bounds__(32) tc_tau_kernel(const uint32_t* __restrict__
       }
     }
   }
-  // warp merge: pop the global minimum `rank` times
-  uint32_t m = 0xFFFFFFFFu;
-  for (int t = 0; t < rank; ++t) {
-    m = __reduce_min_sync(0xffffffffu, best[0]);
-    const unsigned who = __ballot_sync(0xffffffffu, best[0] == m);
-    if (lane == __ffs(who) - 1) {
-#pragma unroll
-      for (int r = 0; r + 1 < R; ++r) best[r] = best[r + 1];
-      best[R - 1] = 0xFFFFFFFFu;
+  warp_pop_rank<R>(best, rank, s_part[warp]);  // the R smallest of this warp's share, ascending
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t one[1];
+    one[0] = lane < (TAU_THREADS / 32) * R ? s_part[lane / R][lane % R] : 0xFFFFFFFFu;
+    const uint32_t m = warp_pop_rank<1>(one, rank, nullptr);
+    if (lane == 0) {
+      // 0xFFFFFFFF: fewer than `rank` valid samples -> admit everything
+      tau[q] = (m == 0xFFFFFFFFu) ? __int_as_float(0x7f800000) : ordered_to_f32(m);
+      cand_cnt[q] = 0;
     }
-  }
-  if (lane == 0) {
-    // 0xFFFFFFFF: fewer than `rank` valid samples -> admit everything
-    tau[q] = (m == 0xFFFFFFFFu) ? __int_as_float(0x7f800000) : ordered_to_f32(m);
-    cand_cnt[q] = 0;
   }
 }
 
@@ -990,7 +1008,8 @@ int tc_set_attributes() {
   return 0;
 }
 
-static int launch_ts_pass(const TcPlan& plan, const TcArgs& a, int sm_count, cudaStream_t st, int* launches) {
+static int launch_ts_pass(const TcPlan& plan, const TcArgs& a, int sm_count, cudaStream_t st, int* launches,
+                          const TcStageHook* hook) {
   const int rows = ts_rows(plan.nblk);
   CUtensorMap tm_x;
   if (int rc = encode_map_box(&tm_x, a.vec, a.n_rows, a.dp, rows)) return rc;
@@ -1016,19 +1035,24 @@ static int launch_ts_pass(const TcPlan& plan, const TcArgs& a, int sm_count, cud
   if (a.bias == nullptr) return fail(1, "tensor-core TS pass needs the per-row bias column");
   const int grid_s = (int)std::min<long long>(sm_count, a.n_sample);
   const int grid_m = (int)std::min<long long>(sm_count, p.n_tiles);
+  if (hook) hook->fn(hook->ctx, 0, 1, st);
   ts_kernel(a.mode, true, plan.nblk, plan.kb)<<<grid_s, TS_THREADS, plan.smem, st>>>(tm_x, p);
   QG_CUDA_OK(cudaGetLastError());
-  tc_tau_kernel<<<a.nq, 32, 0, st>>>(a.sample, a.n_sample * 2, TC_SAMPLE_RANK, a.tau, a.cand_cnt);
+  tc_tau_kernel<<<a.nq, TAU_THREADS, 0, st>>>(a.sample, a.n_sample * 2, TC_SAMPLE_RANK, a.tau, a.cand_cnt);
   QG_CUDA_OK(cudaGetLastError());
+  if (hook) hook->fn(hook->ctx, 0, 0, st);
   p.dbg = a.dbg;
+  if (hook) hook->fn(hook->ctx, 1, 1, st);
   ts_kernel(a.mode, false, plan.nblk, plan.kb)<<<grid_m, TS_THREADS, plan.smem, st>>>(tm_x, p);
   QG_CUDA_OK(cudaGetLastError());
+  if (hook) hook->fn(hook->ctx, 1, 0, st);
   if (launches) *launches += 3;
   return 0;
 }
 
-int launch_tc_pass(const TcPlan& plan, const TcArgs& a, int sm_count, cudaStream_t st, int* launches) {
-  if (plan.variant == 1) return launch_ts_pass(plan, a, sm_count, st, launches);
+int launch_tc_pass(const TcPlan& plan, const TcArgs& a, int sm_count, cudaStream_t st, int* launches,
+                   const TcStageHook* hook) {
+  if (plan.variant == 1) return launch_ts_pass(plan, a, sm_count, st, launches, hook);
   CUtensorMap tm_a, tm_b;
   if (int rc = encode_map(&tm_a, a.vec, a.n_rows, a.dp, TC_TILE_ROWS)) return rc;
   if (int rc = encode_map(&tm_b, a.queries, a.nq, a.dp, plan.n_cols)) return rc;
@@ -1054,20 +1078,24 @@ int launch_tc_pass(const TcPlan& plan, const TcArgs& a, int sm_count, cudaStream
   p.cand_cnt = a.cand_cnt;
   const int grid_s = (int)std::min<long long>(sm_count, a.n_sample);
   const int grid_m = (int)std::min<long long>(sm_count, p.n_tiles);
+  if (hook) hook->fn(hook->ctx, 0, 1, st);
   if (a.mode == MODE_L2) {
     tc_scan_kernel<MODE_L2, true><<<grid_s, TC_THREADS, plan.smem, st>>>(tm_a, tm_b, p);
   } else {
     tc_scan_kernel<MODE_DOT, true><<<grid_s, TC_THREADS, plan.smem, st>>>(tm_a, tm_b, p);
   }
   QG_CUDA_OK(cudaGetLastError());
-  tc_tau_kernel<<<a.nq, 32, 0, st>>>(a.sample, a.n_sample * 2, TC_SAMPLE_RANK, a.tau, a.cand_cnt);
+  tc_tau_kernel<<<a.nq, TAU_THREADS, 0, st>>>(a.sample, a.n_sample * 2, TC_SAMPLE_RANK, a.tau, a.cand_cnt);
   QG_CUDA_OK(cudaGetLastError());
+  if (hook) hook->fn(hook->ctx, 0, 0, st);
+  if (hook) hook->fn(hook->ctx, 1, 1, st);
   if (a.mode == MODE_L2) {
     tc_scan_kernel<MODE_L2, false><<<grid_m, TC_THREADS, plan.smem, st>>>(tm_a, tm_b, p);
   } else {
     tc_scan_kernel<MODE_DOT, false><<<grid_m, TC_THREADS, plan.smem, st>>>(tm_a, tm_b, p);
   }
   QG_CUDA_OK(cudaGetLastError());
+  if (hook) hook->fn(hook->ctx, 1, 0, st);
   if (launches) *launches += 3;
   return 0;
 }

@@ -58,8 +58,15 @@ struct TcArgs {
   unsigned long long* dbg;  // optional [64] per-role cycle counters of CTA 0 of the main scan, else nullptr
 };
 
+// Optional hook called on the launching stream around the two stages of a pass (profiling):
+// stage 0 = sample + threshold kernels, stage 1 = main scan kernel; begin = 1 / end = 0.
+struct TcStageHook {
+  void (*fn)(void* ctx, int stage, int begin, cudaStream_t st);
+  void* ctx;
+};
 // Enqueue sample -> threshold -> main scan for one pass of args.nq <= plan.n_cols queries.
-int launch_tc_pass(const TcPlan& plan, const TcArgs& args, int sm_count, cudaStream_t st, int* launches);
+int launch_tc_pass(const TcPlan& plan, const TcArgs& args, int sm_count, cudaStream_t st, int* launches,
+                   const TcStageHook* hook = nullptr);
 int tc_set_attributes();
 // bias[i] = row i passes (mask nullptr = all rows < n_rows) ? (norm2 ? norm2[i] : 1) : +inf, for i < n_pad.
 int launch_tc_bias(const uint32_t* mask, const float* norm2, long long n_rows, long long n_pad, float* bias,
