@@ -1,0 +1,213 @@
+// Package gpu binds libquivergpu.so (include/quiver_gpu.h) and exposes a core.Index /
+// hybrid.Index implementation backed by one B200.
+//
+// NOTE: this file cannot be compiled in the build image (no Go toolchain); it is the binding a
+// Quiver maintainer adds as pkg/gpu. Everything it calls is exercised through the same C ABI by
+// the C++ host layer (quiver_b200/host) and the Python ctypes tests.
+package gpu
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../../include
+#cgo LDFLAGS: -L${SRCDIR}/../../../quiver_b200/lib -lquivergpu -Wl,-rpath,${SRCDIR}/../../../quiver_b200/lib
+#include <stdlib.h>
+#include "quiver_gpu.h"
+*/
+import "C"
+
+import (
+	"errors"
+	"fmt"
+	"sync"
+	"unsafe"
+
+	"github.com/TFMV/quiver/pkg/types"
+	"github.com/TFMV/quiver/pkg/vectortypes"
+)
+
+// Metric mirrors qg_metric; it replaces the `%p` sniffing of db.go:322-334.
+type Metric int
+
+const (
+	Cosine Metric = iota
+	Euclidean
+	DotProduct
+	SquaredEuclidean
+	Manhattan
+)
+
+// MetricOf maps the reference's DistanceType strings (vectortypes/types.go:19-25).
+func MetricOf(t vectortypes.DistanceType) Metric {
+	switch t {
+	case vectortypes.Euclidean:
+		return Euclidean
+	case vectortypes.DotProduct:
+		return DotProduct
+	case vectortypes.Manhattan:
+		return Manhattan
+	default: // unknown => cosine, types.go:46-47
+		return Cosine
+	}
+}
+
+func lastError(rc C.int) error {
+	return fmt.Errorf("%s (qg_status %d)", C.GoString(C.qg_last_error()), int(rc))
+}
+
+// Index satisfies core.Index and core.BatchIndex (pkg/core/collection.go:78-96) and
+// hybrid.Index (pkg/hybrid/types.go:196-214). String IDs live here; the device sees rows.
+type Index struct {
+	mu     sync.RWMutex // same discipline as exact.go:25: searches share, mutations exclude
+	h      *C.qg_index
+	dim    int
+	ids    []string         // row -> id
+	rows   map[string]int64 // id -> row (live rows only)
+	metric Metric
+}
+
+func New(dim int, metric Metric, device int) (*Index, error) {
+	cfg := C.qg_config{device: C.int(device)}
+	var h *C.qg_index
+	if rc := C.qg_index_create(&h, C.int(dim), C.int(metric), &cfg); rc != 0 {
+		return nil, lastError(rc)
+	}
+	return &Index{h: h, dim: dim, rows: map[string]int64{}, metric: metric}, nil
+}
+
+func (x *Index) Close() { C.qg_index_destroy(x.h) }
+
+// Insert — exact.go:38-58: dimension check, duplicate check, the vector is copied.
+func (x *Index) Insert(id string, v vectortypes.F32) error {
+	x.mu.Lock()
+	defer x.mu.Unlock()
+	if len(v) != x.dim {
+		return fmt.Errorf("vector dimension mismatch: expected %d, got %d", x.dim, len(v))
+	}
+	if _, dup := x.rows[id]; dup {
+		return fmt.Errorf("vector with ID %s already exists", id)
+	}
+	var first C.int64_t
+	if rc := C.qg_index_upload(x.h, (*C.float)(unsafe.Pointer(&v[0])), 1, &first); rc != 0 {
+		return lastError(rc)
+	}
+	x.ids = append(x.ids, id)
+	x.rows[id] = int64(first)
+	return nil
+}
+
+// InsertBatch — core.BatchIndex: one pinned-staged upload for the whole batch.
+func (x *Index) InsertBatch(vs map[string]vectortypes.F32) error {
+	x.mu.Lock()
+	defer x.mu.Unlock()
+	flat := make([]float32, 0, len(vs)*x.dim)
+	ids := make([]string, 0, len(vs))
+	for id, v := range vs {
+		if len(v) != x.dim {
+			return fmt.Errorf("vector dimension mismatch: expected %d, got %d", x.dim, len(v))
+		}
+		if _, dup := x.rows[id]; dup {
+			return fmt.Errorf("vector with ID %s already exists", id)
+		}
+		flat = append(flat, v...)
+		ids = append(ids, id)
+	}
+	if len(ids) == 0 {
+		return nil
+	}
+	var first C.int64_t
+	if rc := C.qg_index_upload(x.h, (*C.float)(unsafe.Pointer(&flat[0])), C.int64_t(len(ids)), &first); rc != 0 {
+		return lastError(rc)
+	}
+	for i, id := range ids {
+		x.ids = append(x.ids, id)
+		x.rows[id] = int64(first) + int64(i)
+	}
+	return nil
+}
+
+// Delete — exact.go:61-70: deleting a missing id is a no-op. Rows become tombstones.
+func (x *Index) Delete(id string) error {
+	x.mu.Lock()
+	defer x.mu.Unlock()
+	row, ok := x.rows[id]
+	if !ok {
+		return nil
+	}
+	r := C.int64_t(row)
+	if rc := C.qg_index_tombstone(x.h, &r, 1); rc != 0 {
+		return lastError(rc)
+	}
+	delete(x.rows, id)
+	return nil
+}
+
+func (x *Index) DeleteBatch(ids []string) error {
+	for _, id := range ids {
+		if err := x.Delete(id); err != nil {
+			return err
+		}
+	}
+	return nil
+}
+
+func (x *Index) Size() int { return int(C.qg_index_size(x.h)) }
+
+// Search — exact.go:92-133.
+func (x *Index) Search(q vectortypes.F32, k int) ([]types.BasicSearchResult, error) {
+	res, err := x.BatchSearch([]vectortypes.F32{q}, k)
+	if err != nil {
+		return nil, err
+	}
+	return res[0], nil
+}
+
+// BatchSearch — hybrid_index.go:677-811 with ForceStrategy = exact: ONE call for all queries.
+func (x *Index) BatchSearch(qs []vectortypes.F32, k int) ([][]types.BasicSearchResult, error) {
+	x.mu.RLock()
+	defer x.mu.RUnlock()
+	n := len(qs)
+	if n == 0 {
+		return nil, nil
+	}
+	dim := len(qs[0])
+	flat := make([]float32, 0, n*dim)
+	for _, q := range qs {
+		if len(q) != dim {
+			return nil, errors.New("queries of one batch must share a dimension")
+		}
+		flat = append(flat, q...)
+	}
+	kk := k
+	if kk < 1 {
+		kk = 1
+	}
+	dist := make([]float32, n*kk)
+	rows := make([]int64, n*kk)
+	cnt := make([]int32, n)
+	rc := C.qg_search_batch(x.h, (*C.float)(unsafe.Pointer(&flat[0])), C.int(n), C.int(dim), C.int(k), nil, nil,
+		(*C.float)(unsafe.Pointer(&dist[0])), nil, (*C.int64_t)(unsafe.Pointer(&rows[0])), (*C.int)(unsafe.Pointer(&cnt[0])))
+	if rc != 0 {
+		return nil, errors.New(C.GoString(C.qg_last_error())) // "k must be positive", "query dimension mismatch: ..."
+	}
+	out := make([][]types.BasicSearchResult, n)
+	for i := range out {
+		out[i] = make([]types.BasicSearchResult, cnt[i])
+		for j := 0; j < int(cnt[i]); j++ {
+			out[i][j] = types.BasicSearchResult{ID: x.ids[rows[i*kk+j]], Distance: dist[i*kk+j]}
+		}
+	}
+	return out, nil
+}
+
+// BatchDistance is the optional hook consulted by hnsw.searchLayer (hnsw.go:536-563) instead of
+// one computeDistance call per neighbour.
+func (x *Index) BatchDistance(q []float32, rows []uint32, out []float32) error {
+	if len(rows) == 0 {
+		return nil
+	}
+	rc := C.qg_batch_distance(x.h, (*C.float)(unsafe.Pointer(&q[0])), C.int(len(q)),
+		(*C.uint32_t)(unsafe.Pointer(&rows[0])), C.int(len(rows)), (*C.float)(unsafe.Pointer(&out[0])))
+	if rc != 0 {
+		return lastError(rc)
+	}
+	return nil
+}
