@@ -1,0 +1,117 @@
+/*
+ * quiver_host.h — C ABI of libquiverhost.so: the host side above libquivergpu.so.
+ *
+ * The reference host is Go; there is no Go toolchain in the build image, so the host logic a
+ * `pkg/gpu` package would carry (string IDs, request validation, negative-example re-rank, the
+ * predicate compiler) is written in C++ and mirrors the reference's names, argument meaning and
+ * error text:
+ *   qh_index       hybrid.HybridIndex in exact mode behind core.Index
+ *                  (pkg/hybrid/hybrid_index.go:86-585, 677-811; pkg/core/collection.go:78-96)
+ *   qh_collection  core.Collection: metadata, facet fields, Search / FluentSearch / SearchWithFacets
+ *                  (pkg/core/collection.go:133-331, 637-807, 874-1108, 1141-1207)
+ * Every function returns 0 or a qg_status code (include/quiver_gpu.h); qh_last_error() returns
+ * the message the reference would have put in its `error`.
+ */
+#ifndef QUIVER_HOST_H
+#define QUIVER_HOST_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qh_index qh_index;
+typedef struct qh_collection qh_collection;
+typedef struct qh_results qh_results;
+
+const char* qh_last_error(void);
+
+/* ---- result sets: one list of (id, distance) per query ------------------------------------ */
+int qh_results_queries(const qh_results* r);
+int qh_results_count(const qh_results* r, int query);
+const char* qh_results_id(const qh_results* r, int query, int j);
+float qh_results_distance(const qh_results* r, int query, int j);
+int qh_results_free(qh_results* r);
+
+/* ---- hybrid index, exact strategy ------------------------------------------------------------
+ * distance: "cosine" | "euclidean" | "dot_product" | "manhattan" | "squared_euclidean" and the
+ * HTTP aliases "l2", "dot", "cos", "" (pkg/api/handlers.go:66-72); unknown => cosine
+ * (pkg/vectortypes/types.go:46-47). arith: 0 = vectortypes float64, 1 = hnsw float32. */
+int qh_index_create(qh_index** out, int dim, const char* distance, int arith, int device);
+int qh_index_destroy(qh_index* idx);
+/* Insert (hybrid_index.go:86-131): dimension and duplicate-ID errors with the reference's text;
+ * the vector is copied. */
+int qh_index_insert(qh_index* idx, const char* id, const float* vec, int dim);
+int qh_index_insert_batch(qh_index* idx, const char* const* ids, const float* vecs, int64_t n, int dim);
+/* Delete (hybrid_index.go:241-290): a missing ID is an error (ExactIndex alone would not mind). */
+int qh_index_delete(qh_index* idx, const char* id);
+int64_t qh_index_size(const qh_index* idx);
+/* Search(query, k) (hybrid_index.go:378; exact.go:92-133). */
+int qh_index_search(qh_index* idx, const float* query, int dim, int k, qh_results** out);
+
+/* SearchWithRequest / BatchSearch (hybrid_index.go:383-469, 677-811). force_strategy: "" or
+ * "exact" run the exact path; "hnsw" is rejected here (the graph walk is not part of this index);
+ * anything else is the reference's "invalid search strategy" error. negatives: nq x dim or NULL;
+ * a negative example is used only when negative_weight > 0 (hybrid_index.go:417). */
+int qh_index_batch_search(qh_index* idx, const float* queries, int nq, int dim, int k, const float* negatives,
+                          int neg_dim, float negative_weight, const char* force_strategy, qh_results** out);
+
+/* ---- collection ------------------------------------------------------------------------------- */
+int qh_collection_create(qh_collection** out, const char* name, int dim, const char* distance, int device);
+int qh_collection_destroy(qh_collection* c);
+/* Add (collection.go:133-215): metadata_json may be NULL. */
+int qh_collection_add(qh_collection* c, const char* id, const float* vec, int dim, const char* metadata_json);
+int qh_collection_add_batch(qh_collection* c, const char* const* ids, const float* vecs, int64_t n, int dim,
+                            const char* const* metadata_json /* n entries, each may be NULL */);
+int qh_collection_delete(qh_collection* c, const char* id);
+int64_t qh_collection_count(const qh_collection* c);
+int qh_collection_set_facet_fields(qh_collection* c, const char* const* fields, int n);
+
+/* types.Filter (pkg/types/search.go:45-52). value_json is the operand as JSON text; a number
+ * written without '.', 'e', 'E' is a Go int, otherwise a float64 (this only matters for its "%v"
+ * text). op: "=", "!=", ">", ">=", "<", "<=", "in", "not_in". */
+typedef struct qh_filter {
+  const char* field;
+  const char* op;
+  const char* value_json;
+} qh_filter;
+/* Collection.Search / FluentSearch.Execute (collection.go:637-807, 1094): ranks the rows that pass
+ * all filters and returns the first k (the reference ranks all rows and filters afterwards; the
+ * result is the same list). k is clamped to Count() like FluentSearch.validate (:924-926). */
+int qh_collection_search(qh_collection* c, const float* query, int dim, int k, const qh_filter* filters, int n_filters,
+                         qh_results** out);
+
+/* facets.Filter implementations (pkg/facets/facets.go). type: 0 equality (value_json), 1 range
+ * (min_json / max_json, NULL or "null" = open; include flags), 2 set (value_json = JSON array),
+ * 3 exists (should_exist). */
+typedef struct qh_facet_filter {
+  int type;
+  const char* field;
+  const char* value_json;
+  const char* min_json;
+  const char* max_json;
+  int include_min, include_max;
+  int should_exist;
+} qh_facet_filter;
+/* Collection.SearchWithFacets (collection.go:1141-1207). */
+int qh_collection_search_with_facets(qh_collection* c, const float* query, int dim, int k,
+                                     const qh_facet_filter* filters, int n_filters, qh_results** out);
+/* Row-pass bits of a predicate set over the rows in insertion order (bit-exactness checks):
+ * mask_out receives count bytes (0/1); ids_out (nullable) the matching row ids are not returned —
+ * use qh_collection_row_id. which: 0 = core filters, 1 = facet filters. */
+int qh_collection_filter_mask(qh_collection* c, int which, const qh_filter* filters, const qh_facet_filter* ffilters,
+                              int n_filters, uint8_t* mask_out, int64_t n_rows);
+int64_t qh_collection_rows(const qh_collection* c);
+const char* qh_collection_row_id(const qh_collection* c, int64_t row);
+
+/* ---- development aids (CPU-only; no device needed) --------------------------------------------- */
+/* fmt.Sprintf("%v", json value) into buf; returns the length or -1 on a JSON error. */
+int qh_debug_sprint_v(const char* value_json, int typed_literals, char* buf, int buf_len);
+/* strings.EqualFold(a, b) as the predicate compiler sees it. */
+int qh_debug_equal_fold(const char* a, const char* b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUIVER_HOST_H */

@@ -1,0 +1,532 @@
+// host.cpp — libquiverhost.so: the host side above the GPU C ABI (include/quiver_host.h).
+// String IDs, request validation with the reference's error text, the negative-example re-rank
+// (pkg/hybrid/hybrid_index.go:515-570) and the predicate pushdown for Collection.Search /
+// SearchWithFacets (pkg/core/collection.go:679-752, 1141-1207).
+#include "../../include/quiver_host.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/quiver_gpu.h"
+#include "filter_compile.hpp"
+#include "value.hpp"
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int gpu_fail(int rc) { return fail(rc, qg_last_error()); }
+
+int metric_of(const char* name) {
+  const std::string s = name ? name : "";
+  if (s == "euclidean" || s == "l2") return QG_L2;
+  if (s == "dot_product" || s == "dot") return QG_DOT;
+  if (s == "manhattan") return QG_L1;
+  if (s == "squared_euclidean") return QG_SQL2;
+  return QG_COSINE;  // "cosine", "cos", "" and anything unknown (types.go:46-47)
+}
+
+struct Hit {
+  std::string id;
+  float distance;
+};
+
+}  // namespace
+
+struct qh_results {
+  std::vector<std::vector<Hit>> lists;
+};
+
+// ---- hybrid index (exact strategy) ---------------------------------------------------------------
+struct qh_index {
+  qg_index* h = nullptr;
+  int dim = 0;
+  mutable std::shared_mutex mu;          // hybrid_index.go:42: searches share, mutations exclude
+  std::vector<std::string> ids;          // row -> id
+  std::unordered_map<std::string, int64_t> rows;  // live id -> row
+};
+
+namespace {
+
+int index_insert_locked(qh_index* idx, const char* const* ids, const float* vecs, int64_t n, int dim) {
+  if (dim != idx->dim)
+    return fail(QG_ERR_DIM, "vector dimension mismatch: expected " + std::to_string(idx->dim) + ", got " +
+                                std::to_string(dim));
+  std::unordered_map<std::string, int> batch;
+  for (int64_t i = 0; i < n; ++i) {
+    const std::string id = ids[i] ? ids[i] : "";
+    if (idx->rows.count(id) || !batch.emplace(id, 1).second)
+      return fail(QG_ERR_INVALID, "vector with ID " + id + " already exists");
+  }
+  int64_t first = 0;
+  if (int rc = qg_index_upload(idx->h, vecs, n, &first)) return gpu_fail(rc);
+  for (int64_t i = 0; i < n; ++i) {
+    idx->ids.push_back(ids[i]);
+    idx->rows[ids[i]] = first + i;
+  }
+  return 0;
+}
+
+// searchWithStrategy, exact branch (hybrid_index.go:515-570) for a batch of queries.
+int index_search_locked(qh_index* idx, const float* queries, int nq, int dim, int k, const float* negatives,
+                        float neg_weight, qg_filter* filter, int64_t n_matching, qh_results* out) {
+  out->lists.assign((size_t)nq, {});
+  if (nq == 0) return 0;
+  const bool has_neg = negatives != nullptr && neg_weight > 0.f;
+  int retrieve = k;
+  if (has_neg && k > 0) {
+    retrieve = std::max(2 * k, 30);  // hybrid_index.go:517-522
+    const int64_t cap = filter ? n_matching : (int64_t)idx->rows.size();
+    if ((int64_t)retrieve > cap) retrieve = (int)std::max<int64_t>(cap, 1);
+  }
+  const int kk = std::max(retrieve, 1);
+  std::vector<float> dist((size_t)nq * kk), negd(has_neg ? (size_t)nq * kk : 0);
+  std::vector<int64_t> row((size_t)nq * kk);
+  std::vector<int> cnt((size_t)nq);
+  if (int rc = qg_search_batch(idx->h, queries, nq, dim, retrieve, filter, has_neg ? negatives : nullptr, dist.data(),
+                               has_neg ? negd.data() : nullptr, row.data(), cnt.data()))
+    return gpu_fail(rc);
+  for (int i = 0; i < nq; ++i) {
+    std::vector<Hit>& list = out->lists[(size_t)i];
+    const int n = cnt[(size_t)i];
+    list.reserve((size_t)n);
+    for (int j = 0; j < n; ++j) {
+      float d = dist[(size_t)i * kk + j];
+      if (has_neg) {
+        // result.Distance - negWeight*negDistance, in float32 like the Go expression (:552);
+        // compiled with -ffp-contract=off so the multiply and the subtract are not fused
+        const float prod = neg_weight * negd[(size_t)i * kk + j];
+        d = d - prod;
+      }
+      list.push_back(Hit{idx->ids[(size_t)row[(size_t)i * kk + j]], d});
+    }
+    if (has_neg) {
+      // sort.SliceStable by (Distance, ID) (:555-560), then the first k (:567-569)
+      std::stable_sort(list.begin(), list.end(), [](const Hit& a, const Hit& b) {
+        if (a.distance == b.distance) return a.id < b.id;
+        return a.distance < b.distance;
+      });
+      if ((int)list.size() > k) list.resize((size_t)k);
+    }
+  }
+  return 0;
+}
+
+}  // namespace
+
+// ---- collection -------------------------------------------------------------------------------------
+struct qh_collection : qh::ColumnSource {
+  std::string name;
+  int dim = 0;
+  qh_index* index = nullptr;
+  std::vector<qh::ValuePtr> metadata;      // per row: parsed metadata object, or nullptr
+  std::vector<std::string> facet_fields;
+  // device columns: one per (family, field); rebuilt lazily after a mutation
+  struct DevCol {
+    int index;
+    uint64_t epoch;
+    qh::Column col;
+  };
+  std::unordered_map<std::string, DevCol> cols;  // key: "m:" + field or "f:" + path
+  uint64_t epoch = 1;
+  int family = 0;  // 0 = metadata columns, 1 = facet columns (set before compiling)
+  std::mutex col_mu;  // column (re)builds touch device state: one search at a time compiles predicates
+
+  const qh::Value* facet_value(const qh::Value& md, const std::string& path) const {
+    // ExtractFacets dot-path walk (facets.go:405-421); nil values are dropped (:423)
+    const qh::Value* v = &md;
+    size_t start = 0;
+    for (;;) {
+      const size_t dot = path.find('.', start);
+      const std::string part = path.substr(start, dot == std::string::npos ? std::string::npos : dot - start);
+      if (v->type != qh::Value::Object) return nullptr;
+      auto it = v->obj.find(part);
+      if (it == v->obj.end()) return nullptr;
+      v = it->second.get();
+      if (dot == std::string::npos) break;
+      start = dot + 1;
+    }
+    return v->type == qh::Value::Null ? nullptr : v;
+  }
+
+  DevCol& ensure(const std::string& field) {
+    const std::string key = (family ? "f:" : "m:") + field;
+    auto it = cols.find(key);
+    if (it == cols.end()) it = cols.emplace(key, DevCol{(int)cols.size(), 0, {}}).first;
+    DevCol& dc = it->second;
+    if (dc.epoch == epoch) return dc;
+    const size_t n = metadata.size();
+    std::vector<qh::CellRef> cells(n);
+    for (size_t r = 0; r < n; ++r) {
+      const qh::Value* md = metadata[r].get();
+      if (!md) { cells[r] = {nullptr, true}; continue; }
+      if (family == 0) {
+        auto f = md->obj.find(field);
+        cells[r] = {f == md->obj.end() ? nullptr : f->second.get(), false};
+      } else {
+        // rows whose facet list is empty never match (MatchesAllFilters, facets.go:437-439)
+        bool any = false;
+        for (const std::string& ff : facet_fields)
+          if (facet_value(*md, ff)) { any = true; break; }
+        const bool is_facet = std::find(facet_fields.begin(), facet_fields.end(), field) != facet_fields.end();
+        if (!any) cells[r] = {nullptr, true};
+        else cells[r] = {is_facet ? facet_value(*md, field) : nullptr, false};
+      }
+    }
+    qh::encode_column(cells, &dc.col);
+    last_rc = qg_facets_set_column(index->h, dc.index, dc.col.kind.data(), dc.col.num.data(), dc.col.scode.data(),
+                                   dc.col.fcode.data(), (int64_t)n);
+    dc.epoch = epoch;
+    return dc;
+  }
+  int last_rc = 0;
+  int field_index(const std::string& name_) override { return ensure(name_).index; }
+  const qh::Column& column(const std::string& name_) override { return ensure(name_).col; }
+};
+
+namespace {
+
+int parse_operand(const char* text, qh::ValuePtr* out) {
+  if (!text) { *out = std::make_shared<qh::Value>(); return 0; }
+  std::string err;
+  *out = qh::parse_json(text, true, &err);
+  if (!*out) return fail(QG_ERR_INVALID, "filter value is not valid JSON: " + err);
+  return 0;
+}
+
+int build_program(qh_collection* c, int which, const qh_filter* filters, const qh_facet_filter* ffilters, int n,
+                  qh::Program* prog) {
+  std::lock_guard<std::mutex> col_lock(c->col_mu);
+  c->family = which;
+  c->last_rc = 0;
+  std::string err;
+  int rc = 0;
+  if (which == 0) {
+    std::vector<qh::CoreFilter> fs((size_t)n);
+    for (int i = 0; i < n; ++i) {
+      fs[(size_t)i].field = filters[i].field ? filters[i].field : "";
+      fs[(size_t)i].op = filters[i].op ? filters[i].op : "";
+      if (int prc = parse_operand(filters[i].value_json, &fs[(size_t)i].value)) return prc;
+    }
+    rc = qh::compile_core_filters(fs, *c, prog, &err);
+  } else {
+    std::vector<qh::FacetFilter> fs((size_t)n);
+    for (int i = 0; i < n; ++i) {
+      qh::FacetFilter& f = fs[(size_t)i];
+      const qh_facet_filter& s = ffilters[i];
+      if (s.type < 0 || s.type > 3) return fail(QG_ERR_INVALID, "unknown facet filter type");
+      f.type = (qh::FacetFilter::Type)s.type;
+      f.field = s.field ? s.field : "";
+      f.include_min = s.include_min != 0;
+      f.include_max = s.include_max != 0;
+      f.should_exist = s.should_exist != 0;
+      if (s.type == 0) {
+        if (int prc = parse_operand(s.value_json, &f.value)) return prc;
+      } else if (s.type == 1) {
+        if (int prc = parse_operand(s.min_json, &f.min)) return prc;
+        if (int prc = parse_operand(s.max_json, &f.max)) return prc;
+      } else if (s.type == 2) {
+        qh::ValuePtr arr;
+        if (int prc = parse_operand(s.value_json, &arr)) return prc;
+        if (arr->type != qh::Value::Array) return fail(QG_ERR_INVALID, "set filter values must be a JSON array");
+        f.values = arr->arr;
+      }
+    }
+    rc = qh::compile_facet_filters(fs, *c, prog, &err);
+  }
+  if (rc) return fail(rc, err);
+  if (c->last_rc) return gpu_fail(c->last_rc);
+  return 0;
+}
+
+struct FilterHandle {
+  qg_filter* f = nullptr;
+  ~FilterHandle() { if (f) qg_filter_destroy(f); }
+};
+
+int make_filter(qh_collection* c, const qh::Program& prog, FilterHandle* out, int64_t* matches) {
+  if (int rc = qg_filter_compile(c->index->h, prog.preds.data(), (int)prog.preds.size(), prog.clauses.data(),
+                                 (int)prog.clauses.size(), prog.iset.data(), (int)prog.iset.size(), prog.fset.data(),
+                                 (int)prog.fset.size(), &out->f))
+    return gpu_fail(rc);
+  if (matches) {
+    if (int rc = qg_filter_eval(c->index->h, out->f, nullptr, matches)) return gpu_fail(rc);
+  }
+  return 0;
+}
+
+}  // namespace
+
+// ======================================================================================================
+extern "C" {
+
+const char* qh_last_error(void) { return g_err.c_str(); }
+
+int qh_results_queries(const qh_results* r) { return r ? (int)r->lists.size() : 0; }
+int qh_results_count(const qh_results* r, int q) {
+  return (r && q >= 0 && q < (int)r->lists.size()) ? (int)r->lists[(size_t)q].size() : 0;
+}
+const char* qh_results_id(const qh_results* r, int q, int j) { return r->lists[(size_t)q][(size_t)j].id.c_str(); }
+float qh_results_distance(const qh_results* r, int q, int j) { return r->lists[(size_t)q][(size_t)j].distance; }
+int qh_results_free(qh_results* r) {
+  delete r;
+  return 0;
+}
+
+int qh_index_create(qh_index** out, int dim, const char* distance, int arith, int device) {
+  if (!out) return fail(QG_ERR_INVALID, "out is null");
+  *out = nullptr;
+  qg_config cfg{};
+  cfg.device = device;
+  cfg.arith = arith;
+  qg_index* h = nullptr;
+  if (int rc = qg_index_create(&h, dim, metric_of(distance), &cfg)) return gpu_fail(rc);
+  qh_index* idx = new qh_index();
+  idx->h = h;
+  idx->dim = dim;
+  *out = idx;
+  return 0;
+}
+
+int qh_index_destroy(qh_index* idx) {
+  if (!idx) return 0;
+  qg_index_destroy(idx->h);
+  delete idx;
+  return 0;
+}
+
+int qh_index_insert(qh_index* idx, const char* id, const float* vec, int dim) {
+  if (!idx || !id || !vec) return fail(QG_ERR_INVALID, "null argument");
+  std::unique_lock<std::shared_mutex> lk(idx->mu);
+  const char* ids[1] = {id};
+  return index_insert_locked(idx, ids, vec, 1, dim);
+}
+
+int qh_index_insert_batch(qh_index* idx, const char* const* ids, const float* vecs, int64_t n, int dim) {
+  if (!idx || (n > 0 && (!ids || !vecs))) return fail(QG_ERR_INVALID, "null argument");
+  std::unique_lock<std::shared_mutex> lk(idx->mu);
+  return index_insert_locked(idx, ids, vecs, n, dim);
+}
+
+int qh_index_delete(qh_index* idx, const char* id) {
+  if (!idx || !id) return fail(QG_ERR_INVALID, "null argument");
+  std::unique_lock<std::shared_mutex> lk(idx->mu);
+  auto it = idx->rows.find(id);
+  if (it == idx->rows.end()) return fail(QG_ERR_INVALID, std::string("vector with ID ") + id + " not found");
+  const int64_t row = it->second;
+  if (int rc = qg_index_tombstone(idx->h, &row, 1)) return gpu_fail(rc);
+  idx->rows.erase(it);
+  return 0;
+}
+
+int64_t qh_index_size(const qh_index* idx) {
+  if (!idx) return 0;
+  std::shared_lock<std::shared_mutex> lk(idx->mu);
+  return (int64_t)idx->rows.size();
+}
+
+int qh_index_search(qh_index* idx, const float* query, int dim, int k, qh_results** out) {
+  return qh_index_batch_search(idx, query, 1, dim, k, nullptr, 0, 0.f, "", out);
+}
+
+int qh_index_batch_search(qh_index* idx, const float* queries, int nq, int dim, int k, const float* negatives,
+                          int neg_dim, float negative_weight, const char* force_strategy, qh_results** out) {
+  if (!idx || !out) return fail(QG_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (nq <= 0) return fail(QG_ERR_INVALID, "no queries provided");  // hybrid_index.go:678-680
+  const std::string strategy = force_strategy ? force_strategy : "";
+  if (strategy == "hnsw")
+    return fail(QG_ERR_UNSUPPORTED, "the GPU index serves the exact strategy; use the HNSW adapter for graph search");
+  if (!strategy.empty() && strategy != "exact") return fail(QG_ERR_INVALID, "invalid search strategy: " + strategy);
+  std::shared_lock<std::shared_mutex> lk(idx->mu);
+  // SearchWithRequest order (hybrid_index.go:392-402): query dim, negative dim, k
+  if (idx->dim > 0 && dim != idx->dim)
+    return fail(QG_ERR_DIM, "query dimension mismatch: expected " + std::to_string(idx->dim) + ", got " +
+                                std::to_string(dim));
+  const bool neg_given = negatives != nullptr && neg_dim > 0;
+  if (neg_given && neg_dim != idx->dim)
+    return fail(QG_ERR_DIM, "negative example dimension mismatch: expected " + std::to_string(idx->dim) + ", got " +
+                                std::to_string(neg_dim));
+  if (k <= 0) return fail(QG_ERR_K, "k must be positive");
+  std::unique_ptr<qh_results> res(new qh_results());
+  if (int rc = index_search_locked(idx, queries, nq, dim, k, neg_given ? negatives : nullptr, negative_weight, nullptr,
+                                   0, res.get()))
+    return rc;
+  *out = res.release();
+  return 0;
+}
+
+// ---- collection ------------------------------------------------------------------------------------
+int qh_collection_create(qh_collection** out, const char* name, int dim, const char* distance, int device) {
+  if (!out) return fail(QG_ERR_INVALID, "out is null");
+  *out = nullptr;
+  qh_index* idx = nullptr;
+  if (int rc = qh_index_create(&idx, dim, distance, 0, device)) return rc;
+  qh_collection* c = new qh_collection();
+  c->name = name ? name : "";
+  c->dim = dim;
+  c->index = idx;
+  *out = c;
+  return 0;
+}
+
+int qh_collection_destroy(qh_collection* c) {
+  if (!c) return 0;
+  qh_index_destroy(c->index);
+  delete c;
+  return 0;
+}
+
+int qh_collection_add_batch(qh_collection* c, const char* const* ids, const float* vecs, int64_t n, int dim,
+                            const char* const* metadata_json) {
+  if (!c || (n > 0 && (!ids || !vecs))) return fail(QG_ERR_INVALID, "null argument");
+  std::vector<qh::ValuePtr> parsed((size_t)n);
+  for (int64_t i = 0; i < n; ++i) {
+    if (!ids[i] || !ids[i][0]) return fail(QG_ERR_INVALID, "vector ID cannot be empty");  // collection.go:143-148
+    if (dim != c->dim)
+      return fail(QG_ERR_DIM, "invalid vector dimension: expected " + std::to_string(c->dim) + ", got " +
+                                  std::to_string(dim));
+    const char* md = metadata_json ? metadata_json[i] : nullptr;
+    if (md && md[0]) {
+      std::string err;
+      qh::ValuePtr v = qh::parse_json(md, false, &err);
+      // json.Unmarshal into map[string]interface{}: objects and null are accepted (collection.go:160-168)
+      if (!v || (v->type != qh::Value::Object && v->type != qh::Value::Null))
+        return fail(QG_ERR_INVALID, "invalid metadata format: " + (v ? std::string("not a JSON object") : err));
+      if (v->type == qh::Value::Object) parsed[(size_t)i] = v;  // a null document decodes to a nil map: no fields
+    }
+    if (c->index->rows.count(ids[i])) return fail(QG_ERR_INVALID, std::string("vector with the same ID already exists: ") + ids[i]);
+  }
+  {
+    std::unique_lock<std::shared_mutex> lk(c->index->mu);
+    if (int rc = index_insert_locked(c->index, ids, vecs, n, dim)) return rc;
+  }
+  for (int64_t i = 0; i < n; ++i) c->metadata.push_back(parsed[(size_t)i]);
+  c->epoch++;
+  return 0;
+}
+
+int qh_collection_add(qh_collection* c, const char* id, const float* vec, int dim, const char* metadata_json) {
+  const char* ids[1] = {id};
+  const char* mds[1] = {metadata_json};
+  return qh_collection_add_batch(c, ids, vec, 1, dim, mds);
+}
+
+int qh_collection_delete(qh_collection* c, const char* id) {
+  if (!c || !id) return fail(QG_ERR_INVALID, "null argument");
+  if (!c->index->rows.count(id)) return fail(QG_ERR_INVALID, "vector not found");  // ErrVectorNotFound
+  return qh_index_delete(c->index, id);
+}
+
+int64_t qh_collection_count(const qh_collection* c) { return c ? qh_index_size(c->index) : 0; }
+int64_t qh_collection_rows(const qh_collection* c) { return c ? (int64_t)c->metadata.size() : 0; }
+const char* qh_collection_row_id(const qh_collection* c, int64_t row) {
+  if (!c || row < 0 || row >= (int64_t)c->index->ids.size()) return "";
+  return c->index->ids[(size_t)row].c_str();
+}
+
+int qh_collection_set_facet_fields(qh_collection* c, const char* const* fields, int n) {
+  if (!c) return fail(QG_ERR_INVALID, "null argument");
+  c->facet_fields.clear();
+  for (int i = 0; i < n; ++i) c->facet_fields.push_back(fields[i] ? fields[i] : "");
+  c->epoch++;  // SetFacetFields re-indexes every row (collection.go:1111-1130)
+  return 0;
+}
+
+static int collection_search(qh_collection* c, int which, const float* query, int dim, int k, const qh_filter* filters,
+                             const qh_facet_filter* ffilters, int n_filters, qh_results** out) {
+  if (!c || !out) return fail(QG_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (which == 0) {
+    // Collection.Search (collection.go:650-665): dimension, then top_k
+    if (dim != c->dim)
+      return fail(QG_ERR_DIM, "invalid vector dimension: expected " + std::to_string(c->dim) + ", got " +
+                                  std::to_string(dim));
+    if (k <= 0) return fail(QG_ERR_K, "top_k must be greater than 0");
+  } else {
+    // SearchWithFacets (collection.go:1146-1151): k, then dimension
+    if (k <= 0) return fail(QG_ERR_K, "k must be positive");
+    if (dim != c->dim)
+      return fail(QG_ERR_DIM, "query vector dimension mismatch, expected " + std::to_string(c->dim) + ", got " +
+                                  std::to_string(dim));
+  }
+  std::unique_ptr<qh_results> res(new qh_results());
+  res->lists.assign(1, {});
+  std::shared_lock<std::shared_mutex> lk(c->index->mu);
+  if (c->index->rows.empty()) {  // empty index: no results, no error (collection.go:666-677, 1179-1182)
+    *out = res.release();
+    return 0;
+  }
+  if (n_filters <= 0) {
+    if (int rc = index_search_locked(c->index, query, 1, dim, k, nullptr, 0.f, nullptr, 0, res.get())) return rc;
+    *out = res.release();
+    return 0;
+  }
+  qh::Program prog;
+  if (int rc = build_program(c, which, filters, ffilters, n_filters, &prog)) return rc;
+  FilterHandle fh;
+  int64_t matches = 0;
+  if (int rc = make_filter(c, prog, &fh, &matches)) return rc;
+  if (int rc = index_search_locked(c->index, query, 1, dim, k, nullptr, 0.f, fh.f, matches, res.get())) return rc;
+  *out = res.release();
+  return 0;
+}
+
+int qh_collection_search(qh_collection* c, const float* query, int dim, int k, const qh_filter* filters, int n_filters,
+                         qh_results** out) {
+  return collection_search(c, 0, query, dim, k, filters, nullptr, n_filters, out);
+}
+
+int qh_collection_search_with_facets(qh_collection* c, const float* query, int dim, int k,
+                                     const qh_facet_filter* filters, int n_filters, qh_results** out) {
+  return collection_search(c, 1, query, dim, k, nullptr, filters, n_filters, out);
+}
+
+int qh_collection_filter_mask(qh_collection* c, int which, const qh_filter* filters, const qh_facet_filter* ffilters,
+                              int n_filters, uint8_t* mask_out, int64_t n_rows) {
+  if (!c || !mask_out) return fail(QG_ERR_INVALID, "null argument");
+  const int64_t rows = (int64_t)c->metadata.size();
+  if (n_rows < rows) return fail(QG_ERR_INVALID, "mask buffer too small");
+  std::shared_lock<std::shared_mutex> lk(c->index->mu);
+  qh::Program prog;
+  if (int rc = build_program(c, which, filters, ffilters, n_filters, &prog)) return rc;
+  FilterHandle fh;
+  if (int rc = make_filter(c, prog, &fh, nullptr)) return rc;
+  std::vector<uint64_t> words((size_t)((rows + 63) / 64) + 1);
+  int64_t matches = 0;
+  if (int rc = qg_filter_eval(c->index->h, fh.f, words.data(), &matches)) return gpu_fail(rc);
+  for (int64_t r = 0; r < rows; ++r) mask_out[r] = (uint8_t)((words[(size_t)(r >> 6)] >> (r & 63)) & 1ull);
+  return 0;
+}
+
+int qh_debug_sprint_v(const char* value_json, int typed_literals, char* buf, int buf_len) {
+  std::string err;
+  qh::ValuePtr v = qh::parse_json(value_json ? value_json : "", typed_literals != 0, &err);
+  if (!v) {
+    g_err = err;
+    return -1;
+  }
+  const std::string s = qh::sprint_v(*v);
+  if (buf && buf_len > 0) {
+    const size_t n = std::min<size_t>(s.size(), (size_t)buf_len - 1);
+    std::memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  }
+  return (int)s.size();
+}
+
+int qh_debug_equal_fold(const char* a, const char* b) {
+  return qh::fold_key(a ? a : "") == qh::fold_key(b ? b : "") ? 1 : 0;
+}
+
+}  // extern "C"
