@@ -208,7 +208,7 @@ def run_native(args):
     d_cnt = torch.empty((Q,), dtype=torch.int32, device=dev)
     if world > 1:
         d_keys = torch.empty((Q, k), dtype=torch.int64, device=dev)  # packed u64 keys
-        d_all = torch.empty((world, Q, k), dtype=torch.int64, device=dev)
+        d_all = torch.empty((world * Q, k), dtype=torch.int64, device=dev)  # rank-major concatenation
 
     def step_device():
         if world == 1:

@@ -1,0 +1,83 @@
+"""Row-sharded exact search across GPUs (no reference counterpart — Quiver is single
+process). One process per GPU: rank g owns the contiguous block [g*ceil(N/G), (g+1)*ceil(N/G)),
+queries are replicated, every rank emits its shard's top-k as packed 64-bit keys
+(order-preserving image of the EXACT float32 distance << 32 | global row), one all-gather
+exchanges Q*k*8 bytes per rank, and every rank merges the G lists.
+
+The key format and the merge are pure integer work, restated here in numpy so that the exchange
+protocol is testable with the gloo backend on CPU; on the GPU the keys come from
+qg_search_shard_keys_device and the merge is qg_merge_shard_keys_device.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import numpy as np
+
+KEY_NONE = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def shard_range(rows: int, world: int, rank: int) -> Tuple[int, int]:
+    """[row0, row1) of `rank`: contiguous blocks of ceil(rows / world)."""
+    per = (rows + world - 1) // world
+    row0 = min(rows, rank * per)
+    return row0, min(rows, row0 + per)
+
+
+def f32_to_ordered(d: np.ndarray) -> np.ndarray:
+    """Same mapping as csrc/common.cuh: unsigned order == float order (negatives flipped)."""
+    b = np.ascontiguousarray(d, dtype=np.float32).view(np.uint32)
+    return np.where(b & np.uint32(0x80000000), ~b, b | np.uint32(0x80000000)).astype(np.uint32)
+
+
+def ordered_to_f32(k: np.ndarray) -> np.ndarray:
+    k = k.astype(np.uint32)
+    b = np.where(k & np.uint32(0x80000000), k & np.uint32(0x7FFFFFFF), ~k).astype(np.uint32)
+    return b.view(np.float32)
+
+
+def pack_keys(dist: np.ndarray, row: np.ndarray, count: np.ndarray, row_base: int) -> np.ndarray:
+    """[Q, k] distances / local rows / counts -> [Q, k] uint64 keys (missing entries = all ones)."""
+    q, k = dist.shape
+    keys = (f32_to_ordered(dist).astype(np.uint64) << np.uint64(32)) | (row.astype(np.int64) + row_base).astype(np.uint64)
+    valid = np.arange(k)[None, :] < np.asarray(count)[:, None]
+    return np.where(valid, keys, KEY_NONE)
+
+
+def merge_keys(gathered: np.ndarray, k: int):
+    """[G, Q, k] keys -> (dist [Q, k], row [Q, k], count [Q]): the k smallest keys per query."""
+    g, q, kk = gathered.shape
+    allk = np.sort(gathered.transpose(1, 0, 2).reshape(q, g * kk), axis=1)[:, :k]
+    valid = allk != KEY_NONE
+    dist = np.where(valid, ordered_to_f32((allk >> np.uint64(32)).astype(np.uint32)), np.float32(np.inf)).astype(np.float32)
+    row = np.where(valid, (allk & np.uint64(0xFFFFFFFF)).astype(np.int64), -1)
+    return dist, row, valid.sum(axis=1).astype(np.int32)
+
+
+class ShardedIndex:
+    """One rank's shard plus the collective. Needs torch.distributed initialised (backend nccl)."""
+
+    def __init__(self, dim: int, metric: int, rows_total: int, device: int = 0):
+        import torch
+        import torch.distributed as dist
+        from . import capi
+        self.torch, self.dist, self.capi = torch, dist, capi
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.row0, self.row1 = shard_range(rows_total, self.world, self.rank)
+        self.device = device
+        self.index = capi.Index(dim, metric, device=device, reserve_rows=max(1, self.row1 - self.row0))
+
+    def search_device(self, d_queries, q: int, k: int, d_dist, d_row, d_count, stream: int = 0):
+        """All tensors on this rank's device; results (global rows) are valid on every rank."""
+        torch = self.torch
+        if self.world == 1:
+            self.index.search_device(d_queries.data_ptr(), q, k, d_dist.data_ptr(), d_row.data_ptr(),
+                                     d_count.data_ptr(), stream=stream)
+            return
+        keys = torch.empty((q, k), dtype=torch.int64, device=d_queries.device)
+        allk = torch.empty((self.world * q, k), dtype=torch.int64, device=d_queries.device)  # rank-major
+        self.index.search_shard_keys_device(d_queries.data_ptr(), q, k, self.row0, keys.data_ptr(), stream=stream)
+        self.dist.all_gather_into_tensor(allk, keys)
+        self.capi.merge_shard_keys_device(self.device, allk.data_ptr(), self.world, q, k, d_dist.data_ptr(),
+                                          d_row.data_ptr(), d_count.data_ptr(), stream=stream)

@@ -1,0 +1,115 @@
+"""Row-sharded search. CPU: the exchange protocol (shard ranges, packed keys, all-gather,
+merge) over gloo with world_size 2 and 3, the per-shard search played by the oracle. GPU: two
+shards of one corpus on one device merged by qg_merge_shard_keys_device equal the unsharded index
+bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, d, k, nq, metric, out):
+    import torch.distributed as dist
+    import torch
+    import oracle
+    from quiver_b200 import sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    corpus = oracle.synth(0, 42, 0, n, d, threads=1)  # every rank could regenerate any row
+    queries = oracle.synth(0, 9999, 0, nq, d, threads=1)
+    row0, row1 = sharded.shard_range(n, world, rank)
+    shard = corpus[row0:row1]
+    dist_l = np.full((nq, k), np.inf, dtype=np.float32)
+    row_l = np.full((nq, k), -1, dtype=np.int64)
+    cnt_l = np.zeros(nq, dtype=np.int32)
+    for i in range(nq):
+        if row1 > row0:
+            od, orow = oracle.exact_search(shard, queries[i], k, metric)
+            dist_l[i, :len(od)], row_l[i, :len(od)], cnt_l[i] = od, orow, len(od)
+    keys = sharded.pack_keys(dist_l, row_l, cnt_l, row0)
+    mine = torch.from_numpy(keys.view(np.int64).copy())
+    allk = torch.empty((world * nq, k), dtype=torch.int64)  # rank-major concatenation
+    dist.all_gather_into_tensor(allk, mine)
+    gd, gr, gc = sharded.merge_keys(allk.numpy().view(np.uint64).reshape(world, nq, k), k)
+    ok = True
+    for i in range(nq):
+        od, orow = oracle.exact_search(corpus, queries[i], k, metric)
+        ok &= gc[i] == len(od) and np.array_equal(gr[i, :len(od)], orow) and \
+            np.array_equal(gd[i, :len(od)].view(np.uint32), od.view(np.uint32))
+    t = torch.tensor([1 if ok else 0])
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        out.put(int(t.item()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 5000), (3, 1001), (2, 1)])
+def test_sharded_exchange_over_gloo(oracle, world, n):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, 32, 10, 4, 1, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert out.get(timeout=5) == 1
+
+
+def test_key_packing_orders_like_floats():
+    from quiver_b200 import sharded
+    d = np.array([-np.inf, -3.5, -0.0, 0.0, 1e-30, 1.0, 2.5, np.inf], dtype=np.float32)
+    o = sharded.f32_to_ordered(d)
+    assert np.all(np.diff(o.astype(np.int64)) >= 0)
+    assert np.array_equal(sharded.ordered_to_f32(o).view(np.uint32), d.view(np.uint32))
+    assert sharded.shard_range(10, 3, 0) == (0, 4) and sharded.shard_range(10, 3, 2) == (8, 10)
+    assert sharded.shard_range(2, 4, 3) == (2, 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nq", [3, 40])
+def test_two_shards_on_one_device_equal_the_unsharded_index(capi, oracle, nq):
+    import torch
+    from quiver_b200 import sharded
+    n, d, k = 70000, 96, 10
+    corpus = oracle.synth(3, 42, 0, n, d)
+    queries = oracle.synth(3, 9999, 0, nq, d)
+    full = capi.Index(d, 1)
+    full.upload(corpus)
+    fd, fr, fc, _ = full.search(queries, k)
+    dq = torch.from_numpy(queries).cuda()
+    world = 2
+    allk = torch.empty((world, nq, k), dtype=torch.int64, device="cuda:0")
+    shards = []
+    for g in range(world):
+        r0, r1 = sharded.shard_range(n, world, g)
+        idx = capi.Index(d, 1)
+        idx.upload(corpus[r0:r1])
+        idx.search_shard_keys_device(dq.data_ptr(), nq, k, r0, allk[g].data_ptr())
+        shards.append(idx)
+    torch.cuda.synchronize()
+    od = torch.empty((nq, k), dtype=torch.float32, device="cuda:0")
+    orow = torch.empty((nq, k), dtype=torch.int64, device="cuda:0")
+    oc = torch.empty((nq,), dtype=torch.int32, device="cuda:0")
+    capi.merge_shard_keys_device(0, allk.data_ptr(), world, nq, k, od.data_ptr(), orow.data_ptr(), oc.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(orow.cpu().numpy(), fr)
+    assert np.array_equal(od.cpu().numpy().view(np.uint32), fd.view(np.uint32))
+    assert np.array_equal(oc.cpu().numpy(), fc)
+    # the numpy merge used by the gloo test agrees with the device merge
+    gd, gr, gc = sharded.merge_keys(allk.cpu().numpy().view(np.uint64), k)
+    assert np.array_equal(gr, fr) and np.array_equal(gd.view(np.uint32), fd.view(np.uint32))
+    for idx in shards + [full]:
+        idx.close()
