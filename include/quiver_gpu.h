@@ -224,6 +224,14 @@ int qg_batch_distance(qg_index* idx, const float* query, int dim, const uint32_t
 int qg_batch_distance_multi(qg_index* idx, const float* queries, int b, int dim,
                             const uint32_t* rows, int m, float* out);
 
+/* The same with the queries resident on the device: a graph walk issues hundreds of expansion
+ * steps for one batch of queries, so the queries are uploaded once. rows is b x m (host), entry
+ * [i*m + j] belongs to query i of the set; 0xFFFFFFFF = skip (+inf). */
+typedef struct qg_queries qg_queries;
+int qg_queries_upload(qg_index* idx, const float* queries, int b, int dim, qg_queries** out);
+int qg_queries_destroy(qg_queries* qs);
+int qg_batch_distance_queries(qg_index* idx, const qg_queries* qs, const uint32_t* rows, int m, float* out);
+
 /* ---- introspection for benchmarks and tests -----------------------------------------*/
 typedef struct qg_scan_stats {
   int64_t rows_scanned;     /* rows whose vector bytes the last scan read            */

@@ -105,6 +105,25 @@ int qh_collection_filter_mask(qh_collection* c, int which, const qh_filter* filt
 int64_t qh_collection_rows(const qh_collection* c);
 const char* qh_collection_row_id(const qh_collection* c, int64_t row);
 
+/* ---- HNSW search with GPU-batched neighbour distances -------------------------------------------
+ * The graph is the reference's (pkg/hnsw/hnsw.go:44-82), viewed as flat arrays; node id = row of
+ * the index (insertion order). The walk is hnsw.Search / searchLayer (hnsw.go:471-580, 602-713)
+ * step for step — same heaps, same visit order, same stop / admit rules — except that the
+ * distances of one expansion step (hnsw.go:536-563, up to MaxM0 = 32 neighbours) of ALL queries
+ * of the batch are evaluated by one qg_batch_distance_queries call. */
+typedef struct qh_hnsw_graph {
+  int64_t n_nodes;
+  int m, max_m0;             /* hnsw.Config M / MaxM0 (hnsw.go:16-25) */
+  int entry_point, current_level, ef_search;
+  const int32_t* level;      /* [n] node level, -1 = deleted node (nil in HNSW.Nodes) */
+  const uint32_t* adj0;      /* [n x max_m0] level-0 connections in list order, 0xFFFFFFFF padded */
+  const int64_t* upper_off;  /* [n+1] start of node i's upper-level block in upper_adj */
+  const uint32_t* upper_adj; /* per node: level[i] blocks of m entries (levels 1..level[i]) */
+} qh_hnsw_graph;
+/* out_evals / out_steps (nullable): distance evaluations per query [nq] and lock-step rounds. */
+int qh_hnsw_search_batch(qh_index* idx, const qh_hnsw_graph* g, const float* queries, int nq, int dim, int k,
+                         qh_results** out, int64_t* out_evals, int64_t* out_steps);
+
 /* ---- development aids (CPU-only; no device needed) --------------------------------------------- */
 /* fmt.Sprintf("%v", json value) into buf; returns the length or -1 on a JSON error. */
 int qh_debug_sprint_v(const char* value_json, int typed_literals, char* buf, int buf_len);

@@ -63,7 +63,8 @@ EXPORTED_SYMBOLS = [
     "qg_index_fetch", "qg_facets_set_column", "qg_filter_compile", "qg_filter_eval", "qg_filter_destroy",
     "qg_search_batch", "qg_search_batch_device", "qg_search_shard_keys_device", "qg_merge_shard_keys_device",
     "qg_batch_distance", "qg_batch_distance_multi", "qg_last_scan_stats", "qg_index_set_profiling",
-    "qg_index_read_profile", "qg_debug_tc_pass",
+    "qg_index_read_profile", "qg_debug_tc_pass", "qg_queries_upload", "qg_queries_destroy",
+    "qg_batch_distance_queries",
 ]
 
 _lib = None
@@ -109,6 +110,9 @@ def load() -> C.CDLL:
     lib.qg_index_set_profiling.argtypes = [vp, i32]
     lib.qg_index_read_profile.argtypes = [vp, C.POINTER(qg_profile)]
     lib.qg_debug_tc_pass.argtypes = [vp, vp, i32, i32, vp, vp, vp, C.POINTER(i32)]
+    lib.qg_queries_upload.argtypes = [vp, vp, i32, i32, C.POINTER(vp)]
+    lib.qg_queries_destroy.argtypes = [vp]
+    lib.qg_batch_distance_queries.argtypes = [vp, vp, vp, i32, vp]
     _lib = lib
     return lib
 

@@ -1373,6 +1373,70 @@ int qg_batch_distance_multi(qg_index* idx, const float* queries, int b, int dim,
   return rc;
 }
 
+struct qg_queries {
+  qg_index* owner = nullptr;
+  int b = 0, dim = 0;
+  DevBuf d_q;
+};
+
+int qg_queries_upload(qg_index* idx, const float* queries, int b, int dim, qg_queries** out) {
+  if (int rc = check_index(idx)) return rc;
+  if (!out) return fail(QG_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (b <= 0 || !queries) return fail(QG_ERR_INVALID, "no queries");
+  if (dim != idx->dim)
+    return fail(QG_ERR_DIM, "query dimension mismatch: expected " + std::to_string(idx->dim) + ", got " +
+                                std::to_string(dim));
+  std::unique_ptr<qg_queries> qs(new qg_queries());
+  qs->owner = idx;
+  qs->b = b;
+  qs->dim = dim;
+  if (int rc = qs->d_q.ensure((size_t)b * dim * 4)) return rc;
+  QG_CUDA_OK(cudaMemcpy(qs->d_q.p, queries, (size_t)b * dim * 4, cudaMemcpyHostToDevice));
+  *out = qs.release();
+  return 0;
+}
+
+int qg_queries_destroy(qg_queries* qs) {
+  if (!qs) return 0;
+  if (qs->owner) cudaSetDevice(qs->owner->device);
+  qs->d_q.release();
+  delete qs;
+  return 0;
+}
+
+int qg_batch_distance_queries(qg_index* idx, const qg_queries* qs, const uint32_t* rows, int m, float* out) {
+  if (int rc = check_index(idx)) return rc;
+  if (!qs || qs->owner != idx) return fail(QG_ERR_INVALID, "query set does not belong to this index");
+  if (m < 0) return fail(QG_ERR_INVALID, "negative batch size");
+  if (m == 0) return 0;
+  if (!rows || !out) return fail(QG_ERR_INVALID, "null buffer");
+  Workspace* w = ws_acquire(idx);
+  if (!w) return fail(QG_ERR_CUDA, "could not create a stream");
+  const size_t rbytes = (size_t)qs->b * m * 4;
+  int rc = 0;
+  do {
+    if ((rc = w->h_in.ensure(rbytes))) break;
+    if ((rc = w->h_out.ensure(rbytes))) break;
+    if ((rc = w->d_rows32.ensure(rbytes))) break;
+    if ((rc = w->d_dist.ensure(rbytes))) break;
+    cudaStream_t st = w->stream;
+    std::memcpy(w->h_in.p, rows, rbytes);
+    cudaError_t e = cudaMemcpyAsync(w->d_rows32.p, w->h_in.p, rbytes, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, cudaGetErrorString(e)); break; }
+    if ((rc = launch_batch_distance(idx->vec, idx->dp, idx->dim, idx->n_rows, idx->metric, idx->arith,
+                                    (const float*)qs->d_q.p, qs->dim, qs->b, (const uint32_t*)w->d_rows32.p, m,
+                                    (float*)w->d_dist.p, st)))
+      break;
+    e = cudaMemcpyAsync(w->h_out.p, w->d_dist.p, rbytes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, cudaGetErrorString(e)); break; }
+    std::memcpy(out, w->h_out.p, rbytes);
+  } while (0);
+  ws_release(idx, w);
+  return rc;
+}
+
 int qg_batch_distance(qg_index* idx, const float* query, int dim, const uint32_t* rows, int n, float* out) {
   return qg_batch_distance_multi(idx, query, 1, dim, rows, n, out);
 }
@@ -1479,6 +1543,35 @@ int qg_debug_tc_pass(qg_index* idx, const float* queries, int nq, int k, float* 
       for (int i = 0; i < 8; ++i)
         fprintf(stderr, "  epilogue warp %d: total %llu wait_xs %llu wait_tmem_full %llu tmem_ld %llu\n", i + 2,
                 h[8 + i * 4], h[9 + i * 4], h[10 + i * 4], h[11 + i * 4]);
+      // finalize of the same pass, with phase time stamps of CTA 0
+      FinalizeCandParams cp{};
+      cp.cand = (const uint64_t*)w->tc_cand.p;
+      cp.cand_cnt = (const int*)w->tc_cnt.p;
+      cp.cap = TC_CAND_CAP;
+      cp.tau = (const float*)w->tc_tau.p;
+      cp.kp = 32;
+      cp.tc_gamma = 1.02 / 512.0 + (double)d / 4194304.0;
+      cudaMemsetAsync(w->counters.p, 0, 64 * 8, st);
+      cp.dbg = (unsigned long long*)w->counters.p;
+      FinalizeParams& fb = cp.base;
+      fb.vec = idx->vec; fb.dp = dp; fb.d = d; fb.metric = idx->metric; fb.arith = idx->arith; fb.mode = mode;
+      fb.cosine = idx->metric == METRIC_COSINE; fb.k = k; fb.gamma = (float)((d + 16) * 5.9604645e-8);
+      fb.max_norm2 = idx->max_norm2; fb.queries = (const float*)w->qpad.p;
+      if (!w->d_dist.ensure((size_t)nq * k * 4) && !w->d_row.ensure((size_t)nq * k * 8) && !w->d_count.ensure((size_t)nq * 4)) {
+        fb.out_dist = (float*)w->d_dist.p; fb.out_row = (long long*)w->d_row.p; fb.out_count = (int*)w->d_count.p;
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+        launch_finalize_cand(cp, nq, st);
+        cudaEventRecord(e1, st);
+        cudaStreamSynchronize(st);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaMemcpy(h, w->counters.p, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "  finalize_cand: %.1f us; CTA 0 cycles: ranked %llu, re-ranked %llu, certified %llu, done %llu "
+                        "(n %llu, nex %llu)\n", ms * 1e3, h[1], h[2], h[3], h[4], h[8], h[9]);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+      }
     }
     if (e == cudaSuccess && tau_out) e = cudaMemcpy(tau_out, w->tc_tau.p, (size_t)nq * 4, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && cnt_out) e = cudaMemcpy(cnt_out, w->tc_cnt.p, (size_t)nq * 4, cudaMemcpyDeviceToHost);

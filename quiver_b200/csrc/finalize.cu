@@ -425,6 +425,10 @@ __global__ void merge_shards_kernel(const uint64_t* __restrict__ keys, int world
 
 int finalize_set_attributes() {
   QG_CUDA_OK(cudaFuncSetAttribute(finalize_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+  // same L1 / shared-memory split as the scan kernels, so that back-to-back launches of a pass do
+  // not make the SMs reconfigure their carve-out
+  QG_CUDA_OK(cudaFuncSetAttribute(finalize_cand_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared));
   QG_CUDA_OK(cudaFuncSetAttribute(merge_shards_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   QG_CUDA_OK(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)finalize_smem(1024)));
@@ -491,39 +495,52 @@ __device__ __forceinline__ float tc_score_upper_bound(int metric, int mode, int 
   return tf;
 }
 
-// dst[rank of src[i]] = src[i] for n distinct keys (n <= FC_RANK_MAX); returns through `my_rank` the
-// rank of the keys this thread owns (i = tid, tid + FC_THREADS). All threads of the block call.
-__device__ __forceinline__ void fc_rank_scatter(const uint64_t* src, int n, uint64_t* dst, int limit,
-                                                int (&my_rank)[FC_RANK_MAX / FC_THREADS]) {
-  const int tid = threadIdx.x;
+// Smallest 32-bit score image P such that at least `want` keys have an image <= P: bitwise
+// bisection with one block-wide count per bit — the cost does not depend on n, unlike all-pairs
+// ranking. The keys stay in registers: thread t owns key t, t + FC_THREADS, ... (KEY_NONE beyond
+// n). s_cnt[3] is scratch. All threads of the block call.
+template <int PER>
+__device__ __forceinline__ uint32_t fc_select_pivot(const uint64_t (&mine)[PER], int want, int* s_cnt) {
+  const int lane = threadIdx.x & 31;
+  uint32_t prefix = 0;
+  if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  for (int bit = 31; bit >= 0; --bit) {
+    const int r = 31 - bit;
+    const uint32_t probe = prefix | ((1u << bit) - 1u);
+    int c = 0;
 #pragma unroll
-  for (int s = 0; s < FC_RANK_MAX / FC_THREADS; ++s) {
-    const int i = tid + s * FC_THREADS;
-    int r = -1;
-    if (i < n) {
-      const uint64_t mine = src[i];
-      r = 0;
-      for (int j = 0; j < n; ++j) r += src[j] < mine;
-      if (r < limit) dst[r] = mine;
-    }
-    my_rank[s] = r;
+    for (int s = 0; s < PER; ++s) c += (mine[s] != KEY_NONE) && ((uint32_t)(mine[s] >> 32) <= probe);
+    c = __reduce_add_sync(0xffffffffu, c);
+    int* slot = s_cnt + (r % 3);
+    if (lane == 0 && c) atomicAdd(slot, c);
+    __syncthreads();
+    if (*slot < want) prefix |= (1u << bit);
+    // three rotating counters: the one reset here was last read before this round's barrier and is
+    // next written after the following round's barrier
+    if (threadIdx.x == 0) s_cnt[(r + 2) % 3] = 0;
   }
   __syncthreads();
+  return prefix;
 }
 
-__global__ void __launch_bounds__(FC_THREADS, 1) finalize_cand_kernel(const FinalizeCandParams cp) {
+__global__ void __launch_bounds__(FC_THREADS, 2) finalize_cand_kernel(const FinalizeCandParams cp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const FinalizeParams& p = cp.base;
   const int q = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cap = cp.cap, k = p.k;
-  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
-  uint64_t* ex = keys + cap;
+  uint64_t* sel = reinterpret_cast<uint64_t*>(smem_raw);  // selected scan keys (unordered), later the output order
+  uint64_t* ex = sel + cap;                               // exact keys
   double* scratch = reinterpret_cast<double*>(ex + cap) + (size_t)warp * (EXACT_SCRATCH_BYTES / 8);
   __shared__ double s_qn2;
   __shared__ int s_extra;
+  __shared__ int s_sel[3];
   __shared__ float s_E;
 
+  long long ts[8];
+  int nts = 0;
+  ts[nts++] = clock64();
   const int n_raw = cp.cand_cnt[q];
   const bool overflow = n_raw > cap;
   const int n = overflow ? cap : n_raw;
@@ -539,34 +556,43 @@ __global__ void __launch_bounds__(FC_THREADS, 1) finalize_cand_kernel(const Fina
   }
   if (tid == 0) s_extra = 0;
   const uint64_t* src = cp.cand + (size_t)q * cap;
-  const bool small = n <= FC_RANK_MAX;
-  int my_rank[FC_RANK_MAX / FC_THREADS];
-  const int nsel = n < cp.kp ? n : cp.kp;
-  uint64_t* sel;  // the best nsel scan keys, ascending
-  if (small) {
-    for (int i = tid; i < n; i += FC_THREADS) keys[i] = __ldcg(src + i);
-    __syncthreads();
-    sel = keys + FC_RANK_MAX;  // n <= FC_RANK_MAX <= cap / 2: the upper half of keys[] is free
-    fc_rank_scatter(keys, n, sel, nsel, my_rank);
-  } else {
-    const int n2 = next_pow2(n);
-    for (int i = tid; i < n2; i += FC_THREADS) keys[i] = i < n ? __ldcg(src + i) : KEY_NONE;
-    block_bitonic_sort(keys, n2);
-    sel = keys;
+  constexpr int PER = 4;  // keys per thread: cap <= PER * FC_THREADS
+  uint64_t mine[PER];
+#pragma unroll
+  for (int s = 0; s < PER; ++s) {
+    const int i = tid + s * FC_THREADS;
+    mine[s] = i < n ? __ldcg(src + i) : KEY_NONE;
   }
+  // the best scan keys = every key whose score image is <= the pivot: at least min(kp, n) keys
+  // (ties on the score image may add a few)
+  const int want = n < cp.kp ? n : cp.kp;
+  const uint32_t pivot = want > 0 ? fc_select_pivot<PER>(mine, want, s_sel) : 0u;
+  if (tid == 0) s_sel[0] = 0;
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < PER; ++s) {
+    if (want > 0 && mine[s] != KEY_NONE && (uint32_t)(mine[s] >> 32) <= pivot) {
+      const int pos = atomicAdd(&s_sel[0], 1);
+      sel[pos] = mine[s];
+    }
+  }
+  __syncthreads();
+  const int nsel = want > 0 ? s_sel[0] : 0;
+  ts[nts++] = clock64();  // keys loaded and selected
 
-  // ---- exact re-rank of the best nsel candidates (one warp per candidate) ----
+  // ---- exact re-rank of the selected candidates (one warp per candidate) ----
   for (int c = warp; c < nsel; c += FC_WARPS) {
     const uint32_t row = key_row(sel[c]);
     const float dist = exact_distance_warp(p.metric, p.arith, qv, p.vec + (size_t)row * p.dp, p.d, scratch);
     if (lane == 0) ex[c] = make_key(dist, row);
   }
   __syncthreads();
+  ts[nts++] = clock64();  // first re-rank done
 
   bool certified = !overflow;
   int nex = nsel;
   if (nsel >= k) {
-    // E = k-th smallest exact distance among the re-ranked candidates
+    // E = k-th smallest exact distance among the re-ranked candidates (all-pairs rank, nsel is small)
     for (int i = tid; i < nsel; i += FC_THREADS) {
       const uint64_t me = ex[i];
       int r = 0;
@@ -578,21 +604,11 @@ __global__ void __launch_bounds__(FC_THREADS, 1) finalize_cand_kernel(const Fina
                                          (double)(p.max_norm2 ? *p.max_norm2 : 0.f));
     if (!(T <= tau) && !all_admitted) certified = false;
     // every further candidate whose scan score is <= T may still belong to the exact top-k
-    if (small) {
 #pragma unroll
-      for (int s = 0; s < FC_RANK_MAX / FC_THREADS; ++s) {
-        const int i = tid + s * FC_THREADS;
-        if (i < n && my_rank[s] >= nsel && key_score(keys[i]) <= T) {
-          const int pos = atomicAdd(&s_extra, 1);
-          if (nsel + pos < cap) ex[nsel + pos] = keys[i];  // scan key for now; replaced by the exact key below
-        }
-      }
-    } else {
-      for (int i = nsel + tid; i < n; i += FC_THREADS) {
-        if (key_score(keys[i]) <= T) {
-          const int pos = atomicAdd(&s_extra, 1);
-          if (nsel + pos < cap) ex[nsel + pos] = keys[i];
-        }
+    for (int s = 0; s < PER; ++s) {
+      if (mine[s] != KEY_NONE && (uint32_t)(mine[s] >> 32) > pivot && key_score(mine[s]) <= T) {
+        const int pos = atomicAdd(&s_extra, 1);
+        if (nsel + pos < cap) ex[nsel + pos] = mine[s];  // scan key for now; replaced by the exact key below
       }
     }
     __syncthreads();
@@ -612,12 +628,12 @@ __global__ void __launch_bounds__(FC_THREADS, 1) finalize_cand_kernel(const Fina
     // fewer than k candidates: complete only if the scan admitted every row
     if (!all_admitted) certified = false;
   }
+  ts[nts++] = clock64();  // certificate + extras done
 
   // ---- order the exact keys and emit the first k ----
   const int kk = nex < k ? nex : k;
-  uint64_t* outk = keys;  // final order (keys[] is no longer needed)
+  uint64_t* outk = sel;  // the scan keys are no longer needed
   if (nex <= FC_RANK_MAX) {
-    __syncthreads();
     for (int i = tid; i < nex; i += FC_THREADS) {
       const uint64_t me = ex[i];
       int r = 0;
@@ -639,27 +655,33 @@ __global__ void __launch_bounds__(FC_THREADS, 1) finalize_cand_kernel(const Fina
       p.out_keys[(size_t)q * k + j] = o;
     }
     if (tid == 0 && p.out_count) p.out_count[q] = certified ? kk : -1;
-    return;
-  }
-  for (int j = tid; j < k; j += FC_THREADS) {
-    const bool ok = j < kk;
-    p.out_dist[(size_t)q * k + j] = ok ? key_score(outk[j]) : __int_as_float(0x7f800000);
-    p.out_row[(size_t)q * k + j] = ok ? (long long)key_row(outk[j]) + p.row_base : -1ll;
-  }
-  if (p.out_negdist != nullptr) {
-    const float* nv = p.negatives + (size_t)q * p.dp;
-    for (int j = warp; j < k; j += FC_WARPS) {
-      float nd = __int_as_float(0x7f800000);
-      if (j < kk) nd = exact_distance_warp(p.metric, p.arith, p.vec + (size_t)key_row(outk[j]) * p.dp, nv, p.d, scratch);
-      if (lane == 0) p.out_negdist[(size_t)q * k + j] = nd;
+  } else {
+    for (int j = tid; j < k; j += FC_THREADS) {
+      const bool ok = j < kk;
+      p.out_dist[(size_t)q * k + j] = ok ? key_score(outk[j]) : __int_as_float(0x7f800000);
+      p.out_row[(size_t)q * k + j] = ok ? (long long)key_row(outk[j]) + p.row_base : -1ll;
     }
+    if (p.out_negdist != nullptr) {
+      const float* nv = p.negatives + (size_t)q * p.dp;
+      for (int j = warp; j < k; j += FC_WARPS) {
+        float nd = __int_as_float(0x7f800000);
+        if (j < kk) nd = exact_distance_warp(p.metric, p.arith, p.vec + (size_t)key_row(outk[j]) * p.dp, nv, p.d, scratch);
+        if (lane == 0) p.out_negdist[(size_t)q * k + j] = nd;
+      }
+    }
+    if (tid == 0) p.out_count[q] = certified ? kk : -1;
   }
-  if (tid == 0) p.out_count[q] = certified ? kk : -1;
+  if (cp.dbg != nullptr && q == 0 && tid == 0) {
+    ts[nts++] = clock64();
+    for (int i = 0; i < nts; ++i) cp.dbg[i] = (unsigned long long)(ts[i] - ts[0]);
+    cp.dbg[8] = (unsigned long long)n;
+    cp.dbg[9] = (unsigned long long)nex;
+  }
 }
 
 int launch_finalize_cand(const FinalizeCandParams& p, int nq, cudaStream_t st) {
   if (nq <= 0) return 0;
-  if (p.cap < 2 * FC_RANK_MAX) return fail(1, "finalize_cand: candidate capacity must be at least 2048");
+  if (p.cap > 4 * FC_THREADS) return fail(1, "finalize_cand: candidate capacity must be at most 2048");
   finalize_cand_kernel<<<nq, FC_THREADS, finalize_cand_smem(p.cap), st>>>(p);
   QG_CUDA_OK(cudaGetLastError());
   return 0;

@@ -1000,6 +1000,10 @@ static int set_attr_ts() {
 }
 
 int tc_set_attributes() {
+  QG_CUDA_OK(cudaFuncSetAttribute(tc_tau_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared));
+  QG_CUDA_OK(cudaFuncSetAttribute(tc_bias_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared));
   if (int e = set_attr_ts()) return e;
   if (int e = set_attr_one<MODE_L2, false>()) return e;
   if (int e = set_attr_one<MODE_L2, true>()) return e;

@@ -1,0 +1,311 @@
+// hnsw_walk.cpp — hnsw.Search (pkg/hnsw/hnsw.go:602-713) over the reference's graph with the
+// per-neighbour distance calls of searchLayer (hnsw.go:536-563) batched on the GPU: all queries
+// of a batch advance in lock step, one expansion step (<= MaxM0 neighbours per query) per
+// qg_batch_distance_queries call. Heaps, visit order, stop and admit rules are the reference's,
+// so with bit-identical distances the walk is step-identical (tests/test_gpu_hnsw.py).
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/quiver_gpu.h"
+#include "../../include/quiver_host.h"
+
+namespace qh_hnsw {
+
+struct Res {
+  uint32_t idx;
+  float dist;
+};
+
+// hnsw.go:101-144 (min-heap) and :153-196 (max-heap): same sift rules, so equal distances leave
+// the heaps in the same shape as the reference.
+struct MinHeap {
+  std::vector<Res> a;
+  void push(Res x) {
+    a.push_back(x);
+    int j = (int)a.size() - 1;
+    for (;;) {
+      int i = (j - 1) / 2;
+      if (i == j || a[j].dist >= a[i].dist) break;
+      std::swap(a[i], a[j]);
+      j = i;
+    }
+  }
+  Res pop() {
+    int n = (int)a.size() - 1;
+    std::swap(a[0], a[n]);
+    int i = 0;
+    for (;;) {
+      int j1 = 2 * i + 1;
+      if (j1 >= n || j1 < 0) break;
+      int j = j1, j2 = j1 + 1;
+      if (j2 < n && a[j2].dist < a[j1].dist) j = j2;
+      if (a[i].dist <= a[j].dist) break;
+      std::swap(a[i], a[j]);
+      i = j;
+    }
+    Res r = a[n];
+    a.pop_back();
+    return r;
+  }
+};
+struct MaxHeap {
+  std::vector<Res> a;
+  void push(Res x) {
+    a.push_back(x);
+    int j = (int)a.size() - 1;
+    for (;;) {
+      int i = (j - 1) / 2;
+      if (i == j || a[j].dist <= a[i].dist) break;
+      std::swap(a[i], a[j]);
+      j = i;
+    }
+  }
+  Res pop() {
+    int n = (int)a.size() - 1;
+    std::swap(a[0], a[n]);
+    int i = 0;
+    for (;;) {
+      int j1 = 2 * i + 1;
+      if (j1 >= n || j1 < 0) break;
+      int j = j1, j2 = j1 + 1;
+      if (j2 < n && a[j2].dist > a[j1].dist) j = j2;
+      if (a[i].dist >= a[j].dist) break;
+      std::swap(a[i], a[j]);
+      i = j;
+    }
+    Res r = a[n];
+    a.pop_back();
+    return r;
+  }
+};
+
+enum Stage { ENTRY_DISTANCE, LAYER_START, EXPAND, DONE };
+
+struct Walk {
+  Stage stage = ENTRY_DISTANCE;
+  int level = 0, ef = 1;
+  uint32_t entry = 0;
+  MinHeap cand;
+  MaxHeap res;
+  std::vector<uint64_t> visited;   // bitset over nodes
+  std::vector<uint32_t> touched;   // words to clear between layers
+  std::vector<uint32_t> pending;   // rows whose distances were requested this round
+  std::vector<Res> layer_result;   // ascending
+  int64_t evals = 0;
+
+  bool test_and_set(uint32_t id) {
+    uint64_t& w = visited[id >> 6];
+    const uint64_t bit = 1ull << (id & 63);
+    if (w & bit) return true;
+    if (w == 0) touched.push_back(id >> 6);
+    w |= bit;
+    return false;
+  }
+  void clear_visited() {
+    for (uint32_t wi : touched) visited[wi] = 0;
+    touched.clear();
+  }
+};
+
+}  // namespace qh_hnsw
+
+// qh_index internals needed here (defined in host.cpp)
+extern "C" int qh_internal_index_handle(qh_index* idx, qg_index** h, int* dim);
+extern "C" const char* qh_internal_row_id(qh_index* idx, int64_t row);
+extern "C" int qh_internal_fail(int code, const char* msg);
+extern "C" qh_results* qh_internal_results_new(int nq);
+extern "C" void qh_internal_results_push(qh_results* r, int q, const char* id, float dist);
+
+extern "C" int qh_hnsw_search_batch(qh_index* idx, const qh_hnsw_graph* g, const float* queries, int nq, int dim,
+                                    int k, qh_results** out, int64_t* out_evals, int64_t* out_steps) {
+  using namespace qh_hnsw;
+  if (!idx || !g || !out) return qh_internal_fail(QG_ERR_INVALID, "null argument");
+  *out = nullptr;
+  qg_index* h = nullptr;
+  int idim = 0;
+  qh_internal_index_handle(idx, &h, &idim);
+  if (nq <= 0 || !queries) return qh_internal_fail(QG_ERR_INVALID, "no queries provided");
+  if (dim != idim) {
+    const std::string msg = "query dimension mismatch: expected " + std::to_string(idim) + ", got " + std::to_string(dim);
+    return qh_internal_fail(QG_ERR_DIM, msg.c_str());
+  }
+  std::unique_ptr<qh_results, int (*)(qh_results*)> res(qh_internal_results_new(nq), qh_results_free);
+  const int64_t n = g->n_nodes;
+  if (n == 0) {  // hnsw.go:606-608: empty graph => no results, no error
+    *out = res.release();
+    return 0;
+  }
+  if (k <= 0) return qh_internal_fail(QG_ERR_K, "k must be positive");
+  const int kk = (int)std::min<int64_t>(k, n);
+  // entry point validation (hnsw.go:620-634)
+  uint32_t entry = (uint32_t)g->entry_point;
+  if ((int64_t)entry >= n || g->level[entry] < 0) {
+    entry = 0xFFFFFFFFu;
+    for (int64_t i = 0; i < n; ++i)
+      if (g->level[i] >= 0) { entry = (uint32_t)i; break; }
+    if (entry == 0xFFFFFFFFu) {
+      *out = res.release();
+      return 0;
+    }
+  }
+  const int ef0 = std::max(g->ef_search, kk);  // hnsw.go:660-663
+  const int m = g->max_m0;                     // rows per query per round
+
+  qg_queries* qs = nullptr;
+  if (int rc = qg_queries_upload(h, queries, nq, dim, &qs)) return qh_internal_fail(rc, qg_last_error());
+  std::vector<Walk> walks((size_t)nq);
+  for (Walk& w : walks) {
+    w.visited.assign((size_t)((n + 63) / 64), 0);
+    w.entry = entry;
+    w.level = g->current_level;
+  }
+  std::vector<uint32_t> rows((size_t)nq * m);
+  std::vector<float> dist((size_t)nq * m);
+  int64_t steps = 0;
+
+  auto connections = [&](uint32_t node, int level, const uint32_t** lst, int* cnt) {
+    if (level == 0) {
+      *lst = g->adj0 + (size_t)node * g->max_m0;
+      *cnt = g->max_m0;
+    } else {
+      *lst = g->upper_adj + g->upper_off[node] + (size_t)(level - 1) * g->m;
+      *cnt = g->m;
+    }
+  };
+  // Advance a walk until it needs distances (fills w.pending) or is done.
+  auto advance = [&](Walk& w) {
+    w.pending.clear();
+    for (;;) {
+      if (w.stage == DONE) return;
+      if (w.stage == ENTRY_DISTANCE) {  // entryDistance, hnsw.go:637 (its value is not used further)
+        w.pending.push_back(w.entry);
+        return;
+      }
+      if (w.stage == LAYER_START) {     // searchLayer prologue, hnsw.go:483-505
+        w.ef = w.level > 0 ? 1 : ef0;
+        w.clear_visited();
+        w.test_and_set(w.entry);
+        w.cand.a.clear();
+        w.res.a.clear();
+        w.pending.push_back(w.entry);
+        return;
+      }
+      // EXPAND: pop candidates (hnsw.go:508-563) until one has unvisited neighbours
+      bool finished = true;
+      while (!w.cand.a.empty()) {
+        const Res cur = w.cand.pop();
+        if ((int)w.res.a.size() >= w.ef && cur.dist > w.res.a[0].dist) break;
+        if (g->level[cur.idx] < 0 || w.level > g->level[cur.idx]) continue;
+        const uint32_t* lst;
+        int cnt;
+        connections(cur.idx, w.level, &lst, &cnt);
+        for (int c = 0; c < cnt; ++c) {
+          const uint32_t id = lst[c];
+          if (id == 0xFFFFFFFFu) break;  // end of the list
+          if ((int64_t)id >= n || g->level[id] < 0) continue;
+          if (!w.test_and_set(id)) w.pending.push_back(id);
+        }
+        if (!w.pending.empty()) { finished = false; break; }
+      }
+      if (!finished) return;
+      // layer finished: drain the max-heap into an ascending list (hnsw.go:567-577)
+      const int rn = (int)w.res.a.size();
+      w.layer_result.resize((size_t)rn);
+      for (int i = rn - 1; i >= 0; --i) w.layer_result[(size_t)i] = w.res.pop();
+      if (w.level > 0) {
+        if (rn > 0) w.entry = w.layer_result[0].idx;  // hnsw.go:650-656
+        w.level--;
+        w.stage = LAYER_START;
+        continue;
+      }
+      w.stage = DONE;
+      return;
+    }
+  };
+  // Feed the distances of the pending rows back, in connection order (hnsw.go:547-560).
+  auto consume = [&](Walk& w, const float* d) {
+    w.evals += (int64_t)w.pending.size();
+    if (w.stage == ENTRY_DISTANCE) {
+      w.stage = LAYER_START;
+      if (w.level <= 0) w.level = 0;
+      return;
+    }
+    if (w.stage == LAYER_START) {
+      const Res e{w.entry, d[0]};
+      w.cand.push(e);
+      w.res.push(e);
+      w.stage = EXPAND;
+      return;
+    }
+    for (size_t j = 0; j < w.pending.size(); ++j) {
+      const float cd = d[j];
+      if ((int)w.res.a.size() < w.ef || cd < w.res.a[0].dist) {
+        const Res r{w.pending[j], cd};
+        w.cand.push(r);
+        w.res.push(r);
+        if ((int)w.res.a.size() > w.ef) w.res.pop();
+      }
+    }
+  };
+
+  int rc = 0;
+  for (;;) {
+    bool any = false;
+    std::fill(rows.begin(), rows.end(), 0xFFFFFFFFu);
+    for (int i = 0; i < nq; ++i) {
+      Walk& w = walks[(size_t)i];
+      advance(w);
+      if (w.stage == DONE) continue;
+      any = true;
+      std::copy(w.pending.begin(), w.pending.end(), rows.begin() + (size_t)i * m);
+    }
+    if (!any) break;
+    ++steps;
+    if ((rc = qg_batch_distance_queries(h, qs, rows.data(), m, dist.data()))) break;
+    for (int i = 0; i < nq; ++i) {
+      Walk& w = walks[(size_t)i];
+      if (w.stage != DONE && !w.pending.empty()) consume(w, dist.data() + (size_t)i * m);
+    }
+  }
+  qg_queries_destroy(qs);
+  if (rc) return qh_internal_fail(rc, qg_last_error());
+
+  // truncate to k (hnsw.go:670-672); under-filled queries get the exact pass (hnsw.go:676-710)
+  std::vector<int> underfilled;
+  for (int i = 0; i < nq; ++i) {
+    Walk& w = walks[(size_t)i];
+    const int cnt = std::min<int>((int)w.layer_result.size(), kk);
+    if (cnt < kk) { underfilled.push_back(i); continue; }
+    for (int j = 0; j < cnt; ++j)
+      qh_internal_results_push(res.get(), i, qh_internal_row_id(idx, w.layer_result[(size_t)j].idx), w.layer_result[(size_t)j].dist);
+  }
+  if (!underfilled.empty()) {
+    const int nu = (int)underfilled.size();
+    std::vector<float> uq((size_t)nu * dim), ud((size_t)nu * kk);
+    std::vector<int64_t> ur((size_t)nu * kk);
+    std::vector<int> uc((size_t)nu);
+    for (int u = 0; u < nu; ++u)
+      std::memcpy(uq.data() + (size_t)u * dim, queries + (size_t)underfilled[(size_t)u] * dim, (size_t)dim * 4);
+    if (int erc = qg_search_batch(h, uq.data(), nu, dim, kk, nullptr, nullptr, ud.data(), nullptr, ur.data(), uc.data()))
+      return qh_internal_fail(erc, qg_last_error());
+    for (int u = 0; u < nu; ++u) {
+      // sort by (Distance, VectorID) like the reference's supplement (hnsw.go:699-704)
+      std::vector<std::pair<float, std::string>> lst;
+      for (int j = 0; j < uc[(size_t)u]; ++j)
+        lst.emplace_back(ud[(size_t)u * kk + j], qh_internal_row_id(idx, ur[(size_t)u * kk + j]));
+      std::stable_sort(lst.begin(), lst.end(), [](const auto& a, const auto& b) {
+        if (a.first == b.first) return a.second < b.second;
+        return a.first < b.first;
+      });
+      for (const auto& e : lst) qh_internal_results_push(res.get(), underfilled[(size_t)u], e.second.c_str(), e.first);
+    }
+  }
+  if (out_evals)
+    for (int i = 0; i < nq; ++i) out_evals[i] = walks[(size_t)i].evals;
+  if (out_steps) *out_steps = steps;
+  *out = res.release();
+  return 0;
+}

@@ -530,3 +530,24 @@ int qh_debug_equal_fold(const char* a, const char* b) {
 }
 
 }  // extern "C"
+
+// ---- internals shared with hnsw_walk.cpp -------------------------------------------------------------
+extern "C" {
+int qh_internal_index_handle(qh_index* idx, qg_index** h, int* dim) {
+  *h = idx->h;
+  *dim = idx->dim;
+  return 0;
+}
+const char* qh_internal_row_id(qh_index* idx, int64_t row) {
+  return (row >= 0 && row < (int64_t)idx->ids.size()) ? idx->ids[(size_t)row].c_str() : "";
+}
+int qh_internal_fail(int code, const char* msg) { return fail(code, msg ? msg : ""); }
+qh_results* qh_internal_results_new(int nq) {
+  qh_results* r = new qh_results();
+  r->lists.assign((size_t)nq, {});
+  return r;
+}
+void qh_internal_results_push(qh_results* r, int q, const char* id, float dist) {
+  r->lists[(size_t)q].push_back(Hit{id, dist});
+}
+}

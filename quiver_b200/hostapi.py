@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "qh_collection_destroy", "qh_collection_add", "qh_collection_add_batch", "qh_collection_delete",
     "qh_collection_count", "qh_collection_set_facet_fields", "qh_collection_search",
     "qh_collection_search_with_facets", "qh_collection_filter_mask", "qh_collection_rows", "qh_collection_row_id",
-    "qh_debug_sprint_v", "qh_debug_equal_fold",
+    "qh_debug_sprint_v", "qh_debug_equal_fold", "qh_hnsw_search_batch",
 ]
 
 
@@ -39,6 +39,12 @@ class qh_facet_filter(C.Structure):
     _fields_ = [("type", C.c_int), ("field", C.c_char_p), ("value_json", C.c_char_p), ("min_json", C.c_char_p),
                 ("max_json", C.c_char_p), ("include_min", C.c_int), ("include_max", C.c_int),
                 ("should_exist", C.c_int)]
+
+
+class qh_hnsw_graph(C.Structure):
+    _fields_ = [("n_nodes", C.c_int64), ("m", C.c_int), ("max_m0", C.c_int), ("entry_point", C.c_int),
+                ("current_level", C.c_int), ("ef_search", C.c_int), ("level", C.c_void_p), ("adj0", C.c_void_p),
+                ("upper_off", C.c_void_p), ("upper_adj", C.c_void_p)]
 
 
 def load() -> C.CDLL:
@@ -82,6 +88,8 @@ def load() -> C.CDLL:
     lib.qh_collection_rows.restype = i64
     lib.qh_collection_row_id.argtypes = [vp, i64]
     lib.qh_collection_row_id.restype = cp
+    lib.qh_hnsw_search_batch.argtypes = [vp, C.POINTER(qh_hnsw_graph), vp, i32, i32, i32, C.POINTER(vp), vp,
+                                         C.POINTER(i64)]
     lib.qh_debug_sprint_v.argtypes = [cp, i32, C.c_char_p, i32]
     lib.qh_debug_equal_fold.argtypes = [cp, cp]
     _lib = lib
@@ -199,6 +207,25 @@ class HybridIndex:
 
     def FluentSearch(self, query):
         return FluentHybridSearch(self, query)
+
+    def HNSWSearchBatch(self, graph: dict, queries, k: int):
+        """hnsw.Search (pkg/hnsw/hnsw.go:602-713) for a batch of queries over the reference's graph
+        (flat arrays, node id = insertion row), neighbour distances batched on the GPU.
+        Returns (results per query, distance evaluations per query, lock-step rounds)."""
+        qs = _f32(queries)
+        level = np.ascontiguousarray(graph["level"], dtype=np.int32)
+        adj0 = np.ascontiguousarray(graph["adj0"], dtype=np.uint32)
+        uoff = np.ascontiguousarray(graph["upper_off"], dtype=np.int64)
+        uadj = np.ascontiguousarray(graph["upper_adj"], dtype=np.uint32)
+        g = qh_hnsw_graph(int(graph["n"]), int(graph["M"]), int(graph["MaxM0"]), int(graph["entry"]),
+                          int(graph["current_level"]), int(graph["EfSearch"]), level.ctypes.data, adj0.ctypes.data,
+                          uoff.ctypes.data, uadj.ctypes.data)
+        evals = np.zeros(qs.shape[0], dtype=np.int64)
+        steps = C.c_int64(0)
+        res = C.c_void_p()
+        _check(self._lib.qh_hnsw_search_batch(self.handle, C.byref(g), _ptr(qs), qs.shape[0], qs.shape[1], k,
+                                              C.byref(res), _ptr(evals), C.byref(steps)))
+        return _take(res), evals, steps.value
 
 
 class FluentHybridSearch:

@@ -1,0 +1,69 @@
+"""T6: HNSW search with GPU-batched neighbour distances (qh_hnsw_search_batch) is step-identical
+to the reference's walk (oracle/hnsw_oracle.c restating pkg/hnsw/hnsw.go): same results, same
+float32 distances, same number of distance evaluations — on the reference's own graph."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def H():
+    from quiver_b200 import hostapi
+    hostapi.load()
+    return hostapi
+
+
+def _underfill_oracle(oracle, corpus, ids, q, k, metric):
+    """hnsw.go:676-710: the under-fill supplement ranks every node by (Distance, VectorID)."""
+    d = oracle.distances(metric, corpus, q)
+    order = sorted(range(len(ids)), key=lambda i: (d[i], ids[i]))[:k]
+    return [(ids[i], d[i]) for i in order]
+
+
+@pytest.mark.parametrize("distance,metric", [("euclidean", 1), ("cosine", 0)])
+def test_batched_walk_is_step_identical(H, oracle, distance, metric):
+    from oracle import hnsw
+    rng = np.random.default_rng(3 + metric)
+    n, d, k, nq = 4000, 48, 10, 96
+    corpus = rng.standard_normal((n, d)).astype(np.float32)
+    graph = hnsw.Graph(corpus, metric, M=16, MaxM0=32, EfConstruction=200, EfSearch=128, seed=5)
+    ids = [f"n{i:05d}" for i in range(n)]
+    idx = H.HybridIndex(d, distance)
+    idx.InsertBatch({ids[i]: corpus[i] for i in range(n)})
+    queries = np.concatenate([rng.standard_normal((nq - 8, d)).astype(np.float32), corpus[:8]])
+    res, evals, steps = idx.HNSWSearchBatch(graph.export(), queries, k)
+    assert steps > 0
+    under = 0
+    for i in range(nq):
+        od, oidx, oev, _ = graph.search(queries[i], k)
+        assert evals[i] == oev, (i, evals[i], oev)
+        if len(oidx) < k:  # graph search under-filled: exact supplement
+            under += 1
+            want = _underfill_oracle(oracle, corpus, ids, queries[i], k, metric)
+            assert [r[0] for r in res[i]] == [w[0] for w in want]
+            continue
+        assert [r[0] for r in res[i]] == [ids[j] for j in oidx], i
+        assert [np.float32(r[1]).view(np.uint32) for r in res[i]] == [np.float32(x).view(np.uint32) for x in od], i
+    # the reference's own lenient property (hnsw_property_test.go:342-395): when the walk reaches an
+    # inserted vector it comes back first at distance 0 — checked against the oracle above; here
+    # only that the batch really ran in lock step
+    assert steps < evals.max() + 8
+    idx.close()
+
+
+def test_walk_edge_cases(H, oracle):
+    from oracle import hnsw
+    rng = np.random.default_rng(9)
+    corpus = rng.random((40, 8), dtype=np.float32)
+    graph = hnsw.Graph(corpus, 1, EfSearch=16, seed=2)
+    idx = H.HybridIndex(8, "euclidean")
+    idx.InsertBatch({f"v{i:02d}": corpus[i] for i in range(40)})
+    q = rng.random((3, 8), dtype=np.float32)
+    with pytest.raises(H.QuiverError, match="k must be positive"):
+        idx.HNSWSearchBatch(graph.export(), q, 0)
+    with pytest.raises(H.QuiverError, match="query dimension mismatch: expected 8, got 7"):
+        idx.HNSWSearchBatch(graph.export(), q[:, :7], 3)
+    res, evals, steps = idx.HNSWSearchBatch(graph.export(), q, 100)  # k > n clamps (hnsw.go:615-617)
+    assert all(len(r) == 40 for r in res)
+    idx.close()
