@@ -437,7 +437,7 @@ struct TsKParams {
   const float* sc;     // [rows padded to 128] 1/|x| (cosine) or nullptr
   const float* queries;
   int dp;
-  uint32_t* sample;  // [n_cols][n_sample][2]
+  uint32_t* sample;  // [n_cols][n_sample][nblk == 2 ? 1 : 2]
   int n_sample;
   const float* tau;
   uint64_t* cand;
@@ -767,14 +767,12 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
         mbar_arrive(&xs_empty[xb]);
       }
       if (SAMPLE && q < p.nq) {
-        // sample[q][w][g]: minimum score of this tile for this query, one slot per epilogue group
-        uint32_t* out = p.sample + ((size_t)q * p.n_sample + (size_t)w) * 2;
+        // minimum score of this tile for this query: sample[q][w] (NBLK == 2) or sample[q][w][group]
         const uint32_t mn = tile_min == __int_as_float(0x7f800000) ? 0xFFFFFFFFu : f32_to_ordered(tile_min);
         if (NBLK == 2) {
-          out[0] = mn;
-          out[1] = 0xFFFFFFFFu;
+          p.sample[(size_t)q * p.n_sample + (size_t)w] = mn;
         } else {
-          out[grp] = mn;
+          p.sample[((size_t)q * p.n_sample + (size_t)w) * 2 + grp] = mn;
         }
       }
     }
@@ -927,7 +925,7 @@ int tc_plan(int dp, int nq, TcPlan* out) {
       out->kb = kb;
       out->stages = stages;
       out->tile_rows = rows;
-      out->sample_vals = 2;
+      out->sample_vals = nblk == 2 ? 1 : 2;
       out->smem = ts_smem_layout(stages, kb, rows).total + 1024;
       return 0;
     }
@@ -1042,7 +1040,8 @@ static int launch_ts_pass(const TcPlan& plan, const TcArgs& a, int sm_count, cud
   if (hook) hook->fn(hook->ctx, 0, 1, st);
   ts_kernel(a.mode, true, plan.nblk, plan.kb)<<<grid_s, TS_THREADS, plan.smem, st>>>(tm_x, p);
   QG_CUDA_OK(cudaGetLastError());
-  tc_tau_kernel<<<a.nq, TAU_THREADS, 0, st>>>(a.sample, a.n_sample * 2, TC_SAMPLE_RANK, a.tau, a.cand_cnt);
+  tc_tau_kernel<<<a.nq, TAU_THREADS, 0, st>>>(a.sample, a.n_sample * plan.sample_vals, TC_SAMPLE_RANK, a.tau,
+                                              a.cand_cnt);
   QG_CUDA_OK(cudaGetLastError());
   if (hook) hook->fn(hook->ctx, 0, 0, st);
   p.dbg = a.dbg;
