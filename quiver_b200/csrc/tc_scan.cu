@@ -421,7 +421,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 //   warps: 0 TMA (corpus tiles + the tile's per-row terms), 1 MMA + TMEM alloc, 2..9 epilogue
 // ================================================================================================
 constexpr int TS_KSTEP_BYTES = 128;               // one swizzle row: 32 floats
-constexpr int TS_THREADS = 320;
+constexpr int TS_EPI_WARPS = 16;                 // epilogue warps: four per TMEM lane quarter
+constexpr int TS_THREADS = 64 + TS_EPI_WARPS * 32;
 constexpr int TS_XS = 8;                          // ring of per-tile row-term buffers
 // corpus rows per tile = MMA N: two resident query blocks leave 64 accumulator columns per buffer,
 // one block leaves 128 (512 TMEM columns = nblk * kb * 32 + nblk * 2 * rows)
@@ -437,7 +438,7 @@ struct TsKParams {
   const float* sc;     // [rows padded to 128] 1/|x| (cosine) or nullptr
   const float* queries;
   int dp;
-  uint32_t* sample;  // [n_cols][n_sample][nblk == 2 ? 1 : 2]
+  uint32_t* sample;  // [n_cols][n_sample][nblk == 2 ? 2 : 4]: one minimum per epilogue sub-group
   int n_sample;
   const float* tau;
   uint64_t* cand;
@@ -504,13 +505,13 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);
+      mbar_init(&tmem_empty[i], TS_EPI_WARPS);
     }
     for (int i = 0; i < TS_XS; ++i) {
       mbar_init(&xs_full[i], 1);
-      mbar_init(&xs_empty[i], 8);
+      mbar_init(&xs_empty[i], TS_EPI_WARPS);
     }
-    mbar_init(a_ready, 8);
+    mbar_init(a_ready, TS_EPI_WARPS);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -628,17 +629,21 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
       p.dbg[5] = (unsigned long long)t_mma_full;
     }
   } else {
-    // ===== epilogue warps: one query per thread, four 16-row chunks per warp and tile =====
+    // ===== epilogue warps: one query per thread, two 16-row chunks per warp and tile =====
+    // 16 warps = 4 per TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31):
+    //   NBLK == 2: group g -> query block g >> 1, chunks {g & 1, (g & 1) + 2} of the 64-row tile
+    //   NBLK == 1: group g -> chunks {g, g + 4} of the 128-row tile
     const int quarter = warp & 3;
-    const int grp = (warp - 2) >> 2;                     // 0 or 1
-    const int blk = NBLK == 2 ? grp : 0;                 // query block of this warp
+    const int grp = (warp - 2) >> 2;                     // 0..3
+    const int blk = NBLK == 2 ? (grp >> 1) : 0;          // query block of this warp
     const int q = blk * 128 + quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    // NBLK == 2: chunks 0..3 of the 64-row tile; NBLK == 1: the two groups interleave the 8 chunks
-    auto chunk_of = [&](int ci) -> int { return NBLK == 2 ? ci : grp + 2 * ci; };
+    constexpr int NCH = 2;                               // chunks per warp and tile
+    auto chunk_of = [&](int ci) -> int { return NBLK == 2 ? (grp & 1) + 2 * ci : grp + 4 * ci; };
+    const bool loads_queries = NBLK == 2 ? (grp & 1) == 0 : grp == 0;
 
     // ---- resident query block -> tensor memory (cosine: pre-scaled by 1/|q|) ----
-    if (NBLK == 2 || grp == 0) {
+    if (loads_queries) {
       float rnq = 1.f;
       if (MODE == MODE_DOT && p.cosine && q < p.nq) {
         float s = 0.f;
@@ -698,13 +703,13 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
       tc_fence_after();
       const uint32_t d_addr = tmem_base + lane_base + (uint32_t)(d_off + (blk * 2 + acc) * ROWS);
       // all of this warp's accumulator chunks are requested before the first one is consumed
-      uint32_t araw[4][16];
+      uint32_t araw[NCH][16];
 #pragma unroll
-      for (int ci = 0; ci < 4; ++ci) tmem_ld16_issue(d_addr + (uint32_t)(chunk_of(ci) * 16), araw[ci]);
+      for (int ci = 0; ci < NCH; ++ci) tmem_ld16_issue(d_addr + (uint32_t)(chunk_of(ci) * 16), araw[ci]);
       tmem_ld_wait();
       float tile_min = __int_as_float(0x7f800000);
 #pragma unroll
-      for (int ci = 0; ci < 4; ++ci) {
+      for (int ci = 0; ci < NCH; ++ci) {
         const int c = chunk_of(ci);
         float v[16];
         const uint32_t boff = (uint32_t)((xb * ROWS + c * 16) * 4);
@@ -770,15 +775,15 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
         // minimum score of this tile for this query: sample[q][w] (NBLK == 2) or sample[q][w][group]
         const uint32_t mn = tile_min == __int_as_float(0x7f800000) ? 0xFFFFFFFFu : f32_to_ordered(tile_min);
         if (NBLK == 2) {
-          p.sample[(size_t)q * p.n_sample + (size_t)w] = mn;
+          p.sample[((size_t)q * p.n_sample + (size_t)w) * 2 + (grp & 1)] = mn;
         } else {
-          p.sample[((size_t)q * p.n_sample + (size_t)w) * 2 + grp] = mn;
+          p.sample[((size_t)q * p.n_sample + (size_t)w) * 4 + grp] = mn;
         }
       }
     }
     if (!SAMPLE && prev_has && prev_pos < TC_CAND_CAP) p.cand[(size_t)q * TC_CAND_CAP + prev_pos] = prev_key;
     if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0) {
-      unsigned long long* o = p.dbg + 8 + (warp - 2) * 4;
+      unsigned long long* o = p.dbg + 8 + ((warp - 2) & 7) * 4;
       o[0] = (unsigned long long)(clock64() - t_epi_begin);
       o[1] = (unsigned long long)t_epi_xs;
       o[2] = (unsigned long long)t_epi_full;
@@ -925,7 +930,7 @@ int tc_plan(int dp, int nq, TcPlan* out) {
       out->kb = kb;
       out->stages = stages;
       out->tile_rows = rows;
-      out->sample_vals = nblk == 2 ? 1 : 2;
+      out->sample_vals = nblk == 2 ? 2 : 4;
       out->smem = ts_smem_layout(stages, kb, rows).total + 1024;
       return 0;
     }
