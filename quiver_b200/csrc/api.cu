@@ -136,13 +136,13 @@ struct Workspace {
     prof_used += 2;
   }
   DevBuf qpad, negpad, partial, mask, counters;
-  DevBuf tc_sample, tc_tau, tc_cand, tc_cnt, tc_bias;
+  DevBuf tc_sample, tc_tau, tc_cand, tc_cnt, tc_bias, tc_apack;
   DevBuf d_q, d_neg, d_dist, d_negdist, d_row, d_count, d_rows32, d_rows64, d_fetch;
   PinBuf h_in, h_out;
   ExhaustiveWork ex;
   void destroy() {
     qpad.release(); negpad.release(); partial.release(); mask.release(); counters.release();
-    tc_sample.release(); tc_tau.release(); tc_cand.release(); tc_cnt.release(); tc_bias.release();
+    tc_sample.release(); tc_tau.release(); tc_cand.release(); tc_cnt.release(); tc_bias.release(); tc_apack.release();
     d_q.release(); d_neg.release(); d_dist.release(); d_negdist.release(); d_row.release(); d_count.release();
     d_rows32.release(); d_rows64.release(); d_fetch.release();
     h_in.release(); h_out.release();
@@ -194,6 +194,9 @@ struct qg_index {
   float* inv_norm = nullptr;
   float* norm2 = nullptr;      // |x|^2, +inf beyond n_rows (tensor-core row term, L2)
   float* unit_bias = nullptr;  // 1.0, +inf beyond n_rows (tensor-core row term, dot / cosine)
+  void* vec16 = nullptr;       // bf16 copy of vec, [cap x dp16]: the tensor-core stream (dim <= 512), else nullptr
+  int dp16 = 0;
+  bool use_bf16 = false;
   uint32_t* live = nullptr;
   float* max_norm2 = nullptr;  // device scalar
   uint64_t live_epoch = 0, facet_epoch = 0;
@@ -294,17 +297,20 @@ static int grow(qg_index* idx, long long need_rows) {
   float* ninv = nullptr;
   float* nn2 = nullptr;
   float* nub = nullptr;
+  void* nv16 = nullptr;
   uint32_t* nlive = nullptr;
   cudaError_t e = cudaMalloc(&nvec, (size_t)ncap * idx->dp * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&ninv, (size_t)ncap * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&nn2, (size_t)ncap * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&nub, (size_t)ncap * sizeof(float));
+  if (e == cudaSuccess && idx->use_bf16) e = cudaMalloc(&nv16, (size_t)ncap * idx->dp16 * 2);
   if (e == cudaSuccess) e = cudaMalloc(&nlive, (size_t)(ncap / 32) * sizeof(uint32_t));
   if (e != cudaSuccess) {
     if (nvec) cudaFree(nvec);
     if (ninv) cudaFree(ninv);
     if (nn2) cudaFree(nn2);
     if (nub) cudaFree(nub);
+    if (nv16) cudaFree(nv16);
     if (nlive) cudaFree(nlive);
     return fail(QG_ERR_OOM, std::string("device allocation for ") + std::to_string(ncap) +
                                 " rows failed: " + cudaGetErrorString(e));
@@ -321,6 +327,9 @@ static int grow(qg_index* idx, long long need_rows) {
                                idx->up_stream));
     QG_CUDA_OK(cudaMemcpyAsync(nub, idx->unit_bias, (size_t)idx->n_rows * sizeof(float), cudaMemcpyDeviceToDevice,
                                idx->up_stream));
+    if (nv16)
+      QG_CUDA_OK(cudaMemcpyAsync(nv16, idx->vec16, (size_t)idx->n_rows * idx->dp16 * 2, cudaMemcpyDeviceToDevice,
+                                 idx->up_stream));
     QG_CUDA_OK(cudaMemcpyAsync(nlive, idx->live, (size_t)((idx->n_rows + 31) / 32) * sizeof(uint32_t),
                                cudaMemcpyDeviceToDevice, idx->up_stream));
   }
@@ -329,7 +338,9 @@ static int grow(qg_index* idx, long long need_rows) {
   if (idx->inv_norm) cudaFree(idx->inv_norm);
   if (idx->norm2) cudaFree(idx->norm2);
   if (idx->unit_bias) cudaFree(idx->unit_bias);
+  if (idx->vec16) cudaFree(idx->vec16);
   if (idx->live) cudaFree(idx->live);
+  idx->vec16 = nv16;
   idx->vec = nvec;
   idx->inv_norm = ninv;
   idx->norm2 = nn2;
@@ -345,6 +356,9 @@ static int finish_append(qg_index* idx, long long n, int64_t* first_row) {
   if (int rc = launch_row_norms(idx->vec, row0, n, idx->dp, idx->dim, idx->inv_norm, idx->norm2, idx->unit_bias,
                                 idx->max_norm2, idx->up_stream))
     return rc;
+  if (idx->use_bf16) {
+    if (int rc = launch_tc_to_bf16(idx->vec, row0, n, idx->dp, idx->dp16, idx->vec16, idx->up_stream)) return rc;
+  }
   if (int rc = launch_set_live(idx->live, row0, n, idx->up_stream)) return rc;
   QG_CUDA_OK(cudaStreamSynchronize(idx->up_stream));
   idx->n_rows += n;
@@ -414,6 +428,11 @@ int qg_index_create(qg_index** out, int dim, int metric, const qg_config* cfg) {
   idx->margin = (cfg && cfg->select_margin > 0) ? cfg->select_margin : 16;
   if (const char* e = std::getenv("QG_TC_MIN_Q")) idx->tc_min_q = std::max(1, std::atoi(e));
   if (const char* e = std::getenv("QG_TC_MIN_ROWS")) idx->tc_min_rows = std::max(128, std::atoi(e));
+  // bf16 copy for the tensor-core stream (+50 % memory): every distance that is RETURNED is still
+  // recomputed from the fp32 rows, the copy only feeds candidate selection. QG_TC_BF16=0 disables it.
+  idx->dp16 = (dim + 7) & ~7;
+  idx->use_bf16 = dim <= 512 && metric != QG_L1;
+  if (const char* e = std::getenv("QG_TC_BF16")) idx->use_bf16 = idx->use_bf16 && std::atoi(e) != 0;
   {
     std::lock_guard<std::mutex> lk(g_dev_mu);
     idx->sm_count = g_dev[device].sm_count;
@@ -446,6 +465,7 @@ int qg_index_destroy(qg_index* idx) {
   if (idx->inv_norm) cudaFree(idx->inv_norm);
   if (idx->norm2) cudaFree(idx->norm2);
   if (idx->unit_bias) cudaFree(idx->unit_bias);
+  if (idx->vec16) cudaFree(idx->vec16);
   if (idx->live) cudaFree(idx->live);
   if (idx->max_norm2) cudaFree(idx->max_norm2);
   if (idx->stage_ev[0]) cudaEventDestroy(idx->stage_ev[0]);
@@ -892,7 +912,7 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
   // ---- tensor-core regime: large query batches over a dense (possibly masked) corpus ----------------
   TcPlan plan{};
   const bool tc_possible = q >= idx->tc_min_q && mode != MODE_L1 && kp <= 128 && idx->n_rows >= idx->tc_min_rows &&
-                           n_pass >= idx->tc_min_rows && tc_available() == 0 && tc_plan(dp, q, &plan) == 0;
+                           n_pass >= idx->tc_min_rows && tc_available() == 0 && tc_plan(dp, q, idx->use_bf16, &plan) == 0;
   if (tc_possible && gather != nullptr) {
     // a selective filter has a compacted row list: the flat scan then reads only the matching rows, but
     // serves at most max_qb queries per pass; the tensor-core scan reads every row (masked) once per
@@ -911,7 +931,15 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
     if (int rc = w->tc_sample.ensure((size_t)plan.n_cols * n_sample * plan.sample_vals * 4)) return rc;
     if (int rc = w->tc_tau.ensure((size_t)TC_MAX_COLS * 4)) return rc;
     if (int rc = w->tc_cand.ensure((size_t)plan.n_cols * TC_CAND_CAP * 8)) return rc;
-    if (int rc = w->tc_cnt.ensure((size_t)TC_MAX_COLS * 4)) return rc;
+    if (int rc = w->tc_cnt.ensure((size_t)(TC_MAX_COLS + 4) * 4)) return rc;
+    if (plan.variant == 1) {
+      // all queries of the search in tensor-memory order, one block per pass
+      if (int rc = w->tc_apack.ensure(tc_pack_bytes(plan, q))) return rc;
+      if (idx->profiling) w->prof_begin(2, st);
+      if (int rc = launch_tc_pack(plan, qpad, q, dp, idx->metric == METRIC_COSINE, w->tc_apack.p, st)) return rc;
+      if (idx->profiling) w->prof_end(st);
+      stats.kernel_launches++;
+    }
     // TS variant: additive row term with the mask folded in (+inf = excluded)
     const float* tc_bias = mode == MODE_L2 ? idx->norm2 : idx->unit_bias;
     if (plan.variant == 1 && mask != nullptr) {
@@ -929,7 +957,9 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
     cp.cap = TC_CAND_CAP;
     cp.tau = (const float*)w->tc_tau.p;
     cp.kp = kp;
-    cp.tc_gamma = 1.02 / 512.0 + (double)d / 4194304.0;
+    // |tensor-core dot - exact dot| <= tc_gamma * |q||x|: both operands truncated to tf32 (2^-10 each) or
+    // rounded to bf16 (2^-9 each), plus the fp32 accumulation
+    cp.tc_gamma = (plan.bf16 ? 1.02 / 256.0 : 1.02 / 512.0) + (double)d / 4194304.0;
     FinalizeParams& fb = cp.base;
     fb.vec = idx->vec;
     fb.dp = dp;
@@ -946,6 +976,8 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
       const int nq = std::min(plan.n_cols, q - p0);
       TcArgs ta{};
       ta.vec = idx->vec;
+      ta.vec16 = idx->vec16;
+      ta.dp16 = idx->dp16;
       ta.n_rows = idx->n_rows;
       ta.dp = dp;
       ta.row_norm2 = idx->norm2;
@@ -953,6 +985,8 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
       ta.mask = mask;
       ta.bias = tc_bias;
       ta.queries = qpad + (size_t)p0 * dp;
+      ta.apack = plan.variant == 1 ? (const char*)w->tc_apack.p + tc_pack_bytes(plan, p0) : nullptr;
+      ta.work_counter = (int*)w->tc_cnt.p + TC_MAX_COLS;
       ta.nq = nq;
       ta.mode = mode;
       ta.cosine = fb.cosine;
@@ -988,7 +1022,9 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
     stats.path = 3;
     stats.queries_per_pass = plan.n_cols;
     stats.rows_scanned = idx->n_rows;
-    stats.bytes_algorithmic = idx->n_rows * (long long)d * 4 + idx->n_rows * 4 + (mask ? idx->n_rows / 8 : 0);
+    stats.bytes_algorithmic = idx->n_rows * (long long)(plan.bf16 ? idx->dp16 * 2 : d * 4) + idx->n_rows * 4 +
+                              (mask ? idx->n_rows / 8 : 0);
+    stats.reserved = plan.bf16;
     idx->stats = stats;
     return 0;
   }
@@ -1500,7 +1536,7 @@ int qg_debug_tc_pass(qg_index* idx, const float* queries, int nq, int k, float* 
   if (idx->n_rows == 0) return fail(QG_ERR_INVALID, "debug_tc_pass: empty index");
   const int mode = scan_mode_of(idx->metric);
   TcPlan plan{};
-  if (mode == MODE_L1 || tc_available() != 0 || tc_plan(idx->dp, nq, &plan) != 0)
+  if (mode == MODE_L1 || tc_available() != 0 || tc_plan(idx->dp, nq, idx->use_bf16, &plan) != 0)
     return fail(QG_ERR_UNSUPPORTED, "tensor-core regime not available for this index");
   Workspace* w = ws_acquire(idx);
   if (!w) return fail(QG_ERR_CUDA, "could not create a stream");
@@ -1518,9 +1554,15 @@ int qg_debug_tc_pass(qg_index* idx, const float* queries, int nq, int k, float* 
     if ((rc = w->tc_sample.ensure((size_t)plan.n_cols * n_sample * plan.sample_vals * 4))) break;
     if ((rc = w->tc_tau.ensure((size_t)TC_MAX_COLS * 4))) break;
     if ((rc = w->tc_cand.ensure((size_t)plan.n_cols * TC_CAND_CAP * 8))) break;
-    if ((rc = w->tc_cnt.ensure((size_t)TC_MAX_COLS * 4))) break;
+    if ((rc = w->tc_cnt.ensure((size_t)(TC_MAX_COLS + 4) * 4))) break;
+    if (plan.variant == 1) {
+      if ((rc = w->tc_apack.ensure(tc_pack_bytes(plan, nq)))) break;
+      if ((rc = launch_tc_pack(plan, (const float*)w->qpad.p, nq, dp, idx->metric == METRIC_COSINE, w->tc_apack.p, st))) break;
+    }
     TcArgs ta{};
     ta.vec = idx->vec;
+    ta.vec16 = idx->vec16;
+    ta.dp16 = idx->dp16;
     ta.n_rows = idx->n_rows;
     ta.dp = dp;
     ta.row_norm2 = idx->norm2;
@@ -1544,6 +1586,8 @@ int qg_debug_tc_pass(qg_index* idx, const float* queries, int nq, int k, float* 
     ta.tau = (float*)w->tc_tau.p;
     ta.cand = (uint64_t*)w->tc_cand.p;
     ta.cand_cnt = (int*)w->tc_cnt.p;
+    ta.apack = w->tc_apack.p;
+    ta.work_counter = (int*)w->tc_cnt.p + TC_MAX_COLS;
     int launches = 0;
     if ((rc = w->counters.ensure(64 * 8))) break;
     cudaMemsetAsync(w->counters.p, 0, 64 * 8, st);
@@ -1555,9 +1599,17 @@ int qg_debug_tc_pass(qg_index* idx, const float* queries, int nq, int k, float* 
       cudaMemcpy(h, w->counters.p, sizeof(h), cudaMemcpyDeviceToHost);
       fprintf(stderr, "tc timing (cycles, CTA 0): producer total %llu wait_xs %llu wait_empty %llu | mma total %llu "
                       "wait_tmem_empty %llu wait_full %llu\n", h[0], h[1], h[2], h[3], h[4], h[5]);
-      for (int i = 0; i < 8; ++i)
-        fprintf(stderr, "  epilogue warp %d: total %llu wait_xs %llu wait_tmem_full %llu tmem_ld %llu\n", i + 2,
-                h[8 + i * 4], h[9 + i * 4], h[10 + i * 4], h[11 + i * 4]);
+      for (int i = 0; i < 4; ++i)
+        fprintf(stderr, "  epilogue warp %d: total %llu wait_xs %llu wait_tmem_full %llu tmem_ld %llu scores+vote %llu "
+                        "publish+release %llu\n", i + 2, h[8 + i * 8], h[9 + i * 8], h[10 + i * 8], h[11 + i * 8],
+                h[12 + i * 8], h[13 + i * 8]);
+      for (int c = 0; c < 2; ++c) {
+        const unsigned long long* t = h + 40 + c * 8;
+        auto us = [&](int i) { return ((double)t[i] - (double)h[40]) * 1e-3; };
+        fprintf(stderr, "  wall clock (us after CTA 0 entry), %s CTA: entry %.1f, tmem allocated %.1f, queries resident "
+                        "%.1f, MMA starts %.1f, first tile drained %.1f, last MMA %.1f, exit %.1f\n",
+                c ? "last" : "first", us(0), us(1), us(2), us(3), us(4), us(5), us(6));
+      }
       // finalize of the same pass, with phase time stamps of CTA 0
       FinalizeCandParams cp{};
       cp.cand = (const uint64_t*)w->tc_cand.p;
@@ -1565,7 +1617,7 @@ int qg_debug_tc_pass(qg_index* idx, const float* queries, int nq, int k, float* 
       cp.cap = TC_CAND_CAP;
       cp.tau = (const float*)w->tc_tau.p;
       cp.kp = 32;
-      cp.tc_gamma = 1.02 / 512.0 + (double)d / 4194304.0;
+      cp.tc_gamma = (plan.bf16 ? 1.02 / 256.0 : 1.02 / 512.0) + (double)d / 4194304.0;
       cudaMemsetAsync(w->counters.p, 0, 64 * 8, st);
       cp.dbg = (unsigned long long*)w->counters.p;
       FinalizeParams& fb = cp.base;

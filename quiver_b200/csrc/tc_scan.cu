@@ -15,9 +15,12 @@
 // Pipelines (mbarriers): full/empty ring of A stages between the TMA warp and the MMA thread;
 // tmem_full/tmem_empty over two accumulator buffers between the MMA thread and the epilogue warps.
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 #include "scan.cuh"
 #include "tc_scan.cuh"
+#include "misc.cuh"
+#include <cstdlib>
 
 namespace qg {
 
@@ -75,6 +78,16 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Same with bf16 operands (kind::f16): K = 16 elements per instruction, twice the tf32 rate.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
       "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -422,7 +435,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 // ================================================================================================
 constexpr int TS_KSTEP_BYTES = 128;               // one swizzle row: 32 floats
 constexpr int TS_EPI_WARPS = 16;                 // epilogue warps: four per TMEM lane quarter
-constexpr int TS_THREADS = 64 + TS_EPI_WARPS * 32;
+constexpr int TS_THREADS = 128 + TS_EPI_WARPS * 32;  // warp group 0: TMA producer, MMA issuer, two idle warps
+constexpr int TS_REGS_CTRL = 56;                 // setmaxnreg: control warp group gives registers away ...
+constexpr int TS_REGS_EPI = 104;                 // ... to the epilogue warp groups (64 accumulator registers each)
+constexpr int TS_MAX_ACC = 4;        // accumulator buffers in tensor memory (as many as fit beside the queries)
+constexpr int TS_CLAIM = 2;          // corpus tiles per work claim of the main scan
 constexpr int TS_XS = 8;                          // ring of per-tile row-term buffers
 // corpus rows per tile = MMA N: two resident query blocks leave 64 accumulator columns per buffer,
 // one block leaves 128 (512 TMEM columns = nblk * kb * 32 + nblk * 2 * rows)
@@ -436,9 +453,10 @@ struct TsKParams {
   int cosine;
   const float* bias;   // [rows padded to 128] additive row term: |x|^2 (L2) or 1 (dot); +inf = row excluded
   const float* sc;     // [rows padded to 128] 1/|x| (cosine) or nullptr
-  const float* queries;
+  const uint32_t* apack;  // this pass's queries in tensor-memory order (tc_pack_kernel)
+  int* work_counter;      // main scan: tiles beyond the first of each CTA are claimed here (zeroed by tc_tau_kernel)
   int dp;
-  uint32_t* sample;  // [n_cols][n_sample][nblk == 2 ? 2 : 4]: one minimum per epilogue sub-group
+  uint32_t* sample;  // [n_cols][n_sample][nblk == 2 ? 1 : 2]: one minimum per tile (and chunk parity)
   int n_sample;
   const float* tau;
   uint64_t* cand;
@@ -447,7 +465,7 @@ struct TsKParams {
 };
 
 struct TsSmem {
-  int off_ring, off_bias, off_sc, off_bars, off_tmem, total;
+  int off_ring, off_bias, off_sc, off_bars, off_tmem, off_tags, total;
 };
 __host__ __device__ inline TsSmem ts_smem_layout(int stages, int kb, int rows) {
   TsSmem s;
@@ -455,10 +473,40 @@ __host__ __device__ inline TsSmem ts_smem_layout(int stages, int kb, int rows) {
   s.off_bias = stages * kb * rows * TS_KSTEP_BYTES;  // one stage = one whole tile (kb k-blocks)
   s.off_sc = s.off_bias + TS_XS * rows * 4;
   s.off_bars = s.off_sc + TS_XS * rows * 4;
-  s.off_tmem = s.off_bars + (2 * stages + 4 + 2 * TS_XS + 1) * 8;
-  s.total = s.off_tmem + 16;
+  s.off_tmem = s.off_bars + (2 * stages + 2 * TS_MAX_ACC + 2 * TS_XS + 1) * 8;
+  s.off_tags = s.off_tmem + 16;  // int ring_tag[stages] (1 = tile, 0 = end of work), int xs_work[TS_XS] (work index, -1 = end)
+  s.total = s.off_tags + (stages + TS_XS) * 4;
   return s;
 }
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// wall-clock stamps of the first and the last CTA (debug counters 40..47 and 48..55)
+__device__ __forceinline__ void dbg_stamp(unsigned long long* dbg, int slot) {
+  if (dbg == nullptr) return;
+  if (blockIdx.x == 0) dbg[40 + slot] = global_ns();
+  else if (blockIdx.x == gridDim.x - 1) dbg[48 + slot] = global_ns();
+}
+
+// Cycle counters of CTA 0 (development aid): laps are added straight to global memory by one lane, so
+// a production launch (dbg == nullptr) carries two dead registers instead of a dozen live counters.
+struct DbgClock {
+  unsigned long long* d;
+  long long t0;
+  __device__ __forceinline__ void start() {
+    if (d != nullptr) t0 = clock64();
+  }
+  __device__ __forceinline__ void lap(int slot) {
+    if (d != nullptr) {
+      const long long t1 = clock64();
+      d[slot] += (unsigned long long)(t1 - t0);
+      t0 = t1;
+    }
+  }
+};
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
@@ -466,11 +514,14 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   return v;
 }
 
-// KB > 0: compile-time number of 32-float blocks per row (MMA issue loop fully unrolled); KB == 0: p.kb.
-template <int MODE, bool SAMPLE, int NBLK, int KB>
+// KB > 0: compile-time number of 128-byte k-blocks per row (MMA issue loop fully unrolled); KB == 0: p.kb.
+// BF16: the corpus stream is the bf16 copy of the index (64 elements per k-block, kind::f16 MMA) and the
+// resident queries are rounded to bf16 — the scores only select candidates, the re-rank stays exact.
+template <int MODE, bool SAMPLE, int NBLK, int KB, bool BF16>
 __global__ void __launch_bounds__(TS_THREADS, 1)
     tc_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const TsKParams p) {
   constexpr int ROWS = ts_rows(NBLK);
+  constexpr int KELEMS = BF16 ? 64 : 32;               // elements per 128-byte k-block
   constexpr int KBLOCK_BYTES = ROWS * TS_KSTEP_BYTES;  // one 32-float block of a tile
   extern __shared__ unsigned char smem_unaligned[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_unaligned) + 1023) &
@@ -484,32 +535,42 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.off_bars);
   uint64_t* empty = full + S;
   uint64_t* tmem_full = empty + S;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* xs_full = tmem_empty + 2;
+  uint64_t* tmem_empty = tmem_full + TS_MAX_ACC;
+  uint64_t* xs_full = tmem_empty + TS_MAX_ACC;
   uint64_t* xs_empty = xs_full + TS_XS;
   uint64_t* a_ready = xs_empty + TS_XS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.off_tmem);
+  volatile int* ring_tag = reinterpret_cast<volatile int*>(smem + L.off_tags);
+  volatile int* xs_work = ring_tag + S;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int a_cols = kb * TC_KBLOCK;             // TMEM columns of one query block
   const int tile_bytes = kb * KBLOCK_BYTES;      // one ring stage = one whole tile
   const int d_off = NBLK * a_cols;               // first accumulator column
+  const int n_acc = min(TS_MAX_ACC, (512 - d_off) / (NBLK * ROWS));  // accumulator buffers of NBLK * ROWS columns
   const long long n_work = SAMPLE ? (long long)p.n_sample : p.n_tiles;
   auto tile_of = [&](long long w) -> long long { return SAMPLE ? (w * p.n_tiles) / p.n_sample : w; };
 
+  // the first two tile claims of the main scan go out before anything else (warp 0, lane 0)
+  int claim_a = 0, claim_b = 0;
+  if (!SAMPLE && threadIdx.x == 0) {
+    claim_a = atomicAdd(p.work_counter, TS_CLAIM);
+    claim_b = atomicAdd(p.work_counter, TS_CLAIM);
+  }
   if (threadIdx.x == 0) {
+    dbg_stamp(p.dbg, 0);
     tma_prefetch_desc(&tm_x);
     for (int i = 0; i < S; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < TS_MAX_ACC; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], TS_EPI_WARPS);
+      mbar_init(&tmem_empty[i], TS_EPI_WARPS / 2);  // a tile is drained by one ping-pong half
     }
     for (int i = 0; i < TS_XS; ++i) {
       mbar_init(&xs_full[i], 1);
-      mbar_init(&xs_empty[i], TS_EPI_WARPS);
+      mbar_init(&xs_empty[i], TS_EPI_WARPS / 2);
     }
     mbar_init(a_ready, TS_EPI_WARPS);
     fence_mbar_init();
@@ -519,7 +580,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) dbg_stamp(p.dbg, 1);
 
+  // register budgets are set inside the role branches (after a merge point ptxas assumes the lower one)
+  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TS_REGS_CTRL));
   if (warp == 0) {
     // ===== TMA producer (converged warp, one elected lane issues): whole corpus tiles and the
     //       tile's per-row terms =====
@@ -528,67 +592,104 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
     long long it = 0;
     const bool with_sc = MODE != MODE_L2 && p.sc != nullptr;
     const uint32_t xs_bytes = (uint32_t)(ROWS * 4 * (with_sc ? 2 : 1));
-    long long t_prod_xs = 0, t_prod_empty = 0;
+    DbgClock clk{(p.dbg != nullptr && blockIdx.x == 0 && lane == 0) ? p.dbg : nullptr, 0};
     const long long t_prod_begin = clock64();
-    for (long long w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-      const long long tile = tile_of(w);
+    // Work distribution of the main scan: tiles are claimed from a global counter, TS_CLAIM at a time
+    // (SMs stream at visibly different rates; a static split leaves the fast ones idle for the last
+    // fifth of the kernel). A claim's round trip is longer than a tile, so two claims are kept in
+    // flight in two different registers (the scoreboard is per register, not per lane). The sample
+    // kernel keeps the static split (its slots are indexed by w). The end of work travels through the
+    // rings as a tag: once through the corpus ring (MMA issuer) and through two consecutive slots of
+    // the row-term ring (one per epilogue half).
+    auto push = [&](long long w, bool live, bool to_ring) {
+      const long long tile = live ? tile_of(w) : 0;
       const int xb = (int)(it % TS_XS);
       const uint32_t xphase = (uint32_t)((it / TS_XS) & 1);
-      long long t0 = 0;
-      if (p.dbg) t0 = clock64();
+      clk.start();
       mbar_wait(&xs_empty[xb], xphase ^ 1u);
-      if (p.dbg) t_prod_xs += clock64() - t0;
+      clk.lap(1);
       if (elect_one()) {
-        mbar_arrive_expect_tx(&xs_full[xb], xs_bytes);
-        bulk_g2s(xs_bias + xb * ROWS, p.bias + tile * ROWS, ROWS * 4, &xs_full[xb]);
-        if (with_sc) bulk_g2s(xs_sc + xb * ROWS, p.sc + tile * ROWS, ROWS * 4, &xs_full[xb]);
+        xs_work[xb] = live ? (int)w : -1;
+        if (live) {
+          mbar_arrive_expect_tx(&xs_full[xb], xs_bytes);
+          bulk_g2s(xs_bias + xb * ROWS, p.bias + tile * ROWS, ROWS * 4, &xs_full[xb]);
+          if (with_sc) bulk_g2s(xs_sc + xb * ROWS, p.sc + tile * ROWS, ROWS * 4, &xs_full[xb]);
+        } else {
+          mbar_arrive(&xs_full[xb]);
+        }
       }
       __syncwarp();
-      if (p.dbg) t0 = clock64();
-      mbar_wait(&empty[stage], phase ^ 1u);
-      if (p.dbg) t_prod_empty += clock64() - t0;
-      if (elect_one()) {
-        unsigned char* dst = ring + (size_t)stage * tile_bytes;
-        mbar_arrive_expect_tx(&full[stage], (uint32_t)tile_bytes);
-        for (int kbi = 0; kbi < kb; ++kbi)
-          tma_load_2d(dst + (size_t)kbi * KBLOCK_BYTES, &tm_x, kbi * TC_KBLOCK, (int)(tile * ROWS), &full[stage]);
+      if (to_ring) {
+        clk.start();
+        mbar_wait(&empty[stage], phase ^ 1u);
+        clk.lap(2);
+        if (elect_one()) {
+          ring_tag[stage] = live ? 1 : 0;
+          if (live) {
+            unsigned char* dst = ring + (size_t)stage * tile_bytes;
+            mbar_arrive_expect_tx(&full[stage], (uint32_t)tile_bytes);
+            for (int kbi = 0; kbi < kb; ++kbi)
+              tma_load_2d(dst + (size_t)kbi * KBLOCK_BYTES, &tm_x, kbi * KELEMS, (int)(tile * ROWS), &full[stage]);
+          } else {
+            mbar_arrive(&full[stage]);
+          }
+        }
+        __syncwarp();
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1u;
+        }
       }
-      __syncwarp();
-      if (++stage == S) {
-        stage = 0;
-        phase ^= 1u;
+      ++it;
+    };
+    if (SAMPLE) {
+      for (long long w = blockIdx.x; w < n_work; w += gridDim.x) push(w, true, true);
+    } else {
+      bool more = true;
+      auto run_claim = [&](int& claim) {
+        const int base = __shfl_sync(0xffffffffu, claim, 0);  // waits for this claim's register only
+        if (base >= n_work) {
+          more = false;
+          return;
+        }
+        if (lane == 0) claim = atomicAdd(p.work_counter, TS_CLAIM);  // re-armed two claims ahead
+        for (int j = 0; j < TS_CLAIM && base + j < n_work; ++j) push(base + j, true, true);
+      };
+      while (more) {
+        run_claim(claim_a);
+        if (more) run_claim(claim_b);
       }
     }
+    push(0, false, true);
+    push(0, false, false);
     if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0) {
       p.dbg[0] = (unsigned long long)(clock64() - t_prod_begin);
-      p.dbg[1] = (unsigned long long)t_prod_xs;
-      p.dbg[2] = (unsigned long long)t_prod_empty;
     }
   } else if (warp == 1) {
     // ===== MMA issuer (converged warp, one elected lane issues) =====
-    long long t_mma_empty = 0, t_mma_full = 0;
+    DbgClock clk{(p.dbg != nullptr && blockIdx.x == 0 && lane == 0) ? p.dbg : nullptr, 0};
     const long long t_mma_begin = clock64();
     mbar_wait(a_ready, 0);
     tc_fence_after();
+    if (lane == 0) dbg_stamp(p.dbg, 3);
     const uint64_t desc0 = make_sdesc(smem_u32(ring));
     const uint32_t idesc = p.idesc;
     int stage = 0;
     uint32_t phase = 0;
     long long it = 0;
-    for (long long w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-      const int acc = (int)(it & 1);
-      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
-      long long t0 = 0;
-      if (p.dbg) t0 = clock64();
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
-      if (p.dbg) t_mma_empty += clock64() - t0;
-      if (p.dbg) t0 = clock64();
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (;; ++it) {
+      clk.start();
       mbar_wait(&full[stage], phase);
-      if (p.dbg) t_mma_full += clock64() - t0;
+      clk.lap(5);
+      if (ring_tag[stage] == 0) break;  // end of work
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+      clk.lap(4);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t d0 = tmem_base + (uint32_t)(d_off + acc * ROWS);
-        const uint32_t d1 = d0 + 2 * ROWS;
+        const uint32_t d0 = tmem_base + (uint32_t)(d_off + acc * NBLK * ROWS);
+        const uint32_t d1 = d0 + ROWS;
         const uint64_t bdesc = desc0 + (uint64_t)((uint32_t)stage * (uint32_t)(tile_bytes >> 4));
         if (KB > 0) {
 #pragma unroll
@@ -597,8 +698,13 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
             for (int k = 0; k < 4; ++k) {
               const uint64_t bd = bdesc + (uint64_t)(kbi * (KBLOCK_BYTES >> 4) + k * 2);
               const uint32_t aa = tmem_base + (uint32_t)(kbi * TC_KBLOCK + k * 8);
-              umma_tf32_ts(d0, aa, bd, idesc, (kbi | k) != 0 ? 1u : 0u);
-              if (NBLK == 2) umma_tf32_ts(d1, aa + (uint32_t)(KB * TC_KBLOCK), bd, idesc, (kbi | k) != 0 ? 1u : 0u);
+              if (BF16) {
+                umma_bf16_ts(d0, aa, bd, idesc, (kbi | k) != 0 ? 1u : 0u);
+                if (NBLK == 2) umma_bf16_ts(d1, aa + (uint32_t)(KB * TC_KBLOCK), bd, idesc, (kbi | k) != 0 ? 1u : 0u);
+              } else {
+                umma_tf32_ts(d0, aa, bd, idesc, (kbi | k) != 0 ? 1u : 0u);
+                if (NBLK == 2) umma_tf32_ts(d1, aa + (uint32_t)(KB * TC_KBLOCK), bd, idesc, (kbi | k) != 0 ? 1u : 0u);
+              }
             }
           }
         } else {
@@ -607,8 +713,13 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
           for (int kbi = 0; kbi < kb; ++kbi) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              umma_tf32_ts(d0, a0 + k * 8, bd0 + (uint64_t)(k * 2), idesc, (kbi | k) != 0 ? 1u : 0u);
-              if (NBLK == 2) umma_tf32_ts(d1, a0 + a_cols + k * 8, bd0 + (uint64_t)(k * 2), idesc, (kbi | k) != 0 ? 1u : 0u);
+              if (BF16) {
+                umma_bf16_ts(d0, a0 + k * 8, bd0 + (uint64_t)(k * 2), idesc, (kbi | k) != 0 ? 1u : 0u);
+                if (NBLK == 2) umma_bf16_ts(d1, a0 + a_cols + k * 8, bd0 + (uint64_t)(k * 2), idesc, (kbi | k) != 0 ? 1u : 0u);
+              } else {
+                umma_tf32_ts(d0, a0 + k * 8, bd0 + (uint64_t)(k * 2), idesc, (kbi | k) != 0 ? 1u : 0u);
+                if (NBLK == 2) umma_tf32_ts(d1, a0 + a_cols + k * 8, bd0 + (uint64_t)(k * 2), idesc, (kbi | k) != 0 ? 1u : 0u);
+              }
             }
             bd0 += (uint64_t)(KBLOCK_BYTES >> 4);
             a0 += TC_KBLOCK;
@@ -622,46 +733,51 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
         stage = 0;
         phase ^= 1u;
       }
+      if (++acc == n_acc) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
     }
+    if (lane == 0) dbg_stamp(p.dbg, 5);
     if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0) {
       p.dbg[3] = (unsigned long long)(clock64() - t_mma_begin);
-      p.dbg[4] = (unsigned long long)t_mma_empty;
-      p.dbg[5] = (unsigned long long)t_mma_full;
     }
-  } else {
-    // ===== epilogue warps: one query per thread, two 16-row chunks per warp and tile =====
-    // 16 warps = 4 per TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31):
-    //   NBLK == 2: group g -> query block g >> 1, chunks {g & 1, (g & 1) + 2} of the 64-row tile
-    //   NBLK == 1: group g -> chunks {g, g + 4} of the 128-row tile
+  } else if (warp >= 4) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TS_REGS_EPI));
+    // ===== epilogue warps: one query per thread; two ping-pong halves of 8 warps alternate tiles =====
+    // A tile's epilogue is a latency chain (barrier waits, tcgen05.ld, the dependent min tree), so
+    // even tiles go to half 0 (accumulator buffer 0) and odd tiles to half 1 (buffer 1): the two
+    // chains overlap. 16 warps = 4 per TMEM lane quarter (a warp may only touch lanes
+    // 32*(warp%4)..+31); within a half:
+    //   NBLK == 2: the two warps of a quarter take one query block each, all 4 chunks of the 64-row tile
+    //   NBLK == 1: they split the 8 chunks of the 128-row tile (even / odd chunks)
     const int quarter = warp & 3;
-    const int grp = (warp - 2) >> 2;                     // 0..3
-    const int blk = NBLK == 2 ? (grp >> 1) : 0;          // query block of this warp
+    const int grp = (warp - 4) >> 2;                     // 0..3
+    const int pp = grp & 1;                              // ping-pong half = tile parity = accumulator buffer
+    const int sub = grp >> 1;
+    const int blk = NBLK == 2 ? sub : 0;                 // query block of this warp
     const int q = blk * 128 + quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    constexpr int NCH = 2;                               // chunks per warp and tile
-    auto chunk_of = [&](int ci) -> int { return NBLK == 2 ? (grp & 1) + 2 * ci : grp + 4 * ci; };
-    const bool loads_queries = NBLK == 2 ? (grp & 1) == 0 : grp == 0;
+    constexpr int NCH = 4;                               // chunks per warp and tile
+    auto chunk_of = [&](int ci) -> int { return NBLK == 2 ? ci : sub + 2 * ci; };
 
     // ---- resident query block -> tensor memory (cosine: pre-scaled by 1/|q|) ----
-    if (loads_queries) {
-      float rnq = 1.f;
-      if (MODE == MODE_DOT && p.cosine && q < p.nq) {
-        float s = 0.f;
-        const float* qv = p.queries + (size_t)q * p.dp;
-        for (int i = 0; i < p.dp; ++i) s = fmaf(qv[i], qv[i], s);
-        rnq = s > 0.f ? rsqrtf(s) : 0.f;
-      }
-      for (int c = 0; c < a_cols / 16; ++c) {
+    // (tc_pack_kernel laid them out so that a warp reads 2 KB contiguous per 16 columns; the 16 warps
+    //  split the 16-column groups of their query block between them)
+    {
+      const int nch = a_cols / 16;
+      const int cpart = NBLK == 2 ? pp : grp, nparts = NBLK == 2 ? 2 : 4;
+      const uint4* ap = reinterpret_cast<const uint4*>(p.apack) +
+                        ((size_t)blk * nch * 128 + (size_t)(quarter * 32 + lane)) * 4;
+      for (int c = cpart; c < nch; c += nparts) {
         float v[16];
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
-          const int col = c * 16 + j4 * 4;
-          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (q < p.nq && col < p.dp) t = __ldg(reinterpret_cast<const float4*>(p.queries + (size_t)q * p.dp + col));
-          v[j4 * 4 + 0] = t.x * rnq;
-          v[j4 * 4 + 1] = t.y * rnq;
-          v[j4 * 4 + 2] = t.z * rnq;
-          v[j4 * 4 + 3] = t.w * rnq;
+          const uint4 t = __ldg(ap + (size_t)c * 128 * 4 + j4);
+          v[j4 * 4 + 0] = __uint_as_float(t.x);
+          v[j4 * 4 + 1] = __uint_as_float(t.y);
+          v[j4 * 4 + 2] = __uint_as_float(t.z);
+          v[j4 * 4 + 3] = __uint_as_float(t.w);
         }
         tmem_st16(tmem_base + lane_base + (uint32_t)(blk * a_cols + c * 16), v);
       }
@@ -670,6 +786,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(a_ready);
+    if (warp == 4 && lane == 0) dbg_stamp(p.dbg, 2);
 
     float tau_me = -__int_as_float(0x7f800000);
     if (!SAMPLE && q < p.nq) tau_me = __ldg(p.tau + q);
@@ -680,82 +797,112 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
     uint64_t pend_key = 0, prev_key = 0;
     int prev_pos = 0;
     bool has_pend = false, prev_has = false;
-    long long t_epi_xs = 0, t_epi_full = 0;
+    DbgClock clk{(p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && warp < 8) ? p.dbg + 8 + (warp - 4) * 8 : nullptr, 0};
     const long long t_epi_begin = clock64();
 
-    long long it = 0;
-    for (long long w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-      const long long tile = tile_of(w);
-      const int acc = (int)(it & 1);
-      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+    int acc = pp;  // tile it uses buffer it % n_acc; this half sees every second tile
+    uint32_t acc_phase = 0;
+    for (long long it = pp;; it += 2) {
       const int xb = (int)(it % TS_XS);
       const uint32_t xphase = (uint32_t)((it / TS_XS) & 1);
-      long long t0 = 0;
-      if (p.dbg) t0 = clock64();
+      clk.start();
       mbar_wait(&xs_full[xb], xphase);
-      if (p.dbg) {
-        const long long t1 = clock64();
-        t_epi_xs += t1 - t0;
-        t0 = t1;
-      }
+      const long long w = xs_work[xb];
+      if (w < 0) break;  // end of work
+      const long long tile = tile_of(w);
+      clk.lap(1);
       mbar_wait(&tmem_full[acc], acc_phase);
-      if (p.dbg) t_epi_full += clock64() - t0;
+      clk.lap(2);
+      if (it == 0 && warp == 4 && lane == 0) dbg_stamp(p.dbg, 4);
       tc_fence_after();
-      const uint32_t d_addr = tmem_base + lane_base + (uint32_t)(d_off + (blk * 2 + acc) * ROWS);
+      const uint32_t d_addr = tmem_base + lane_base + (uint32_t)(d_off + (acc * NBLK + blk) * ROWS);
       // all of this warp's accumulator chunks are requested before the first one is consumed
       uint32_t araw[NCH][16];
 #pragma unroll
       for (int ci = 0; ci < NCH; ++ci) tmem_ld16_issue(d_addr + (uint32_t)(chunk_of(ci) * 16), araw[ci]);
       tmem_ld_wait();
-      float tile_min = __int_as_float(0x7f800000);
+      clk.lap(3);
+      // the accumulator now lives in registers: hand the buffer back before the min tree runs
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc += 2;
+      if (acc >= n_acc) {
+        acc -= n_acc;
+        acc_phase ^= 1u;
+      }
+      // scores of the warp's NCH chunks (in place) and their minima: independent chains, one vote per tile
+      float cmin[NCH];
 #pragma unroll
       for (int ci = 0; ci < NCH; ++ci) {
-        const int c = chunk_of(ci);
-        float v[16];
-        const uint32_t boff = (uint32_t)((xb * ROWS + c * 16) * 4);
+        const uint32_t boff = (uint32_t)((xb * ROWS + chunk_of(ci) * 16) * 4);
+        uint32_t(&v)[16] = araw[ci];
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
           const float4 bb = lds128(bias_s + boff + j4 * 16);
-          const float a0 = __uint_as_float(araw[ci][j4 * 4 + 0]), a1 = __uint_as_float(araw[ci][j4 * 4 + 1]);
-          const float a2 = __uint_as_float(araw[ci][j4 * 4 + 2]), a3 = __uint_as_float(araw[ci][j4 * 4 + 3]);
+          const float a0 = __uint_as_float(v[j4 * 4 + 0]), a1 = __uint_as_float(v[j4 * 4 + 1]);
+          const float a2 = __uint_as_float(v[j4 * 4 + 2]), a3 = __uint_as_float(v[j4 * 4 + 3]);
+          float r0, r1, r2, r3;
           if (MODE == MODE_L2) {
-            v[j4 * 4 + 0] = fmaf(-2.f, a0, bb.x);
-            v[j4 * 4 + 1] = fmaf(-2.f, a1, bb.y);
-            v[j4 * 4 + 2] = fmaf(-2.f, a2, bb.z);
-            v[j4 * 4 + 3] = fmaf(-2.f, a3, bb.w);
+            r0 = fmaf(-2.f, a0, bb.x);
+            r1 = fmaf(-2.f, a1, bb.y);
+            r2 = fmaf(-2.f, a2, bb.z);
+            r3 = fmaf(-2.f, a3, bb.w);
           } else {
             float4 ss = make_float4(1.f, 1.f, 1.f, 1.f);
             if (has_sc) ss = lds128(sc_s + boff + j4 * 16);
-            v[j4 * 4 + 0] = fmaf(-a0, ss.x, bb.x);
-            v[j4 * 4 + 1] = fmaf(-a1, ss.y, bb.y);
-            v[j4 * 4 + 2] = fmaf(-a2, ss.z, bb.z);
-            v[j4 * 4 + 3] = fmaf(-a3, ss.w, bb.w);
+            r0 = fmaf(-a0, ss.x, bb.x);
+            r1 = fmaf(-a1, ss.y, bb.y);
+            r2 = fmaf(-a2, ss.z, bb.z);
+            r3 = fmaf(-a3, ss.w, bb.w);
           }
+          v[j4 * 4 + 0] = __float_as_uint(r0);
+          v[j4 * 4 + 1] = __float_as_uint(r1);
+          v[j4 * 4 + 2] = __float_as_uint(r2);
+          v[j4 * 4 + 3] = __float_as_uint(r3);
+          const float m4 = fminf(fminf(r0, r1), fminf(r2, r3));
+          cmin[ci] = j4 == 0 ? m4 : fminf(cmin[ci], m4);
         }
-        const float m = fminf(fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])), fminf(fminf(v[4], v[5]), fminf(v[6], v[7]))),
-                              fminf(fminf(fminf(v[8], v[9]), fminf(v[10], v[11])),
-                                    fminf(fminf(v[12], v[13]), fminf(v[14], v[15]))));
-        if (SAMPLE) {
-          tile_min = fminf(tile_min, m);
-        } else {
-          const bool lane_hit = m <= tau_me;
-          if (__any_sync(0xffffffffu, lane_hit)) {
-            if (lane_hit) {  // usually a single lane: the others skip the 16 comparisons
+      }
+      float tile_min = cmin[0];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                if (v[j] <= tau_me) {
-                  if (has_pend) {  // second hit of this lane within one tile (rare): publish the first now
-                    const int pos = atomicAdd(p.cand_cnt + q, 1);
-                    if (pos < TC_CAND_CAP) p.cand[(size_t)q * TC_CAND_CAP + pos] = pend_key;
-                  }
-                  pend_key = make_key(v[j], (uint32_t)(tile * ROWS + c * 16 + j));
+      for (int ci = 1; ci < NCH; ++ci) tile_min = fminf(tile_min, cmin[ci]);
+      if (!SAMPLE) {
+        const bool lane_hit = tile_min <= tau_me;
+        if (__any_sync(0xffffffffu, lane_hit)) {
+          if (lane_hit) {  // usually a single lane with a single admitted row
+#pragma unroll
+            for (int ci = 0; ci < NCH; ++ci) {
+              if (cmin[ci] <= tau_me) {
+                // branch-free count of admitted rows of the chunk and the index of the last one; a
+                // single admitted row is the chunk minimum itself
+                int n_hit = 0, j_hit = 0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const bool h = __uint_as_float(araw[ci][j]) <= tau_me;
+                  n_hit += h ? 1 : 0;
+                  j_hit = h ? j : j_hit;
+                }
+                const uint32_t row0 = (uint32_t)(tile * ROWS + chunk_of(ci) * 16);
+                if (n_hit == 1 && !has_pend) {
+                  pend_key = make_key(cmin[ci], row0 + (uint32_t)j_hit);
                   has_pend = true;
+                } else {  // several admitted rows in one tile for this query (rare): publish directly
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    const float vj = __uint_as_float(araw[ci][j]);
+                    if (vj <= tau_me) {
+                      const int pos = atomicAdd(p.cand_cnt + q, 1);
+                      if (pos < TC_CAND_CAP) p.cand[(size_t)q * TC_CAND_CAP + pos] = make_key(vj, row0 + (uint32_t)j);
+                    }
+                  }
                 }
               }
             }
           }
         }
       }
+      clk.lap(4);
       if (!SAMPLE) {
         if (prev_has && prev_pos < TC_CAND_CAP) p.cand[(size_t)q * TC_CAND_CAP + prev_pos] = prev_key;
         prev_has = has_pend;
@@ -765,29 +912,22 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
           has_pend = false;
         }
       }
-      tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&tmem_empty[acc]);
-        mbar_arrive(&xs_empty[xb]);
-      }
+      if (lane == 0) mbar_arrive(&xs_empty[xb]);
+      clk.lap(5);
       if (SAMPLE && q < p.nq) {
         // minimum score of this tile for this query: sample[q][w] (NBLK == 2) or sample[q][w][group]
         const uint32_t mn = tile_min == __int_as_float(0x7f800000) ? 0xFFFFFFFFu : f32_to_ordered(tile_min);
         if (NBLK == 2) {
-          p.sample[((size_t)q * p.n_sample + (size_t)w) * 2 + (grp & 1)] = mn;
+          p.sample[(size_t)q * p.n_sample + (size_t)w] = mn;
         } else {
-          p.sample[((size_t)q * p.n_sample + (size_t)w) * 4 + grp] = mn;
+          p.sample[((size_t)q * p.n_sample + (size_t)w) * 2 + sub] = mn;
         }
       }
     }
     if (!SAMPLE && prev_has && prev_pos < TC_CAND_CAP) p.cand[(size_t)q * TC_CAND_CAP + prev_pos] = prev_key;
     if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0) {
-      unsigned long long* o = p.dbg + 8 + ((warp - 2) & 7) * 4;
-      o[0] = (unsigned long long)(clock64() - t_epi_begin);
-      o[1] = (unsigned long long)t_epi_xs;
-      o[2] = (unsigned long long)t_epi_full;
-      o[3] = 0;
+      if (warp < 8) p.dbg[8 + (warp - 4) * 8] = (unsigned long long)(clock64() - t_epi_begin);  // one warp per lane quarter reports
     }
   }
 
@@ -795,6 +935,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (threadIdx.x == 0) dbg_stamp(p.dbg, 6);
 }
 
 // Threshold per query: the TC_SAMPLE_RANK-th smallest sampled score (+inf when the sample holds
@@ -822,7 +963,8 @@ __device__ __forceinline__ uint32_t warp_pop_rank(uint32_t (&best)[R], int rank,
 constexpr int TAU_THREADS = 128;
 
 __global__ void __launch_bounds__(TAU_THREADS) tc_tau_kernel(const uint32_t* __restrict__ sample, int n_vals, int rank,
-                                                             float* __restrict__ tau, int* __restrict__ cand_cnt) {
+                                                             float* __restrict__ tau, int* __restrict__ cand_cnt,
+                                                             int* __restrict__ work_counter) {
   const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t* vals = sample + (size_t)q * n_vals;
   constexpr int R = TC_SAMPLE_RANK;
@@ -851,6 +993,7 @@ __global__ void __launch_bounds__(TAU_THREADS) tc_tau_kernel(const uint32_t* __r
       // 0xFFFFFFFF: fewer than `rank` valid samples -> admit everything
       tau[q] = (m == 0xFFFFFFFFu) ? __int_as_float(0x7f800000) : ordered_to_f32(m);
       cand_cnt[q] = 0;
+      if (q == 0 && work_counter != nullptr) *work_counter = 0;
     }
   }
 }
@@ -876,6 +1019,84 @@ int launch_tc_bias(const uint32_t* mask, const float* norm2, long long n_rows, l
   return 0;
 }
 
+// Queries of a search in tensor-memory order, one block of n_cols queries per pass:
+//   apack[pass][blk][c][r][j] = 32-bit column c*16+j of query pass*n_cols + blk*128 + r
+// (fp32 value, or two consecutive bf16 values, low half first; cosine: pre-scaled by 1/|q|; zero
+// beyond nq and beyond dp). One warp per query slot.
+__global__ void __launch_bounds__(256) tc_pack_kernel(const float* __restrict__ queries, int nq, int dp, int n_cols,
+                                                      int a_cols, int bf16, int cosine, uint32_t* __restrict__ apack,
+                                                      long long n_slots) {
+  const int lane = threadIdx.x & 31;
+  const long long slot = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (slot >= n_slots) return;
+  const long long pass = slot / n_cols;
+  const int qi = (int)(slot - pass * n_cols), blk = qi >> 7, r = qi & 127;
+  const bool valid = slot < nq;
+  const float* qv = queries + (size_t)slot * dp;
+  float rnq = 1.f;
+  if (cosine && valid) {
+    float s = 0.f;
+    for (int e = lane; e < dp; e += 32) s = fmaf(qv[e], qv[e], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    rnq = s > 0.f ? rsqrtf(s) : 0.f;
+  }
+  const int nch = a_cols >> 4;
+  uint32_t* dst = apack + (size_t)pass * n_cols * a_cols;
+  for (int col = lane; col < a_cols; col += 32) {
+    uint32_t bits = 0;
+    if (valid) {
+      if (bf16) {
+        const int e = col * 2;
+        const float a = e < dp ? qv[e] * rnq : 0.f, b = e + 1 < dp ? qv[e + 1] * rnq : 0.f;
+        const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        bits = *reinterpret_cast<const uint32_t*>(&h);
+      } else {
+        bits = col < dp ? __float_as_uint(qv[col] * rnq) : 0u;
+      }
+    }
+    dst[((size_t)(blk * nch + (col >> 4)) * 128 + r) * 16 + (col & 15)] = bits;
+  }
+}
+
+size_t tc_pack_bytes(const TcPlan& plan, int nq) {
+  const long long passes = (nq + plan.n_cols - 1) / plan.n_cols;
+  return (size_t)passes * plan.n_cols * plan.kb * TC_KBLOCK * 4;
+}
+
+int launch_tc_pack(const TcPlan& plan, const float* queries, int nq, int dp, int cosine, void* apack, cudaStream_t st) {
+  if (plan.variant != 1 || nq <= 0) return 0;
+  const long long passes = (nq + plan.n_cols - 1) / plan.n_cols;
+  const long long n_slots = passes * plan.n_cols;
+  tc_pack_kernel<<<(int)((n_slots + 7) / 8), 256, 0, st>>>(queries, nq, dp, plan.n_cols, plan.kb * TC_KBLOCK, plan.bf16,
+                                                           cosine, (uint32_t*)apack, n_slots);
+  QG_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// bf16 copy of the corpus for the tensor-core stream: round to nearest even, rows padded to dp16.
+__global__ void __launch_bounds__(256) tc_to_bf16_kernel(const float* __restrict__ vec, long long row0, long long n,
+                                                         int dp, int dp16, __nv_bfloat16* __restrict__ out) {
+  const long long total = n * (dp16 / 2);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (dp16 / 2);
+    const int c = (int)(i - r * (dp16 / 2)) * 2;
+    const float* src = vec + (size_t)(row0 + r) * dp;
+    const float a = c < dp ? src[c] : 0.f, b = c + 1 < dp ? src[c + 1] : 0.f;
+    reinterpret_cast<__nv_bfloat162*>(out + (size_t)(row0 + r) * dp16)[c / 2] = __floats2bfloat162_rn(a, b);
+  }
+}
+
+int launch_tc_to_bf16(const float* vec, long long row0, long long n, int dp, int dp16, void* out, cudaStream_t st) {
+  if (n <= 0) return 0;
+  long long blocks = (n * (dp16 / 2) + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  tc_to_bf16_kernel<<<(int)blocks, 256, 0, st>>>(vec, row0, n, dp, dp16, reinterpret_cast<__nv_bfloat16*>(out));
+  QG_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // ---- host side --------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -895,27 +1116,49 @@ int tc_available() {
   return g_encode ? 0 : -1;
 }
 
-static int encode_map(CUtensorMap* map, const float* base, long long rows, int dp, int box_rows) {
+static int encode_map(CUtensorMap* map, const void* base, long long rows, int dp, int box_rows, bool bf16 = false) {
   if (tc_available() != 0) return fail(4, "cuTensorMapEncodeTiled is not available from this driver");
+  const int esz = bf16 ? 2 : 4;
   cuuint64_t dims[2] = {(cuuint64_t)dp, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)dp * 4};
-  cuuint32_t box[2] = {(cuuint32_t)TC_KBLOCK, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)dp * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+  CUresult r = g_encode(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                        const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(4, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
   return 0;
 }
 
-static int encode_map_box(CUtensorMap* map, const float* base, long long rows, int dp, int box_rows) {
-  return encode_map(map, base, rows, dp, box_rows);
-}
 
-int tc_plan(int dp, int nq, TcPlan* out) {
+int tc_plan(int dp, int nq, bool bf16, TcPlan* out) {
   if (dp < 4 || dp % 4 != 0) return -1;
-  const int kb = (dp + TC_KBLOCK - 1) / TC_KBLOCK;
+  int kb = (dp + TC_KBLOCK - 1) / TC_KBLOCK;
   const int budget = 227 * 1024 - 1024;  // alignment slack
+  out->bf16 = 0;
+  if (bf16) {
+    // bf16 stream: 64 elements per 128-byte k-block; rows of the bf16 copy are padded to 8 elements
+    const int kb16 = (dp + 63) / 64;
+    if (kb16 <= 8) {
+      const int nblk = (kb16 <= 4 && nq > 128) ? 2 : 1;
+      const int rows = ts_rows(nblk);
+      int stages = (budget - ts_smem_layout(0, kb16, rows).total) / (kb16 * rows * TS_KSTEP_BYTES + 16);
+      stages = std::min(stages, 12);
+      if (stages >= 2) {
+        out->variant = 1;
+        out->bf16 = 1;
+        out->nblk = nblk;
+        out->n_cols = 128 * nblk;
+        out->kb = kb16;
+        out->stages = stages;
+        out->tile_rows = rows;
+        out->sample_vals = nblk == 2 ? 1 : 2;
+        out->smem = ts_smem_layout(stages, kb16, rows).total + 1024;
+        return 0;
+      }
+    }
+  }
   // TS variant: queries resident in tensor memory. 512 columns = nblk * kb * 32 (queries) +
   // nblk * 2 * 64 (double-buffered accumulators).
   if (kb <= 8) {
@@ -930,7 +1173,7 @@ int tc_plan(int dp, int nq, TcPlan* out) {
       out->kb = kb;
       out->stages = stages;
       out->tile_rows = rows;
-      out->sample_vals = nblk == 2 ? 2 : 4;
+      out->sample_vals = nblk == 2 ? 1 : 2;
       out->smem = ts_smem_layout(stages, kb, rows).total + 1024;
       return 0;
     }
@@ -972,24 +1215,26 @@ static int set_attr_one() {
 
 typedef void (*TsKernelFn)(const CUtensorMap, const TsKParams);
 
-template <int MODE, bool SAMPLE, int NBLK>
+template <int MODE, bool SAMPLE, int NBLK, bool BF16>
 static TsKernelFn ts_kernel_kb(int kb) {
   switch (kb) {
-    case 1: return tc_ts_kernel<MODE, SAMPLE, NBLK, 1>;
-    case 2: return tc_ts_kernel<MODE, SAMPLE, NBLK, 2>;
-    case 3: return tc_ts_kernel<MODE, SAMPLE, NBLK, 3>;
-    case 4: return tc_ts_kernel<MODE, SAMPLE, NBLK, 4>;
-    default: return tc_ts_kernel<MODE, SAMPLE, NBLK, 0>;
+    case 1: return tc_ts_kernel<MODE, SAMPLE, NBLK, 1, BF16>;
+    case 2: return tc_ts_kernel<MODE, SAMPLE, NBLK, 2, BF16>;
+    case 3: return tc_ts_kernel<MODE, SAMPLE, NBLK, 3, BF16>;
+    case 4: return tc_ts_kernel<MODE, SAMPLE, NBLK, 4, BF16>;
+    default: return tc_ts_kernel<MODE, SAMPLE, NBLK, 0, BF16>;
   }
 }
 
-static TsKernelFn ts_kernel(int mode, bool sample, int nblk, int kb) {
-  if (mode == MODE_L2) {
-    if (sample) return nblk == 2 ? ts_kernel_kb<MODE_L2, true, 2>(kb) : ts_kernel_kb<MODE_L2, true, 1>(kb);
-    return nblk == 2 ? ts_kernel_kb<MODE_L2, false, 2>(kb) : ts_kernel_kb<MODE_L2, false, 1>(kb);
-  }
-  if (sample) return nblk == 2 ? ts_kernel_kb<MODE_DOT, true, 2>(kb) : ts_kernel_kb<MODE_DOT, true, 1>(kb);
-  return nblk == 2 ? ts_kernel_kb<MODE_DOT, false, 2>(kb) : ts_kernel_kb<MODE_DOT, false, 1>(kb);
+template <int MODE, bool BF16>
+static TsKernelFn ts_kernel_ms(bool sample, int nblk, int kb) {
+  if (sample) return nblk == 2 ? ts_kernel_kb<MODE, true, 2, BF16>(kb) : ts_kernel_kb<MODE, true, 1, BF16>(kb);
+  return nblk == 2 ? ts_kernel_kb<MODE, false, 2, BF16>(kb) : ts_kernel_kb<MODE, false, 1, BF16>(kb);
+}
+
+static TsKernelFn ts_kernel(int mode, bool sample, int nblk, int kb, bool bf16) {
+  if (mode == MODE_L2) return bf16 ? ts_kernel_ms<MODE_L2, true>(sample, nblk, kb) : ts_kernel_ms<MODE_L2, false>(sample, nblk, kb);
+  return bf16 ? ts_kernel_ms<MODE_DOT, true>(sample, nblk, kb) : ts_kernel_ms<MODE_DOT, false>(sample, nblk, kb);
 }
 
 static int set_attr_ts() {
@@ -997,8 +1242,9 @@ static int set_attr_ts() {
     for (int sample = 0; sample < 2; ++sample)
       for (int nblk = 1; nblk <= 2; ++nblk)
         for (int kb = 0; kb <= 4; ++kb)
-          QG_CUDA_OK(cudaFuncSetAttribute(ts_kernel(mode, sample != 0, nblk, kb == 0 ? 9 : kb),
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          for (int bf = 0; bf < 2; ++bf)
+            QG_CUDA_OK(cudaFuncSetAttribute(ts_kernel(mode, sample != 0, nblk, kb == 0 ? 9 : kb, bf != 0),
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   return 0;
 }
 
@@ -1018,8 +1264,14 @@ int tc_set_attributes() {
 static int launch_ts_pass(const TcPlan& plan, const TcArgs& a, int sm_count, cudaStream_t st, int* launches,
                           const TcStageHook* hook) {
   const int rows = ts_rows(plan.nblk);
+  const bool bf16 = plan.bf16 != 0;
   CUtensorMap tm_x;
-  if (int rc = encode_map_box(&tm_x, a.vec, a.n_rows, a.dp, rows)) return rc;
+  if (bf16) {
+    if (a.vec16 == nullptr) return fail(1, "tensor-core bf16 pass needs the bf16 copy of the corpus");
+    if (int rc = encode_map(&tm_x, a.vec16, a.n_rows, a.dp16, rows, true)) return rc;
+  } else {
+    if (int rc = encode_map(&tm_x, a.vec, a.n_rows, a.dp, rows)) return rc;
+  }
   TsKParams p{};
   p.n_rows = a.n_rows;
   p.n_tiles = (a.n_rows + rows - 1) / rows;
@@ -1027,11 +1279,13 @@ static int launch_ts_pass(const TcPlan& plan, const TcArgs& a, int sm_count, cud
   p.stages = plan.stages;
   p.nq = a.nq;
   p.nblk = plan.nblk;
-  p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(rows >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t fmt = bf16 ? 1u : 2u;  // F16F32Format: BF16 = 1, TF32 = 2
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(rows >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   p.cosine = a.cosine;
   p.bias = a.bias;
   p.sc = a.cosine ? a.inv_norm : nullptr;
-  p.queries = a.queries;
+  p.apack = static_cast<const uint32_t*>(a.apack);
+  p.work_counter = a.work_counter;
   p.dp = a.dp;
   p.sample = a.sample;
   p.n_sample = a.n_sample;
@@ -1039,19 +1293,22 @@ static int launch_ts_pass(const TcPlan& plan, const TcArgs& a, int sm_count, cud
   p.cand = a.cand;
   p.cand_cnt = a.cand_cnt;
   p.dbg = nullptr;
+  if (a.apack == nullptr || a.work_counter == nullptr) return fail(1, "tensor-core TS pass needs packed queries and a work counter");
   if (a.bias == nullptr) return fail(1, "tensor-core TS pass needs the per-row bias column");
   const int grid_s = (int)std::min<long long>(sm_count, a.n_sample);
   const int grid_m = (int)std::min<long long>(sm_count, p.n_tiles);
   if (hook) hook->fn(hook->ctx, 0, 1, st);
-  ts_kernel(a.mode, true, plan.nblk, plan.kb)<<<grid_s, TS_THREADS, plan.smem, st>>>(tm_x, p);
+  ts_kernel(a.mode, true, plan.nblk, plan.kb, bf16)<<<grid_s, TS_THREADS, plan.smem, st>>>(tm_x, p);
   QG_CUDA_OK(cudaGetLastError());
   tc_tau_kernel<<<a.nq, TAU_THREADS, 0, st>>>(a.sample, a.n_sample * plan.sample_vals, TC_SAMPLE_RANK, a.tau,
-                                              a.cand_cnt);
+                                              a.cand_cnt, a.work_counter);
   QG_CUDA_OK(cudaGetLastError());
+  if (a.dbg != nullptr && std::getenv("QG_TC_NOHIT"))  // development aid: a scan that admits nothing
+    launch_fill_f32(a.tau, a.nq, -__builtin_huge_valf(), st);
   if (hook) hook->fn(hook->ctx, 0, 0, st);
   p.dbg = a.dbg;
   if (hook) hook->fn(hook->ctx, 1, 1, st);
-  ts_kernel(a.mode, false, plan.nblk, plan.kb)<<<grid_m, TS_THREADS, plan.smem, st>>>(tm_x, p);
+  ts_kernel(a.mode, false, plan.nblk, plan.kb, bf16)<<<grid_m, TS_THREADS, plan.smem, st>>>(tm_x, p);
   QG_CUDA_OK(cudaGetLastError());
   if (hook) hook->fn(hook->ctx, 1, 0, st);
   if (launches) *launches += 3;
@@ -1093,7 +1350,7 @@ int launch_tc_pass(const TcPlan& plan, const TcArgs& a, int sm_count, cudaStream
     tc_scan_kernel<MODE_DOT, true><<<grid_s, TC_THREADS, plan.smem, st>>>(tm_a, tm_b, p);
   }
   QG_CUDA_OK(cudaGetLastError());
-  tc_tau_kernel<<<a.nq, TAU_THREADS, 0, st>>>(a.sample, a.n_sample * 2, TC_SAMPLE_RANK, a.tau, a.cand_cnt);
+  tc_tau_kernel<<<a.nq, TAU_THREADS, 0, st>>>(a.sample, a.n_sample * 2, TC_SAMPLE_RANK, a.tau, a.cand_cnt, nullptr);
   QG_CUDA_OK(cudaGetLastError());
   if (hook) hook->fn(hook->ctx, 0, 0, st);
   if (hook) hook->fn(hook->ctx, 1, 1, st);

@@ -23,6 +23,7 @@ constexpr int TC_CAND_CAP = 2048;       // candidate capacity per query per pass
 
 struct TcPlan {
   int variant;      // 1 = TS (queries resident in tensor memory, dp <= 256), 0 = SS (queries in shared memory)
+  int bf16;         // TS only: stream the bf16 copy of the corpus (kind::f16) instead of the fp32 rows (kind::tf32)
   int nblk;         // TS: resident blocks of 128 queries (1 or 2)
   int n_cols;       // queries per pass
   int kb;           // 32-float blocks per row
@@ -33,10 +34,12 @@ struct TcPlan {
 };
 
 // Geometry for a padded dimension dp and nq queries; returns 0 when the tensor path fits.
-int tc_plan(int dp, int nq, TcPlan* out);
+int tc_plan(int dp, int nq, bool bf16, TcPlan* out);
 
 struct TcArgs {
   const float* vec;         // [n_rows x dp]
+  const void* vec16;        // [n_rows x dp16] bf16 copy (plan.bf16), else nullptr
+  int dp16;
   long long n_rows;
   int dp;
   const float* row_norm2;   // [n_rows] |x|^2 (L2 scores)
@@ -45,6 +48,8 @@ struct TcArgs {
   const float* bias;        // TS variant: [rows padded to 64] |x|^2 (L2) or 1 (dot), +inf for rows that
                             // may not match (mask already applied) and for the padding
   const float* queries;     // [nq x dp] device
+  const void* apack;        // TS variant: this pass's block of the packed queries (launch_tc_pack)
+  int* work_counter;        // TS variant: one int of scratch (tile claims of the main scan)
   int nq;
   int mode;                 // MODE_L2 / MODE_DOT (scan.cuh)
   int cosine;
@@ -68,6 +73,12 @@ struct TcStageHook {
 int launch_tc_pass(const TcPlan& plan, const TcArgs& args, int sm_count, cudaStream_t st, int* launches,
                    const TcStageHook* hook = nullptr);
 int tc_set_attributes();
+// TS variant: all nq queries of a search in tensor-memory order, one block of plan.n_cols queries per
+// pass (pass i starts at byte i * tc_pack_bytes(plan, plan.n_cols)). Cosine queries are pre-scaled.
+size_t tc_pack_bytes(const TcPlan& plan, int nq);
+int launch_tc_pack(const TcPlan& plan, const float* queries, int nq, int dp, int cosine, void* apack, cudaStream_t st);
+// out[row0 + r][0..dp16) = bf16(vec[row0 + r][0..dp)) (round to nearest even, zero padded)
+int launch_tc_to_bf16(const float* vec, long long row0, long long n, int dp, int dp16, void* out, cudaStream_t st);
 // bias[i] = row i passes (mask nullptr = all rows < n_rows) ? (norm2 ? norm2[i] : 1) : +inf, for i < n_pad.
 int launch_tc_bias(const uint32_t* mask, const float* norm2, long long n_rows, long long n_pad, float* bias,
                    cudaStream_t st);
