@@ -266,8 +266,6 @@ def run_native(args):
     for _ in range(max(3, args.warmup)):
         step_device()
     barrier()
-    idx.read_profile()
-    idx.set_profiling(True)
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -279,6 +277,17 @@ def run_native(args):
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
+    # the same K steps once more with an event pair around every kernel (prep / scan / finalize): the
+    # per-kernel durations behind the roofline. Kept out of `value`: ~500 event records per step cost ~10 %.
+    idx.read_profile()
+    idx.set_profiling(True)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(args.steps):
+        step_device()
+    p1.record()
+    barrier()
+    ms_profiled = p0.elapsed_time(p1)
     clk = clocks.stop() if rank == 0 else None
     idx.set_profiling(False)
     prof = idx.read_profile()
@@ -332,26 +341,40 @@ def run_native(args):
     bytes_per_launch = stats["bytes_algorithmic"]  # rows*dim*4 (+ row-term / mask columns read); one corpus pass
     achieved = bytes_per_launch / (scan_launch_ms * 1e-3) / 1e9 if scan_launch_ms > 0 else 0.0
     tc = stats["path"] == 3
-    kernel_name = "tc_ts_kernel (main scan, tcgen05.mma kind::tf32)" if tc else "scan_fast_kernel"
-    total_ms = ms_step * args.steps
+    bf16_stream = tc and stats.get("reserved", 0) == 1
+    kernel_name = ("tc_ts_kernel (main scan, tcgen05.mma kind::%s, queries resident in TMEM)" % ("f16 on a bf16 copy of the corpus" if bf16_stream else "tf32")) if tc else "scan_fast_kernel"
+    total_ms = ms_profiled
+    hbm = {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+           "frac_of_nominal_8TBs": achieved / 8000.0}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "kernel": kernel_name, "launch_ms": scan_launch_ms,
                 "bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
-                "frac_of_nominal_8TBs": achieved / 8000.0,
+                "timed": f"CUDA events around every launch during a second pass of the same {args.steps} steps "
+                         f"({ms_profiled / args.steps:.3f} ms per step with the events, {ms_step:.3f} without)",
                 "scan_share_of_step": prof["scan_ms"] / total_ms if total_ms > 0 else None,
                 "prep_share_of_step": prof["prep_ms"] / total_ms if total_ms > 0 else None,
                 "finalize_share_of_step": prof["finalize_ms"] / total_ms if total_ms > 0 else None,
                 "finalize_launch_ms": prof["finalize_ms"] / max(1, prof["finalize_launches"]),
                 "prep_launch_ms": prof["prep_ms"] / max(1, prof["prep_launches"]) if prof["prep_launches"] else None}
     if tc:
+        # a [rows x d] x [d x queries] contraction per pass: the binding roof is whichever floor is higher,
+        # the corpus stream (HBM) or the MMA work (tensor pipe; tf32 runs at half the bf16 rate)
         qpp = min(Q, stats["queries_per_pass"])
         flops = 2.0 * qpp * nloc * d
         tfl = flops / (scan_launch_ms * 1e-3) / 1e12 if scan_launch_ms > 0 else 0.0
         bf16 = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        roofline["tensor"] = {"achieved_tflops": tfl, "queries_per_pass": qpp,
-                              "peak_bf16_tflops_measured": bf16, "frac_of_bf16_peak": tfl / bf16,
-                              "note": "kind::tf32 runs at half the bf16 rate: at 256 queries per pass the "
-                                      "scan sits at the HBM / tf32-tensor crossover"}
+        tpeak = bf16 if bf16_stream else bf16 / 2
+        t_hbm, t_tensor = bytes_per_launch / (peak * 1e9), flops / (tpeak * 1e12)
+        tensor = {"achieved": tfl, "peak": tpeak, "unit": "TFLOP/s", "frac": tfl / tpeak, "queries_per_pass": qpp,
+                  "flops_per_launch": flops,
+                  "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained%s)" % ("" if bf16_stream else " / 2 for tf32")
+                                 if "bf16_tflops_sustained" in peaks else "fallback 1400 TFLOP/s"}
+        if t_tensor > t_hbm:
+            roofline.update({"bound": "tensor", "achieved": tfl, "peak": tpeak, "unit": "TFLOP/s", "frac": tfl / tpeak,
+                             "peak_source": tensor["peak_source"], "flops_per_launch": flops, "hbm": hbm})
+        else:
+            roofline["tensor"] = tensor
+        roofline["floors_us"] = {"hbm": t_hbm * 1e6, "tensor": t_tensor * 1e6}
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         roofline["traffic"] = tr.get("tc_ts_kernel_bytes_per_launch" if tc else "scan_fast_kernel_bytes_per_launch")
@@ -392,7 +415,7 @@ def run_native(args):
     line = {
         "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "tf32 tensor-core scan (f32 flat scan for small batches) + f64 re-rank", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32 (returned distances: the reference's f32/f64 arithmetic; candidate selection: bf16 tensor-core scan for batches, f32 flat scan for single queries)", "data": "synthetic",
         "config": {"workload": f"flat {args.metric} exact search {args.rows}x{d} fp32 (SIFT-shaped synthetic, "
                                f"oracle/synth.h kind {args.kind} seed {args.seed}), query batch {Q}, k={k}",
                    "rows": args.rows, "dim": d, "k": k, "queries_per_step": Q,
