@@ -135,6 +135,9 @@ struct Workspace {
     cudaEventRecord(prof_ev[prof_used + 1], st);
     prof_used += 2;
   }
+  // host-buffer searches stage their queries chunk by chunk on a copy stream, one event per chunk
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> chunk_ev;
   DevBuf qpad, negpad, partial, mask, counters;
   DevBuf tc_sample, tc_tau, tc_cand, tc_cnt, tc_bias, tc_apack;
   DevBuf d_q, d_neg, d_dist, d_negdist, d_row, d_count, d_rows32, d_rows64, d_fetch;
@@ -148,6 +151,8 @@ struct Workspace {
     h_in.release(); h_out.release();
     exhaustive_free(ex);
     for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : chunk_ev) cudaEventDestroy(e);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
     prof_ev.clear();
     if (done) cudaEventDestroy(done);
     if (stream) cudaStreamDestroy(stream);
@@ -357,7 +362,10 @@ static int finish_append(qg_index* idx, long long n, int64_t* first_row) {
                                 idx->max_norm2, idx->up_stream))
     return rc;
   if (idx->use_bf16) {
-    if (int rc = launch_tc_to_bf16(idx->vec, row0, n, idx->dp, idx->dp16, idx->vec16, idx->up_stream)) return rc;
+    if (int rc = launch_tc_to_bf16(idx->vec, row0, n, idx->dp, idx->dim, idx->dp16,
+                                   tc_extra_cols(idx->dim, scan_mode_of(idx->metric) == MODE_L2) ? idx->norm2 : nullptr,
+                                   idx->metric == METRIC_COSINE ? idx->inv_norm : nullptr, idx->vec16, idx->up_stream))
+      return rc;
   }
   if (int rc = launch_set_live(idx->live, row0, n, idx->up_stream)) return rc;
   QG_CUDA_OK(cudaStreamSynchronize(idx->up_stream));
@@ -430,7 +438,7 @@ int qg_index_create(qg_index** out, int dim, int metric, const qg_config* cfg) {
   if (const char* e = std::getenv("QG_TC_MIN_ROWS")) idx->tc_min_rows = std::max(128, std::atoi(e));
   // bf16 copy for the tensor-core stream (+50 % memory): every distance that is RETURNED is still
   // recomputed from the fp32 rows, the copy only feeds candidate selection. QG_TC_BF16=0 disables it.
-  idx->dp16 = (dim + 7) & ~7;
+  idx->dp16 = tc_dp16(dim, scan_mode_of(metric) == MODE_L2);
   idx->use_bf16 = dim <= 512 && metric != QG_L1;
   if (const char* e = std::getenv("QG_TC_BF16")) idx->use_bf16 = idx->use_bf16 && std::atoi(e) != 0;
   {
@@ -912,7 +920,8 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
   // ---- tensor-core regime: large query batches over a dense (possibly masked) corpus ----------------
   TcPlan plan{};
   const bool tc_possible = q >= idx->tc_min_q && mode != MODE_L1 && kp <= 128 && idx->n_rows >= idx->tc_min_rows &&
-                           n_pass >= idx->tc_min_rows && tc_available() == 0 && tc_plan(dp, q, idx->use_bf16, &plan) == 0;
+                           n_pass >= idx->tc_min_rows && tc_available() == 0 &&
+                           tc_plan(dp, d + tc_extra_cols(d, mode == MODE_L2), q, idx->use_bf16, &plan) == 0;
   if (tc_possible && gather != nullptr) {
     // a selective filter has a compacted row list: the flat scan then reads only the matching rows, but
     // serves at most max_qb queries per pass; the tensor-core scan reads every row (masked) once per
@@ -932,11 +941,16 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
     if (int rc = w->tc_tau.ensure((size_t)TC_MAX_COLS * 4)) return rc;
     if (int rc = w->tc_cand.ensure((size_t)plan.n_cols * TC_CAND_CAP * 8)) return rc;
     if (int rc = w->tc_cnt.ensure((size_t)(TC_MAX_COLS + 4) * 4)) return rc;
+    // raw scan: bf16 stream without a mask — the norm columns of the bf16 rows make the MMA output the score
+    const bool tc_raw = plan.variant == 1 && plan.bf16 && mask == nullptr && idx->n_rows >= plan.tile_rows &&
+                        tc_raw_supported(d, mode == MODE_L2);
     if (plan.variant == 1) {
       // all queries of the search in tensor-memory order, one block per pass
       if (int rc = w->tc_apack.ensure(tc_pack_bytes(plan, q))) return rc;
       if (idx->profiling) w->prof_begin(2, st);
-      if (int rc = launch_tc_pack(plan, qpad, q, dp, idx->metric == METRIC_COSINE, w->tc_apack.p, st)) return rc;
+      if (int rc = launch_tc_pack(plan, qpad, q, dp, d, tc_raw ? tc_extra_cols(d, mode == MODE_L2) : 0,
+                                  idx->metric == METRIC_COSINE, w->tc_apack.p, st))
+        return rc;
       if (idx->profiling) w->prof_end(st);
       stats.kernel_launches++;
     }
@@ -960,6 +974,7 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
     // |tensor-core dot - exact dot| <= tc_gamma * |q||x|: both operands truncated to tf32 (2^-10 each) or
     // rounded to bf16 (2^-9 each), plus the fp32 accumulation
     cp.tc_gamma = (plan.bf16 ? 1.02 / 256.0 : 1.02 / 512.0) + (double)d / 4194304.0;
+    cp.tc_norm_gamma = (tc_raw && mode == MODE_L2) ? (double)(d + 16) / 4194304.0 : 0.0;
     FinalizeParams& fb = cp.base;
     fb.vec = idx->vec;
     fb.dp = dp;
@@ -986,6 +1001,7 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
       ta.bias = tc_bias;
       ta.queries = qpad + (size_t)p0 * dp;
       ta.apack = plan.variant == 1 ? (const char*)w->tc_apack.p + tc_pack_bytes(plan, p0) : nullptr;
+      ta.raw = tc_raw;
       ta.work_counter = (int*)w->tc_cnt.p + TC_MAX_COLS;
       ta.nq = nq;
       ta.mode = mode;
@@ -1022,8 +1038,8 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
     stats.path = 3;
     stats.queries_per_pass = plan.n_cols;
     stats.rows_scanned = idx->n_rows;
-    stats.bytes_algorithmic = idx->n_rows * (long long)(plan.bf16 ? idx->dp16 * 2 : d * 4) + idx->n_rows * 4 +
-                              (mask ? idx->n_rows / 8 : 0);
+    stats.bytes_algorithmic = idx->n_rows * (long long)(plan.bf16 ? idx->dp16 * 2 : d * 4) +
+                              (tc_raw ? 0 : idx->n_rows * 4) + (mask ? idx->n_rows / 8 : 0);
     stats.reserved = plan.bf16;
     idx->stats = stats;
     return 0;
@@ -1279,17 +1295,52 @@ int qg_search_batch(qg_index* idx, const float* queries, int q, int dim, int k, 
     if ((rc = w->d_row.ensure(obytes * 8))) break;
     if ((rc = w->d_count.ensure((size_t)q * 4))) break;
     cudaStream_t st = w->stream;
-    std::memcpy(w->h_in.p, queries, qbytes);
-    cudaError_t e = cudaMemcpyAsync(w->d_q.p, w->h_in.p, qbytes, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess && negatives) {
-      std::memcpy((char*)w->h_in.p + qbytes, negatives, qbytes);
-      e = cudaMemcpyAsync(w->d_neg.p, (char*)w->h_in.p + qbytes, qbytes, cudaMemcpyHostToDevice, st);
+    // Large batches are staged and enqueued in chunks: the host copy into pinned memory and the H2D copy
+    // of chunk c + 1 (copy stream) run while the device scans chunk c.
+    constexpr int CHUNK = 2048;
+    const int n_chunks = (q + CHUNK - 1) / CHUNK;
+    if (n_chunks > 1 && !w->copy_stream &&
+        cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      rc = fail(QG_ERR_CUDA, "could not create the copy stream");
+      break;
     }
-    if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, cudaGetErrorString(e)); break; }
-    SearchArgs a{(const float*)w->d_q.p, q, k, filter, negatives ? (const float*)w->d_neg.p : nullptr,
-                 (float*)w->d_dist.p, negatives ? (float*)w->d_negdist.p : nullptr, (long long*)w->d_row.p,
-                 (int*)w->d_count.p, nullptr, 0};
-    if ((rc = search_enqueue(idx, w, a, st))) break;
+    while (n_chunks > 1 && (int)w->chunk_ev.size() < n_chunks) {
+      cudaEvent_t ev = nullptr;
+      if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) break;
+      w->chunk_ev.push_back(ev);
+    }
+    if (n_chunks > 1 && (int)w->chunk_ev.size() < n_chunks) { rc = fail(QG_ERR_CUDA, "could not create events"); break; }
+    cudaError_t e = cudaSuccess;
+    qg_scan_stats total{};
+    for (int c = 0; c < n_chunks && !rc; ++c) {
+      const int q0 = c * CHUNK, qc = std::min(CHUNK, q - q0);
+      const size_t off = (size_t)q0 * dim * 4, cb = (size_t)qc * dim * 4;
+      cudaStream_t cs = n_chunks > 1 ? w->copy_stream : st;
+      std::memcpy((char*)w->h_in.p + off, (const char*)queries + off, cb);
+      e = cudaMemcpyAsync((char*)w->d_q.p + off, (char*)w->h_in.p + off, cb, cudaMemcpyHostToDevice, cs);
+      if (e == cudaSuccess && negatives) {
+        std::memcpy((char*)w->h_in.p + qbytes + off, (const char*)negatives + off, cb);
+        e = cudaMemcpyAsync((char*)w->d_neg.p + off, (char*)w->h_in.p + qbytes + off, cb, cudaMemcpyHostToDevice, cs);
+      }
+      if (e == cudaSuccess && n_chunks > 1) {
+        e = cudaEventRecord(w->chunk_ev[c], cs);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, w->chunk_ev[c], 0);
+      }
+      if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, cudaGetErrorString(e)); break; }
+      SearchArgs a{(const float*)w->d_q.p + (size_t)q0 * dim, qc, k, filter,
+                   negatives ? (const float*)w->d_neg.p + (size_t)q0 * dim : nullptr,
+                   (float*)w->d_dist.p + (size_t)q0 * k, negatives ? (float*)w->d_negdist.p + (size_t)q0 * k : nullptr,
+                   (long long*)w->d_row.p + (size_t)q0 * k, (int*)w->d_count.p + q0, nullptr, 0};
+      if ((rc = search_enqueue(idx, w, a, st))) break;
+      if (c == 0) {
+        total = idx->stats;
+      } else {
+        total.passes += idx->stats.passes;
+        total.kernel_launches += idx->stats.kernel_launches;
+      }
+    }
+    if (rc) break;
+    idx->stats = total;
     char* ho = (char*)w->h_out.p;
     float* h_dist = (float*)ho;
     float* h_neg = (float*)(ho + obytes * 4);
@@ -1536,11 +1587,13 @@ int qg_debug_tc_pass(qg_index* idx, const float* queries, int nq, int k, float* 
   if (idx->n_rows == 0) return fail(QG_ERR_INVALID, "debug_tc_pass: empty index");
   const int mode = scan_mode_of(idx->metric);
   TcPlan plan{};
-  if (mode == MODE_L1 || tc_available() != 0 || tc_plan(idx->dp, nq, idx->use_bf16, &plan) != 0)
+  if (mode == MODE_L1 || tc_available() != 0 ||
+      tc_plan(idx->dp, idx->dim + tc_extra_cols(idx->dim, mode == MODE_L2), nq, idx->use_bf16, &plan) != 0)
     return fail(QG_ERR_UNSUPPORTED, "tensor-core regime not available for this index");
   Workspace* w = ws_acquire(idx);
   if (!w) return fail(QG_ERR_CUDA, "could not create a stream");
   int rc = 0;
+  bool dbg_raw = false;
   do {
     cudaStream_t st = w->stream;
     const int dp = idx->dp, d = idx->dim;
@@ -1557,7 +1610,11 @@ int qg_debug_tc_pass(qg_index* idx, const float* queries, int nq, int k, float* 
     if ((rc = w->tc_cnt.ensure((size_t)(TC_MAX_COLS + 4) * 4))) break;
     if (plan.variant == 1) {
       if ((rc = w->tc_apack.ensure(tc_pack_bytes(plan, nq)))) break;
-      if ((rc = launch_tc_pack(plan, (const float*)w->qpad.p, nq, dp, idx->metric == METRIC_COSINE, w->tc_apack.p, st))) break;
+      dbg_raw = plan.bf16 && idx->n_live == idx->n_rows && idx->n_rows >= plan.tile_rows &&
+                tc_raw_supported(d, mode == MODE_L2);
+      if ((rc = launch_tc_pack(plan, (const float*)w->qpad.p, nq, dp, d, dbg_raw ? tc_extra_cols(d, mode == MODE_L2) : 0,
+                               idx->metric == METRIC_COSINE, w->tc_apack.p, st)))
+        break;
     }
     TcArgs ta{};
     ta.vec = idx->vec;
@@ -1587,6 +1644,7 @@ int qg_debug_tc_pass(qg_index* idx, const float* queries, int nq, int k, float* 
     ta.cand = (uint64_t*)w->tc_cand.p;
     ta.cand_cnt = (int*)w->tc_cnt.p;
     ta.apack = w->tc_apack.p;
+    ta.raw = dbg_raw;
     ta.work_counter = (int*)w->tc_cnt.p + TC_MAX_COLS;
     int launches = 0;
     if ((rc = w->counters.ensure(64 * 8))) break;
@@ -1618,6 +1676,7 @@ int qg_debug_tc_pass(qg_index* idx, const float* queries, int nq, int k, float* 
       cp.tau = (const float*)w->tc_tau.p;
       cp.kp = 32;
       cp.tc_gamma = (plan.bf16 ? 1.02 / 256.0 : 1.02 / 512.0) + (double)d / 4194304.0;
+      cp.tc_norm_gamma = (dbg_raw && mode == MODE_L2) ? (double)(d + 16) / 4194304.0 : 0.0;
       cudaMemsetAsync(w->counters.p, 0, 64 * 8, st);
       cp.dbg = (unsigned long long*)w->counters.p;
       FinalizeParams& fb = cp.base;

@@ -495,30 +495,49 @@ __device__ __forceinline__ float tc_score_upper_bound(int metric, int mode, int 
   return tf;
 }
 
-// Smallest 32-bit score image P such that at least `want` keys have an image <= P: bitwise
-// bisection with one block-wide count per bit — the cost does not depend on n, unlike all-pairs
-// ranking. The keys stay in registers: thread t owns key t, t + FC_THREADS, ... (KEY_NONE beyond
-// n). s_cnt[3] is scratch. All threads of the block call.
+// Smallest 32-bit score image P such that at least `want` keys have an image <= P: radix select, four
+// bits per round (eight block-wide rounds whatever n is, unlike all-pairs ranking). The keys stay in
+// registers: thread t owns key t, t + FC_THREADS, ... (KEY_NONE beyond n). Each round histograms the
+// next digit of the keys that still match the prefix (warp-aggregated with match.any, one shared
+// atomic per distinct digit and warp), then every thread walks the 16 counters itself. s_hist[48] is
+// scratch: three rotating histograms — the one cleared after a round's barrier was last read before
+// that barrier and is next written after the following one. All threads of the block call.
 template <int PER>
-__device__ __forceinline__ uint32_t fc_select_pivot(const uint64_t (&mine)[PER], int want, int* s_cnt) {
+__device__ __forceinline__ uint32_t fc_select_pivot(const uint64_t (&mine)[PER], int want, int* s_hist) {
   const int lane = threadIdx.x & 31;
   uint32_t prefix = 0;
-  if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+  int below = 0;  // keys below the prefix range
+  if (threadIdx.x < 48) s_hist[threadIdx.x] = 0;
   __syncthreads();
-  for (int bit = 31; bit >= 0; --bit) {
-    const int r = 31 - bit;
-    const uint32_t probe = prefix | ((1u << bit) - 1u);
-    int c = 0;
+#pragma unroll 1
+  for (int r = 0; r < 8; ++r) {
+    const int shift = 28 - 4 * r;
+    int* h = s_hist + (r % 3) * 16;
 #pragma unroll
-    for (int s = 0; s < PER; ++s) c += (mine[s] != KEY_NONE) && ((uint32_t)(mine[s] >> 32) <= probe);
-    c = __reduce_add_sync(0xffffffffu, c);
-    int* slot = s_cnt + (r % 3);
-    if (lane == 0 && c) atomicAdd(slot, c);
+    for (int s = 0; s < PER; ++s) {
+      const uint32_t img = (uint32_t)(mine[s] >> 32);
+      // r == 0: every key matches; later: the bits above the digit must equal the prefix
+      const bool active = mine[s] != KEY_NONE && (r == 0 || (img >> (shift + 4)) == (prefix >> (shift + 4)));
+      const int digit = active ? (int)((img >> shift) & 15u) : 16;
+      const unsigned peers = __match_any_sync(0xffffffffu, digit);
+      if (active && lane == __ffs(peers) - 1) atomicAdd(h + digit, __popc(peers));
+    }
     __syncthreads();
-    if (*slot < want) prefix |= (1u << bit);
-    // three rotating counters: the one reset here was last read before this round's barrier and is
-    // next written after the following round's barrier
-    if (threadIdx.x == 0) s_cnt[(r + 2) % 3] = 0;
+    int cum = below, pick = 15, before = below;
+    bool found = false;
+#pragma unroll
+    for (int dgt = 0; dgt < 16; ++dgt) {
+      const int c = h[dgt];
+      if (!found && cum + c >= want) {
+        found = true;
+        pick = dgt;
+        before = cum;
+      }
+      cum += c;
+    }
+    prefix |= (uint32_t)pick << shift;
+    below = before;
+    if (threadIdx.x < 16) s_hist[((r + 2) % 3) * 16 + threadIdx.x] = 0;
   }
   __syncthreads();
   return prefix;
@@ -535,7 +554,7 @@ __global__ void __launch_bounds__(FC_THREADS, 2) finalize_cand_kernel(const Fina
   double* scratch = reinterpret_cast<double*>(ex + cap) + (size_t)warp * (EXACT_SCRATCH_BYTES / 8);
   __shared__ double s_qn2;
   __shared__ int s_extra;
-  __shared__ int s_sel[3];
+  __shared__ int s_sel[48];
   __shared__ float s_E;
 
   long long ts[8];
@@ -581,6 +600,11 @@ __global__ void __launch_bounds__(FC_THREADS, 2) finalize_cand_kernel(const Fina
   ts[nts++] = clock64();  // keys loaded and selected
 
   // ---- exact re-rank of the selected candidates (one warp per candidate) ----
+  // the rows are scattered over the corpus: the warp's later candidates are pulled towards L2 / L1 first
+  for (int c = warp + FC_WARPS; c < nsel; c += FC_WARPS) {
+    const char* rowp = reinterpret_cast<const char*>(p.vec + (size_t)key_row(sel[c]) * p.dp);
+    if (lane * 128 < p.dp * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + lane * 128));
+  }
   for (int c = warp; c < nsel; c += FC_WARPS) {
     const uint32_t row = key_row(sel[c]);
     const float dist = exact_distance_warp(p.metric, p.arith, qv, p.vec + (size_t)row * p.dp, p.d, scratch);
@@ -600,8 +624,13 @@ __global__ void __launch_bounds__(FC_THREADS, 2) finalize_cand_kernel(const Fina
       if (r == k - 1) s_E = key_score(me);
     }
     __syncthreads();
-    const float T = tc_score_upper_bound(p.metric, p.mode, p.cosine, s_E, cp.tc_gamma, (double)p.gamma, s_qn2,
-                                         (double)(p.max_norm2 ? *p.max_norm2 : 0.f));
+    float T = tc_score_upper_bound(p.metric, p.mode, p.cosine, s_E, cp.tc_gamma, (double)p.gamma, s_qn2,
+                                   (double)(p.max_norm2 ? *p.max_norm2 : 0.f));
+    if (cp.tc_norm_gamma > 0.0) {  // raw L2 scan: the norm term is accumulated by the tensor core as well
+      const double t2 = (double)T + cp.tc_norm_gamma * (double)(p.max_norm2 ? *p.max_norm2 : 0.f);
+      T = (float)t2;
+      if ((double)T < t2) T = nextafterf(T, __int_as_float(0x7f800000));
+    }
     if (!(T <= tau) && !all_admitted) certified = false;
     // every further candidate whose scan score is <= T may still belong to the exact top-k
 #pragma unroll

@@ -448,7 +448,8 @@ __host__ __device__ constexpr int ts_rows(int nblk) { return nblk == 2 ? 64 : 12
 struct TsKParams {
   long long n_rows;
   long long n_tiles;
-  int kb, stages, nq, nblk;
+  long long n_sample_from;  // tiles the sample is drawn from (raw scan: full tiles only, the out-of-bounds rows of a partial tile read as zeros)
+  int kb, ksteps, a_cols, stages, nq, nblk;
   uint32_t idesc;
   int cosine;
   const float* bias;   // [rows padded to 128] additive row term: |x|^2 (L2) or 1 (dot); +inf = row excluded
@@ -474,8 +475,10 @@ __host__ __device__ inline TsSmem ts_smem_layout(int stages, int kb, int rows) {
   s.off_sc = s.off_bias + TS_XS * rows * 4;
   s.off_bars = s.off_sc + TS_XS * rows * 4;
   s.off_tmem = s.off_bars + (2 * stages + 2 * TS_MAX_ACC + 2 * TS_XS + 1) * 8;
-  s.off_tags = s.off_tmem + 16;  // int ring_tag[stages] (1 = tile, 0 = end of work), int xs_work[TS_XS] (work index, -1 = end)
-  s.total = s.off_tags + (stages + TS_XS) * 4;
+  // int ring_tag[stages], xs_work[TS_XS], acc_work[TS_MAX_ACC]: the work index travelling with a ring
+  // stage / row-term slot / accumulator buffer (-1 = end of work)
+  s.off_tags = s.off_tmem + 16;
+  s.total = s.off_tags + (stages + TS_XS + TS_MAX_ACC) * 4;
   return s;
 }
 
@@ -517,7 +520,10 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 // KB > 0: compile-time number of 128-byte k-blocks per row (MMA issue loop fully unrolled); KB == 0: p.kb.
 // BF16: the corpus stream is the bf16 copy of the index (64 elements per k-block, kind::f16 MMA) and the
 // resident queries are rounded to bf16 — the scores only select candidates, the re-rank stays exact.
-template <int MODE, bool SAMPLE, int NBLK, int KB, bool BF16>
+// RAW (BF16 only, no mask): the bf16 rows carry the pieces of -|x|^2 / 2 behind the vector and the
+// queries carry ones there, so the accumulator already holds q.x - |x|^2 / 2 (L2) or q.x (dot, cosine on
+// normalised rows): no row-term ring, the epilogue is a max tree over the raw accumulator.
+template <int MODE, bool SAMPLE, int NBLK, int KB, bool BF16, bool RAW>
 __global__ void __launch_bounds__(TS_THREADS, 1)
     tc_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const TsKParams p) {
   constexpr int ROWS = ts_rows(NBLK);
@@ -542,14 +548,16 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.off_tmem);
   volatile int* ring_tag = reinterpret_cast<volatile int*>(smem + L.off_tags);
   volatile int* xs_work = ring_tag + S;
+  volatile int* acc_work = xs_work + TS_XS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int a_cols = kb * TC_KBLOCK;             // TMEM columns of one query block
+  const int a_cols = p.a_cols;                   // TMEM columns of one query block
+  const int ksteps = p.ksteps;                   // MMA k-steps per row (the last k-block may be partial)
   const int tile_bytes = kb * KBLOCK_BYTES;      // one ring stage = one whole tile
   const int d_off = NBLK * a_cols;               // first accumulator column
   const int n_acc = min(TS_MAX_ACC, (512 - d_off) / (NBLK * ROWS));  // accumulator buffers of NBLK * ROWS columns
   const long long n_work = SAMPLE ? (long long)p.n_sample : p.n_tiles;
-  auto tile_of = [&](long long w) -> long long { return SAMPLE ? (w * p.n_tiles) / p.n_sample : w; };
+  auto tile_of = [&](long long w) -> long long { return SAMPLE ? (w * p.n_sample_from) / p.n_sample : w; };
 
   // the first two tile claims of the main scan go out before anything else (warp 0, lane 0)
   int claim_a = 0, claim_b = 0;
@@ -603,28 +611,30 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
     // the row-term ring (one per epilogue half).
     auto push = [&](long long w, bool live, bool to_ring) {
       const long long tile = live ? tile_of(w) : 0;
-      const int xb = (int)(it % TS_XS);
-      const uint32_t xphase = (uint32_t)((it / TS_XS) & 1);
-      clk.start();
-      mbar_wait(&xs_empty[xb], xphase ^ 1u);
-      clk.lap(1);
-      if (elect_one()) {
-        xs_work[xb] = live ? (int)w : -1;
-        if (live) {
-          mbar_arrive_expect_tx(&xs_full[xb], xs_bytes);
-          bulk_g2s(xs_bias + xb * ROWS, p.bias + tile * ROWS, ROWS * 4, &xs_full[xb]);
-          if (with_sc) bulk_g2s(xs_sc + xb * ROWS, p.sc + tile * ROWS, ROWS * 4, &xs_full[xb]);
-        } else {
-          mbar_arrive(&xs_full[xb]);
+      if (!RAW) {
+        const int xb = (int)(it % TS_XS);
+        const uint32_t xphase = (uint32_t)((it / TS_XS) & 1);
+        clk.start();
+        mbar_wait(&xs_empty[xb], xphase ^ 1u);
+        clk.lap(1);
+        if (elect_one()) {
+          xs_work[xb] = live ? (int)w : -1;
+          if (live) {
+            mbar_arrive_expect_tx(&xs_full[xb], xs_bytes);
+            bulk_g2s(xs_bias + xb * ROWS, p.bias + tile * ROWS, ROWS * 4, &xs_full[xb]);
+            if (with_sc) bulk_g2s(xs_sc + xb * ROWS, p.sc + tile * ROWS, ROWS * 4, &xs_full[xb]);
+          } else {
+            mbar_arrive(&xs_full[xb]);
+          }
         }
+        __syncwarp();
       }
-      __syncwarp();
       if (to_ring) {
         clk.start();
         mbar_wait(&empty[stage], phase ^ 1u);
         clk.lap(2);
         if (elect_one()) {
-          ring_tag[stage] = live ? 1 : 0;
+          ring_tag[stage] = live ? (int)w : -1;
           if (live) {
             unsigned char* dst = ring + (size_t)stage * tile_bytes;
             mbar_arrive_expect_tx(&full[stage], (uint32_t)tile_bytes);
@@ -661,7 +671,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
       }
     }
     push(0, false, true);
-    push(0, false, false);
+    if (!RAW) push(0, false, false);
     if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0) {
       p.dbg[0] = (unsigned long long)(clock64() - t_prod_begin);
     }
@@ -683,11 +693,16 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
       clk.start();
       mbar_wait(&full[stage], phase);
       clk.lap(5);
-      if (ring_tag[stage] == 0) break;  // end of work
+      const int wtag = ring_tag[stage];
+      if (wtag < 0) break;  // end of work
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
       clk.lap(4);
       tc_fence_after();
       if (elect_one()) {
+        if (RAW) {  // the work index travels with the accumulator buffer
+          acc_work[acc] = wtag;
+          __threadfence_block();
+        }
         const uint32_t d0 = tmem_base + (uint32_t)(d_off + acc * NBLK * ROWS);
         const uint32_t d1 = d0 + ROWS;
         const uint64_t bdesc = desc0 + (uint64_t)((uint32_t)stage * (uint32_t)(tile_bytes >> 4));
@@ -696,14 +711,15 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
           for (int kbi = 0; kbi < (KB > 0 ? KB : 1); ++kbi) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
+              if (kbi * 4 + k >= ksteps) continue;
               const uint64_t bd = bdesc + (uint64_t)(kbi * (KBLOCK_BYTES >> 4) + k * 2);
               const uint32_t aa = tmem_base + (uint32_t)(kbi * TC_KBLOCK + k * 8);
               if (BF16) {
                 umma_bf16_ts(d0, aa, bd, idesc, (kbi | k) != 0 ? 1u : 0u);
-                if (NBLK == 2) umma_bf16_ts(d1, aa + (uint32_t)(KB * TC_KBLOCK), bd, idesc, (kbi | k) != 0 ? 1u : 0u);
+                if (NBLK == 2) umma_bf16_ts(d1, aa + (uint32_t)a_cols, bd, idesc, (kbi | k) != 0 ? 1u : 0u);
               } else {
                 umma_tf32_ts(d0, aa, bd, idesc, (kbi | k) != 0 ? 1u : 0u);
-                if (NBLK == 2) umma_tf32_ts(d1, aa + (uint32_t)(KB * TC_KBLOCK), bd, idesc, (kbi | k) != 0 ? 1u : 0u);
+                if (NBLK == 2) umma_tf32_ts(d1, aa + (uint32_t)a_cols, bd, idesc, (kbi | k) != 0 ? 1u : 0u);
               }
             }
           }
@@ -713,6 +729,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
           for (int kbi = 0; kbi < kb; ++kbi) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
+              if (kbi * 4 + k >= ksteps) continue;
               if (BF16) {
                 umma_bf16_ts(d0, a0 + k * 8, bd0 + (uint64_t)(k * 2), idesc, (kbi | k) != 0 ? 1u : 0u);
                 if (NBLK == 2) umma_bf16_ts(d1, a0 + a_cols + k * 8, bd0 + (uint64_t)(k * 2), idesc, (kbi | k) != 0 ? 1u : 0u);
@@ -736,6 +753,22 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
       if (++acc == n_acc) {
         acc = 0;
         acc_phase ^= 1u;
+      }
+    }
+    if (RAW) {
+      // end of work for the two epilogue halves: the next two accumulator buffers carry the tag
+      for (int e = 0; e < 2; ++e) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        if (elect_one()) {
+          acc_work[acc] = -1;
+          __threadfence_block();
+          mbar_arrive(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++acc == n_acc) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
       }
     }
     if (lane == 0) dbg_stamp(p.dbg, 5);
@@ -790,6 +823,13 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
 
     float tau_me = -__int_as_float(0x7f800000);
     if (!SAMPLE && q < p.nq) tau_me = __ldg(p.tau + q);
+    // raw scan: a row is admitted when its accumulator value a' >= theta. L2: score = -2 a' exactly, so
+    // theta = -tau / 2; dot / cosine: score = 1 - a' is rounded, so theta is lowered by a few ulps (a
+    // few more rows are admitted; every admitted row carries its own score).
+    float theta_me = __int_as_float(0x7f800000);
+    if (RAW && !SAMPLE && q < p.nq)
+      theta_me = MODE == MODE_L2 ? -0.5f * tau_me : (1.f - tau_me) - 4e-7f * (1.f + fabsf(tau_me));
+    auto raw_score = [](float a) -> float { return MODE == MODE_L2 ? -2.f * a : 1.f - a; };
     const bool has_sc = MODE != MODE_L2 && p.sc != nullptr;
     const uint32_t bias_s = smem_u32(xs_bias), sc_s = smem_u32(xs_sc);
     // a lane's hit is parked in registers and published one tile later, so the round trip of the
@@ -806,13 +846,21 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
       const int xb = (int)(it % TS_XS);
       const uint32_t xphase = (uint32_t)((it / TS_XS) & 1);
       clk.start();
-      mbar_wait(&xs_full[xb], xphase);
-      const long long w = xs_work[xb];
-      if (w < 0) break;  // end of work
+      long long w;
+      if (RAW) {
+        mbar_wait(&tmem_full[acc], acc_phase);
+        w = acc_work[acc];
+        if (w < 0) break;  // end of work
+        clk.lap(2);
+      } else {
+        mbar_wait(&xs_full[xb], xphase);
+        w = xs_work[xb];
+        if (w < 0) break;  // end of work
+        clk.lap(1);
+        mbar_wait(&tmem_full[acc], acc_phase);
+        clk.lap(2);
+      }
       const long long tile = tile_of(w);
-      clk.lap(1);
-      mbar_wait(&tmem_full[acc], acc_phase);
-      clk.lap(2);
       if (it == 0 && warp == 4 && lane == 0) dbg_stamp(p.dbg, 4);
       tc_fence_after();
       const uint32_t d_addr = tmem_base + lane_base + (uint32_t)(d_off + (acc * NBLK + blk) * ROWS);
@@ -831,69 +879,123 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
         acc -= n_acc;
         acc_phase ^= 1u;
       }
-      // scores of the warp's NCH chunks (in place) and their minima: independent chains, one vote per tile
-      float cmin[NCH];
+      float tile_min;  // smallest score of the warp's rows of this tile (sample stage)
+      if (RAW) {
+        // the accumulator is the (negated, scaled) score: a max tree per chunk, one vote per tile
+        float cmax[NCH];
 #pragma unroll
-      for (int ci = 0; ci < NCH; ++ci) {
-        const uint32_t boff = (uint32_t)((xb * ROWS + chunk_of(ci) * 16) * 4);
-        uint32_t(&v)[16] = araw[ci];
+        for (int ci = 0; ci < NCH; ++ci) {
+          const uint32_t(&v)[16] = araw[ci];
+          float m = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 bb = lds128(bias_s + boff + j4 * 16);
-          const float a0 = __uint_as_float(v[j4 * 4 + 0]), a1 = __uint_as_float(v[j4 * 4 + 1]);
-          const float a2 = __uint_as_float(v[j4 * 4 + 2]), a3 = __uint_as_float(v[j4 * 4 + 3]);
-          float r0, r1, r2, r3;
-          if (MODE == MODE_L2) {
-            r0 = fmaf(-2.f, a0, bb.x);
-            r1 = fmaf(-2.f, a1, bb.y);
-            r2 = fmaf(-2.f, a2, bb.z);
-            r3 = fmaf(-2.f, a3, bb.w);
-          } else {
-            float4 ss = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (has_sc) ss = lds128(sc_s + boff + j4 * 16);
-            r0 = fmaf(-a0, ss.x, bb.x);
-            r1 = fmaf(-a1, ss.y, bb.y);
-            r2 = fmaf(-a2, ss.z, bb.z);
-            r3 = fmaf(-a3, ss.w, bb.w);
-          }
-          v[j4 * 4 + 0] = __float_as_uint(r0);
-          v[j4 * 4 + 1] = __float_as_uint(r1);
-          v[j4 * 4 + 2] = __float_as_uint(r2);
-          v[j4 * 4 + 3] = __float_as_uint(r3);
-          const float m4 = fminf(fminf(r0, r1), fminf(r2, r3));
-          cmin[ci] = j4 == 0 ? m4 : fminf(cmin[ci], m4);
+          for (int j = 2; j < 16; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+          cmax[ci] = m;
         }
-      }
-      float tile_min = cmin[0];
+        float tile_max = cmax[0];
 #pragma unroll
-      for (int ci = 1; ci < NCH; ++ci) tile_min = fminf(tile_min, cmin[ci]);
-      if (!SAMPLE) {
-        const bool lane_hit = tile_min <= tau_me;
-        if (__any_sync(0xffffffffu, lane_hit)) {
-          if (lane_hit) {  // usually a single lane with a single admitted row
+        for (int ci = 1; ci < NCH; ++ci) tile_max = fmaxf(tile_max, cmax[ci]);
+        tile_min = raw_score(tile_max);
+        if (!SAMPLE) {
+          const bool lane_hit = tile_max >= theta_me;
+          if (__any_sync(0xffffffffu, lane_hit)) {
+            if (lane_hit) {  // usually a single lane with a single admitted row
 #pragma unroll
-            for (int ci = 0; ci < NCH; ++ci) {
-              if (cmin[ci] <= tau_me) {
-                // branch-free count of admitted rows of the chunk and the index of the last one; a
-                // single admitted row is the chunk minimum itself
-                int n_hit = 0, j_hit = 0;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const bool h = __uint_as_float(araw[ci][j]) <= tau_me;
-                  n_hit += h ? 1 : 0;
-                  j_hit = h ? j : j_hit;
-                }
-                const uint32_t row0 = (uint32_t)(tile * ROWS + chunk_of(ci) * 16);
-                if (n_hit == 1 && !has_pend) {
-                  pend_key = make_key(cmin[ci], row0 + (uint32_t)j_hit);
-                  has_pend = true;
-                } else {  // several admitted rows in one tile for this query (rare): publish directly
+              for (int ci = 0; ci < NCH; ++ci) {
+                if (cmax[ci] >= theta_me) {
+                  int n_hit = 0, j_hit = 0;
 #pragma unroll
                   for (int j = 0; j < 16; ++j) {
-                    const float vj = __uint_as_float(araw[ci][j]);
-                    if (vj <= tau_me) {
-                      const int pos = atomicAdd(p.cand_cnt + q, 1);
-                      if (pos < TC_CAND_CAP) p.cand[(size_t)q * TC_CAND_CAP + pos] = make_key(vj, row0 + (uint32_t)j);
+                    const bool h = __uint_as_float(araw[ci][j]) >= theta_me;
+                    n_hit += h ? 1 : 0;
+                    j_hit = h ? j : j_hit;
+                  }
+                  const long long row0 = tile * ROWS + chunk_of(ci) * 16;
+                  if (n_hit == 1 && !has_pend) {
+                    if (row0 + j_hit < p.n_rows) {  // rows past the end of the corpus read as zeros
+                      pend_key = make_key(raw_score(cmax[ci]), (uint32_t)(row0 + j_hit));
+                      has_pend = true;
+                    }
+                  } else {  // several admitted rows in one tile for this query (rare): publish directly
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                      const float aj = __uint_as_float(araw[ci][j]);
+                      if (aj >= theta_me && row0 + j < p.n_rows) {
+                        const int pos = atomicAdd(p.cand_cnt + q, 1);
+                        if (pos < TC_CAND_CAP)
+                          p.cand[(size_t)q * TC_CAND_CAP + pos] = make_key(raw_score(aj), (uint32_t)(row0 + j));
+                      }
+                    }
+                  }
+                }
+              }
+            }
+          }
+        }
+      } else {
+        // scores of the warp's NCH chunks (in place) and their minima: independent chains, one vote per tile
+        float cmin[NCH];
+  #pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) {
+          const uint32_t boff = (uint32_t)((xb * ROWS + chunk_of(ci) * 16) * 4);
+          uint32_t(&v)[16] = araw[ci];
+  #pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 bb = lds128(bias_s + boff + j4 * 16);
+            const float a0 = __uint_as_float(v[j4 * 4 + 0]), a1 = __uint_as_float(v[j4 * 4 + 1]);
+            const float a2 = __uint_as_float(v[j4 * 4 + 2]), a3 = __uint_as_float(v[j4 * 4 + 3]);
+            float r0, r1, r2, r3;
+            if (MODE == MODE_L2) {
+              r0 = fmaf(-2.f, a0, bb.x);
+              r1 = fmaf(-2.f, a1, bb.y);
+              r2 = fmaf(-2.f, a2, bb.z);
+              r3 = fmaf(-2.f, a3, bb.w);
+            } else {
+              float4 ss = make_float4(1.f, 1.f, 1.f, 1.f);
+              if (has_sc) ss = lds128(sc_s + boff + j4 * 16);
+              r0 = fmaf(-a0, ss.x, bb.x);
+              r1 = fmaf(-a1, ss.y, bb.y);
+              r2 = fmaf(-a2, ss.z, bb.z);
+              r3 = fmaf(-a3, ss.w, bb.w);
+            }
+            v[j4 * 4 + 0] = __float_as_uint(r0);
+            v[j4 * 4 + 1] = __float_as_uint(r1);
+            v[j4 * 4 + 2] = __float_as_uint(r2);
+            v[j4 * 4 + 3] = __float_as_uint(r3);
+            const float m4 = fminf(fminf(r0, r1), fminf(r2, r3));
+            cmin[ci] = j4 == 0 ? m4 : fminf(cmin[ci], m4);
+          }
+        }
+        tile_min = cmin[0];
+  #pragma unroll
+        for (int ci = 1; ci < NCH; ++ci) tile_min = fminf(tile_min, cmin[ci]);
+        if (!SAMPLE) {
+          const bool lane_hit = tile_min <= tau_me;
+          if (__any_sync(0xffffffffu, lane_hit)) {
+            if (lane_hit) {  // usually a single lane with a single admitted row
+  #pragma unroll
+              for (int ci = 0; ci < NCH; ++ci) {
+                if (cmin[ci] <= tau_me) {
+                  // branch-free count of admitted rows of the chunk and the index of the last one; a
+                  // single admitted row is the chunk minimum itself
+                  int n_hit = 0, j_hit = 0;
+  #pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    const bool h = __uint_as_float(araw[ci][j]) <= tau_me;
+                    n_hit += h ? 1 : 0;
+                    j_hit = h ? j : j_hit;
+                  }
+                  const uint32_t row0 = (uint32_t)(tile * ROWS + chunk_of(ci) * 16);
+                  if (n_hit == 1 && !has_pend) {
+                    pend_key = make_key(cmin[ci], row0 + (uint32_t)j_hit);
+                    has_pend = true;
+                  } else {  // several admitted rows in one tile for this query (rare): publish directly
+  #pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                      const float vj = __uint_as_float(araw[ci][j]);
+                      if (vj <= tau_me) {
+                        const int pos = atomicAdd(p.cand_cnt + q, 1);
+                        if (pos < TC_CAND_CAP) p.cand[(size_t)q * TC_CAND_CAP + pos] = make_key(vj, row0 + (uint32_t)j);
+                      }
                     }
                   }
                 }
@@ -912,8 +1014,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
           has_pend = false;
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&xs_empty[xb]);
+      if (!RAW) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xs_empty[xb]);
+      }
       clk.lap(5);
       if (SAMPLE && q < p.nq) {
         // minimum score of this tile for this query: sample[q][w] (NBLK == 2) or sample[q][w][group]
@@ -1023,9 +1127,9 @@ int launch_tc_bias(const uint32_t* mask, const float* norm2, long long n_rows, l
 //   apack[pass][blk][c][r][j] = 32-bit column c*16+j of query pass*n_cols + blk*128 + r
 // (fp32 value, or two consecutive bf16 values, low half first; cosine: pre-scaled by 1/|q|; zero
 // beyond nq and beyond dp). One warp per query slot.
-__global__ void __launch_bounds__(256) tc_pack_kernel(const float* __restrict__ queries, int nq, int dp, int n_cols,
-                                                      int a_cols, int bf16, int cosine, uint32_t* __restrict__ apack,
-                                                      long long n_slots) {
+__global__ void __launch_bounds__(256) tc_pack_kernel(const float* __restrict__ queries, int nq, int dp, int d, int ones,
+                                                      int n_cols, int a_cols, int bf16, int cosine,
+                                                      uint32_t* __restrict__ apack, long long n_slots) {
   const int lane = threadIdx.x & 31;
   const long long slot = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (slot >= n_slots) return;
@@ -1047,8 +1151,10 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const float* __restrict__ 
     uint32_t bits = 0;
     if (valid) {
       if (bf16) {
+        // elements d .. d + ones - 1 face the norm columns of the bf16 rows (raw L2 scan)
         const int e = col * 2;
-        const float a = e < dp ? qv[e] * rnq : 0.f, b = e + 1 < dp ? qv[e + 1] * rnq : 0.f;
+        const float a = e < d ? qv[e] * rnq : (e < d + ones ? 1.f : 0.f);
+        const float b = e + 1 < d ? qv[e + 1] * rnq : (e + 1 < d + ones ? 1.f : 0.f);
         const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
         bits = *reinterpret_cast<const uint32_t*>(&h);
       } else {
@@ -1061,38 +1167,61 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const float* __restrict__ 
 
 size_t tc_pack_bytes(const TcPlan& plan, int nq) {
   const long long passes = (nq + plan.n_cols - 1) / plan.n_cols;
-  return (size_t)passes * plan.n_cols * plan.kb * TC_KBLOCK * 4;
+  return (size_t)passes * plan.n_cols * plan.a_cols * 4;
 }
 
-int launch_tc_pack(const TcPlan& plan, const float* queries, int nq, int dp, int cosine, void* apack, cudaStream_t st) {
+int launch_tc_pack(const TcPlan& plan, const float* queries, int nq, int dp, int d, int ones, int cosine, void* apack,
+                   cudaStream_t st) {
   if (plan.variant != 1 || nq <= 0) return 0;
   const long long passes = (nq + plan.n_cols - 1) / plan.n_cols;
   const long long n_slots = passes * plan.n_cols;
-  tc_pack_kernel<<<(int)((n_slots + 7) / 8), 256, 0, st>>>(queries, nq, dp, plan.n_cols, plan.kb * TC_KBLOCK, plan.bf16,
-                                                           cosine, (uint32_t*)apack, n_slots);
+  tc_pack_kernel<<<(int)((n_slots + 7) / 8), 256, 0, st>>>(queries, nq, dp, d, plan.bf16 ? ones : 0, plan.n_cols,
+                                                           plan.a_cols, plan.bf16, cosine, (uint32_t*)apack, n_slots);
   QG_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-// bf16 copy of the corpus for the tensor-core stream: round to nearest even, rows padded to dp16.
+// bf16 copy of the corpus for the tensor-core stream (round to nearest even): the d vector elements
+// (cosine: scaled by 1/|x|), then for L2 the three bf16 pieces of -|x|^2 / 2 (their sum is exact),
+// zero padded to dp16.
 __global__ void __launch_bounds__(256) tc_to_bf16_kernel(const float* __restrict__ vec, long long row0, long long n,
-                                                         int dp, int dp16, __nv_bfloat16* __restrict__ out) {
+                                                         int dp, int d, int dp16, const float* __restrict__ norm2,
+                                                         const float* __restrict__ inv_norm,
+                                                         __nv_bfloat16* __restrict__ out) {
   const long long total = n * (dp16 / 2);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / (dp16 / 2);
     const int c = (int)(i - r * (dp16 / 2)) * 2;
     const float* src = vec + (size_t)(row0 + r) * dp;
-    const float a = c < dp ? src[c] : 0.f, b = c + 1 < dp ? src[c + 1] : 0.f;
-    reinterpret_cast<__nv_bfloat162*>(out + (size_t)(row0 + r) * dp16)[c / 2] = __floats2bfloat162_rn(a, b);
+    const float sc = inv_norm ? __ldg(inv_norm + row0 + r) : 1.f;
+    float v[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int e = c + t;
+      float x = 0.f;
+      if (e < d) {
+        x = src[e] * sc;
+      } else if (norm2 != nullptr && e < d + 3) {
+        const float s0 = -0.5f * __ldg(norm2 + row0 + r);
+        const float hi = __bfloat162float(__float2bfloat16_rn(s0));
+        const float r1 = s0 - hi;
+        const float mid = __bfloat162float(__float2bfloat16_rn(r1));
+        x = e == d ? hi : (e == d + 1 ? mid : r1 - mid);
+      }
+      v[t] = x;
+    }
+    reinterpret_cast<__nv_bfloat162*>(out + (size_t)(row0 + r) * dp16)[c / 2] = __floats2bfloat162_rn(v[0], v[1]);
   }
 }
 
-int launch_tc_to_bf16(const float* vec, long long row0, long long n, int dp, int dp16, void* out, cudaStream_t st) {
+int launch_tc_to_bf16(const float* vec, long long row0, long long n, int dp, int d, int dp16, const float* norm2,
+                      const float* inv_norm, void* out, cudaStream_t st) {
   if (n <= 0) return 0;
   long long blocks = (n * (dp16 / 2) + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  tc_to_bf16_kernel<<<(int)blocks, 256, 0, st>>>(vec, row0, n, dp, dp16, reinterpret_cast<__nv_bfloat16*>(out));
+  tc_to_bf16_kernel<<<(int)blocks, 256, 0, st>>>(vec, row0, n, dp, d, dp16, norm2, inv_norm,
+                                                 reinterpret_cast<__nv_bfloat16*>(out));
   QG_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -1132,16 +1261,19 @@ static int encode_map(CUtensorMap* map, const void* base, long long rows, int dp
 }
 
 
-int tc_plan(int dp, int nq, bool bf16, TcPlan* out) {
+int tc_plan(int dp, int d16, int nq, bool bf16, TcPlan* out) {
   if (dp < 4 || dp % 4 != 0) return -1;
   int kb = (dp + TC_KBLOCK - 1) / TC_KBLOCK;
   const int budget = 227 * 1024 - 1024;  // alignment slack
   out->bf16 = 0;
   if (bf16) {
-    // bf16 stream: 64 elements per 128-byte k-block; rows of the bf16 copy are padded to 8 elements
-    const int kb16 = (dp + 63) / 64;
-    if (kb16 <= 8) {
-      const int nblk = (kb16 <= 4 && nq > 128) ? 2 : 1;
+    // bf16 stream: 16 elements per MMA k-step, 64 per 128-byte k-block; d16 counts the vector and the
+    // norm columns. 512 TMEM columns = nblk * a_cols (queries) + at least two accumulator buffers.
+    const int ksteps = (d16 + 15) / 16;
+    const int kb16 = (ksteps + 3) / 4;
+    const int a_cols = (ksteps * 8 + 15) & ~15;
+    if (a_cols <= 256) {
+      const int nblk = (a_cols <= 128 && nq > 128) ? 2 : 1;
       const int rows = ts_rows(nblk);
       int stages = (budget - ts_smem_layout(0, kb16, rows).total) / (kb16 * rows * TS_KSTEP_BYTES + 16);
       stages = std::min(stages, 12);
@@ -1151,6 +1283,8 @@ int tc_plan(int dp, int nq, bool bf16, TcPlan* out) {
         out->nblk = nblk;
         out->n_cols = 128 * nblk;
         out->kb = kb16;
+        out->ksteps = ksteps;
+        out->a_cols = a_cols;
         out->stages = stages;
         out->tile_rows = rows;
         out->sample_vals = nblk == 2 ? 1 : 2;
@@ -1171,6 +1305,8 @@ int tc_plan(int dp, int nq, bool bf16, TcPlan* out) {
       out->nblk = nblk;
       out->n_cols = 128 * nblk;
       out->kb = kb;
+      out->ksteps = kb * 4;
+      out->a_cols = kb * TC_KBLOCK;
       out->stages = stages;
       out->tile_rows = rows;
       out->sample_vals = nblk == 2 ? 1 : 2;
@@ -1215,26 +1351,31 @@ static int set_attr_one() {
 
 typedef void (*TsKernelFn)(const CUtensorMap, const TsKParams);
 
-template <int MODE, bool SAMPLE, int NBLK, bool BF16>
+template <int MODE, bool SAMPLE, int NBLK, bool BF16, bool RAW>
 static TsKernelFn ts_kernel_kb(int kb) {
   switch (kb) {
-    case 1: return tc_ts_kernel<MODE, SAMPLE, NBLK, 1, BF16>;
-    case 2: return tc_ts_kernel<MODE, SAMPLE, NBLK, 2, BF16>;
-    case 3: return tc_ts_kernel<MODE, SAMPLE, NBLK, 3, BF16>;
-    case 4: return tc_ts_kernel<MODE, SAMPLE, NBLK, 4, BF16>;
-    default: return tc_ts_kernel<MODE, SAMPLE, NBLK, 0, BF16>;
+    case 1: return tc_ts_kernel<MODE, SAMPLE, NBLK, 1, BF16, RAW>;
+    case 2: return tc_ts_kernel<MODE, SAMPLE, NBLK, 2, BF16, RAW>;
+    case 3: return tc_ts_kernel<MODE, SAMPLE, NBLK, 3, BF16, RAW>;
+    case 4: return tc_ts_kernel<MODE, SAMPLE, NBLK, 4, BF16, RAW>;
+    default: return tc_ts_kernel<MODE, SAMPLE, NBLK, 0, BF16, RAW>;
   }
 }
 
-template <int MODE, bool BF16>
+template <int MODE, bool BF16, bool RAW>
 static TsKernelFn ts_kernel_ms(bool sample, int nblk, int kb) {
-  if (sample) return nblk == 2 ? ts_kernel_kb<MODE, true, 2, BF16>(kb) : ts_kernel_kb<MODE, true, 1, BF16>(kb);
-  return nblk == 2 ? ts_kernel_kb<MODE, false, 2, BF16>(kb) : ts_kernel_kb<MODE, false, 1, BF16>(kb);
+  if (sample) return nblk == 2 ? ts_kernel_kb<MODE, true, 2, BF16, RAW>(kb) : ts_kernel_kb<MODE, true, 1, BF16, RAW>(kb);
+  return nblk == 2 ? ts_kernel_kb<MODE, false, 2, BF16, RAW>(kb) : ts_kernel_kb<MODE, false, 1, BF16, RAW>(kb);
 }
 
-static TsKernelFn ts_kernel(int mode, bool sample, int nblk, int kb, bool bf16) {
-  if (mode == MODE_L2) return bf16 ? ts_kernel_ms<MODE_L2, true>(sample, nblk, kb) : ts_kernel_ms<MODE_L2, false>(sample, nblk, kb);
-  return bf16 ? ts_kernel_ms<MODE_DOT, true>(sample, nblk, kb) : ts_kernel_ms<MODE_DOT, false>(sample, nblk, kb);
+// raw kernels exist for the bf16 stream only
+static TsKernelFn ts_kernel(int mode, bool sample, int nblk, int kb, bool bf16, bool raw) {
+  if (mode == MODE_L2) {
+    if (!bf16) return ts_kernel_ms<MODE_L2, false, false>(sample, nblk, kb);
+    return raw ? ts_kernel_ms<MODE_L2, true, true>(sample, nblk, kb) : ts_kernel_ms<MODE_L2, true, false>(sample, nblk, kb);
+  }
+  if (!bf16) return ts_kernel_ms<MODE_DOT, false, false>(sample, nblk, kb);
+  return raw ? ts_kernel_ms<MODE_DOT, true, true>(sample, nblk, kb) : ts_kernel_ms<MODE_DOT, true, false>(sample, nblk, kb);
 }
 
 static int set_attr_ts() {
@@ -1242,8 +1383,8 @@ static int set_attr_ts() {
     for (int sample = 0; sample < 2; ++sample)
       for (int nblk = 1; nblk <= 2; ++nblk)
         for (int kb = 0; kb <= 4; ++kb)
-          for (int bf = 0; bf < 2; ++bf)
-            QG_CUDA_OK(cudaFuncSetAttribute(ts_kernel(mode, sample != 0, nblk, kb == 0 ? 9 : kb, bf != 0),
+          for (int bf = 0; bf < 3; ++bf)  // tf32, bf16 with row terms, bf16 raw
+            QG_CUDA_OK(cudaFuncSetAttribute(ts_kernel(mode, sample != 0, nblk, kb == 0 ? 9 : kb, bf != 0, bf == 2),
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   return 0;
 }
@@ -1265,6 +1406,7 @@ static int launch_ts_pass(const TcPlan& plan, const TcArgs& a, int sm_count, cud
                           const TcStageHook* hook) {
   const int rows = ts_rows(plan.nblk);
   const bool bf16 = plan.bf16 != 0;
+  const bool raw = bf16 && a.raw != 0;
   CUtensorMap tm_x;
   if (bf16) {
     if (a.vec16 == nullptr) return fail(1, "tensor-core bf16 pass needs the bf16 copy of the corpus");
@@ -1275,15 +1417,19 @@ static int launch_ts_pass(const TcPlan& plan, const TcArgs& a, int sm_count, cud
   TsKParams p{};
   p.n_rows = a.n_rows;
   p.n_tiles = (a.n_rows + rows - 1) / rows;
+  p.n_sample_from = raw ? a.n_rows / rows : p.n_tiles;
   p.kb = plan.kb;
+  p.ksteps = plan.ksteps;
+  p.a_cols = plan.a_cols;
   p.stages = plan.stages;
   p.nq = a.nq;
   p.nblk = plan.nblk;
+  if (raw && p.n_sample_from <= 0) return fail(1, "raw tensor-core scan needs at least one full tile");
   const uint32_t fmt = bf16 ? 1u : 2u;  // F16F32Format: BF16 = 1, TF32 = 2
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(rows >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   p.cosine = a.cosine;
   p.bias = a.bias;
-  p.sc = a.cosine ? a.inv_norm : nullptr;
+  p.sc = (a.cosine && !bf16) ? a.inv_norm : nullptr;  // the bf16 rows of a cosine index are stored normalised
   p.apack = static_cast<const uint32_t*>(a.apack);
   p.work_counter = a.work_counter;
   p.dp = a.dp;
@@ -1294,11 +1440,11 @@ static int launch_ts_pass(const TcPlan& plan, const TcArgs& a, int sm_count, cud
   p.cand_cnt = a.cand_cnt;
   p.dbg = nullptr;
   if (a.apack == nullptr || a.work_counter == nullptr) return fail(1, "tensor-core TS pass needs packed queries and a work counter");
-  if (a.bias == nullptr) return fail(1, "tensor-core TS pass needs the per-row bias column");
+  if (!raw && a.bias == nullptr) return fail(1, "tensor-core TS pass needs the per-row bias column");
   const int grid_s = (int)std::min<long long>(sm_count, a.n_sample);
   const int grid_m = (int)std::min<long long>(sm_count, p.n_tiles);
   if (hook) hook->fn(hook->ctx, 0, 1, st);
-  ts_kernel(a.mode, true, plan.nblk, plan.kb, bf16)<<<grid_s, TS_THREADS, plan.smem, st>>>(tm_x, p);
+  ts_kernel(a.mode, true, plan.nblk, plan.kb, bf16, raw)<<<grid_s, TS_THREADS, plan.smem, st>>>(tm_x, p);
   QG_CUDA_OK(cudaGetLastError());
   tc_tau_kernel<<<a.nq, TAU_THREADS, 0, st>>>(a.sample, a.n_sample * plan.sample_vals, TC_SAMPLE_RANK, a.tau,
                                               a.cand_cnt, a.work_counter);
@@ -1308,7 +1454,7 @@ static int launch_ts_pass(const TcPlan& plan, const TcArgs& a, int sm_count, cud
   if (hook) hook->fn(hook->ctx, 0, 0, st);
   p.dbg = a.dbg;
   if (hook) hook->fn(hook->ctx, 1, 1, st);
-  ts_kernel(a.mode, false, plan.nblk, plan.kb, bf16)<<<grid_m, TS_THREADS, plan.smem, st>>>(tm_x, p);
+  ts_kernel(a.mode, false, plan.nblk, plan.kb, bf16, raw)<<<grid_m, TS_THREADS, plan.smem, st>>>(tm_x, p);
   QG_CUDA_OK(cudaGetLastError());
   if (hook) hook->fn(hook->ctx, 1, 0, st);
   if (launches) *launches += 3;

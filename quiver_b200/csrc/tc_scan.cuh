@@ -26,20 +26,38 @@ struct TcPlan {
   int bf16;         // TS only: stream the bf16 copy of the corpus (kind::f16) instead of the fp32 rows (kind::tf32)
   int nblk;         // TS: resident blocks of 128 queries (1 or 2)
   int n_cols;       // queries per pass
-  int kb;           // 32-float blocks per row
+  int kb;           // 128-byte k-blocks per row (32 floats or 64 bf16 elements)
+  int ksteps;       // TS: MMA k-steps per row (8 floats or 16 bf16 elements each)
+  int a_cols;       // TS: tensor-memory columns of one resident query block
   int stages;       // corpus ring depth
   int tile_rows;    // corpus rows per tile (sample granularity)
   int sample_vals;  // sampled scores kept per tile and query
   int smem;         // dynamic shared memory bytes
 };
 
-// Geometry for a padded dimension dp and nq queries; returns 0 when the tensor path fits.
-int tc_plan(int dp, int nq, bool bf16, TcPlan* out);
+// Columns the bf16 copy of a row carries after the d vector elements: for L2 the three bf16 pieces of
+// -|x|^2 / 2 (hi + mid + lo is exact to 24 bits), so that the MMA itself produces q.x - |x|^2 / 2 and the
+// epilogue of an unmasked scan is a bare max tree ("raw" scan). They are only added where they fit the
+// padding of the last 128-byte k-block (d = 96, 100, 200 ...): a whole extra k-block for three columns
+// (d = 128) costs more shared-memory traffic than the lighter epilogue returns (measured: 126 us against
+// 120 us per 256-query pass over 1M x 128). Dot / cosine rows need none (cosine rows are stored
+// normalised), so their unmasked scans are always raw.
+inline int tc_extra_cols(int d, int mode_l2) {
+  if (!mode_l2) return 0;
+  return (d + 3 + 63) / 64 == (d + 63) / 64 ? 3 : 0;
+}
+inline bool tc_raw_supported(int d, int mode_l2) { return !mode_l2 || tc_extra_cols(d, mode_l2) == 3; }
+inline int tc_dp16(int d, int mode_l2) { return (d + tc_extra_cols(d, mode_l2) + 7) & ~7; }
+
+// Geometry for a padded dimension dp (fp32 rows), d16 used elements per bf16 row (vector + extra
+// columns) and nq queries; returns 0 when the tensor path fits.
+int tc_plan(int dp, int d16, int nq, bool bf16, TcPlan* out);
 
 struct TcArgs {
   const float* vec;         // [n_rows x dp]
   const void* vec16;        // [n_rows x dp16] bf16 copy (plan.bf16), else nullptr
   int dp16;
+  int raw;                  // plan.bf16 only, no mask: scores come straight out of the MMA (no row-term column)
   long long n_rows;
   int dp;
   const float* row_norm2;   // [n_rows] |x|^2 (L2 scores)
@@ -75,10 +93,14 @@ int launch_tc_pass(const TcPlan& plan, const TcArgs& args, int sm_count, cudaStr
 int tc_set_attributes();
 // TS variant: all nq queries of a search in tensor-memory order, one block of plan.n_cols queries per
 // pass (pass i starts at byte i * tc_pack_bytes(plan, plan.n_cols)). Cosine queries are pre-scaled.
+// `ones`: query elements d .. d + ones - 1 are set to 1 (raw L2 scan: they pick up the norm columns).
 size_t tc_pack_bytes(const TcPlan& plan, int nq);
-int launch_tc_pack(const TcPlan& plan, const float* queries, int nq, int dp, int cosine, void* apack, cudaStream_t st);
-// out[row0 + r][0..dp16) = bf16(vec[row0 + r][0..dp)) (round to nearest even, zero padded)
-int launch_tc_to_bf16(const float* vec, long long row0, long long n, int dp, int dp16, void* out, cudaStream_t st);
+int launch_tc_pack(const TcPlan& plan, const float* queries, int nq, int dp, int d, int ones, int cosine, void* apack,
+                   cudaStream_t st);
+// out[row0 + r][0..d) = bf16(vec[row0 + r][i] * (inv_norm ? inv_norm[row0 + r] : 1)), then the
+// tc_extra_cols() columns (norm2 != nullptr: the three pieces of -norm2 / 2), zero padded to dp16.
+int launch_tc_to_bf16(const float* vec, long long row0, long long n, int dp, int d, int dp16, const float* norm2,
+                      const float* inv_norm, void* out, cudaStream_t st);
 // bias[i] = row i passes (mask nullptr = all rows < n_rows) ? (norm2 ? norm2[i] : 1) : +inf, for i < n_pad.
 int launch_tc_bias(const uint32_t* mask, const float* norm2, long long n_rows, long long n_pad, float* bias,
                    cudaStream_t st);
