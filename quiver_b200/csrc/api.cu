@@ -26,6 +26,13 @@ int fail(int code, const std::string& msg) {
   g_error = msg;
   return code;
 }
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("QG_PDL");
+    return e == nullptr || std::atoi(e) != 0;
+  }();
+  return on;
+}
 
 // ---- per-device one-time state ----------------------------------------------------------------
 struct DeviceState {
@@ -223,12 +230,12 @@ struct qg_index {
 namespace qg {
 
 // Number of corpus tiles the sample stage scores: chosen so that about G rows per query fall under
-// the TC_SAMPLE_RANK-th smallest sampled score (G ~ 256 for k = 10).
+// the tc_sample_rank(k)-th smallest sampled score (G ~ 256 for k = 10).
 static long long tc_sample_tiles(const TcPlan& plan, long long n_rows, int k) {
   const long long n_tiles = (n_rows + plan.tile_rows - 1) / plan.tile_rows;
   const long long G = std::max<long long>(256, 6ll * (k + 24));
-  long long n_sample = ((long long)TC_SAMPLE_RANK * n_rows + G * plan.tile_rows - 1) / (G * plan.tile_rows);
-  // the sampled fraction is TC_SAMPLE_RANK / G (~3 %) of the corpus whatever its size
+  long long n_sample = ((long long)tc_sample_rank(k) * n_rows + G * plan.tile_rows - 1) / (G * plan.tile_rows);
+  // the sampled fraction is rank / G (~3 %) of the corpus whatever its size
   return std::max<long long>(16, std::min<long long>(n_sample, std::min<long long>(n_tiles, 1 << 17)));
 }
 
@@ -1008,6 +1015,8 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
       ta.cosine = fb.cosine;
       ta.sample = (uint32_t*)w->tc_sample.p;
       ta.n_sample = (int)n_sample;
+    ta.sample_rank = tc_sample_rank(k);
+      ta.sample_rank = tc_sample_rank(k);
       ta.tau = (float*)w->tc_tau.p;
       ta.cand = (uint64_t*)w->tc_cand.p;
       ta.cand_cnt = (int*)w->tc_cnt.p;
@@ -1640,6 +1649,7 @@ int qg_debug_tc_pass(qg_index* idx, const float* queries, int nq, int k, float* 
     ta.cosine = idx->metric == METRIC_COSINE;
     ta.sample = (uint32_t*)w->tc_sample.p;
     ta.n_sample = (int)n_sample;
+    ta.sample_rank = tc_sample_rank(k);
     ta.tau = (float*)w->tc_tau.p;
     ta.cand = (uint64_t*)w->tc_cand.p;
     ta.cand_cnt = (int*)w->tc_cnt.p;

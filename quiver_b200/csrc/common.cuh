@@ -96,4 +96,33 @@ __device__ __forceinline__ void st_volatile_s32(int* p, int v) {
 }
 #endif  // __CUDACC__
 
+
+// ---- programmatic dependent launch -------------------------------------------------------------------
+// The four kernels of a tensor-core pass (sample, threshold, scan, finalize) are chained with
+// cudaLaunchAttributeProgrammaticStreamSerialization: every kernel lets its successor's CTAs be launched
+// as soon as all of its own CTAs run (pdl_launch_dependents at the top), and the successor blocks in
+// pdl_wait() before it touches anything the predecessor writes — the launch latency and the
+// predecessor-independent part of the prologue (barrier setup, TMEM allocation, query load) overlap the
+// predecessor's tail. Both instructions are no-ops in a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();  // QG_PDL=0 switches the attribute off (api.cu)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                  Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace qg

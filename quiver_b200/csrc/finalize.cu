@@ -560,6 +560,8 @@ __global__ void __launch_bounds__(FC_THREADS, 2) finalize_cand_kernel(const Fina
   long long ts[8];
   int nts = 0;
   ts[nts++] = clock64();
+  pdl_launch_dependents();
+  pdl_wait();  // candidate lists, counts and thresholds come from the scan / threshold kernels just before
   const int n_raw = cp.cand_cnt[q];
   const bool overflow = n_raw > cap;
   const int n = overflow ? cap : n_raw;
@@ -711,8 +713,7 @@ __global__ void __launch_bounds__(FC_THREADS, 2) finalize_cand_kernel(const Fina
 int launch_finalize_cand(const FinalizeCandParams& p, int nq, cudaStream_t st) {
   if (nq <= 0) return 0;
   if (p.cap > 4 * FC_THREADS) return fail(1, "finalize_cand: candidate capacity must be at most 2048");
-  finalize_cand_kernel<<<nq, FC_THREADS, finalize_cand_smem(p.cap), st>>>(p);
-  QG_CUDA_OK(cudaGetLastError());
+  QG_CUDA_OK(launch_chained(finalize_cand_kernel, dim3(nq), dim3(FC_THREADS), finalize_cand_smem(p.cap), st, p));
   return 0;
 }
 

@@ -4,7 +4,7 @@
 // One pass serves up to 256 queries (the MMA N dimension). Three kernels per pass:
 //   1. tc_scan_kernel<MODE, SAMPLE=true>   scores of a strided sample of corpus tiles; per tile and
 //      query the two smallest scores are kept;
-//   2. tc_tau_kernel                       per query, the TC_SAMPLE_RANK-th smallest sampled score
+//   2. tc_tau_kernel                       per query, the sample_rank-th smallest sampled score
 //      becomes the admission threshold tau (expected ~256 corpus rows pass per query);
 //   3. tc_scan_kernel<MODE, SAMPLE=false>  persistent scan of every tile: 128 x N accumulator tile
 //      in TMEM -> score -> `score <= tau` -> (rare) append of the (score,row) key to the query's
@@ -559,12 +559,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
   const long long n_work = SAMPLE ? (long long)p.n_sample : p.n_tiles;
   auto tile_of = [&](long long w) -> long long { return SAMPLE ? (w * p.n_sample_from) / p.n_sample : w; };
 
-  // the first two tile claims of the main scan go out before anything else (warp 0, lane 0)
-  int claim_a = 0, claim_b = 0;
-  if (!SAMPLE && threadIdx.x == 0) {
-    claim_a = atomicAdd(p.work_counter, TS_CLAIM);
-    claim_b = atomicAdd(p.work_counter, TS_CLAIM);
-  }
+  // Chained launch: the successor may be launched right away; this kernel's own setup (barriers, TMEM,
+  // resident queries) does not depend on the predecessor, everything after pdl_wait() may.
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     dbg_stamp(p.dbg, 0);
     tma_prefetch_desc(&tm_x);
@@ -602,6 +599,14 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
     const uint32_t xs_bytes = (uint32_t)(ROWS * 4 * (with_sc ? 2 : 1));
     DbgClock clk{(p.dbg != nullptr && blockIdx.x == 0 && lane == 0) ? p.dbg : nullptr, 0};
     const long long t_prod_begin = clock64();
+    // the threshold kernel zeroes the work counter (main scan); the previous pass's finalize still reads
+    // nothing this kernel writes before this point
+    pdl_wait();
+    int claim_a = 0, claim_b = 0;
+    if (!SAMPLE && lane == 0) {
+      claim_a = atomicAdd(p.work_counter, TS_CLAIM);
+      claim_b = atomicAdd(p.work_counter, TS_CLAIM);
+    }
     // Work distribution of the main scan: tiles are claimed from a global counter, TS_CLAIM at a time
     // (SMs stream at visibly different rates; a static split leaves the fast ones idle for the last
     // fifth of the kernel). A claim's round trip is longer than a tile, so two claims are kept in
@@ -794,6 +799,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
     constexpr int NCH = 4;                               // chunks per warp and tile
     auto chunk_of = [&](int ci) -> int { return NBLK == 2 ? ci : sub + 2 * ci; };
 
+    // the sample stage may directly follow the kernel that packs the queries; the main scan's
+    // predecessor (threshold kernel) never touches them, so its query load overlaps that kernel
+    if (SAMPLE) pdl_wait();
     // ---- resident query block -> tensor memory (cosine: pre-scaled by 1/|q|) ----
     // (tc_pack_kernel laid them out so that a warp reads 2 KB contiguous per 16 columns; the 16 warps
     //  split the 16-column groups of their query block between them)
@@ -821,8 +829,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
     if (lane == 0) mbar_arrive(a_ready);
     if (warp == 4 && lane == 0) dbg_stamp(p.dbg, 2);
 
+    pdl_wait();  // thresholds (main scan) / the buffers the previous pass still reads (sample stage)
     float tau_me = -__int_as_float(0x7f800000);
-    if (!SAMPLE && q < p.nq) tau_me = __ldg(p.tau + q);
+    if (!SAMPLE && q < p.nq) tau_me = __ldcg(p.tau + q);
     // raw scan: a row is admitted when its accumulator value a' >= theta. L2: score = -2 a' exactly, so
     // theta = -tau / 2; dot / cosine: score = 1 - a' is rounded, so theta is lowered by a few ulps (a
     // few more rows are admitted; every admitted row carries its own score).
@@ -1042,7 +1051,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
   if (threadIdx.x == 0) dbg_stamp(p.dbg, 6);
 }
 
-// Threshold per query: the TC_SAMPLE_RANK-th smallest sampled score (+inf when the sample holds
+// Threshold per query: the rank-th smallest sampled score (+inf when the sample holds
 // fewer valid scores). One warp per query; bitwise binary search over the ordered-float images.
 // Also clears the candidate counters of the pass.
 // Pop the warp-wide minimum `rank` times from per-lane ascending lists best[0..R); returns the last
@@ -1070,14 +1079,16 @@ __global__ void __launch_bounds__(TAU_THREADS) tc_tau_kernel(const uint32_t* __r
                                                              float* __restrict__ tau, int* __restrict__ cand_cnt,
                                                              int* __restrict__ work_counter) {
   const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_launch_dependents();
+  pdl_wait();  // the sample comes from the kernel just before; tau / cand_cnt are read by the one before that
   const uint32_t* vals = sample + (size_t)q * n_vals;
-  constexpr int R = TC_SAMPLE_RANK;
+  constexpr int R = TC_SAMPLE_RANK_MAX;
   __shared__ uint32_t s_part[TAU_THREADS / 32][R];
   uint32_t best[R];  // this lane's R smallest values, ascending
 #pragma unroll
   for (int r = 0; r < R; ++r) best[r] = 0xFFFFFFFFu;
   for (int i = tid; i < n_vals; i += TAU_THREADS) {
-    uint32_t x = __ldg(vals + i);
+    uint32_t x = __ldcg(vals + i);
     if (x < best[R - 1]) {
 #pragma unroll
       for (int r = 0; r < R; ++r) {
@@ -1087,12 +1098,17 @@ __global__ void __launch_bounds__(TAU_THREADS) tc_tau_kernel(const uint32_t* __r
       }
     }
   }
-  warp_pop_rank<R>(best, rank, s_part[warp]);  // the R smallest of this warp's share, ascending
+  if (lane < R) s_part[warp][lane] = 0xFFFFFFFFu;
+  __syncwarp();
+  warp_pop_rank<R>(best, rank, s_part[warp]);  // the `rank` smallest of this warp's share, ascending
   __syncthreads();
   if (warp == 0) {
-    uint32_t one[1];
-    one[0] = lane < (TAU_THREADS / 32) * R ? s_part[lane / R][lane % R] : 0xFFFFFFFFu;
-    const uint32_t m = warp_pop_rank<1>(one, rank, nullptr);
+    // 4 warps x 16 ascending values: every lane takes two consecutive ones
+    static_assert((TAU_THREADS / 32) * R == 64, "final merge assumes 64 partial values");
+    uint32_t two[2];
+    two[0] = s_part[lane / 8][(lane % 8) * 2];
+    two[1] = s_part[lane / 8][(lane % 8) * 2 + 1];
+    const uint32_t m = warp_pop_rank<2>(two, rank, nullptr);
     if (lane == 0) {
       // 0xFFFFFFFF: fewer than `rank` valid samples -> admit everything
       tau[q] = (m == 0xFFFFFFFFu) ? __int_as_float(0x7f800000) : ordered_to_f32(m);
@@ -1407,6 +1423,7 @@ static int launch_ts_pass(const TcPlan& plan, const TcArgs& a, int sm_count, cud
   const int rows = ts_rows(plan.nblk);
   const bool bf16 = plan.bf16 != 0;
   const bool raw = bf16 && a.raw != 0;
+  const int sample_rank = std::min(TC_SAMPLE_RANK_MAX, std::max(1, a.sample_rank));
   CUtensorMap tm_x;
   if (bf16) {
     if (a.vec16 == nullptr) return fail(1, "tensor-core bf16 pass needs the bf16 copy of the corpus");
@@ -1444,18 +1461,17 @@ static int launch_ts_pass(const TcPlan& plan, const TcArgs& a, int sm_count, cud
   const int grid_s = (int)std::min<long long>(sm_count, a.n_sample);
   const int grid_m = (int)std::min<long long>(sm_count, p.n_tiles);
   if (hook) hook->fn(hook->ctx, 0, 1, st);
-  ts_kernel(a.mode, true, plan.nblk, plan.kb, bf16, raw)<<<grid_s, TS_THREADS, plan.smem, st>>>(tm_x, p);
-  QG_CUDA_OK(cudaGetLastError());
-  tc_tau_kernel<<<a.nq, TAU_THREADS, 0, st>>>(a.sample, a.n_sample * plan.sample_vals, TC_SAMPLE_RANK, a.tau,
-                                              a.cand_cnt, a.work_counter);
-  QG_CUDA_OK(cudaGetLastError());
+  QG_CUDA_OK(launch_chained(ts_kernel(a.mode, true, plan.nblk, plan.kb, bf16, raw), dim3(grid_s), dim3(TS_THREADS),
+                            (size_t)plan.smem, st, tm_x, p));
+  QG_CUDA_OK(launch_chained(tc_tau_kernel, dim3(a.nq), dim3(TAU_THREADS), (size_t)0, st, (const uint32_t*)a.sample,
+                            a.n_sample * plan.sample_vals, sample_rank, a.tau, a.cand_cnt, a.work_counter));
   if (a.dbg != nullptr && std::getenv("QG_TC_NOHIT"))  // development aid: a scan that admits nothing
     launch_fill_f32(a.tau, a.nq, -__builtin_huge_valf(), st);
   if (hook) hook->fn(hook->ctx, 0, 0, st);
   p.dbg = a.dbg;
   if (hook) hook->fn(hook->ctx, 1, 1, st);
-  ts_kernel(a.mode, false, plan.nblk, plan.kb, bf16, raw)<<<grid_m, TS_THREADS, plan.smem, st>>>(tm_x, p);
-  QG_CUDA_OK(cudaGetLastError());
+  QG_CUDA_OK(launch_chained(ts_kernel(a.mode, false, plan.nblk, plan.kb, bf16, raw), dim3(grid_m), dim3(TS_THREADS),
+                            (size_t)plan.smem, st, tm_x, p));
   if (hook) hook->fn(hook->ctx, 1, 0, st);
   if (launches) *launches += 3;
   return 0;
@@ -1496,7 +1512,9 @@ int launch_tc_pass(const TcPlan& plan, const TcArgs& a, int sm_count, cudaStream
     tc_scan_kernel<MODE_DOT, true><<<grid_s, TC_THREADS, plan.smem, st>>>(tm_a, tm_b, p);
   }
   QG_CUDA_OK(cudaGetLastError());
-  tc_tau_kernel<<<a.nq, TAU_THREADS, 0, st>>>(a.sample, a.n_sample * 2, TC_SAMPLE_RANK, a.tau, a.cand_cnt, nullptr);
+  tc_tau_kernel<<<a.nq, TAU_THREADS, 0, st>>>(a.sample, a.n_sample * 2,
+                                              std::min(TC_SAMPLE_RANK_MAX, std::max(1, a.sample_rank)), a.tau, a.cand_cnt,
+                                              nullptr);
   QG_CUDA_OK(cudaGetLastError());
   if (hook) hook->fn(hook->ctx, 0, 0, st);
   if (hook) hook->fn(hook->ctx, 1, 1, st);

@@ -18,7 +18,10 @@ constexpr int TC_KBLOCK = 32;           // floats per 128-byte swizzle row
 constexpr int TC_STAGE_BYTES = TC_TILE_ROWS * TC_KBLOCK * 4;
 constexpr int TC_MAX_COLS = 256;        // MMA N (queries per pass)
 constexpr int TC_THREADS = 320;         // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int TC_SAMPLE_RANK = 8;       // order statistic of the sample used as threshold
+constexpr int TC_SAMPLE_RANK_MAX = 16;  // largest order statistic of the sample the threshold kernel can take
+// Order statistic used as threshold: the spread of the admitted count is Gamma(rank) / rank, so larger k
+// (fewer admitted rows per wanted row) takes a higher rank from a proportionally larger sample.
+inline int tc_sample_rank(int k) { return k > 32 ? 16 : 8; }
 constexpr int TC_CAND_CAP = 2048;       // candidate capacity per query per pass
 
 struct TcPlan {
@@ -74,6 +77,7 @@ struct TcArgs {
   // sample stage
   uint32_t* sample;         // [n_cols][n_sample][plan.sample_vals] ordered-float images
   int n_sample;             // sampled tiles
+  int sample_rank;          // order statistic of the sample that becomes the threshold (<= TC_SAMPLE_RANK_MAX)
   float* tau;               // [n_cols] thresholds (written by the threshold kernel)
   // main stage
   uint64_t* cand;           // [n_cols][TC_CAND_CAP] scan keys
