@@ -1704,8 +1704,9 @@ int qg_debug_tc_pass(qg_index* idx, const float* queries, int nq, int k, float* 
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
         cudaMemcpy(h, w->counters.p, sizeof(h), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "  finalize_cand: %.1f us; CTA 0 cycles: ranked %llu, re-ranked %llu, certified %llu, done %llu "
-                        "(n %llu, nex %llu)\n", ms * 1e3, h[1], h[2], h[3], h[4], h[8], h[9]);
+        fprintf(stderr, "  finalize_cand: %.1f us; CTA 0 cycles: keys %llu, pivot %llu, selected %llu, re-ranked %llu, "
+                        "certified %llu, done %llu (n %llu, nex %llu)\n", ms * 1e3, h[10], h[11], h[1], h[2], h[3], h[4],
+                h[8], h[9]);
         cudaEventDestroy(e0); cudaEventDestroy(e1);
       }
     }

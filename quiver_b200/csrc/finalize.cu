@@ -503,7 +503,7 @@ __device__ __forceinline__ float tc_score_upper_bound(int metric, int mode, int 
 // scratch: three rotating histograms — the one cleared after a round's barrier was last read before
 // that barrier and is next written after the following one. All threads of the block call.
 template <int PER>
-__device__ __forceinline__ uint32_t fc_select_pivot(const uint64_t (&mine)[PER], int want, int* s_hist) {
+__device__ __forceinline__ uint32_t fc_select_pivot(const uint64_t (&mine)[PER], int n, int want, int* s_hist) {
   const int lane = threadIdx.x & 31;
   uint32_t prefix = 0;
   int below = 0;  // keys below the prefix range
@@ -515,6 +515,7 @@ __device__ __forceinline__ uint32_t fc_select_pivot(const uint64_t (&mine)[PER],
     int* h = s_hist + (r % 3) * 16;
 #pragma unroll
     for (int s = 0; s < PER; ++s) {
+      if (s * FC_THREADS >= n) break;  // block-uniform: slots beyond n hold no key in any thread
       const uint32_t img = (uint32_t)(mine[s] >> 32);
       // r == 0: every key matches; later: the bits above the digit must equal the prefix
       const bool active = mine[s] != KEY_NONE && (r == 0 || (img >> (shift + 4)) == (prefix >> (shift + 4)));
@@ -523,20 +524,20 @@ __device__ __forceinline__ uint32_t fc_select_pivot(const uint64_t (&mine)[PER],
       if (active && lane == __ffs(peers) - 1) atomicAdd(h + digit, __popc(peers));
     }
     __syncthreads();
-    int cum = below, pick = 15, before = below;
-    bool found = false;
+    // lanes 0..15 take one counter each; inclusive warp scan; the first digit whose running count
+    // reaches `want` is the next digit of the pivot
+    const int c = lane < 16 ? h[lane] : 0;
+    int inc = c;
 #pragma unroll
-    for (int dgt = 0; dgt < 16; ++dgt) {
-      const int c = h[dgt];
-      if (!found && cum + c >= want) {
-        found = true;
-        pick = dgt;
-        before = cum;
-      }
-      cum += c;
+    for (int o = 1; o < 16; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += up;
     }
+    const unsigned reach = __ballot_sync(0xffffffffu, lane < 16 && below + inc >= want);
+    const int pick = reach ? __ffs(reach) - 1 : 15;
+    const int before = __shfl_sync(0xffffffffu, inc - c, pick);
     prefix |= (uint32_t)pick << shift;
-    below = before;
+    below += before;
     if (threadIdx.x < 16) s_hist[((r + 2) % 3) * 16 + threadIdx.x] = 0;
   }
   __syncthreads();
@@ -587,7 +588,12 @@ __global__ void __launch_bounds__(FC_THREADS, 2) finalize_cand_kernel(const Fina
   // the best scan keys = every key whose score image is <= the pivot: at least min(kp, n) keys
   // (ties on the score image may add a few)
   const int want = n < cp.kp ? n : cp.kp;
-  const uint32_t pivot = want > 0 ? fc_select_pivot<PER>(mine, want, s_sel) : 0u;
+  long long t_keys = 0, t_pivot = 0;
+  if (cp.dbg != nullptr) {
+    t_keys = (long long)(mine[0] & 1) + clock64();  // (depends on the first key: stamped once it has arrived)
+  }
+  const uint32_t pivot = want > 0 ? fc_select_pivot<PER>(mine, n, want, s_sel) : 0u;
+  if (cp.dbg != nullptr) t_pivot = clock64();
   if (tid == 0) s_sel[0] = 0;
   __syncthreads();
 #pragma unroll
@@ -707,6 +713,8 @@ __global__ void __launch_bounds__(FC_THREADS, 2) finalize_cand_kernel(const Fina
     for (int i = 0; i < nts; ++i) cp.dbg[i] = (unsigned long long)(ts[i] - ts[0]);
     cp.dbg[8] = (unsigned long long)n;
     cp.dbg[9] = (unsigned long long)nex;
+    cp.dbg[10] = (unsigned long long)(t_keys - ts[0]);
+    cp.dbg[11] = (unsigned long long)(t_pivot - ts[0]);
   }
 }
 

@@ -172,6 +172,14 @@ class HybridIndex:
         arr = (C.c_char_p * len(ids))(*[i.encode() for i in ids])
         _check(self._lib.qh_index_insert_batch(self.handle, arr, _ptr(mat), len(ids), mat.shape[1]))
 
+    def InsertBatchArrays(self, ids: Sequence[str], matrix) -> None:
+        """InsertBatch for rows that already sit in one [n x dim] matrix (Arrow / Parquet ingest)."""
+        mat = _f32(matrix)
+        if len(ids) == 0:
+            return
+        arr = (C.c_char_p * len(ids))(*[i.encode() for i in ids])
+        _check(self._lib.qh_index_insert_batch(self.handle, arr, _ptr(mat), len(ids), mat.shape[1]))
+
     def Delete(self, id: str) -> None:
         _check(self._lib.qh_index_delete(self.handle, id.encode()))
 
