@@ -185,6 +185,9 @@ def run_native(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL prints its version banner (and anything NCCL_DEBUG asks for) to stdout by default; stdout
+        # carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     import oracle  # checker + cpu_baseline only
