@@ -46,6 +46,9 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--shard", default="auto", choices=["auto", "rows", "queries"],
+                    help="multi-GPU layout (quiver_b200/sharded.py choose_layout): row-sharded corpus + all-gather "
+                         "merge, or replicated corpus + query-split batch")
     return ap.parse_args()
 
 
@@ -164,7 +167,7 @@ def run_reference(args):
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_native(args):
@@ -195,10 +198,20 @@ def run_native(args):
 
     mid = METRIC_ID[args.metric]
     Q, k, d = args.queries, args.k, args.dim
-    # row shard of this rank (contiguous block)
-    per = (args.rows + world - 1) // world
-    row0 = min(args.rows, rank * per)
-    nloc = max(0, min(args.rows, row0 + per) - row0)
+    from quiver_b200 import sharded
+    layout = "rows" if world == 1 else (args.shard if args.shard != "auto" else
+                                        sharded.choose_layout(args.rows, d, Q, world))
+    by_queries = layout == "queries"
+    if by_queries:
+        # replicated corpus, this rank answers a contiguous slice of the batch
+        row0, nloc = 0, args.rows
+        qper = (Q + world - 1) // world
+        q0, q1 = sharded.query_range(Q, world, rank)
+    else:
+        # row shard of this rank (contiguous block)
+        per = (args.rows + world - 1) // world
+        row0 = min(args.rows, rank * per)
+        nloc = max(0, min(args.rows, row0 + per) - row0)
     idx = capi.Index(d, mid, device=local_rank, reserve_rows=max(nloc, 1))
     idx.upload_synthetic(args.kind, args.seed, row0, nloc)
 
@@ -209,13 +222,23 @@ def run_native(args):
     d_dist = torch.empty((Q, k), dtype=torch.float32, device=dev)
     d_row = torch.empty((Q, k), dtype=torch.int64, device=dev)
     d_cnt = torch.empty((Q,), dtype=torch.int32, device=dev)
-    if world > 1:
+    if world > 1 and by_queries:
+        blk = torch.zeros(sharded.ReplicatedIndex.block_bytes(qper, k), dtype=torch.uint8, device=dev)
+        b_row, b_dist, b_cnt = sharded.unpack_block(blk, qper, k)
+        d_allb = torch.empty(world * blk.numel(), dtype=torch.uint8, device=dev)  # rank-major result blocks
+    elif world > 1:
         d_keys = torch.empty((Q, k), dtype=torch.int64, device=dev)  # packed u64 keys
         d_all = torch.empty((world * Q, k), dtype=torch.int64, device=dev)  # rank-major concatenation
 
     def step_device():
         if world == 1:
             idx.search_device(dq.data_ptr(), Q, k, d_dist.data_ptr(), d_row.data_ptr(), d_cnt.data_ptr(), stream=st)
+        elif by_queries:
+            # the results stay in block layout (per rank: rows | distances | counts); every rank gets all
+            if q1 > q0:
+                idx.search_device(dq[q0:q1].data_ptr(), q1 - q0, k, b_dist.data_ptr(), b_row.data_ptr(),
+                                  b_cnt.data_ptr(), stream=st)
+            dist.all_gather_into_tensor(d_allb, blk)
         else:
             idx.search_shard_keys_device(dq.data_ptr(), Q, k, row0, d_keys.data_ptr(), stream=st)
             dist.all_gather_into_tensor(d_all, d_keys)
@@ -230,6 +253,9 @@ def run_native(args):
     # ---- parity gate before any timing is reported ------------------------------------------------
     step_device()
     torch.cuda.synchronize()
+    if world > 1 and by_queries:
+        sharded.scatter_blocks(d_allb, world, qper, Q, k, d_dist, d_row, d_cnt)
+        torch.cuda.synchronize()
     checked = None
     host_corpus = None
     if not args.no_check and rank == 0:
@@ -300,6 +326,7 @@ def run_native(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
     qps = Q / (ms_step * 1e-3)
+    Q_gpu = (q1 - q0) if (world > 1 and by_queries) else Q  # queries one GPU's kernels serve per step
 
     # ---- e2e: host buffers through the C ABI call a Go caller would make ----------------------------------
     e2e_steps = max(10, min(args.steps, 100))
@@ -310,6 +337,10 @@ def run_native(args):
         h_keys = torch.empty((Q, k), dtype=torch.int64).pin_memory()
 
         def step_e2e():
+            if by_queries:
+                dq[q0:q1].copy_(q_pin[q0:q1], non_blocking=True)
+                step_device()
+                return d_allb.cpu()
             dq.copy_(q_pin, non_blocking=True)
             step_device()
             out = (d_dist.cpu(), d_row.cpu(), d_cnt.cpu())
@@ -362,7 +393,7 @@ def run_native(args):
     if tc:
         # a [rows x d] x [d x queries] contraction per pass: the binding roof is whichever floor is higher,
         # the corpus stream (HBM) or the MMA work (tensor pipe; tf32 runs at half the bf16 rate)
-        qpp = min(Q, stats["queries_per_pass"])
+        qpp = min(Q_gpu, stats["queries_per_pass"])
         flops = 2.0 * qpp * nloc * d
         tfl = flops / (scan_launch_ms * 1e-3) / 1e12 if scan_launch_ms > 0 else 0.0
         bf16 = float(peaks.get("bf16_tflops_sustained", 1400.0))
@@ -414,7 +445,7 @@ def run_native(args):
             oracle.synth(args.kind, args.seed, 0, args.rows, d, threads=min(16, host_cores()))
         cpu_base, _ = cpu_reference_qps(oracle, args, corpus, steps=2, warmup=1, budget_s=args.cpu_seconds)
 
-    launches_per_step = stats["kernel_launches"] + (1 if world > 1 else 0)
+    launches_per_step = stats["kernel_launches"] + (1 if (world > 1 and not by_queries) else 0)  # + merge kernel
     line = {
         "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
@@ -422,29 +453,53 @@ def run_native(args):
         "config": {"workload": f"flat {args.metric} exact search {args.rows}x{d} fp32 (SIFT-shaped synthetic, "
                                f"oracle/synth.h kind {args.kind} seed {args.seed}), query batch {Q}, k={k}",
                    "rows": args.rows, "dim": d, "k": k, "queries_per_step": Q,
-                   "parallelism": "single GPU" if world == 1 else f"row-sharded x{world}, NCCL all-gather of per-shard top-k",
+                   "parallelism": "single GPU" if world == 1 else (
+                       f"corpus replicated x{world} ({args.rows*d*6/1e9:.2f} GB per GPU with the bf16 copy), batch split "
+                       f"in contiguous blocks of {qper} queries, one NCCL all-gather of the result blocks"
+                       if by_queries else f"row-sharded x{world}, NCCL all-gather of per-shard top-k"),
                    "l2_policy": f"inputs larger than L2: every step streams the {args.rows*d*4/1e6:.0f} MB corpus "
                                 f"({nloc*d*4/1e6:.0f} MB per GPU)",
                    "parity_check": checked},
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": Q * d * 4,
                 "d2h_bytes_per_step": Q * k * 12 + Q * 4, "steps": e2e_steps,
-                "api": "qg_search_batch (host buffers, pinned staging)" if world == 1 else
-                       "pinned H2D + shard search + all-gather + merge + D2H"},
+                "api": "qg_search_batch (host buffers, pinned staging)" if world == 1 else (
+                       "pinned H2D of the rank's query block + search + all-gather + D2H of all results" if by_queries
+                       else "pinned H2D + shard search + all-gather + merge + D2H")},
         "gpu_launches": launches_per_step * args.steps,
         "kernels_per_step": {"passes": stats["passes"], "launches": stats["kernel_launches"],
                              "path": {0: "exhaustive", 1: "flat scan", 2: "gather scan", 3: "tensor-core"}[stats["path"]],
-                             "queries_per_pass": stats["queries_per_pass"], "merge": 1 if world > 1 else 0},
+                             "queries_per_pass": stats["queries_per_pass"],
+                             "merge": 1 if (world > 1 and not by_queries) else 0},
         "small_batch_regime": small,
         "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_base,
         "host_cores": host_cores(), "device": capi.device_info(local_rank)["name"],
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_OUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly one JSON line: keep a private handle on the real stdout for it and point
+    fd 1 at stderr, so library chatter (NCCL's version banner, compiler notes ...) cannot join it."""
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

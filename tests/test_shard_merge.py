@@ -113,3 +113,65 @@ def test_two_shards_on_one_device_equal_the_unsharded_index(capi, oracle, nq):
     assert np.array_equal(gr, fr) and np.array_equal(gd.view(np.uint32), fd.view(np.uint32))
     for idx in shards + [full]:
         idx.close()
+
+
+def _worker_queries(rank, world, port, n, d, k, nq, metric, out):
+    """The "queries" layout: every rank holds the corpus, answers its slice, one all-gather of blocks."""
+    import torch.distributed as dist
+    import torch
+    import oracle
+    from quiver_b200 import sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    corpus = oracle.synth(0, 42, 0, n, d, threads=1)
+    queries = oracle.synth(0, 9999, 0, nq, d, threads=1)
+    per = (nq + world - 1) // world
+    q0, q1 = sharded.query_range(nq, world, rank)
+    mine = torch.zeros(sharded.ReplicatedIndex.block_bytes(per, k), dtype=torch.uint8)
+    rows, dists, cnts = sharded.unpack_block(mine, per, k)
+    for i in range(q0, q1):
+        od, orow = oracle.exact_search(corpus, queries[i], k, metric)
+        dists[i - q0, :len(od)] = torch.from_numpy(od)
+        rows[i - q0, :len(od)] = torch.from_numpy(orow.astype(np.int64))
+        cnts[i - q0] = len(od)
+    allb = torch.empty(world * mine.numel(), dtype=torch.uint8)
+    dist.all_gather_into_tensor(allb, mine)
+    gd = torch.empty((nq, k), dtype=torch.float32)
+    gr = torch.empty((nq, k), dtype=torch.int64)
+    gc = torch.empty((nq,), dtype=torch.int32)
+    sharded.scatter_blocks(allb, world, per, nq, k, gd, gr, gc)
+    ok = True
+    for i in range(nq):
+        od, orow = oracle.exact_search(corpus, queries[i], k, metric)
+        ok &= int(gc[i]) == len(od) and np.array_equal(gr[i, :len(od)].numpy(), orow) and \
+            np.array_equal(gd[i, :len(od)].numpy().view(np.uint32), od.view(np.uint32))
+    t = torch.tensor([1 if ok else 0])
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        out.put(int(t.item()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nq", [(2, 7), (3, 10), (3, 2)])
+def test_query_split_exchange_over_gloo(oracle, world, nq):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_queries, args=(r, world, port, 500, 16, 5, nq, 1, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert out.get(timeout=5) == 1
+
+
+def test_layout_choice():
+    from quiver_b200 import sharded
+    assert sharded.choose_layout(1_000_000, 128, 10_000, 8) == "queries"     # 0.77 GB corpus, 1250 queries per GPU
+    assert sharded.choose_layout(1_000_000, 128, 1, 8) == "rows"            # a single query is shortened by rows
+    assert sharded.choose_layout(100_000_000, 96, 1024, 8) == "rows"        # 57.6 GB with the bf16 copy: shard it
+    assert sharded.choose_layout(1_000_000, 128, 10_000, 1) == "rows"
+    assert sharded.query_range(10, 3, 2) == (8, 10) and sharded.query_range(2, 3, 2) == (2, 2)
