@@ -114,9 +114,8 @@ int qg_index_fetch(qg_index* idx, const int64_t* rows, int64_t n, float* out /* 
  *           -1 when kind is MISSING
  *   fcode : dictionary code of the case-folded string (strings.EqualFold,
  *           facets.go:73-77) for STRING rows, else -1
- * Array-valued facets (facets.go:304-316) are out of the device path: mark them
- * QG_KIND_OTHER; predicates that would need their elements return QG_ERR_UNSUPPORTED
- * at compile time rather than a wrong mask. */
+ * Array / map values are QG_KIND_OTHER; the elements of arrays travel separately
+ * (qg_facets_set_array_column) for the one predicate that looks inside them (QG_OP_ELEM_IN). */
 typedef enum qg_value_kind {
   QG_KIND_MISSING = 0, /* field absent from the row's metadata / facets */
   QG_KIND_NULL = 1,    /* present, JSON null                            */
@@ -129,6 +128,15 @@ typedef enum qg_value_kind {
 
 int qg_facets_set_column(qg_index* idx, int field, const uint8_t* kind, const double* num,
                          const int32_t* scode, const int32_t* fcode, int64_t n);
+
+/* Elements of the array-valued rows of a column (facets.go:308-320: a SetFilter matches an array
+ * facet when ANY element equals ANY filter value under valuesEqual). CSR layout: row r owns
+ * elem_codes[offsets[r] .. offsets[r+1]); rows that are not arrays own nothing. The codes come from a
+ * per-column dictionary kept by the host (equal codes <=> valuesEqual elements: numbers by float64
+ * value, everything else by reflect.DeepEqual). Call after qg_facets_set_column for the same field;
+ * n must equal that column's n. */
+int qg_facets_set_array_column(qg_index* idx, int field, const int32_t* offsets /* n + 1 */,
+                               const int32_t* elem_codes, int64_t n, int64_t n_elems);
 
 /* A predicate is already lowered by the host-side compiler (quiver_b200/host) from the
  * reference's filter objects into this normal form; the device evaluates
@@ -151,7 +159,10 @@ typedef enum qg_clause_op {
   QG_OP_FCODE_IN = 11,    /* kind STRING and fcode in set[ia .. ia+ic)                  */
   QG_OP_NUM_IN_TOL = 12,  /* kind NUMBER and any |num - fset[ia+j]| <= fb, j < ic       */
   QG_OP_NUM_IN = 13,      /* kinds in mask ib and num == fset[ia+j] for some j < ic     */
-  QG_OP_NUM_BITS_EQ = 14  /* kind NUMBER and bit pattern of num == bits(fa)             */
+  QG_OP_NUM_BITS_EQ = 14, /* kind NUMBER and bit pattern of num == bits(fa)             */
+  QG_OP_ELEM_IN = 15      /* kind OTHER and any element code of the row's array in
+                             set[ia .. ia+ic) (SetFilter over array facets, facets.go:308-320;
+                             needs qg_facets_set_array_column)                           */
 } qg_clause_op;
 
 typedef struct qg_clause {

@@ -60,7 +60,7 @@ EXPORTED_SYMBOLS = [
     "qg_abi_version", "qg_last_error", "qg_device_count", "qg_device_info", "qg_index_create",
     "qg_index_destroy", "qg_index_upload", "qg_index_upload_device", "qg_index_upload_synthetic",
     "qg_index_tombstone", "qg_index_size", "qg_index_rows", "qg_index_dim", "qg_index_metric",
-    "qg_index_fetch", "qg_facets_set_column", "qg_filter_compile", "qg_filter_eval", "qg_filter_destroy",
+    "qg_index_fetch", "qg_facets_set_column", "qg_facets_set_array_column", "qg_filter_compile", "qg_filter_eval", "qg_filter_destroy",
     "qg_search_batch", "qg_search_batch_device", "qg_search_shard_keys_device", "qg_merge_shard_keys_device",
     "qg_batch_distance", "qg_batch_distance_multi", "qg_last_scan_stats", "qg_index_set_profiling",
     "qg_index_read_profile", "qg_debug_tc_pass", "qg_queries_upload", "qg_queries_destroy",
@@ -97,6 +97,7 @@ def load() -> C.CDLL:
     lib.qg_index_metric.argtypes = [vp]
     lib.qg_index_fetch.argtypes = [vp, vp, i64, vp]
     lib.qg_facets_set_column.argtypes = [vp, i32, vp, vp, vp, vp, i64]
+    lib.qg_facets_set_array_column.argtypes = [vp, i32, vp, vp, i64, i64]
     lib.qg_filter_compile.argtypes = [vp, vp, i32, vp, i32, vp, i32, vp, i32, C.POINTER(vp)]
     lib.qg_filter_eval.argtypes = [vp, vp, vp, C.POINTER(i64)]
     lib.qg_filter_destroy.argtypes = [vp]

@@ -170,6 +170,8 @@ struct FacetColumn {
   bool set = false;
   long long n = 0;
   DevBuf kind, num, scode, fcode;
+  DevBuf arr_off, arr_code;  // optional CSR of array elements (qg_facets_set_array_column)
+  long long arr_rows = -1;   // rows covered by arr_off, -1 = none
 };
 
 }  // namespace qg
@@ -472,6 +474,7 @@ int qg_index_destroy(qg_index* idx) {
   for (auto& w : idx->ws_async) w->destroy();
   for (auto& c : idx->cols) {
     c.kind.release(); c.num.release(); c.scode.release(); c.fcode.release();
+    c.arr_off.release(); c.arr_code.release();
   }
   idx->col_table.release();
   idx->stage[0].release();
@@ -648,6 +651,32 @@ int qg_facets_set_column(qg_index* idx, int field, const uint8_t* kind, const do
   QG_CUDA_OK(cudaStreamSynchronize(idx->up_stream));
   c.set = true;
   c.n = n;
+  c.arr_rows = -1;  // a new column invalidates the element lists of the old one
+  idx->facet_epoch++;
+  idx->col_table_dirty = true;
+  return 0;
+}
+
+int qg_facets_set_array_column(qg_index* idx, int field, const int32_t* offsets, const int32_t* elem_codes, int64_t n,
+                               int64_t n_elems) {
+  if (int rc = check_index(idx)) return rc;
+  if (field < 0 || (size_t)field >= idx->cols.size() || !idx->cols[field].set)
+    return fail(QG_ERR_INVALID, "set the column with qg_facets_set_column first");
+  FacetColumn& c = idx->cols[field];
+  if (n != c.n) return fail(QG_ERR_RANGE, "array column must cover the same rows as the column");
+  if (n_elems < 0 || !offsets || (n_elems > 0 && !elem_codes)) return fail(QG_ERR_INVALID, "null array column buffer");
+  if (offsets[0] != 0 || offsets[n] != n_elems) return fail(QG_ERR_INVALID, "offsets must run from 0 to n_elems");
+  for (int64_t i = 0; i < n; ++i)
+    if (offsets[i + 1] < offsets[i]) return fail(QG_ERR_INVALID, "offsets must be non-decreasing");
+  // rows appended later own no elements: the offsets are padded with n_elems up to the capacity
+  const size_t cap = (size_t)std::max<long long>(idx->cap, 1);
+  std::vector<int32_t> off(cap + 1, (int32_t)n_elems);
+  std::copy(offsets, offsets + n + 1, off.begin());
+  if (int rc = c.arr_off.ensure((cap + 1) * 4)) return rc;
+  if (int rc = c.arr_code.ensure(std::max<size_t>(1, (size_t)n_elems) * 4)) return rc;
+  QG_CUDA_OK(cudaMemcpy(c.arr_off.p, off.data(), (cap + 1) * 4, cudaMemcpyHostToDevice));
+  if (n_elems > 0) QG_CUDA_OK(cudaMemcpy(c.arr_code.p, elem_codes, (size_t)n_elems * 4, cudaMemcpyHostToDevice));
+  c.arr_rows = (long long)cap;
   idx->facet_epoch++;
   idx->col_table_dirty = true;
   return 0;
@@ -667,11 +696,11 @@ int qg_filter_compile(qg_index* idx, const qg_pred* preds, int n_preds, const qg
   }
   for (int i = 0; i < n_clauses; ++i) {
     const qg_clause& c = clauses[i];
-    if (c.op < QG_OP_FALSE || c.op > QG_OP_NUM_BITS_EQ) return fail(QG_ERR_UNSUPPORTED, "unknown clause op");
+    if (c.op < QG_OP_FALSE || c.op > QG_OP_ELEM_IN) return fail(QG_ERR_UNSUPPORTED, "unknown clause op");
     if (c.op >= QG_OP_KIND_IN) {
       if (c.field < 0 || c.field >= 4096) return fail(QG_ERR_INVALID, "clause field out of range");
     }
-    if (c.op == QG_OP_SCODE_IN || c.op == QG_OP_FCODE_IN) {
+    if (c.op == QG_OP_SCODE_IN || c.op == QG_OP_FCODE_IN || c.op == QG_OP_ELEM_IN) {
       if (c.ia < 0 || c.ic < 0 || c.ia + c.ic > n_iset) return fail(QG_ERR_INVALID, "clause int-set out of bounds");
     }
     if (c.op == QG_OP_NUM_IN_TOL || c.op == QG_OP_NUM_IN) {
@@ -753,6 +782,10 @@ static int prepare_columns(qg_index* idx, const qg_filter* f) {
       tab[i].num = (const double*)idx->cols[i].num.p;
       tab[i].scode = (const int32_t*)idx->cols[i].scode.p;
       tab[i].fcode = (const int32_t*)idx->cols[i].fcode.p;
+      // only rows below the column's n can be arrays, and the element lists cover those
+      const bool arr_ok = idx->cols[i].arr_rows >= 0;
+      tab[i].arr_off = arr_ok ? (const int32_t*)idx->cols[i].arr_off.p : nullptr;
+      tab[i].arr_code = arr_ok ? (const int32_t*)idx->cols[i].arr_code.p : nullptr;
     }
     if (int rc = idx->col_table.ensure(tab.size() * sizeof(FacetColDev))) return rc;
     QG_CUDA_OK(cudaMemcpy(idx->col_table.p, tab.data(), tab.size() * sizeof(FacetColDev), cudaMemcpyHostToDevice));

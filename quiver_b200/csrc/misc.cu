@@ -180,6 +180,15 @@ __device__ __forceinline__ bool eval_clause(const qg_clause& c, const FacetColDe
       case QG_OP_NUM_BITS_EQ:
         r = kind == QG_KIND_NUMBER && __double_as_longlong(col.num[row]) == __double_as_longlong(c.fa);
         break;
+      case QG_OP_ELEM_IN:
+        if (kind == QG_KIND_OTHER && col.arr_off != nullptr) {
+          const int e1 = col.arr_off[row + 1];
+          for (int e = col.arr_off[row]; e < e1 && !r; ++e) {
+            const int v = col.arr_code[e];
+            for (int j = 0; j < c.ic; ++j) r |= prog.iset[c.ia + j] == v;
+          }
+        }
+        break;
       default:
         r = false;
     }

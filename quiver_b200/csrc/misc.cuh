@@ -11,6 +11,8 @@ struct FacetColDev {
   const double* num;
   const int32_t* scode;
   const int32_t* fcode;
+  const int32_t* arr_off;   // [rows + 1] CSR offsets of the array-valued rows' elements, or nullptr
+  const int32_t* arr_code;  // element codes
 };
 
 struct FilterProgDev {

@@ -3,6 +3,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstring>
 
 namespace qh {
 
@@ -100,7 +102,51 @@ void exists_pred(Builder& b, int field) {
   b.end_pred(first, false);
 }
 
+std::string hex_bits(double x) {
+  if (x == 0.0) x = 0.0;  // -0 == +0 under ==
+  uint64_t u;
+  static_assert(sizeof(u) == sizeof(x), "double is 64 bits");
+  std::memcpy(&u, &x, 8);
+  char buf[17];
+  std::snprintf(buf, sizeof buf, "%016llx", (unsigned long long)u);
+  return buf;
+}
+
+// reflect.DeepEqual below the top level is type-sensitive: a decoded float64 never equals a Go int.
+std::string nested_key(const Value& v) {
+  switch (v.type) {
+    case Value::Null: return "z";
+    case Value::Bool: return v.b ? "b1" : "b0";
+    case Value::Number: return "f" + hex_bits(v.num);
+    case Value::Int: return "i" + hex_bits(v.num);
+    case Value::String: return "s" + std::to_string(v.str.size()) + ":" + v.str;
+    case Value::Array: {
+      std::string k = "a[";
+      for (const ValuePtr& e : v.arr) k += (e ? nested_key(*e) : std::string("z")) + ",";
+      return k + "]";
+    }
+    case Value::Object: {
+      std::string k = "o{";
+      for (const auto& kv : v.obj)
+        k += std::to_string(kv.first.size()) + ":" + kv.first + "=" + (kv.second ? nested_key(*kv.second) : std::string("z")) + ",";
+      return k + "}";
+    }
+  }
+  return "?";
+}
+
+int elem_code(const Column& col, const std::string& key) {
+  auto it = std::lower_bound(col.elem_keys.begin(), col.elem_keys.end(), key);
+  if (it == col.elem_keys.end() || *it != key) return -1;
+  return (int)(it - col.elem_keys.begin());
+}
+
 }  // namespace
+
+std::string element_key(const Value& v) {
+  if (v.is_numeric()) return "n" + hex_bits(v.num);  // toFloat64(a) == toFloat64(b)
+  return nested_key(v);
+}
 
 void encode_column(const std::vector<CellRef>& cells, Column* out) {
   const size_t n = cells.size();
@@ -111,6 +157,11 @@ void encode_column(const std::vector<CellRef>& cells, Column* out) {
   out->texts.clear();
   out->folded.clear();
   out->has_array_rows = false;
+  out->arr_off.assign(n + 1, 0);
+  out->arr_code.clear();
+  out->elem_keys.clear();
+  std::vector<std::string> elems;       // element keys in row order
+  std::vector<int32_t> elem_count(n, 0);
   std::vector<std::string> text(n), fold(n);
   for (size_t i = 0; i < n; ++i) {
     if (cells[i].no_row) { out->kind[i] = QG_KIND_NOROW; continue; }
@@ -129,10 +180,17 @@ void encode_column(const std::vector<CellRef>& cells, Column* out) {
       case Value::Array:
         out->kind[i] = (uint8_t)(K_OTHER | (v->arr.empty() ? 0 : 0x80));
         out->has_array_rows = true;
+        for (const ValuePtr& e : v->arr) {
+          static const Value kNil;
+          elems.push_back(element_key(e ? *e : kNil));
+        }
+        elem_count[i] = (int32_t)v->arr.size();
         break;
       case Value::Object:
         out->kind[i] = (uint8_t)(K_OTHER | (v->obj.empty() ? 0 : 0x80));
         out->has_array_rows = true;
+        elems.push_back(element_key(*v));  // a map is compared whole (facets.go:322-328)
+        elem_count[i] = 1;
         break;
     }
   }
@@ -146,6 +204,12 @@ void encode_column(const std::vector<CellRef>& cells, Column* out) {
   out->texts.erase(std::unique(out->texts.begin(), out->texts.end()), out->texts.end());
   std::sort(out->folded.begin(), out->folded.end());
   out->folded.erase(std::unique(out->folded.begin(), out->folded.end()), out->folded.end());
+  out->elem_keys = elems;
+  std::sort(out->elem_keys.begin(), out->elem_keys.end());
+  out->elem_keys.erase(std::unique(out->elem_keys.begin(), out->elem_keys.end()), out->elem_keys.end());
+  out->arr_code.reserve(elems.size());
+  for (const std::string& k : elems) out->arr_code.push_back(elem_code(*out, k));
+  for (size_t i = 0; i < n; ++i) out->arr_off[i + 1] = out->arr_off[i] + elem_count[i];
   for (size_t i = 0; i < n; ++i) {
     const int k = out->kind[i] & 0x7f;
     if (k == K_MISSING || k == QG_KIND_NOROW) continue;
@@ -244,9 +308,21 @@ int compile_facet_filters(const std::vector<FacetFilter>& filters, ColumnSource&
         break;
       }
       case FacetFilter::Set: {
+        // array facet: any element valuesEqual to any member; map facet: the whole value
+        // (facets.go:308-328) — both through the column's element dictionary
         if (col.has_array_rows) {
-          if (err) *err = "set filter over array-valued facets is not supported on the device path";
-          return QG_ERR_UNSUPPORTED;
+          const int e0 = (int)out->iset.size();
+          for (const ValuePtr& v : f.values) {
+            static const Value kNil;
+            const int code = elem_code(col, element_key(v ? *v : kNil));
+            if (code >= 0) out->iset.push_back(code);
+          }
+          if ((int)out->iset.size() > e0) {
+            qg_clause c = clause(QG_OP_ELEM_IN, field);
+            c.ia = e0;
+            c.ic = (int)out->iset.size() - e0;
+            b.add(c);
+          }
         }
         // string facet: EqualFold against the string members (facets.go:296-307)
         const int i0 = (int)out->iset.size();

@@ -22,8 +22,17 @@ struct Column {
   std::vector<int32_t> fcode;   // id of the case-folded string in `folded` (sorted, unique); -1 otherwise
   std::vector<std::string> texts;
   std::vector<std::string> folded;
-  bool has_array_rows = false;  // a row holds an array/map value (element-wise predicates are unsupported)
+  bool has_array_rows = false;  // a row holds an array / map value
+  // Elements of the array-valued rows (CSR over all rows; a map counts as its own single element:
+  // facets.go:322-328 compares it whole). elem_keys is the sorted, unique dictionary of element_key()
+  // strings; arr_code holds indices into it.
+  std::vector<int32_t> arr_off, arr_code;
+  std::vector<std::string> elem_keys;
 };
+
+// Dictionary key of one value under facets.valuesEqual (facets.go:515-520): equal keys <=> valuesEqual.
+// Numbers compare as float64 whatever their Go type, everything else by reflect.DeepEqual.
+std::string element_key(const Value& v);
 
 // value == nullptr: the field is absent (MISSING); no_row: the row has no metadata / facet entry.
 struct CellRef {

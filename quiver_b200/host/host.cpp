@@ -186,6 +186,9 @@ struct qh_collection : qh::ColumnSource {
     qh::encode_column(cells, &dc.col);
     last_rc = qg_facets_set_column(index->h, dc.index, dc.col.kind.data(), dc.col.num.data(), dc.col.scode.data(),
                                    dc.col.fcode.data(), (int64_t)n);
+    if (!last_rc && dc.col.has_array_rows)
+      last_rc = qg_facets_set_array_column(index->h, dc.index, dc.col.arr_off.data(), dc.col.arr_code.data(), (int64_t)n,
+                                           (int64_t)dc.col.arr_code.size());
     dc.epoch = epoch;
     return dc;
   }
