@@ -40,7 +40,7 @@ $(LIBDIR)/libquivergpu.so: $(CU_OBJS)
 # exists in this image). -ffp-contract=off: the rerank arithmetic must not fuse (hybrid_index.go:552).
 $(LIBDIR)/libquiverhost.so: $(HOST_SRCS) $(HOST_HDRS) $(LIBDIR)/libquivergpu.so
 	@mkdir -p $(LIBDIR)
-	$(CXX) -std=c++17 -O2 -fPIC -shared -ffp-contract=off -Wall -Iinclude -o $@ $(HOST_SRCS) \
+	$(CXX) -std=c++17 -O2 -fPIC -shared -pthread -ffp-contract=off -Wall -Iinclude -o $@ $(HOST_SRCS) \
 	    -L$(LIBDIR) -lquivergpu -Wl,-rpath,'$$ORIGIN'
 
 # The oracle is test infrastructure: strict IEEE, no contraction (Go/amd64 never fuses).

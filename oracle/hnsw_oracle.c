@@ -207,6 +207,8 @@ qo_hnsw* qo_hnsw_build(const float* vec, int64_t n, int d, int metric, int arith
   h->visited = (uint8_t*)calloc((size_t)n + 1, 1);
   qh_res* buf = (qh_res*)malloc(sizeof(qh_res) * (size_t)(ef_construction + max_m0 + M + 8));
   qh_res* nd = (qh_res*)malloc(sizeof(qh_res) * (size_t)(max_m0 + M + 8));
+  const char* std_env = getenv("QO_HNSW_STANDARD");
+  const int standard = std_env != NULL && std_env[0] == '1';
   for (int64_t i = 0; i < n; ++i) {
     /* Insert, hnsw.go:266-334 */
     int level = random_level(h, seed, (uint64_t)i);
@@ -252,7 +254,10 @@ qo_hnsw* qo_hnsw_build(const float* vec, int64_t n, int d, int metric, int arith
           h->conn_n[nb][lc] = keep;
         }
       }
-      if (ns > 0) ep = (uint32_t)i;
+      /* hnsw.go sets the next layer's entry point to the node being inserted (which has no links
+       * there yet) - kept faithfully. QO_HNSW_STANDARD=1 descends from the closest neighbour found
+       * instead (the textbook algorithm): measurement aid only, never used by a parity test. */
+      if (ns > 0) ep = standard ? buf[0].idx : (uint32_t)i;
     }
     if (level > old_level) {
       h->entry = (uint32_t)i;

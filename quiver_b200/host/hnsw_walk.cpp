@@ -8,6 +8,11 @@
 #include <memory>
 #include <string>
 #include <vector>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 
 #include "../../include/quiver_gpu.h"
 #include "../../include/quiver_host.h"
@@ -83,6 +88,79 @@ struct MaxHeap {
 };
 
 enum Stage { ENTRY_DISTANCE, LAYER_START, EXPAND, DONE };
+
+// The walks of a batch are independent between two distance rounds: their heap work (the part the
+// GPU does not take over) is spread over the host cores by a small persistent pool.
+class WalkPool {
+ public:
+  explicit WalkPool(int n_threads) {
+    for (int t = 1; t < n_threads; ++t) workers_.emplace_back([this] { loop(); });
+  }
+  ~WalkPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+      ++gen_;
+    }
+    cv_.notify_all();
+    for (std::thread& t : workers_) t.join();
+  }
+  // fn(i) for every i in [0, n), in chunks claimed from a shared counter; returns when all are done.
+  void run(int n, const std::function<void(int)>& fn) {
+    if (workers_.empty() || n < 256) {
+      for (int i = 0; i < n; ++i) fn(i);
+      return;
+    }
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      fn_ = &fn;
+      n_ = n;
+      next_.store(0);
+      busy_ = (int)workers_.size();
+      ++gen_;
+    }
+    cv_.notify_all();
+    work();
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [this] { return busy_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void work() {
+    const int chunk = 64;
+    for (;;) {
+      const int i0 = next_.fetch_add(chunk);
+      if (i0 >= n_) break;
+      const int i1 = std::min(n_, i0 + chunk);
+      for (int i = i0; i < i1; ++i) (*fn_)(i);
+    }
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+      }
+      work();
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--busy_ == 0) done_cv_.notify_one();
+      }
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_cv_;
+  const std::function<void(int)>* fn_ = nullptr;
+  std::atomic<int> next_{0};
+  int n_ = 0, busy_ = 0;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+};
 
 struct Walk {
   Stage stage = ENTRY_DISTANCE;
@@ -252,23 +330,29 @@ extern "C" int qh_hnsw_search_batch(qh_index* idx, const qh_hnsw_graph* g, const
   };
 
   int rc = 0;
+  const int n_threads = (int)std::max(1u, std::min({std::thread::hardware_concurrency(), 32u, (unsigned)(nq / 256 + 1)}));
+  WalkPool pool(n_threads);
+  std::atomic<int> any{0};
+  const std::function<void(int)> do_advance = [&](int i) {
+    Walk& w = walks[(size_t)i];
+    uint32_t* slot = rows.data() + (size_t)i * m;
+    advance(w);
+    const size_t np = w.stage == DONE ? 0 : w.pending.size();
+    std::copy(w.pending.begin(), w.pending.begin() + (long)np, slot);
+    std::fill(slot + np, slot + m, 0xFFFFFFFFu);
+    if (w.stage != DONE) any.store(1, std::memory_order_relaxed);
+  };
+  const std::function<void(int)> do_consume = [&](int i) {
+    Walk& w = walks[(size_t)i];
+    if (w.stage != DONE && !w.pending.empty()) consume(w, dist.data() + (size_t)i * m);
+  };
   for (;;) {
-    bool any = false;
-    std::fill(rows.begin(), rows.end(), 0xFFFFFFFFu);
-    for (int i = 0; i < nq; ++i) {
-      Walk& w = walks[(size_t)i];
-      advance(w);
-      if (w.stage == DONE) continue;
-      any = true;
-      std::copy(w.pending.begin(), w.pending.end(), rows.begin() + (size_t)i * m);
-    }
-    if (!any) break;
+    any.store(0);
+    pool.run(nq, do_advance);
+    if (!any.load()) break;
     ++steps;
     if ((rc = qg_batch_distance_queries(h, qs, rows.data(), m, dist.data()))) break;
-    for (int i = 0; i < nq; ++i) {
-      Walk& w = walks[(size_t)i];
-      if (w.stage != DONE && !w.pending.empty()) consume(w, dist.data() + (size_t)i * m);
-    }
+    pool.run(nq, do_consume);
   }
   qg_queries_destroy(qs);
   if (rc) return qh_internal_fail(rc, qg_last_error());
