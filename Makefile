@@ -7,6 +7,10 @@ CXX       ?= g++
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := -std=c++17 -O3 $(ARCH) -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unused-function \
              --expt-relaxed-constexpr -Xptxas -warn-spills
+# make TC_INSTRUMENT=1: per-role cycle counters inside the tensor-core scan (tools/tc_timing.py)
+ifeq ($(TC_INSTRUMENT),1)
+NVFLAGS   += -DQG_TC_INSTRUMENT
+endif
 CSRC      := quiver_b200/csrc
 BUILD     := build/csrc
 LIBDIR    := quiver_b200/lib

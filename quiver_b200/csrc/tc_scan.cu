@@ -487,9 +487,18 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+// The per-role cycle counters and wall-clock stamps below cost ~35 predicated instructions per tile and
+// epilogue warp even when switched off at run time, so they are compiled in only with
+// -DQG_TC_INSTRUMENT (make TC_INSTRUMENT=1; tools/tc_timing.py needs that build).
+#ifdef QG_TC_INSTRUMENT
+constexpr bool TS_INSTRUMENT = true;
+#else
+constexpr bool TS_INSTRUMENT = false;
+#endif
+
 // wall-clock stamps of the first and the last CTA (debug counters 40..47 and 48..55)
 __device__ __forceinline__ void dbg_stamp(unsigned long long* dbg, int slot) {
-  if (dbg == nullptr) return;
+  if (!TS_INSTRUMENT || dbg == nullptr) return;
   if (blockIdx.x == 0) dbg[40 + slot] = global_ns();
   else if (blockIdx.x == gridDim.x - 1) dbg[48 + slot] = global_ns();
 }
@@ -500,16 +509,22 @@ struct DbgClock {
   unsigned long long* d;
   long long t0;
   __device__ __forceinline__ void start() {
-    if (d != nullptr) t0 = clock64();
+    if (TS_INSTRUMENT && d != nullptr) t0 = clock64();
   }
   __device__ __forceinline__ void lap(int slot) {
-    if (d != nullptr) {
+    if (TS_INSTRUMENT && d != nullptr) {
       const long long t1 = clock64();
       d[slot] += (unsigned long long)(t1 - t0);
       t0 = t1;
     }
   }
 };
+
+__device__ __forceinline__ int lds_s32(const volatile int* p) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(const_cast<const int*>(p))) : "memory");
+  return v;
+}
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
@@ -598,7 +613,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
     const bool with_sc = MODE != MODE_L2 && p.sc != nullptr;
     const uint32_t xs_bytes = (uint32_t)(ROWS * 4 * (with_sc ? 2 : 1));
     DbgClock clk{(p.dbg != nullptr && blockIdx.x == 0 && lane == 0) ? p.dbg : nullptr, 0};
-    const long long t_prod_begin = clock64();
+    const long long t_prod_begin = TS_INSTRUMENT ? clock64() : 0;
     // the threshold kernel zeroes the work counter (main scan); the previous pass's finalize still reads
     // nothing this kernel writes before this point
     pdl_wait();
@@ -677,13 +692,13 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
     }
     push(0, false, true);
     if (!RAW) push(0, false, false);
-    if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0) {
+    if (TS_INSTRUMENT && p.dbg != nullptr && blockIdx.x == 0 && lane == 0) {
       p.dbg[0] = (unsigned long long)(clock64() - t_prod_begin);
     }
   } else if (warp == 1) {
     // ===== MMA issuer (converged warp, one elected lane issues) =====
     DbgClock clk{(p.dbg != nullptr && blockIdx.x == 0 && lane == 0) ? p.dbg : nullptr, 0};
-    const long long t_mma_begin = clock64();
+    const long long t_mma_begin = TS_INSTRUMENT ? clock64() : 0;
     mbar_wait(a_ready, 0);
     tc_fence_after();
     if (lane == 0) dbg_stamp(p.dbg, 3);
@@ -698,7 +713,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
       clk.start();
       mbar_wait(&full[stage], phase);
       clk.lap(5);
-      const int wtag = ring_tag[stage];
+      const int wtag = lds_s32(&ring_tag[stage]);
       if (wtag < 0) break;  // end of work
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
       clk.lap(4);
@@ -777,7 +792,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
       }
     }
     if (lane == 0) dbg_stamp(p.dbg, 5);
-    if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0) {
+    if (TS_INSTRUMENT && p.dbg != nullptr && blockIdx.x == 0 && lane == 0) {
       p.dbg[3] = (unsigned long long)(clock64() - t_mma_begin);
     }
   } else if (warp >= 4) {
@@ -847,7 +862,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
     int prev_pos = 0;
     bool has_pend = false, prev_has = false;
     DbgClock clk{(p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && warp < 8) ? p.dbg + 8 + (warp - 4) * 8 : nullptr, 0};
-    const long long t_epi_begin = clock64();
+    const long long t_epi_begin = TS_INSTRUMENT ? clock64() : 0;
 
     int acc = pp;  // tile it uses buffer it % n_acc; this half sees every second tile
     uint32_t acc_phase = 0;
@@ -858,12 +873,12 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
       long long w;
       if (RAW) {
         mbar_wait(&tmem_full[acc], acc_phase);
-        w = acc_work[acc];
+        w = lds_s32(&acc_work[acc]);
         if (w < 0) break;  // end of work
         clk.lap(2);
       } else {
         mbar_wait(&xs_full[xb], xphase);
-        w = xs_work[xb];
+        w = lds_s32(&xs_work[xb]);
         if (w < 0) break;  // end of work
         clk.lap(1);
         mbar_wait(&tmem_full[acc], acc_phase);
@@ -1039,7 +1054,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
       }
     }
     if (!SAMPLE && prev_has && prev_pos < TC_CAND_CAP) p.cand[(size_t)q * TC_CAND_CAP + prev_pos] = prev_key;
-    if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0) {
+    if (TS_INSTRUMENT && p.dbg != nullptr && blockIdx.x == 0 && lane == 0) {
       if (warp < 8) p.dbg[8 + (warp - 4) * 8] = (unsigned long long)(clock64() - t_epi_begin);  // one warp per lane quarter reports
     }
   }

@@ -1,4 +1,5 @@
-"""Development aid: per-role cycle counters of the tensor-core scan (QG_TC_TIMING)."""
+"""Development aid: per-role cycle counters of the tensor-core scan (QG_TC_TIMING).
+Needs the instrumented build: make -B lib TC_INSTRUMENT=1 (the counters are compiled out by default)."""
 import os, sys
 import numpy as np
 os.environ["QG_TC_TIMING"] = "1"
