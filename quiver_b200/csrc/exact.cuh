@@ -129,4 +129,55 @@ __device__ __forceinline__ float exact_distance_warp(int metric, int arith, cons
   return (float)(1.0 - sim);                                  // distances.go:39
 }
 
+// Up to three stored rows against one query in a single pass of the warp: the reference's float64
+// sums are strictly sequential (one lane per sum, ~20 cycles per addition), so the three staging arrays
+// that cosine needs for one row carry one row each for L2 / L1 / dot and lanes 0..2 run the three
+// chains side by side. Same operation order per row as exact_distance_warp, hence the same bits.
+// out[j] is valid on every lane for j < nb. Metrics / arithmetic modes that need more than one array per
+// row (cosine, the float32 variants) fall back to one row at a time.
+__device__ __forceinline__ void exact_distance_warp3(int metric, int arith, const float* __restrict__ a,
+                                                     const float* const* b, int nb, int d, double* scratch,
+                                                     float* out) {
+  const bool one_array = arith != ARITH_HNSW_F32 && (metric == METRIC_L2 || metric == METRIC_L1 || metric == METRIC_DOT);
+  if (!one_array || nb == 1) {
+    for (int j = 0; j < nb; ++j) out[j] = exact_distance_warp(metric, arith, a, b[j], d, scratch);
+    return;
+  }
+  const int lane = threadIdx.x & 31;
+  double s = 0.0;  // lane j < nb: the sum of row j
+  for (int base = 0; base < d; base += EXACT_CHUNK) {
+    const int n = min(EXACT_CHUNK, d - base);
+    for (int i = lane; i < n; i += 32) {
+      const float x = a[base + i];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        if (j >= nb) break;
+        const float y = b[j][base + i];
+        double t;
+        if (metric == METRIC_L2) {
+          const double df = (double)__fsub_rn(x, y);
+          t = df * df;
+        } else if (metric == METRIC_L1) {
+          t = fabs((double)__fsub_rn(x, y));
+        } else {
+          t = (double)x * (double)y;
+        }
+        scratch[j * EXACT_CHUNK + i] = t;
+      }
+    }
+    __syncwarp();
+    if (lane < nb) {
+      const double* t = scratch + lane * EXACT_CHUNK;
+      for (int i = 0; i < n; ++i) s = __dadd_rn(s, t[i]);
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (j >= nb) break;
+    const double sj = __shfl_sync(0xffffffffu, s, j);
+    out[j] = metric == METRIC_L2 ? (float)sqrt(sj) : (metric == METRIC_L1 ? (float)sj : (float)(1.0 - sj));
+  }
+}
+
 }  // namespace qg

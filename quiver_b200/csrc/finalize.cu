@@ -613,10 +613,18 @@ __global__ void __launch_bounds__(FC_THREADS, 2) finalize_cand_kernel(const Fina
     const char* rowp = reinterpret_cast<const char*>(p.vec + (size_t)key_row(sel[c]) * p.dp);
     if (lane * 128 < p.dp * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + lane * 128));
   }
-  for (int c = warp; c < nsel; c += FC_WARPS) {
-    const uint32_t row = key_row(sel[c]);
-    const float dist = exact_distance_warp(p.metric, p.arith, qv, p.vec + (size_t)row * p.dp, p.d, scratch);
-    if (lane == 0) ex[c] = make_key(dist, row);
+  for (int c = warp; c < nsel; c += 3 * FC_WARPS) {  // three candidates of the warp per pass
+    const float* rows3[3];
+    uint32_t rid[3];
+    int nb = 0;
+    for (int j = 0; j < 3 && c + j * FC_WARPS < nsel; ++j, ++nb) {
+      rid[j] = key_row(sel[c + j * FC_WARPS]);
+      rows3[j] = p.vec + (size_t)rid[j] * p.dp;
+    }
+    float dist3[3];
+    exact_distance_warp3(p.metric, p.arith, qv, rows3, nb, p.d, scratch, dist3);
+    if (lane == 0)
+      for (int j = 0; j < nb; ++j) ex[c + j * FC_WARPS] = make_key(dist3[j], rid[j]);
   }
   __syncthreads();
   ts[nts++] = clock64();  // first re-rank done
@@ -654,10 +662,19 @@ __global__ void __launch_bounds__(FC_THREADS, 2) finalize_cand_kernel(const Fina
       extra = cap - nsel;
       certified = false;
     }
-    for (int c = warp; c < extra; c += FC_WARPS) {
-      const uint32_t row = key_row(ex[nsel + c]);
-      const float dist = exact_distance_warp(p.metric, p.arith, qv, p.vec + (size_t)row * p.dp, p.d, scratch);
-      if (lane == 0) ex[nsel + c] = make_key(dist, row);
+    for (int c = warp; c < extra; c += 3 * FC_WARPS) {
+      const float* rows3[3];
+      uint32_t rid[3];
+      int nb = 0;
+      for (int j = 0; j < 3 && c + j * FC_WARPS < extra; ++j, ++nb) {
+        rid[j] = key_row(ex[nsel + c + j * FC_WARPS]);
+        rows3[j] = p.vec + (size_t)rid[j] * p.dp;
+      }
+      float dist3[3];
+      exact_distance_warp3(p.metric, p.arith, qv, rows3, nb, p.d, scratch, dist3);
+      __syncwarp();
+      if (lane == 0)
+        for (int j = 0; j < nb; ++j) ex[nsel + c + j * FC_WARPS] = make_key(dist3[j], rid[j]);
     }
     __syncthreads();
     nex = nsel + extra;
