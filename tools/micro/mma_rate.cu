@@ -54,7 +54,7 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
 // CHAINS independent accumulators used round-robin; every MMA accumulates into its chain's D. The issue
 // loop is unrolled 16x inside one elected region so that descriptor arithmetic stays off the critical path.
 template <int N, int CHAINS, bool SS>
-__global__ void bench(int iters, unsigned long long* out) {
+__global__ void bench(int iters, unsigned long long* out, int delay = 0) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint32_t slot;
@@ -88,6 +88,10 @@ __global__ void bench(int iters, unsigned long long* out) {
         }
       }
       __syncwarp();
+      if (delay > 0) {  // the issuer is busy elsewhere (barrier polls) between groups of 16 MMAs
+        const long long until = clock64() + delay;
+        while (clock64() < until) {}
+      }
     }
     const long long t1 = clock64();
     if (elect_one()) umma_commit(&bar);
@@ -128,9 +132,25 @@ void run_all(unsigned long long* d_out) {
   run<256, 1, SS>(d_out);
 }
 
+// How deep is the MMA queue? 16 MMAs (N = 64: 512 cycles of tensor work) then `delay` cycles in which the
+// issuer does something else: if the total per group stays 512 the queue absorbs the gap.
+void run_delay(unsigned long long* d_out) {
+  const int iters = 4096;
+  cudaFuncSetAttribute(bench<64, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  for (int delay : {0, 100, 200, 300, 400, 600}) {
+    bench<64, 2, false><<<148, 128, 70 * 1024>>>(iters, d_out, delay);
+    cudaDeviceSynchronize();
+    unsigned long long h[2];
+    cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
+    printf("TS N=64 groups of 16 MMAs + %3d idle issuer cycles: %.1f cycles per group (tensor work 512)\n", delay,
+           (double)h[1] / (iters / 16));
+  }
+}
+
 int main() {
   unsigned long long* d_out;
   cudaMalloc(&d_out, 16 * 148);
+  run_delay(d_out);
   run_all<false>(d_out);
   run_all<true>(d_out);
   cudaFree(d_out);
