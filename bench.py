@@ -334,17 +334,28 @@ def run_native(args):
         def step_e2e():
             return idx.search(q_host, k)
     else:
-        h_keys = torch.empty((Q, k), dtype=torch.int64).pin_memory()
+        # results land in pinned host buffers (a pageable .cpu() would add a staging copy per step)
+        if by_queries:
+            h_allb = torch.empty(d_allb.numel(), dtype=torch.uint8).pin_memory()
+        else:
+            h_dist = torch.empty((Q, k), dtype=torch.float32).pin_memory()
+            h_row = torch.empty((Q, k), dtype=torch.int64).pin_memory()
+            h_cnt = torch.empty((Q,), dtype=torch.int32).pin_memory()
 
         def step_e2e():
             if by_queries:
                 dq[q0:q1].copy_(q_pin[q0:q1], non_blocking=True)
                 step_device()
-                return d_allb.cpu()
+                h_allb.copy_(d_allb, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                return h_allb
             dq.copy_(q_pin, non_blocking=True)
             step_device()
-            out = (d_dist.cpu(), d_row.cpu(), d_cnt.cpu())
-            return out
+            h_dist.copy_(d_dist, non_blocking=True)
+            h_row.copy_(d_row, non_blocking=True)
+            h_cnt.copy_(d_cnt, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return h_dist, h_row, h_cnt
     for _ in range(3):
         step_e2e()
     barrier()

@@ -441,9 +441,9 @@ constexpr int TS_REGS_EPI = 104;                 // ... to the epilogue warp gro
 constexpr int TS_MAX_ACC = 4;        // accumulator buffers in tensor memory (as many as fit beside the queries)
 constexpr int TS_CLAIM = 2;          // corpus tiles per work claim of the main scan
 constexpr int TS_XS = 8;                          // ring of per-tile row-term buffers
-// corpus rows per tile = MMA N: two resident query blocks leave 64 accumulator columns per buffer,
-// one block leaves 128 (512 TMEM columns = nblk * kb * 32 + nblk * 2 * rows)
-__host__ __device__ constexpr int ts_rows(int nblk) { return nblk == 2 ? 64 : 128; }
+// corpus rows per tile = MMA N = 128. The accumulator of one (tile, query block) pair is a *unit* of
+// 128 TMEM columns; as many unit buffers as fit beside the resident queries rotate (2 or 3).
+__host__ __device__ constexpr int ts_rows(int /*nblk*/) { return 128; }
 
 struct TsKParams {
   long long n_rows;
@@ -457,7 +457,7 @@ struct TsKParams {
   const uint32_t* apack;  // this pass's queries in tensor-memory order (tc_pack_kernel)
   int* work_counter;      // main scan: tiles beyond the first of each CTA are claimed here (zeroed by tc_tau_kernel)
   int dp;
-  uint32_t* sample;  // [n_cols][n_sample][nblk == 2 ? 1 : 2]: one minimum per tile (and chunk parity)
+  uint32_t* sample;  // [n_cols][n_sample][2]: one minimum per tile and chunk parity
   int n_sample;
   const float* tau;
   uint64_t* cand;
@@ -570,7 +570,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
   const int ksteps = p.ksteps;                   // MMA k-steps per row (the last k-block may be partial)
   const int tile_bytes = kb * KBLOCK_BYTES;      // one ring stage = one whole tile
   const int d_off = NBLK * a_cols;               // first accumulator column
-  const int n_acc = min(TS_MAX_ACC, (512 - d_off) / (NBLK * ROWS));  // accumulator buffers of NBLK * ROWS columns
+  // Accumulator units: one (tile, query block) pair = ROWS columns. Unit u of iteration `it` is
+  // u = it (one block) or 2 * it + blk (two blocks); it lives in buffer u % n_acc and is drained by
+  // epilogue group u & 1 — the tile-parity ping-pong half (one block) or the block's warps (two blocks).
+  const int n_acc = min(TS_MAX_ACC, (512 - d_off) / ROWS);
   const long long n_work = SAMPLE ? (long long)p.n_sample : p.n_tiles;
   auto tile_of = [&](long long w) -> long long { return SAMPLE ? (w * p.n_sample_from) / p.n_sample : w; };
 
@@ -586,11 +589,11 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
     }
     for (int i = 0; i < TS_MAX_ACC; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], TS_EPI_WARPS / 2);  // a tile is drained by one ping-pong half
+      mbar_init(&tmem_empty[i], TS_EPI_WARPS / 2);  // a unit is drained by one group of 8 warps
     }
     for (int i = 0; i < TS_XS; ++i) {
       mbar_init(&xs_full[i], 1);
-      mbar_init(&xs_empty[i], TS_EPI_WARPS / 2);
+      mbar_init(&xs_empty[i], NBLK == 2 ? TS_EPI_WARPS : TS_EPI_WARPS / 2);  // both blocks read a tile's row terms
     }
     mbar_init(a_ready, TS_EPI_WARPS);
     fence_mbar_init();
@@ -691,7 +694,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
       }
     }
     push(0, false, true);
-    if (!RAW) push(0, false, false);
+    if (!RAW && NBLK == 1) push(0, false, false);  // one end tag per ping-pong half in the row-term ring
     if (TS_INSTRUMENT && p.dbg != nullptr && blockIdx.x == 0 && lane == 0) {
       p.dbg[0] = (unsigned long long)(clock64() - t_prod_begin);
     }
@@ -715,64 +718,57 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
       clk.lap(5);
       const int wtag = lds_s32(&ring_tag[stage]);
       if (wtag < 0) break;  // end of work
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
-      clk.lap(4);
-      tc_fence_after();
-      if (elect_one()) {
-        if (RAW) {  // the work index travels with the accumulator buffer
-          acc_work[acc] = wtag;
-          __threadfence_block();
-        }
-        const uint32_t d0 = tmem_base + (uint32_t)(d_off + acc * NBLK * ROWS);
-        const uint32_t d1 = d0 + ROWS;
-        const uint64_t bdesc = desc0 + (uint64_t)((uint32_t)stage * (uint32_t)(tile_bytes >> 4));
-        if (KB > 0) {
+      const uint64_t bdesc = desc0 + (uint64_t)((uint32_t)stage * (uint32_t)(tile_bytes >> 4));
 #pragma unroll
-          for (int kbi = 0; kbi < (KB > 0 ? KB : 1); ++kbi) {
+      for (int blk = 0; blk < NBLK; ++blk) {  // one accumulator unit per resident query block
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        clk.lap(4);
+        tc_fence_after();
+        if (elect_one()) {
+          if (RAW) {  // the work index travels with the accumulator buffer
+            acc_work[acc] = wtag;
+            __threadfence_block();
+          }
+          const uint32_t du = tmem_base + (uint32_t)(d_off + acc * ROWS);
+          const uint32_t au = tmem_base + (uint32_t)(blk * a_cols);
+          if (KB > 0) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (kbi * 4 + k >= ksteps) continue;
-              const uint64_t bd = bdesc + (uint64_t)(kbi * (KBLOCK_BYTES >> 4) + k * 2);
-              const uint32_t aa = tmem_base + (uint32_t)(kbi * TC_KBLOCK + k * 8);
-              if (BF16) {
-                umma_bf16_ts(d0, aa, bd, idesc, (kbi | k) != 0 ? 1u : 0u);
-                if (NBLK == 2) umma_bf16_ts(d1, aa + (uint32_t)a_cols, bd, idesc, (kbi | k) != 0 ? 1u : 0u);
-              } else {
-                umma_tf32_ts(d0, aa, bd, idesc, (kbi | k) != 0 ? 1u : 0u);
-                if (NBLK == 2) umma_tf32_ts(d1, aa + (uint32_t)a_cols, bd, idesc, (kbi | k) != 0 ? 1u : 0u);
+            for (int kbi = 0; kbi < (KB > 0 ? KB : 1); ++kbi) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (kbi * 4 + k >= ksteps) continue;
+                const uint64_t bd = bdesc + (uint64_t)(kbi * (KBLOCK_BYTES >> 4) + k * 2);
+                const uint32_t aa = au + (uint32_t)(kbi * TC_KBLOCK + k * 8);
+                if (BF16) umma_bf16_ts(du, aa, bd, idesc, (kbi | k) != 0 ? 1u : 0u);
+                else umma_tf32_ts(du, aa, bd, idesc, (kbi | k) != 0 ? 1u : 0u);
               }
             }
-          }
-        } else {
-          uint64_t bd0 = bdesc;
-          uint32_t a0 = tmem_base;
-          for (int kbi = 0; kbi < kb; ++kbi) {
+          } else {
+            uint64_t bd0 = bdesc;
+            uint32_t a0 = au;
+            for (int kbi = 0; kbi < kb; ++kbi) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (kbi * 4 + k >= ksteps) continue;
-              if (BF16) {
-                umma_bf16_ts(d0, a0 + k * 8, bd0 + (uint64_t)(k * 2), idesc, (kbi | k) != 0 ? 1u : 0u);
-                if (NBLK == 2) umma_bf16_ts(d1, a0 + a_cols + k * 8, bd0 + (uint64_t)(k * 2), idesc, (kbi | k) != 0 ? 1u : 0u);
-              } else {
-                umma_tf32_ts(d0, a0 + k * 8, bd0 + (uint64_t)(k * 2), idesc, (kbi | k) != 0 ? 1u : 0u);
-                if (NBLK == 2) umma_tf32_ts(d1, a0 + a_cols + k * 8, bd0 + (uint64_t)(k * 2), idesc, (kbi | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) {
+                if (kbi * 4 + k >= ksteps) continue;
+                if (BF16) umma_bf16_ts(du, a0 + k * 8, bd0 + (uint64_t)(k * 2), idesc, (kbi | k) != 0 ? 1u : 0u);
+                else umma_tf32_ts(du, a0 + k * 8, bd0 + (uint64_t)(k * 2), idesc, (kbi | k) != 0 ? 1u : 0u);
               }
+              bd0 += (uint64_t)(KBLOCK_BYTES >> 4);
+              a0 += TC_KBLOCK;
             }
-            bd0 += (uint64_t)(KBLOCK_BYTES >> 4);
-            a0 += TC_KBLOCK;
           }
+          if (blk == NBLK - 1) umma_commit(&empty[stage]);  // the stage is free once the last block has read it
+          umma_commit(&tmem_full[acc]);
         }
-        umma_commit(&empty[stage]);
-        umma_commit(&tmem_full[acc]);
+        __syncwarp();
+        if (++acc == n_acc) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
       }
-      __syncwarp();
       if (++stage == S) {
         stage = 0;
         phase ^= 1u;
-      }
-      if (++acc == n_acc) {
-        acc = 0;
-        acc_phase ^= 1u;
       }
     }
     if (RAW) {
@@ -806,13 +802,13 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
     //   NBLK == 1: they split the 8 chunks of the 128-row tile (even / odd chunks)
     const int quarter = warp & 3;
     const int grp = (warp - 4) >> 2;                     // 0..3
-    const int pp = grp & 1;                              // ping-pong half = tile parity = accumulator buffer
-    const int sub = grp >> 1;
-    const int blk = NBLK == 2 ? sub : 0;                 // query block of this warp
+    const int pp = grp & 1;                              // epilogue group: drains the units with u & 1 == pp
+    const int sub = grp >> 1;                            // which half of the unit's chunks (even / odd)
+    const int blk = NBLK == 2 ? pp : 0;                  // query block of this warp
     const int q = blk * 128 + quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    constexpr int NCH = 4;                               // chunks per warp and tile
-    auto chunk_of = [&](int ci) -> int { return NBLK == 2 ? ci : sub + 2 * ci; };
+    constexpr int NCH = 4;                               // chunks per warp and unit (8 chunks of 16 rows, two warps)
+    auto chunk_of = [&](int ci) -> int { return sub + 2 * ci; };
 
     // the sample stage may directly follow the kernel that packs the queries; the main scan's
     // predecessor (threshold kernel) never touches them, so its query load overlaps that kernel
@@ -822,7 +818,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
     //  split the 16-column groups of their query block between them)
     {
       const int nch = a_cols / 16;
-      const int cpart = NBLK == 2 ? pp : grp, nparts = NBLK == 2 ? 2 : 4;
+      const int cpart = NBLK == 2 ? sub : grp, nparts = NBLK == 2 ? 2 : 4;
       const uint4* ap = reinterpret_cast<const uint4*>(p.apack) +
                         ((size_t)blk * nch * 128 + (size_t)(quarter * 32 + lane)) * 4;
       for (int c = cpart; c < nch; c += nparts) {
@@ -864,9 +860,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
     DbgClock clk{(p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && warp < 8) ? p.dbg + 8 + (warp - 4) * 8 : nullptr, 0};
     const long long t_epi_begin = TS_INSTRUMENT ? clock64() : 0;
 
-    int acc = pp;  // tile it uses buffer it % n_acc; this half sees every second tile
+    int acc = pp;  // unit u uses buffer u % n_acc; this group drains every second unit
     uint32_t acc_phase = 0;
-    for (long long it = pp;; it += 2) {
+    // one block: units are tiles and the group sees every second tile; two blocks: every tile, its block
+    for (long long it = (NBLK == 2 ? 0 : pp);; it += (NBLK == 2 ? 1 : 2)) {
       const int xb = (int)(it % TS_XS);
       const uint32_t xphase = (uint32_t)((it / TS_XS) & 1);
       clk.start();
@@ -887,7 +884,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
       const long long tile = tile_of(w);
       if (it == 0 && warp == 4 && lane == 0) dbg_stamp(p.dbg, 4);
       tc_fence_after();
-      const uint32_t d_addr = tmem_base + lane_base + (uint32_t)(d_off + (acc * NBLK + blk) * ROWS);
+      const uint32_t d_addr = tmem_base + lane_base + (uint32_t)(d_off + acc * ROWS);
       // all of this warp's accumulator chunks are requested before the first one is consumed
       uint32_t araw[NCH][16];
 #pragma unroll
@@ -1046,11 +1043,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
       if (SAMPLE && q < p.nq) {
         // minimum score of this tile for this query: sample[q][w] (NBLK == 2) or sample[q][w][group]
         const uint32_t mn = tile_min == __int_as_float(0x7f800000) ? 0xFFFFFFFFu : f32_to_ordered(tile_min);
-        if (NBLK == 2) {
-          p.sample[(size_t)q * p.n_sample + (size_t)w] = mn;
-        } else {
-          p.sample[((size_t)q * p.n_sample + (size_t)w) * 2 + sub] = mn;
-        }
+        p.sample[((size_t)q * p.n_sample + (size_t)w) * 2 + sub] = mn;
       }
     }
     if (!SAMPLE && prev_has && prev_pos < TC_CAND_CAP) p.cand[(size_t)q * TC_CAND_CAP + prev_pos] = prev_key;
@@ -1318,7 +1311,7 @@ int tc_plan(int dp, int d16, int nq, bool bf16, TcPlan* out) {
         out->a_cols = a_cols;
         out->stages = stages;
         out->tile_rows = rows;
-        out->sample_vals = nblk == 2 ? 1 : 2;
+        out->sample_vals = 2;
         out->smem = ts_smem_layout(stages, kb16, rows).total + 1024;
         return 0;
       }
@@ -1340,7 +1333,7 @@ int tc_plan(int dp, int d16, int nq, bool bf16, TcPlan* out) {
       out->a_cols = kb * TC_KBLOCK;
       out->stages = stages;
       out->tile_rows = rows;
-      out->sample_vals = nblk == 2 ? 1 : 2;
+      out->sample_vals = 2;
       out->smem = ts_smem_layout(stages, kb, rows).total + 1024;
       return 0;
     }
