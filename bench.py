@@ -258,6 +258,7 @@ def run_native(args):
         torch.cuda.synchronize()
     checked = None
     host_corpus = None
+    uncertified = 0  # queries the device API returned with count -1 (not counted as served)
     if not args.no_check and rank == 0:
         nchk = min(Q, 8)
         chk_ids = sorted(set(int(x) for x in np.linspace(0, Q - 1, nchk)))
@@ -267,18 +268,28 @@ def run_native(args):
             corpus_chk = oracle.synth(args.kind, args.seed, 0, sub_rows, d, threads=min(16, host_cores()))
             host_corpus = corpus_chk
             got_d, got_r = d_dist.cpu().numpy(), d_row.cpu().numpy()
-            assert (d_cnt.cpu().numpy() == min(k, args.rows)).all(), "uncertified queries in the device-API run"
+            cnt_host = d_cnt.cpu().numpy()
+            uncertified = int((cnt_host < 0).sum())
+            # the device API marks a query whose selection could not be proven with count -1 (the host API
+            # re-runs it through the flat scan); a sampled threshold makes that rare, not impossible
+            assert uncertified <= max(1, Q // 2000), f"{uncertified} uncertified queries in the device-API run"
+            assert ((cnt_host == min(k, args.rows)) | (cnt_host < 0)).all()
+            chk_ids = [i for i in chk_ids if cnt_host[i] >= 0]
             for i in chk_ids:
                 od, orow = oracle.exact_search(corpus_chk, q_host[i], k, mid)
                 assert np.array_equal(got_r[i, :len(orow)], orow), (i, got_r[i], orow)
                 assert np.array_equal(got_d[i, :len(od)].view(np.uint32), od.view(np.uint32))
             checked = (f"{len(chk_ids)} queries spread over the batch bit-identical to the oracle over all "
-                       f"{sub_rows} rows; all {Q} queries certified")
+                       f"{sub_rows} rows; {Q - uncertified} of {Q} queries certified in the device-API run")
         else:
             # full-size property: distances of the returned rows equal the oracle's pairwise arithmetic,
             # ascending, and no row of a 200k-row prefix beats the k-th result
             corpus_chk = oracle.synth(args.kind, args.seed, 0, sub_rows, d, threads=min(16, host_cores()))
             got_d, got_r = d_dist.cpu().numpy(), d_row.cpu().numpy()
+            cnt_host = d_cnt.cpu().numpy()
+            uncertified = int((cnt_host < 0).sum())
+            assert uncertified <= max(1, Q // 2000), f"{uncertified} uncertified queries in the device-API run"
+            chk_ids = [i for i in chk_ids if cnt_host[i] >= 0]
             for i in chk_ids:
                 rows_i = got_r[i]
                 vecs = np.stack([oracle.synth(args.kind, args.seed, int(r), 1, d, threads=1)[0] for r in rows_i])
@@ -325,7 +336,7 @@ def run_native(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
-    qps = Q / (ms_step * 1e-3)
+    qps = (Q - uncertified) / (ms_step * 1e-3)
     Q_gpu = (q1 - q0) if (world > 1 and by_queries) else Q  # queries one GPU's kernels serve per step
 
     # ---- e2e: host buffers through the C ABI call a Go caller would make ----------------------------------
@@ -481,6 +492,7 @@ def run_native(args):
                              "path": {0: "exhaustive", 1: "flat scan", 2: "gather scan", 3: "tensor-core"}[stats["path"]],
                              "queries_per_pass": stats["queries_per_pass"],
                              "merge": 1 if (world > 1 and not by_queries) else 0},
+        "uncertified_queries_device_api": uncertified,
         "small_batch_regime": small,
         "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_base,
         "host_cores": host_cores(), "device": capi.device_info(local_rank)["name"],
