@@ -977,8 +977,12 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
   }
   if (tc_possible && !gather) {
     const long long n_sample = tc_sample_tiles(plan, idx->n_rows, k);
-    if (int rc = w->tc_sample.ensure((size_t)plan.n_cols * n_sample * plan.sample_vals * 4)) return rc;
-    if (int rc = w->tc_tau.ensure((size_t)TC_MAX_COLS * 4)) return rc;
+    // TS variant: the sample + threshold stage runs once for all passes of the search
+    const int n_pass_tc = (q + plan.n_cols - 1) / plan.n_cols;
+    const bool hoist = plan.variant == 1 && n_pass_tc > 1;
+    const size_t q_slots = hoist ? (size_t)n_pass_tc * plan.n_cols : (size_t)plan.n_cols;
+    if (int rc = w->tc_sample.ensure(q_slots * n_sample * plan.sample_vals * 4)) return rc;
+    if (int rc = w->tc_tau.ensure(std::max<size_t>(q_slots, TC_MAX_COLS) * 4)) return rc;
     if (int rc = w->tc_cand.ensure((size_t)plan.n_cols * TC_CAND_CAP * 8)) return rc;
     if (int rc = w->tc_cnt.ensure((size_t)(TC_MAX_COLS + 4) * 4)) return rc;
     // raw scan: bf16 stream without a mask — the norm columns of the bf16 rows make the MMA output the score
@@ -1027,9 +1031,25 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
     fb.gamma = (float)((d + 16) * 5.9604645e-8);
     fb.max_norm2 = idx->max_norm2;
     fb.row_base = a.row_base;
-    for (int p0 = 0; p0 < q; p0 += plan.n_cols) {
-      const int nq = std::min(plan.n_cols, q - p0);
+    // profiling: kind 2 = sample + threshold kernels, kind 0 = main scan kernel
+    TcStageHook hook{[](void* ctx, int stage, int begin, cudaStream_t s) {
+                       Workspace* ws = static_cast<Workspace*>(ctx);
+                       if (begin) ws->prof_begin(stage == 0 ? 2 : 0, s);
+                       else ws->prof_end(s);
+                     },
+                     w};
+    if (hoist) {
+      cp.reset_cnt = (int*)w->tc_cnt.p;
+      cp.reset_work = (int*)w->tc_cnt.p + TC_MAX_COLS;
+    }
+    for (int p0 = hoist ? -1 : 0; p0 < q; p0 = p0 < 0 ? 0 : p0 + plan.n_cols) {
+      // p0 == -1: the sample + threshold stage of every pass at once (hoisted out of the loop)
+      const bool all = p0 < 0;
+      const int q0 = all ? 0 : p0;
+      const int nq = all ? q : std::min(plan.n_cols, q - p0);
       TcArgs ta{};
+      ta.sample_only = all ? 1 : 0;
+      ta.presampled = hoist ? 1 : 0;
       ta.vec = idx->vec;
       ta.vec16 = idx->vec16;
       ta.dp16 = idx->dp16;
@@ -1039,8 +1059,8 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
       ta.inv_norm = idx->metric == METRIC_COSINE ? idx->inv_norm : nullptr;
       ta.mask = mask;
       ta.bias = tc_bias;
-      ta.queries = qpad + (size_t)p0 * dp;
-      ta.apack = plan.variant == 1 ? (const char*)w->tc_apack.p + tc_pack_bytes(plan, p0) : nullptr;
+      ta.queries = qpad + (size_t)q0 * dp;
+      ta.apack = plan.variant == 1 ? (const char*)w->tc_apack.p + tc_pack_bytes(plan, q0) : nullptr;
       ta.raw = tc_raw;
       ta.work_counter = (int*)w->tc_cnt.p + TC_MAX_COLS;
       ta.nq = nq;
@@ -1048,22 +1068,16 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
       ta.cosine = fb.cosine;
       ta.sample = (uint32_t*)w->tc_sample.p;
       ta.n_sample = (int)n_sample;
-    ta.sample_rank = tc_sample_rank(k);
       ta.sample_rank = tc_sample_rank(k);
-      ta.tau = (float*)w->tc_tau.p;
+      ta.tau = (float*)w->tc_tau.p + (hoist ? q0 : 0);
       ta.cand = (uint64_t*)w->tc_cand.p;
       ta.cand_cnt = (int*)w->tc_cnt.p;
-      // profiling: kind 2 = sample + threshold kernels, kind 0 = main scan kernel
-      TcStageHook hook{[](void* ctx, int stage, int begin, cudaStream_t s) {
-                         Workspace* ws = static_cast<Workspace*>(ctx);
-                         if (begin) ws->prof_begin(stage == 0 ? 2 : 0, s);
-                         else ws->prof_end(s);
-                       },
-                       w};
       const int rc = launch_tc_pass(plan, ta, idx->sm_count, st, &stats.kernel_launches,
                                     idx->profiling ? &hook : nullptr);
       if (rc) return rc;
+      if (all) continue;
       stats.passes++;
+      cp.tau = (const float*)w->tc_tau.p + (hoist ? q0 : 0);
       fb.queries = qpad + (size_t)p0 * dp;
       fb.negatives = negpad ? negpad + (size_t)p0 * dp : nullptr;
       fb.out_dist = a.d_dist ? a.d_dist + (size_t)p0 * k : nullptr;

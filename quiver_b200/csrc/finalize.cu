@@ -725,6 +725,12 @@ __global__ void __launch_bounds__(FC_THREADS, 2) finalize_cand_kernel(const Fina
     }
     if (tid == 0) p.out_count[q] = certified ? kk : -1;
   }
+  // the next pass of the search reuses the candidate lists: its scan starts only after this kernel
+  // has completed (dependent launch), so the counters can be handed back zeroed from here
+  if (tid == 0 && cp.reset_cnt != nullptr) {
+    cp.reset_cnt[q] = 0;
+    if (q == 0 && cp.reset_work != nullptr) *cp.reset_work = 0;
+  }
   if (cp.dbg != nullptr && q == 0 && tid == 0) {
     ts[nts++] = clock64();
     for (int i = 0; i < nts; ++i) cp.dbg[i] = (unsigned long long)(ts[i] - ts[0]);

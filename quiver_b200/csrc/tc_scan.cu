@@ -455,6 +455,8 @@ struct TsKParams {
   const float* bias;   // [rows padded to 128] additive row term: |x|^2 (L2) or 1 (dot); +inf = row excluded
   const float* sc;     // [rows padded to 128] 1/|x| (cosine) or nullptr
   const uint32_t* apack;  // this pass's queries in tensor-memory order (tc_pack_kernel)
+  long long pass_stride;  // sample stage over a whole search: 32-bit words between two passes' query blocks
+                          // (blockIdx.y = pass); nq then counts all queries of the search
   int* work_counter;      // main scan: tiles beyond the first of each CTA are claimed here (zeroed by tc_tau_kernel)
   int dp;
   uint32_t* sample;  // [n_cols][n_sample][2]: one minimum per tile and chunk parity
@@ -575,6 +577,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
   // epilogue group u & 1 — the tile-parity ping-pong half (one block) or the block's warps (two blocks).
   const int n_acc = min(TS_MAX_ACC, (512 - d_off) / ROWS);
   const long long n_work = SAMPLE ? (long long)p.n_sample : p.n_tiles;
+  const int py = SAMPLE ? (int)blockIdx.y : 0;  // pass of the search this CTA samples for
   auto tile_of = [&](long long w) -> long long { return SAMPLE ? (w * p.n_sample_from) / p.n_sample : w; };
 
   // Chained launch: the successor may be launched right away; this kernel's own setup (barriers, TMEM,
@@ -805,7 +808,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
     const int pp = grp & 1;                              // epilogue group: drains the units with u & 1 == pp
     const int sub = grp >> 1;                            // which half of the unit's chunks (even / odd)
     const int blk = NBLK == 2 ? pp : 0;                  // query block of this warp
-    const int q = blk * 128 + quarter * 32 + lane;
+    const int q = py * (NBLK * 128) + blk * 128 + quarter * 32 + lane;  // query index (within p.nq)
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     constexpr int NCH = 4;                               // chunks per warp and unit (8 chunks of 16 rows, two warps)
     auto chunk_of = [&](int ci) -> int { return sub + 2 * ci; };
@@ -819,7 +822,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
     {
       const int nch = a_cols / 16;
       const int cpart = NBLK == 2 ? sub : grp, nparts = NBLK == 2 ? 2 : 4;
-      const uint4* ap = reinterpret_cast<const uint4*>(p.apack) +
+      const uint4* ap = reinterpret_cast<const uint4*>(p.apack + (size_t)py * (size_t)p.pass_stride) +
                         ((size_t)blk * nch * 128 + (size_t)(quarter * 32 + lane)) * 4;
       for (int c = cpart; c < nch; c += nparts) {
         float v[16];
@@ -1085,7 +1088,7 @@ constexpr int TAU_THREADS = 128;
 
 __global__ void __launch_bounds__(TAU_THREADS) tc_tau_kernel(const uint32_t* __restrict__ sample, int n_vals, int rank,
                                                              float* __restrict__ tau, int* __restrict__ cand_cnt,
-                                                             int* __restrict__ work_counter) {
+                                                             int n_cnt, int* __restrict__ work_counter) {
   const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   pdl_launch_dependents();
   pdl_wait();  // the sample comes from the kernel just before; tau / cand_cnt are read by the one before that
@@ -1120,7 +1123,7 @@ __global__ void __launch_bounds__(TAU_THREADS) tc_tau_kernel(const uint32_t* __r
     if (lane == 0) {
       // 0xFFFFFFFF: fewer than `rank` valid samples -> admit everything
       tau[q] = (m == 0xFFFFFFFFu) ? __int_as_float(0x7f800000) : ordered_to_f32(m);
-      cand_cnt[q] = 0;
+      if (q < n_cnt) cand_cnt[q] = 0;  // the first pass's counters (finalize_cand re-zeroes them for the next)
       if (q == 0 && work_counter != nullptr) *work_counter = 0;
     }
   }
@@ -1466,22 +1469,33 @@ static int launch_ts_pass(const TcPlan& plan, const TcArgs& a, int sm_count, cud
   p.dbg = nullptr;
   if (a.apack == nullptr || a.work_counter == nullptr) return fail(1, "tensor-core TS pass needs packed queries and a work counter");
   if (!raw && a.bias == nullptr) return fail(1, "tensor-core TS pass needs the per-row bias column");
-  const int grid_s = (int)std::min<long long>(sm_count, a.n_sample);
   const int grid_m = (int)std::min<long long>(sm_count, p.n_tiles);
-  if (hook) hook->fn(hook->ctx, 0, 1, st);
-  QG_CUDA_OK(launch_chained(ts_kernel(a.mode, true, plan.nblk, plan.kb, bf16, raw), dim3(grid_s), dim3(TS_THREADS),
-                            (size_t)plan.smem, st, tm_x, p));
-  QG_CUDA_OK(launch_chained(tc_tau_kernel, dim3(a.nq), dim3(TAU_THREADS), (size_t)0, st, (const uint32_t*)a.sample,
-                            a.n_sample * plan.sample_vals, sample_rank, a.tau, a.cand_cnt, a.work_counter));
-  if (a.dbg != nullptr && std::getenv("QG_TC_NOHIT"))  // development aid: a scan that admits nothing
-    launch_fill_f32(a.tau, a.nq, -__builtin_huge_valf(), st);
-  if (hook) hook->fn(hook->ctx, 0, 0, st);
+  if (a.sample_only || !a.presampled) {
+    // sample + threshold: for this pass, or (sample_only) for all passes of a search in one launch each
+    // — the sample depends on nothing but the queries, and hoisting it out of the pass loop pays its
+    // launch, TMEM allocation and pipeline ramp once per search instead of once per 256 queries
+    const int n_pass = a.sample_only ? (a.nq + plan.n_cols - 1) / plan.n_cols : 1;
+    int gx = (int)std::min<long long>(sm_count, a.n_sample);
+    if (n_pass > 1) gx = (int)std::max<long long>(1, std::min<long long>(a.n_sample, sm_count / n_pass));
+    p.pass_stride = (long long)plan.n_cols * plan.a_cols;
+    if (hook) hook->fn(hook->ctx, 0, 1, st);
+    QG_CUDA_OK(launch_chained(ts_kernel(a.mode, true, plan.nblk, plan.kb, bf16, raw), dim3(gx, n_pass), dim3(TS_THREADS),
+                              (size_t)plan.smem, st, tm_x, p));
+    QG_CUDA_OK(launch_chained(tc_tau_kernel, dim3(a.nq), dim3(TAU_THREADS), (size_t)0, st, (const uint32_t*)a.sample,
+                              a.n_sample * plan.sample_vals, sample_rank, a.tau, a.cand_cnt, plan.n_cols,
+                              a.work_counter));
+    if (a.dbg != nullptr && std::getenv("QG_TC_NOHIT"))  // development aid: a scan that admits nothing
+      launch_fill_f32(a.tau, a.nq, -__builtin_huge_valf(), st);
+    if (hook) hook->fn(hook->ctx, 0, 0, st);
+    if (launches) *launches += 2;
+    if (a.sample_only) return 0;
+  }
   p.dbg = a.dbg;
   if (hook) hook->fn(hook->ctx, 1, 1, st);
   QG_CUDA_OK(launch_chained(ts_kernel(a.mode, false, plan.nblk, plan.kb, bf16, raw), dim3(grid_m), dim3(TS_THREADS),
                             (size_t)plan.smem, st, tm_x, p));
   if (hook) hook->fn(hook->ctx, 1, 0, st);
-  if (launches) *launches += 3;
+  if (launches) *launches += 1;
   return 0;
 }
 
@@ -1522,7 +1536,7 @@ int launch_tc_pass(const TcPlan& plan, const TcArgs& a, int sm_count, cudaStream
   QG_CUDA_OK(cudaGetLastError());
   tc_tau_kernel<<<a.nq, TAU_THREADS, 0, st>>>(a.sample, a.n_sample * 2,
                                               std::min(TC_SAMPLE_RANK_MAX, std::max(1, a.sample_rank)), a.tau, a.cand_cnt,
-                                              nullptr);
+                                              a.nq, nullptr);
   QG_CUDA_OK(cudaGetLastError());
   if (hook) hook->fn(hook->ctx, 0, 0, st);
   if (hook) hook->fn(hook->ctx, 1, 1, st);

@@ -63,6 +63,10 @@ struct TcArgs {
   const void* vec16;        // [n_rows x dp16] bf16 copy (plan.bf16), else nullptr
   int dp16;
   int raw;                  // plan.bf16 only, no mask: scores come straight out of the MMA (no row-term column)
+  // TS variant, multi-pass searches: launch_tc_pass with sample_only = 1 runs the sample + threshold stage
+  // for ALL nq queries of the search (apack / sample / tau sized for every pass); the per-pass calls then
+  // set presampled = 1 and point apack / tau at their pass.
+  int sample_only, presampled;
   long long n_rows;
   int dp;
   const float* row_norm2;   // [n_rows] |x|^2 (L2 scores)
