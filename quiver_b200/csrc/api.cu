@@ -983,8 +983,12 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
     const size_t q_slots = hoist ? (size_t)n_pass_tc * plan.n_cols : (size_t)plan.n_cols;
     if (int rc = w->tc_sample.ensure(q_slots * n_sample * plan.sample_vals * 4)) return rc;
     if (int rc = w->tc_tau.ensure(std::max<size_t>(q_slots, TC_MAX_COLS) * 4)) return rc;
-    if (int rc = w->tc_cand.ensure((size_t)plan.n_cols * TC_CAND_CAP * 8)) return rc;
-    if (int rc = w->tc_cnt.ensure((size_t)(TC_MAX_COLS + 4) * 4)) return rc;
+    // hoisted searches finalize TC_PASS_GROUP passes per launch: candidate lists, counters and tile-claim
+    // counters exist once per pass of a group
+    const int group = hoist ? TC_PASS_GROUP : 1;
+    const size_t cnt_slots = (size_t)group * TC_MAX_COLS;  // work counters follow at [cnt_slots ..)
+    if (int rc = w->tc_cand.ensure((size_t)group * plan.n_cols * TC_CAND_CAP * 8)) return rc;
+    if (int rc = w->tc_cnt.ensure((cnt_slots + 8) * 4)) return rc;
     // raw scan: bf16 stream without a mask — the norm columns of the bf16 rows make the MMA output the score
     const bool tc_raw = plan.variant == 1 && plan.bf16 && mask == nullptr && idx->n_rows >= plan.tile_rows &&
                         tc_raw_supported(d, mode == MODE_L2);
@@ -1040,8 +1044,10 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
                      w};
     if (hoist) {
       cp.reset_cnt = (int*)w->tc_cnt.p;
-      cp.reset_work = (int*)w->tc_cnt.p + TC_MAX_COLS;
+      cp.reset_work = (int*)w->tc_cnt.p + cnt_slots;
+      cp.n_reset_work = group;
     }
+    int pass_no = 0;  // pass index within the search
     for (int p0 = hoist ? -1 : 0; p0 < q; p0 = p0 < 0 ? 0 : p0 + plan.n_cols) {
       // p0 == -1: the sample + threshold stage of every pass at once (hoisted out of the loop)
       const bool all = p0 < 0;
@@ -1062,7 +1068,9 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
       ta.queries = qpad + (size_t)q0 * dp;
       ta.apack = plan.variant == 1 ? (const char*)w->tc_apack.p + tc_pack_bytes(plan, q0) : nullptr;
       ta.raw = tc_raw;
-      ta.work_counter = (int*)w->tc_cnt.p + TC_MAX_COLS;
+      const int slot = all ? 0 : pass_no % group;  // this pass's lists inside its group
+      ta.work_counter = (int*)w->tc_cnt.p + cnt_slots + slot;
+      ta.n_cnt = group * plan.n_cols;
       ta.nq = nq;
       ta.mode = mode;
       ta.cosine = fb.cosine;
@@ -1070,23 +1078,30 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
       ta.n_sample = (int)n_sample;
       ta.sample_rank = tc_sample_rank(k);
       ta.tau = (float*)w->tc_tau.p + (hoist ? q0 : 0);
-      ta.cand = (uint64_t*)w->tc_cand.p;
-      ta.cand_cnt = (int*)w->tc_cnt.p;
+      ta.cand = (uint64_t*)w->tc_cand.p + (size_t)slot * plan.n_cols * TC_CAND_CAP;
+      ta.cand_cnt = (int*)w->tc_cnt.p + (size_t)slot * plan.n_cols;
       const int rc = launch_tc_pass(plan, ta, idx->sm_count, st, &stats.kernel_launches,
                                     idx->profiling ? &hook : nullptr);
       if (rc) return rc;
       if (all) continue;
       stats.passes++;
-      cp.tau = (const float*)w->tc_tau.p + (hoist ? q0 : 0);
-      fb.queries = qpad + (size_t)p0 * dp;
-      fb.negatives = negpad ? negpad + (size_t)p0 * dp : nullptr;
-      fb.out_dist = a.d_dist ? a.d_dist + (size_t)p0 * k : nullptr;
-      fb.out_negdist = a.d_negdist ? a.d_negdist + (size_t)p0 * k : nullptr;
-      fb.out_row = a.d_row ? a.d_row + (size_t)p0 * k : nullptr;
-      fb.out_count = a.d_count ? a.d_count + p0 : nullptr;
-      fb.out_keys = a.d_keys ? a.d_keys + (size_t)p0 * k : nullptr;
+      ++pass_no;
+      // finalize once per group of passes (a partial pass can only be the last one of the search, so the
+      // queries of a group are contiguous: the lists of its passes sit one after the other)
+      const bool group_done = pass_no % group == 0 || p0 + plan.n_cols >= q;
+      if (!group_done) continue;
+      const int g0 = (pass_no - 1) / group * group * plan.n_cols;  // first query of the group
+      const int gq = p0 + nq - g0;                                  // queries in the group
+      cp.tau = (const float*)w->tc_tau.p + (hoist ? g0 : 0);
+      fb.queries = qpad + (size_t)g0 * dp;
+      fb.negatives = negpad ? negpad + (size_t)g0 * dp : nullptr;
+      fb.out_dist = a.d_dist ? a.d_dist + (size_t)g0 * k : nullptr;
+      fb.out_negdist = a.d_negdist ? a.d_negdist + (size_t)g0 * k : nullptr;
+      fb.out_row = a.d_row ? a.d_row + (size_t)g0 * k : nullptr;
+      fb.out_count = a.d_count ? a.d_count + g0 : nullptr;
+      fb.out_keys = a.d_keys ? a.d_keys + (size_t)g0 * k : nullptr;
       const bool prof2 = idx->profiling && w->prof_begin(1, st) == 0;
-      const int frc = launch_finalize_cand(cp, nq, st);
+      const int frc = launch_finalize_cand(cp, gq, st);
       if (prof2) w->prof_end(st);
       if (frc) return frc;
       stats.kernel_launches++;

@@ -729,7 +729,7 @@ __global__ void __launch_bounds__(FC_THREADS, 2) finalize_cand_kernel(const Fina
   // has completed (dependent launch), so the counters can be handed back zeroed from here
   if (tid == 0 && cp.reset_cnt != nullptr) {
     cp.reset_cnt[q] = 0;
-    if (q == 0 && cp.reset_work != nullptr) *cp.reset_work = 0;
+    if (q < cp.n_reset_work && cp.reset_work != nullptr) cp.reset_work[q] = 0;
   }
   if (cp.dbg != nullptr && q == 0 && tid == 0) {
     ts[nts++] = clock64();

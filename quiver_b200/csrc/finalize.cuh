@@ -35,7 +35,8 @@ struct FinalizeCandParams {
   const float* tau;         // [nq] admission threshold the scan used (+inf = every row admitted)
   int kp;                   // candidates re-ranked before the certificate (pow2 >= k + margin)
   int* reset_cnt;           // optional: [nq] candidate counters zeroed for the next pass (hoisted sample stage) ...
-  int* reset_work;          // ... and the main scan's tile-claim counter
+  int* reset_work;          // ... and the main scans' tile-claim counters
+  int n_reset_work;         // how many of them (one per pass of the group this launch finalizes)
   double tc_gamma;          // bound on |tensor-core dot - exact dot| / (|q| |x|)
   double tc_norm_gamma;     // raw L2 scan: bound on the extra accumulation error / |x|^2 (the norm rides in the MMA), else 0
   unsigned long long* dbg;  // optional [16] phase time stamps of CTA 0 (development aid), else nullptr

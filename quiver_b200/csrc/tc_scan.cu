@@ -1088,7 +1088,8 @@ constexpr int TAU_THREADS = 128;
 
 __global__ void __launch_bounds__(TAU_THREADS) tc_tau_kernel(const uint32_t* __restrict__ sample, int n_vals, int rank,
                                                              float* __restrict__ tau, int* __restrict__ cand_cnt,
-                                                             int n_cnt, int* __restrict__ work_counter) {
+                                                             int n_cnt, int* __restrict__ work_counter,
+                                                             int n_work_counters) {
   const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   pdl_launch_dependents();
   pdl_wait();  // the sample comes from the kernel just before; tau / cand_cnt are read by the one before that
@@ -1124,7 +1125,7 @@ __global__ void __launch_bounds__(TAU_THREADS) tc_tau_kernel(const uint32_t* __r
       // 0xFFFFFFFF: fewer than `rank` valid samples -> admit everything
       tau[q] = (m == 0xFFFFFFFFu) ? __int_as_float(0x7f800000) : ordered_to_f32(m);
       if (q < n_cnt) cand_cnt[q] = 0;  // the first pass's counters (finalize_cand re-zeroes them for the next)
-      if (q == 0 && work_counter != nullptr) *work_counter = 0;
+      if (q < n_work_counters && work_counter != nullptr) work_counter[q] = 0;
     }
   }
 }
@@ -1482,8 +1483,9 @@ static int launch_ts_pass(const TcPlan& plan, const TcArgs& a, int sm_count, cud
     QG_CUDA_OK(launch_chained(ts_kernel(a.mode, true, plan.nblk, plan.kb, bf16, raw), dim3(gx, n_pass), dim3(TS_THREADS),
                               (size_t)plan.smem, st, tm_x, p));
     QG_CUDA_OK(launch_chained(tc_tau_kernel, dim3(a.nq), dim3(TAU_THREADS), (size_t)0, st, (const uint32_t*)a.sample,
-                              a.n_sample * plan.sample_vals, sample_rank, a.tau, a.cand_cnt, plan.n_cols,
-                              a.work_counter));
+                              a.n_sample * plan.sample_vals, sample_rank, a.tau, a.cand_cnt,
+                              a.sample_only ? a.n_cnt : plan.n_cols, a.work_counter,
+                              a.sample_only ? std::max(1, a.n_cnt / plan.n_cols) : 1));
     if (a.dbg != nullptr && std::getenv("QG_TC_NOHIT"))  // development aid: a scan that admits nothing
       launch_fill_f32(a.tau, a.nq, -__builtin_huge_valf(), st);
     if (hook) hook->fn(hook->ctx, 0, 0, st);
@@ -1536,7 +1538,7 @@ int launch_tc_pass(const TcPlan& plan, const TcArgs& a, int sm_count, cudaStream
   QG_CUDA_OK(cudaGetLastError());
   tc_tau_kernel<<<a.nq, TAU_THREADS, 0, st>>>(a.sample, a.n_sample * 2,
                                               std::min(TC_SAMPLE_RANK_MAX, std::max(1, a.sample_rank)), a.tau, a.cand_cnt,
-                                              a.nq, nullptr);
+                                              a.nq, nullptr, 0);
   QG_CUDA_OK(cudaGetLastError());
   if (hook) hook->fn(hook->ctx, 0, 0, st);
   if (hook) hook->fn(hook->ctx, 1, 1, st);

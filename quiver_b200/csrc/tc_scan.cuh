@@ -25,6 +25,7 @@ constexpr int TC_SAMPLE_RANK_MAX = 16;  // largest order statistic of the sample
 // could not be certified); rank 12 puts that below 1e-6 per query for a sample 1.5x as large.
 inline int tc_sample_rank(int k) { return k > 32 ? 16 : 12; }
 constexpr int TC_CAND_CAP = 2048;       // candidate capacity per query per pass
+constexpr int TC_PASS_GROUP = 8;        // passes of a multi-pass search finalized by one finalize_cand launch
 
 struct TcPlan {
   int variant;      // 1 = TS (queries resident in tensor memory, dp <= 256), 0 = SS (queries in shared memory)
@@ -67,6 +68,8 @@ struct TcArgs {
   // for ALL nq queries of the search (apack / sample / tau sized for every pass); the per-pass calls then
   // set presampled = 1 and point apack / tau at their pass.
   int sample_only, presampled;
+  int n_cnt;                // sample_only: candidate counters (and n_cnt / n_cols work counters) the threshold
+                            // kernel zeroes for the first group of passes
   long long n_rows;
   int dp;
   const float* row_norm2;   // [n_rows] |x|^2 (L2 scores)
