@@ -985,8 +985,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
             v[j4 * 4 + 1] = __float_as_uint(r1);
             v[j4 * 4 + 2] = __float_as_uint(r2);
             v[j4 * 4 + 3] = __float_as_uint(r3);
-            const float m4 = fminf(fminf(r0, r1), fminf(r2, r3));
-            cmin[ci] = j4 == 0 ? m4 : fminf(cmin[ci], m4);
+            // three-input minima (FMNMX3): two values per instruction on the half-rate ALU pipe
+            if (j4 == 0) cmin[ci] = fminf(fminf(r0, r1), r2);
+            else cmin[ci] = fminf(fminf(cmin[ci], r0), fminf(r1, r2));
+            cmin[ci] = fminf(cmin[ci], r3);
           }
         }
         tile_min = cmin[0];
