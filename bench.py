@@ -342,8 +342,11 @@ def run_native(args):
     # ---- e2e: host buffers through the C ABI call a Go caller would make ----------------------------------
     e2e_steps = max(10, min(args.steps, 100))
     if world == 1:
+        e2e_out = [None]
+
         def step_e2e():
-            return idx.search(q_host, k)
+            e2e_out[0] = idx.search(q_host, k, out=e2e_out[0])  # result buffers reused from step to step
+            return e2e_out[0]
     else:
         # results land in pinned host buffers (a pageable .cpu() would add a staging copy per step)
         if by_queries:

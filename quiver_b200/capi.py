@@ -250,20 +250,27 @@ class Index:
 
     # -- search --------------------------------------------------------------------------------
     def search(self, queries: np.ndarray, k: int, filter: Optional[Filter] = None,
-               negatives: Optional[np.ndarray] = None):
-        """Host-buffer search. Returns (dist [q,k], row [q,k], count [q], negdist or None)."""
+               negatives: Optional[np.ndarray] = None, out=None):
+        """Host-buffer search. Returns (dist [q,k], row [q,k], count [q], negdist or None).
+        `out` = (dist, row, count[, negdist]) from an earlier call of the same shape reuses the result
+        buffers (the library overwrites every element), as a caller holding result slices would."""
         queries = np.ascontiguousarray(queries, dtype=np.float32)
         if queries.ndim == 1:
             queries = queries[None, :]
         q, dim = queries.shape
         kk = max(k, 0)
-        dist = np.full((q, kk), np.inf, dtype=np.float32)
-        row = np.full((q, kk), -1, dtype=np.int64)
-        cnt = np.zeros(q, dtype=np.int32)
+        if out is not None and out[0].shape == (q, kk) and out[0].dtype == np.float32 and out[1].dtype == np.int64:
+            dist, row, cnt = out[0], out[1], out[2]
+        else:
+            out = None
+            dist = np.full((q, kk), np.inf, dtype=np.float32)
+            row = np.full((q, kk), -1, dtype=np.int64)
+            cnt = np.zeros(q, dtype=np.int32)
         neg = negd = None
         if negatives is not None:
             neg = np.ascontiguousarray(negatives, dtype=np.float32).reshape(q, -1)
-            negd = np.full((q, kk), np.inf, dtype=np.float32)
+            negd = out[3] if (out is not None and len(out) > 3 and out[3] is not None) else \
+                np.full((q, kk), np.inf, dtype=np.float32)
         _check(self._lib.qg_search_batch(self.handle, _ptr(queries), q, dim, k,
                                          filter.handle if filter is not None else None, _ptr(neg), _ptr(dist),
                                          _ptr(negd), _ptr(row), _ptr(cnt)))

@@ -143,8 +143,8 @@ struct Workspace {
     prof_used += 2;
   }
   // host-buffer searches stage their queries chunk by chunk on a copy stream, one event per chunk
-  cudaStream_t copy_stream = nullptr;
-  std::vector<cudaEvent_t> chunk_ev;
+  cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
+  std::vector<cudaEvent_t> chunk_ev;  // per chunk: queries staged, chunk computed, results on the host
   DevBuf qpad, negpad, partial, mask, counters;
   DevBuf tc_sample, tc_tau, tc_cand, tc_cnt, tc_bias, tc_apack;
   DevBuf d_q, d_neg, d_dist, d_negdist, d_row, d_count, d_rows32, d_rows64, d_fetch;
@@ -160,6 +160,7 @@ struct Workspace {
     for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : chunk_ev) cudaEventDestroy(e);
     if (copy_stream) cudaStreamDestroy(copy_stream);
+    if (d2h_stream) cudaStreamDestroy(d2h_stream);
     prof_ev.clear();
     if (done) cudaEventDestroy(done);
     if (stream) cudaStreamDestroy(stream);
@@ -1371,16 +1372,22 @@ int qg_search_batch(qg_index* idx, const float* queries, int q, int dim, int k, 
     constexpr int CHUNK = 2048;
     const int n_chunks = (q + CHUNK - 1) / CHUNK;
     if (n_chunks > 1 && !w->copy_stream &&
-        cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
-      rc = fail(QG_ERR_CUDA, "could not create the copy stream");
+        (cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+         cudaStreamCreateWithFlags(&w->d2h_stream, cudaStreamNonBlocking) != cudaSuccess)) {
+      rc = fail(QG_ERR_CUDA, "could not create the copy streams");
       break;
     }
-    while (n_chunks > 1 && (int)w->chunk_ev.size() < n_chunks) {
+    while (n_chunks > 1 && (int)w->chunk_ev.size() < 3 * n_chunks) {
       cudaEvent_t ev = nullptr;
       if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) break;
       w->chunk_ev.push_back(ev);
     }
-    if (n_chunks > 1 && (int)w->chunk_ev.size() < n_chunks) { rc = fail(QG_ERR_CUDA, "could not create events"); break; }
+    if (n_chunks > 1 && (int)w->chunk_ev.size() < 3 * n_chunks) { rc = fail(QG_ERR_CUDA, "could not create events"); break; }
+    char* const ho = (char*)w->h_out.p;
+    float* const h_dist = (float*)ho;
+    float* const h_neg = (float*)(ho + obytes * 4);
+    long long* const h_row = (long long*)(ho + obytes * 8);
+    int* const h_cnt = (int*)(ho + obytes * 16);
     cudaError_t e = cudaSuccess;
     qg_scan_stats total{};
     for (int c = 0; c < n_chunks && !rc; ++c) {
@@ -1409,20 +1416,49 @@ int qg_search_batch(qg_index* idx, const float* queries, int q, int dim, int k, 
         total.passes += idx->stats.passes;
         total.kernel_launches += idx->stats.kernel_launches;
       }
+      if (n_chunks > 1) {
+        // this chunk's results travel to the host (second copy stream) while the next chunks are scanned
+        cudaEvent_t done = w->chunk_ev[n_chunks + c], landed = w->chunk_ev[2 * n_chunks + c];
+        cudaStream_t ds = w->d2h_stream;
+        const size_t o0 = (size_t)q0 * k, on = (size_t)qc * k;
+        e = cudaEventRecord(done, st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ds, done, 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_dist + o0, (float*)w->d_dist.p + o0, on * 4, cudaMemcpyDeviceToHost, ds);
+        if (e == cudaSuccess && negatives)
+          e = cudaMemcpyAsync(h_neg + o0, (float*)w->d_negdist.p + o0, on * 4, cudaMemcpyDeviceToHost, ds);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_row + o0, (long long*)w->d_row.p + o0, on * 8, cudaMemcpyDeviceToHost, ds);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_cnt + q0, (int*)w->d_count.p + q0, (size_t)qc * 4, cudaMemcpyDeviceToHost, ds);
+        if (e == cudaSuccess) e = cudaEventRecord(landed, ds);
+        if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, cudaGetErrorString(e)); break; }
+      }
     }
     if (rc) break;
     idx->stats = total;
-    char* ho = (char*)w->h_out.p;
-    float* h_dist = (float*)ho;
-    float* h_neg = (float*)(ho + obytes * 4);
-    long long* h_row = (long long*)(ho + obytes * 8);
-    int* h_cnt = (int*)(ho + obytes * 16);
-    e = cudaMemcpyAsync(h_dist, w->d_dist.p, obytes * 4, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && negatives) e = cudaMemcpyAsync(h_neg, w->d_negdist.p, obytes * 4, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h_row, w->d_row.p, obytes * 8, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h_cnt, w->d_count.p, (size_t)q * 4, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, std::string("search: ") + cudaGetErrorString(e)); break; }
+    bool copied_out = false;
+    if (n_chunks > 1) {
+      // hand every chunk to the caller's buffers as soon as it has landed (later chunks are still in flight)
+      for (int c = 0; c < n_chunks && e == cudaSuccess; ++c) {
+        const int q0 = c * CHUNK, qc = std::min(CHUNK, q - q0);
+        const size_t o0 = (size_t)q0 * k, on = (size_t)qc * k;
+        e = cudaEventSynchronize(w->chunk_ev[2 * n_chunks + c]);
+        if (e != cudaSuccess) break;
+        std::memcpy(out_dist + o0, h_dist + o0, on * 4);
+        if (negatives) std::memcpy(out_negdist + o0, h_neg + o0, on * 4);
+        std::memcpy(out_row + o0, h_row + o0, on * 8);
+        std::memcpy(out_count + q0, h_cnt + q0, (size_t)qc * 4);
+      }
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, std::string("search: ") + cudaGetErrorString(e)); break; }
+      copied_out = true;
+    }
+    if (!copied_out) {
+      e = cudaMemcpyAsync(h_dist, w->d_dist.p, obytes * 4, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess && negatives) e = cudaMemcpyAsync(h_neg, w->d_negdist.p, obytes * 4, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(h_row, w->d_row.p, obytes * 8, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(h_cnt, w->d_count.p, (size_t)q * 4, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, std::string("search: ") + cudaGetErrorString(e)); break; }
+    }
     int escalations = 0;
     // queries the tensor-core regime could not certify: redo one by one with the flat scan
     if (idx->stats.path == 3) {
@@ -1497,10 +1533,12 @@ int qg_search_batch(qg_index* idx, const float* queries, int q, int dim, int k, 
     }
     if (rc) break;
     idx->stats.escalations = escalations;
-    std::memcpy(out_dist, h_dist, obytes * 4);
-    if (negatives) std::memcpy(out_negdist, h_neg, obytes * 4);
-    std::memcpy(out_row, h_row, obytes * 8);
-    std::memcpy(out_count, h_cnt, (size_t)q * 4);
+    if (!copied_out || escalations > 0) {  // (re-run queries changed their rows in the staging buffers)
+      std::memcpy(out_dist, h_dist, obytes * 4);
+      if (negatives) std::memcpy(out_negdist, h_neg, obytes * 4);
+      std::memcpy(out_row, h_row, obytes * 8);
+      std::memcpy(out_count, h_cnt, (size_t)q * 4);
+    }
   } while (0);
   ws_release(idx, w);
   return rc;
