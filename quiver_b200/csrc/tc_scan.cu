@@ -1,19 +1,24 @@
-// tc_scan.cu — see tc_scan.cuh. sm_100a only: TMA (cp.async.bulk.tensor), tcgen05.mma kind::tf32,
-// TMEM accumulators, tcgen05.ld epilogue.
+// tc_scan.cu — see tc_scan.cuh. sm_100a only: TMA (cp.async.bulk.tensor), tcgen05.mma kind::f16 (bf16
+// stream) / kind::tf32, TMEM accumulators, tcgen05.ld epilogue.
 //
-// One pass serves up to 256 queries (the MMA N dimension). Three kernels per pass:
-//   1. tc_scan_kernel<MODE, SAMPLE=true>   scores of a strided sample of corpus tiles; per tile and
-//      query the two smallest scores are kept;
-//   2. tc_tau_kernel                       per query, the sample_rank-th smallest sampled score
-//      becomes the admission threshold tau (expected ~256 corpus rows pass per query);
-//   3. tc_scan_kernel<MODE, SAMPLE=false>  persistent scan of every tile: 128 x N accumulator tile
-//      in TMEM -> score -> `score <= tau` -> (rare) append of the (score,row) key to the query's
-//      candidate list in global memory.
-// finalize_cand_kernel (finalize.cu) then re-ranks the candidates exactly and certifies the result:
-// tau is only a performance heuristic, never a correctness assumption.
+// One pass serves up to 256 queries. Kernels:
+//   1. tc_ts_kernel<.., SAMPLE=true>   scores of a strided sample of corpus tiles; per tile and query
+//      the minimum of each half of the tile's chunks is kept. For a multi-pass search it runs ONCE
+//      for all passes (grid.y = pass);
+//   2. tc_tau_kernel                   per query, the sample_rank-th smallest sampled score becomes the
+//      admission threshold tau (expected ~256 corpus rows pass per query); also once per search;
+//   3. tc_ts_kernel<.., SAMPLE=false>  persistent scan of every tile of one pass: queries resident in
+//      TMEM (A operand), corpus tiles through a TMA ring (B operand), one 128-column accumulator unit
+//      per (tile, query block) -> score -> `score <= tau` -> (rare) append of the (score,row) key to
+//      the query's candidate list in global memory.
+//   (tc_scan_kernel is the SS form for dims too large to keep the queries in TMEM.)
+// finalize_cand_kernel (finalize.cu) then re-ranks the candidates exactly and certifies the result
+// (once per group of TC_PASS_GROUP passes): tau is only a performance heuristic, never a correctness
+// assumption. All launches of a search are chained with programmatic dependent launch.
 //
-// Pipelines (mbarriers): full/empty ring of A stages between the TMA warp and the MMA thread;
-// tmem_full/tmem_empty over two accumulator buffers between the MMA thread and the epilogue warps.
+// Pipelines (mbarriers): full/empty ring of corpus stages between the TMA warp and the MMA issuer;
+// tmem_full/tmem_empty over 2-3 accumulator units between the MMA issuer and the two epilogue groups;
+// xs_full/xs_empty ring of per-tile row terms (masked / non-raw scans only).
 #include <cuda.h>
 #include <cuda_bf16.h>
 

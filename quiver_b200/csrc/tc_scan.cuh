@@ -3,11 +3,13 @@
 // For Q >= ~8 queries the distance scan of hybrid.ExactIndex.Search / HybridIndex.BatchSearch
 // (reference pkg/hybrid/exact.go:114-129, hybrid_index.go:703-795: one goroutine per query, each
 // a full pass over the corpus) is a dense [rows x d] x [d x Q] contraction. tc_scan.cu runs it on
-// the 5th-generation tensor cores: TMA stages fp32 corpus tiles (128 rows x 32 floats, 128-byte
-// swizzle) in shared memory, one thread issues tcgen05.mma kind::tf32 with the accumulators in
-// TMEM, and the epilogue warps read them back with tcgen05.ld and keep only the rows whose score
-// is below a per-query threshold. The tf32 scores only SELECT candidates; returned distances are
-// recomputed in the reference's arithmetic and the selection is certified (finalize.cu).
+// the 5th-generation tensor cores: TMA stages tiles of a bf16 copy of the corpus (128 rows x 64
+// elements, 128-byte swizzle; the fp32 rows with kind::tf32 when there is no bf16 copy) in shared
+// memory, the queries sit in tensor memory, one elected thread issues tcgen05.mma with the
+// accumulators in TMEM, and the epilogue warps read them back with tcgen05.ld and keep only the rows
+// whose score is below a per-query threshold. The low-precision scores only SELECT candidates;
+// returned distances are recomputed in the reference's arithmetic and the selection is certified
+// (finalize.cu).
 #pragma once
 #include "common.cuh"
 
@@ -17,7 +19,7 @@ constexpr int TC_TILE_ROWS = 128;       // MMA M
 constexpr int TC_KBLOCK = 32;           // floats per 128-byte swizzle row
 constexpr int TC_STAGE_BYTES = TC_TILE_ROWS * TC_KBLOCK * 4;
 constexpr int TC_MAX_COLS = 256;        // MMA N (queries per pass)
-constexpr int TC_THREADS = 320;         // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int TC_THREADS = 320;         // SS form: warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int TC_SAMPLE_RANK_MAX = 16;  // largest order statistic of the sample the threshold kernel can take
 // Order statistic used as threshold: the spread of the admitted count is Gamma(rank) / rank, so larger k
 // (fewer admitted rows per wanted row) takes a higher rank from a proportionally larger sample.
