@@ -1,5 +1,5 @@
-"""Tensor-core regime (tc_scan.cu: TMA + tcgen05.mma kind::tf32 + TMEM) against the CPU oracle.
-The tf32 scores only select candidates; the returned lists must still be bit-identical to the
+"""Tensor-core regime (tc_scan.cu: TMA + tcgen05.mma kind::f16 / kind::tf32 + TMEM) against the CPU oracle.
+The bf16 / tf32 scores only select candidates; the returned lists must still be bit-identical to the
 oracle (exact re-rank + certificate), for every metric, ragged dimensions, masks and batch sizes."""
 import numpy as np
 import pytest
@@ -118,3 +118,27 @@ def test_tc_device_api_matches_flat_path(capi):
     assert np.array_equal(row[:4].cpu().numpy(), r1)
     assert np.array_equal(dist[:4].cpu().numpy().view(np.uint32), d1.view(np.uint32))
     idx.close()
+
+
+@pytest.mark.parametrize("nq,k", [(600, 10), (2100, 10), (2300, 100)])
+def test_tc_multi_pass_groups_and_chunks(capi, oracle, nq, k):
+    """Searches longer than one pass: the sample + threshold stage runs once for all passes, finalize
+    once per group of passes, and the host-buffer call stages queries / results in chunks of 2 048 —
+    with tombstones, so the masked (row-term) epilogue is the one exercised, and on raw L2 / cosine."""
+    rng = np.random.default_rng(nq + k)
+    n, d = 60000, 96  # 45 000 live rows after the tombstones: still above the tensor-core threshold
+    corpus = rng.standard_normal((n, d)).astype(np.float32)
+    queries = rng.standard_normal((nq, d)).astype(np.float32)
+    which = sorted(set([0, 255, 256, 511, nq // 2, 2047 % nq, 2048 % nq, nq - 1]))
+    for metric in (1, 0):
+        idx = capi.Index(d, metric)
+        idx.upload(corpus)
+        st = _check(oracle, idx, corpus, queries, k, metric, which, label=f"multi/m{metric}/Q{nq}/k{k}")
+        assert st["path"] == 3 and st["passes"] == (nq + 255) // 256, st
+        dead = rng.choice(n, n // 4, replace=False)
+        idx.tombstone(dead)
+        live = np.ones(n, dtype=np.uint8)
+        live[dead] = 0
+        st = _check(oracle, idx, corpus, queries, k, metric, which, live=live, label=f"multi+dead/m{metric}/Q{nq}")
+        assert st["path"] == 3, st
+        idx.close()
