@@ -451,6 +451,10 @@ int qg_index_create(qg_index** out, int dim, int metric, const qg_config* cfg) {
   idx->dp16 = tc_dp16(dim, scan_mode_of(metric) == MODE_L2);
   idx->use_bf16 = dim <= 512 && metric != QG_L1;
   if (const char* e = std::getenv("QG_TC_BF16")) idx->use_bf16 = idx->use_bf16 && std::atoi(e) != 0;
+  // With the bf16 copy a tensor-core pass streams half the bytes of the flat fp32 scan, so it wins from two
+  // queries on (1M x 128: 77 us for 2..8 queries against 134 / 220 us for 2 / 4 queries on the flat scan).
+  // A single query stays on the flat scan: it is also the re-run path of an uncertified tensor-core query.
+  if (idx->use_bf16 && std::getenv("QG_TC_MIN_Q") == nullptr) idx->tc_min_q = 2;
   {
     std::lock_guard<std::mutex> lk(g_dev_mu);
     idx->sm_count = g_dev[device].sm_count;

@@ -111,8 +111,13 @@ def test_tc_device_api_matches_flat_path(capi):
     idx.search_device(q.data_ptr(), nq, k, dist.data_ptr(), row.data_ptr(), cnt.data_ptr(), stream=st)
     torch.cuda.synchronize()
     assert idx.stats()["path"] == 3
-    d1, r1, c1, _ = idx.search(q[:4].cpu().numpy(), k)  # 4 queries: flat scan
-    assert idx.stats()["path"] == 1
+    r1, d1 = [], []
+    for i in range(4):  # one query at a time: flat scan
+        di, ri, _, _ = idx.search(q[i:i + 1].cpu().numpy(), k)
+        assert idx.stats()["path"] == 1
+        r1.append(ri[0])
+        d1.append(di[0])
+    r1, d1 = np.stack(r1), np.stack(d1)
     ok = cnt[:4].cpu().numpy() >= 0
     assert ok.all()
     assert np.array_equal(row[:4].cpu().numpy(), r1)
