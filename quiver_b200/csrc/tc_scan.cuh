@@ -1,6 +1,6 @@
 // tc_scan.cuh — tensor-core regime of the exact scan (large query batches).
 //
-// For Q >= ~8 queries the distance scan of hybrid.ExactIndex.Search / HybridIndex.BatchSearch
+// For batches (Q >= 2 with a bf16 copy, else Q >= 8) the distance scan of ExactIndex.Search / HybridIndex.BatchSearch
 // (reference pkg/hybrid/exact.go:114-129, hybrid_index.go:703-795: one goroutine per query, each
 // a full pass over the corpus) is a dense [rows x d] x [d x Q] contraction. tc_scan.cu runs it on
 // the 5th-generation tensor cores: TMA stages tiles of a bf16 copy of the corpus (128 rows x 64
