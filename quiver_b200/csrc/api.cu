@@ -227,7 +227,7 @@ struct qg_index {
   qg_scan_stats stats{};
   bool profiling = false;
   int tc_min_q = 8;             // query batches at least this large use the tensor-core regime
-  long long tc_min_rows = 32768;
+  long long tc_min_rows = 8192;  // below this the sampled threshold admits too few rows (rank * rows / 2048) and the flat scan is cheap
 };
 
 namespace qg {
