@@ -147,3 +147,36 @@ def test_tc_multi_pass_groups_and_chunks(capi, oracle, nq, k):
         st = _check(oracle, idx, corpus, queries, k, metric, which, live=live, label=f"multi+dead/m{metric}/Q{nq}")
         assert st["path"] == 3, st
         idx.close()
+
+
+def test_concurrent_searches_share_one_index(capi):
+    """The reference serves searches under a shared RLock (collection.go:647; hybrid_stress_test.go:29-74):
+    many callers at once on one index. qg_search_batch is re-entrant (per-call workspace + streams); the
+    answers of 8 threads hammering every regime must equal the ones computed one call at a time."""
+    import threading
+    rng = np.random.default_rng(77)
+    n, d, k = 50000, 64, 10
+    idx = capi.Index(d, 1)
+    idx.upload(rng.random((n, d), dtype=np.float32))
+    batches = [rng.random((q, d), dtype=np.float32) for q in (1, 4, 64, 300, 2, 700, 33, 1)]
+    want = [idx.search(b, k) for b in batches]
+    errors = []
+
+    def worker(t):
+        try:
+            for it in range(6):
+                j = (t + it) % len(batches)
+                dist, row, cnt, _ = idx.search(batches[j], k)
+                if not (np.array_equal(row, want[j][1]) and np.array_equal(cnt, want[j][2]) and
+                        np.array_equal(dist.view(np.uint32), want[j][0].view(np.uint32))):
+                    errors.append((t, it, j))
+        except Exception as e:  # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(8)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(120)
+    assert not errors, errors[:5]
+    idx.close()
