@@ -1,3 +1,5 @@
+"""Development check (run by hand on a GPU box): how many of the bench batch's 10 000 queries come back
+uncertified from the device API, and why (candidate count against the sampled threshold)."""
 import os, sys, numpy as np, torch
 sys.path.insert(0, os.getcwd())
 from quiver_b200 import capi
