@@ -205,7 +205,12 @@ int qg_search_batch(qg_index* idx, const float* queries, int q, int dim, int k,
 
 /* Same with every buffer resident on the index's device and the work enqueued on
  * `stream` (a cudaStream_t passed as void*; NULL = the legacy default stream). Returns
- * after enqueueing; results are valid once the stream has been synchronised. */
+ * after enqueueing; results are valid once the stream has been synchronised.
+ * The scans only select candidates and a certificate proves the selection; a query whose
+ * certificate failed (rare: the sampled threshold admitted too few rows, or adversarial data)
+ * comes back with out_count = -1 and unspecified rows. qg_search_batch repeats such queries
+ * through the flat scan and the exhaustive path before it returns; a caller of this
+ * asynchronous form checks the counts and re-submits those queries one at a time. */
 int qg_search_batch_device(qg_index* idx, const void* d_queries, int q, int dim, int k,
                            qg_filter* filter, const void* d_negatives, void* d_out_dist,
                            void* d_out_negdist, void* d_out_row, void* d_out_count,
@@ -215,7 +220,8 @@ int qg_search_batch_device(qg_index* idx, const void* d_queries, int q, int dim,
  * Per-shard top-k as packed 64-bit keys: high 32 bits = order-preserving image of the
  * exact float32 distance, low 32 bits = global row (row_base + local row). Missing
  * entries are all-ones. The keys of all shards are exchanged by the host layer (NCCL
- * all-gather) and merged by qg_merge_shard_keys_device. */
+ * all-gather) and merged by qg_merge_shard_keys_device. Uncertified queries (see above) are
+ * repeated by the exhaustive path inside the call, which therefore synchronises `stream` once. */
 int qg_search_shard_keys_device(qg_index* idx, const void* d_queries, int q, int dim, int k,
                                 qg_filter* filter, int64_t row_base, void* d_out_keys /* q x k u64 */,
                                 void* stream);

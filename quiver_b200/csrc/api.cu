@@ -1321,6 +1321,30 @@ int qg_search_shard_keys_device(qg_index* idx, const void* d_queries, int q, int
                  (uint64_t*)d_out_keys, row_base};
     rc = search_enqueue(idx, w, a, st);
   }
+  // The keys are merged with other shards' keys without any count travelling along, so a query whose
+  // selection could not be certified is repeated here by the exhaustive path (rare; this is why the call
+  // synchronises the stream once before it returns).
+  if (!rc) {
+    std::vector<int> h_cnt((size_t)q);
+    cudaError_t e = cudaMemcpyAsync(h_cnt.data(), w->d_count.p, (size_t)q * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fail(QG_ERR_CUDA, std::string("shard search: ") + cudaGetErrorString(e));
+    const uint32_t* mask = filter ? (const uint32_t*)filter->comb_mask.p
+                                  : (idx->n_live < idx->n_rows ? idx->live : nullptr);
+    const size_t rowb = (size_t)idx->dp * 4, srcb = (size_t)idx->dim * 4;
+    for (int i = 0; i < q && !rc; ++i) {
+      if (h_cnt[(size_t)i] >= 0) continue;
+      if ((rc = w->qpad.ensure(rowb))) break;
+      e = cudaMemsetAsync(w->qpad.p, 0, rowb, st);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(w->qpad.p, (const float*)d_queries + (size_t)i * idx->dim, srcb, cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, cudaGetErrorString(e)); break; }
+      rc = exhaustive_search(w->ex, idx->vec, idx->n_rows, idx->dp, idx->dim, mask, (const float*)w->qpad.p, nullptr,
+                             idx->metric, idx->arith, k, nullptr, nullptr, nullptr, (int*)w->d_count.p + i,
+                             (uint64_t*)d_out_keys + (size_t)i * k, row_base, st);
+      idx->stats.escalations++;
+    }
+  }
   ws_release_async(idx, w, st);
   return rc;
 }

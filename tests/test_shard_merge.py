@@ -175,3 +175,30 @@ def test_layout_choice():
     assert sharded.choose_layout(100_000_000, 96, 1024, 8) == "rows"        # 57.6 GB with the bf16 copy: shard it
     assert sharded.choose_layout(1_000_000, 128, 10_000, 1) == "rows"
     assert sharded.query_range(10, 3, 2) == (8, 10) and sharded.query_range(2, 3, 2) == (2, 2)
+
+
+@pytest.mark.gpu
+def test_shard_keys_repeat_uncertified_queries(capi, oracle):
+    """The packed keys of a shard travel without counts, so a query whose selection could not be
+    certified must already be exact when qg_search_shard_keys_device returns: adversarial rows (the
+    neighbours of one query clustered in one stretch, 400 near-duplicates) through the keys API."""
+    import torch
+    from quiver_b200 import sharded
+    rng = np.random.default_rng(6)
+    n, d, k, nq = 40000, 64, 10, 16
+    corpus = rng.random((n, d), dtype=np.float32)
+    corpus = np.ascontiguousarray(corpus[np.argsort(corpus[:, 0])])
+    queries = rng.random((nq, d), dtype=np.float32)
+    corpus[1000:1400] = queries[0] + 1e-3 * rng.standard_normal((400, d)).astype(np.float32)
+    idx = capi.Index(d, 1)
+    idx.upload(corpus)
+    dq = torch.from_numpy(queries).cuda()
+    keys = torch.empty((1, nq, k), dtype=torch.int64, device="cuda:0")
+    idx.search_shard_keys_device(dq.data_ptr(), nq, k, 0, keys.data_ptr())
+    torch.cuda.synchronize()
+    gd, gr, gc = sharded.merge_keys(keys.cpu().numpy().view(np.uint64), k)
+    for i in range(nq):
+        od, orow = oracle.exact_search(corpus, queries[i], k, 1)
+        assert gc[i] == k and np.array_equal(gr[i], orow), (i, gr[i], orow, idx.stats())
+        assert np.array_equal(gd[i].view(np.uint32), od.view(np.uint32))
+    idx.close()
