@@ -98,8 +98,19 @@ int qg_index_upload_synthetic(qg_index* idx, int kind, uint64_t seed, int64_t gl
                               int64_t n, int64_t* first_row);
 /* Mark rows deleted (Delete, exact.go:61-70). Already-deleted rows are a no-op. */
 int qg_index_tombstone(qg_index* idx, const int64_t* rows, int64_t n);
+/* Squeeze the tombstoned rows out of every per-row array (vectors, bf16 copy, norms, facet
+ * columns and their element lists): live rows keep their relative order and are renumbered
+ * 0 .. size-1, the capacity shrinks to fit, qg_index_rows() == qg_index_size() afterwards.
+ * The reference drops a deleted vector from its map at once (exact.go:61-70,
+ * hybrid_index.go:244-290), so a Go index never scans dead entries; this call gives the device
+ * index the same property after a burst of deletes. old_to_new (nullable) receives, for each of
+ * the qg_index_rows() rows before the call, its new row or -1; the caller renumbers its
+ * id <-> row tables with it. Works out of place (the live part of the index must fit a second
+ * time; QG_ERR_OOM leaves the index untouched). Needs the same external exclusion as upload /
+ * tombstone; compiled filters stay valid and are re-evaluated on their next use. */
+int qg_index_compact(qg_index* idx, int64_t* old_to_new /*nullable*/, int64_t* out_rows /*nullable*/);
 int64_t qg_index_size(const qg_index* idx);  /* live rows                    */
-int64_t qg_index_rows(const qg_index* idx);  /* rows ever uploaded           */
+int64_t qg_index_rows(const qg_index* idx);  /* rows held (uploaded and not yet compacted away) */
 int qg_index_dim(const qg_index* idx);
 int qg_index_metric(const qg_index* idx);
 /* Copy stored vectors back (IncludeVectors, collection.go:766-770). */

@@ -47,6 +47,11 @@ int qh_index_insert_batch(qh_index* idx, const char* const* ids, const float* ve
 /* Delete (hybrid_index.go:241-290): a missing ID is an error (ExactIndex alone would not mind). */
 int qh_index_delete(qh_index* idx, const char* id);
 int64_t qh_index_size(const qh_index* idx);
+/* Drop the rows of deleted vectors from the device arrays (qg_index_compact) and renumber the
+ * id <-> row tables. The reference frees a vector the moment it is deleted (exact.go:61-70,
+ * hybrid_index.go:244-290); a wrapper calls this when deleted rows outnumber live ones, under the
+ * write lock it already holds for Delete (collection.go:376). *out_removed (nullable) = rows dropped. */
+int qh_index_compact(qh_index* idx, int64_t* out_removed);
 /* Search(query, k) (hybrid_index.go:378; exact.go:92-133). */
 int qh_index_search(qh_index* idx, const float* query, int dim, int k, qh_results** out);
 
@@ -66,6 +71,8 @@ int qh_collection_add_batch(qh_collection* c, const char* const* ids, const floa
                             const char* const* metadata_json /* n entries, each may be NULL */);
 int qh_collection_delete(qh_collection* c, const char* id);
 int64_t qh_collection_count(const qh_collection* c);
+/* qh_index_compact for the collection's index; the per-row metadata moves with the rows. */
+int qh_collection_compact(qh_collection* c, int64_t* out_removed);
 int qh_collection_set_facet_fields(qh_collection* c, const char* const* fields, int n);
 
 /* types.Filter (pkg/types/search.go:45-52). value_json is the operand as JSON text; a number

@@ -59,7 +59,7 @@ class qg_profile(C.Structure):
 EXPORTED_SYMBOLS = [
     "qg_abi_version", "qg_last_error", "qg_device_count", "qg_device_info", "qg_index_create",
     "qg_index_destroy", "qg_index_upload", "qg_index_upload_device", "qg_index_upload_synthetic",
-    "qg_index_tombstone", "qg_index_size", "qg_index_rows", "qg_index_dim", "qg_index_metric",
+    "qg_index_tombstone", "qg_index_compact", "qg_index_size", "qg_index_rows", "qg_index_dim", "qg_index_metric",
     "qg_index_fetch", "qg_facets_set_column", "qg_facets_set_array_column", "qg_filter_compile", "qg_filter_eval", "qg_filter_destroy",
     "qg_search_batch", "qg_search_batch_device", "qg_search_shard_keys_device", "qg_merge_shard_keys_device",
     "qg_batch_distance", "qg_batch_distance_multi", "qg_last_scan_stats", "qg_index_set_profiling",
@@ -89,6 +89,7 @@ def load() -> C.CDLL:
     lib.qg_index_upload_device.argtypes = [vp, vp, i64, C.POINTER(i64)]
     lib.qg_index_upload_synthetic.argtypes = [vp, i32, C.c_uint64, i64, i64, C.POINTER(i64)]
     lib.qg_index_tombstone.argtypes = [vp, vp, i64]
+    lib.qg_index_compact.argtypes = [vp, vp, C.POINTER(i64)]
     lib.qg_index_size.argtypes = [vp]
     lib.qg_index_size.restype = i64
     lib.qg_index_rows.argtypes = [vp]
@@ -233,6 +234,14 @@ class Index:
         r = np.ascontiguousarray(rows, dtype=np.int64)
         _check(self._lib.qg_index_tombstone(self.handle, _ptr(r), r.size))
 
+    def compact(self) -> np.ndarray:
+        """Squeeze tombstoned rows out (qg_index_compact); returns old row -> new row (-1 = deleted)."""
+        old_to_new = np.empty(self.rows, dtype=np.int64)
+        n_new = C.c_int64(0)
+        _check(self._lib.qg_index_compact(self.handle, _ptr(old_to_new), C.byref(n_new)))
+        assert n_new.value == self.rows
+        return old_to_new
+
     def fetch(self, rows) -> np.ndarray:
         r = np.ascontiguousarray(rows, dtype=np.int64)
         out = np.empty((r.size, self.dim), dtype=np.float32)
@@ -247,6 +256,14 @@ class Index:
         fcode = np.ascontiguousarray(fcode, dtype=np.int32)
         _check(self._lib.qg_facets_set_column(self.handle, field, _ptr(kind), _ptr(num), _ptr(scode), _ptr(fcode),
                                               kind.size))
+
+    def set_array_column(self, field: int, offsets: np.ndarray, elem_codes: np.ndarray):
+        """CSR element lists of the array-valued rows of a column already set (qg_facets_set_array_column)."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+        elem_codes = np.ascontiguousarray(elem_codes, dtype=np.int32)
+        _check(self._lib.qg_facets_set_array_column(self.handle, field, _ptr(offsets),
+                                                    _ptr(elem_codes) if elem_codes.size else None,
+                                                    offsets.size - 1, elem_codes.size))
 
     # -- search --------------------------------------------------------------------------------
     def search(self, queries: np.ndarray, k: int, filter: Optional[Filter] = None,

@@ -12,6 +12,7 @@
 
 #include "../../include/quiver_gpu.h"
 #include "common.cuh"
+#include "compact.cuh"
 #include "exact.cuh"
 #include "finalize.cuh"
 #include "misc.cuh"
@@ -173,6 +174,7 @@ struct FacetColumn {
   DevBuf kind, num, scode, fcode;
   DevBuf arr_off, arr_code;  // optional CSR of array elements (qg_facets_set_array_column)
   long long arr_rows = -1;   // rows covered by arr_off, -1 = none
+  bool synthetic = false;    // created by prepare_columns for a field nobody set (every row MISSING)
 };
 
 }  // namespace qg
@@ -601,6 +603,180 @@ int qg_index_tombstone(qg_index* idx, const int64_t* rows, int64_t n) {
   return 0;
 }
 
+// Tombstone compaction. Out of place: the map old row -> new row comes from a prefix sum over the live
+// mask, one warp per old row then moves the row's slice of every array; the index switches to the new
+// arrays only after everything succeeded.
+int qg_index_compact(qg_index* idx, int64_t* old_to_new, int64_t* out_rows) {
+  if (int rc = check_index(idx)) return rc;
+  QG_CUDA_OK(cudaDeviceSynchronize());  // nothing may still read the arrays that are about to be replaced
+  const long long n_old = idx->n_rows, n_new = idx->n_live;
+  if (out_rows) *out_rows = n_new;
+  if (n_old == n_new) {
+    if (old_to_new)
+      for (long long r = 0; r < n_old; ++r) old_to_new[r] = r;
+    return 0;
+  }
+  cudaStream_t st = idx->up_stream;
+  const long long n_words = (n_old + 31) / 32;
+  long long ncap = (std::max<long long>(n_new, 1024) + 1023) & ~1023ll;
+
+  struct NewCol {
+    DevBuf kind, num, scode, fcode, arr_off, arr_code, arr_cnt;
+    long long n = 0;
+    bool arr = false;
+    void drop() {
+      kind.release(); num.release(); scode.release(); fcode.release();
+      arr_off.release(); arr_code.release(); arr_cnt.release();
+    }
+  };
+  DevBuf cnt, woff, tmp, map, nvec, ninv, nn2, nub, nv16, nlive;
+  std::vector<NewCol> ncols(idx->cols.size());
+  std::vector<uint32_t> h_map;
+  auto cleanup = [&](int rc) {
+    cnt.release(); woff.release(); tmp.release(); map.release();
+    nvec.release(); ninv.release(); nn2.release(); nub.release(); nv16.release(); nlive.release();
+    for (auto& c : ncols) c.drop();
+    return rc;
+  };
+  auto cuda_rc = [&](cudaError_t e) {
+    return e == cudaSuccess ? 0 : fail(e == cudaErrorMemoryAllocation ? QG_ERR_OOM : QG_ERR_CUDA, cudaGetErrorString(e));
+  };
+  int rc = 0;
+  // ---- old row -> new row ---------------------------------------------------------------------------
+  if ((rc = cnt.ensure((size_t)n_words * 4)) || (rc = woff.ensure((size_t)(n_words + 1) * 4)) ||
+      (rc = tmp.ensure((size_t)scan_tmp_words(std::max(n_words, ncap)) * 4)) || (rc = map.ensure((size_t)n_old * 4)))
+    return cleanup(rc);
+  if ((rc = launch_word_popcount(idx->live, n_words, (uint32_t*)cnt.p, st)) ||
+      (rc = launch_exclusive_scan_u32((const uint32_t*)cnt.p, (uint32_t*)woff.p, n_words, (uint32_t*)tmp.p, st)) ||
+      (rc = launch_compact_map(idx->live, (const uint32_t*)woff.p, n_old, (uint32_t*)map.p, st)))
+    return cleanup(rc);
+  uint32_t total = 0;
+  if ((rc = cuda_rc(cudaMemcpyAsync(&total, (uint32_t*)woff.p + n_words, 4, cudaMemcpyDeviceToHost, st))) ||
+      (rc = cuda_rc(cudaStreamSynchronize(st))))
+    return cleanup(rc);
+  if ((long long)total != n_new)
+    return cleanup(fail(QG_ERR_CUDA, "compact: live mask holds " + std::to_string(total) + " rows, expected " +
+                                             std::to_string(n_new)));
+  bool any_col = false;
+  for (const FacetColumn& c : idx->cols) any_col = any_col || (c.set && !c.synthetic);
+  if (old_to_new || any_col) {
+    h_map.resize((size_t)n_old);
+    if ((rc = cuda_rc(cudaMemcpyAsync(h_map.data(), map.p, (size_t)n_old * 4, cudaMemcpyDeviceToHost, st))) ||
+        (rc = cuda_rc(cudaStreamSynchronize(st))))
+      return cleanup(rc);
+  }
+  // ---- vectors, bf16 copy, norms, live mask -------------------------------------------------------------
+  if ((rc = nvec.ensure((size_t)ncap * idx->dp * 4)) || (rc = ninv.ensure((size_t)ncap * 4)) ||
+      (rc = nn2.ensure((size_t)ncap * 4)) || (rc = nub.ensure((size_t)ncap * 4)) ||
+      (idx->use_bf16 && (rc = nv16.ensure((size_t)ncap * idx->dp16 * 2))) || (rc = nlive.ensure((size_t)(ncap / 32) * 4)))
+    return cleanup(rc);
+  if ((rc = cuda_rc(cudaMemsetAsync(nlive.p, 0, (size_t)(ncap / 32) * 4, st))) ||
+      (rc = launch_fill_f32((float*)nn2.p, ncap, INFINITY, st)) || (rc = launch_fill_f32((float*)nub.p, ncap, INFINITY, st)))
+    return cleanup(rc);
+  {
+    CompactRowsArgs a{};
+    a.map = (const uint32_t*)map.p;
+    a.n_rows = n_old;
+    a.vec = idx->vec; a.vec_out = (float*)nvec.p; a.dp = idx->dp;
+    a.vec16 = idx->use_bf16 ? idx->vec16 : nullptr; a.vec16_out = nv16.p; a.dp16 = idx->dp16;
+    a.inv_norm = idx->inv_norm; a.inv_norm_out = (float*)ninv.p;
+    a.norm2 = idx->norm2; a.norm2_out = (float*)nn2.p;
+    a.unit_bias = idx->unit_bias; a.unit_bias_out = (float*)nub.p;
+    if ((rc = launch_compact_rows(a, idx->sm_count, st)) || (rc = launch_set_live((uint32_t*)nlive.p, 0, n_new, st)))
+      return cleanup(rc);
+  }
+  // ---- facet columns ----------------------------------------------------------------------------------
+  for (size_t i = 0; i < idx->cols.size(); ++i) {
+    const FacetColumn& c = idx->cols[i];
+    if (!c.set || c.synthetic) continue;
+    NewCol& nc = ncols[i];
+    // rows the column covers after the move: the live ones among its first c.n rows
+    nc.n = 0;
+    for (long long r = c.n - 1; r >= 0; --r)
+      if (h_map[(size_t)r] != 0xFFFFFFFFu) { nc.n = (long long)h_map[(size_t)r] + 1; break; }
+    nc.arr = c.arr_rows >= 0;
+    if ((rc = nc.kind.ensure((size_t)ncap)) || (rc = nc.num.ensure((size_t)ncap * 8)) ||
+        (rc = nc.scode.ensure((size_t)ncap * 4)) || (rc = nc.fcode.ensure((size_t)ncap * 4)))
+      return cleanup(rc);
+    if ((rc = cuda_rc(cudaMemsetAsync(nc.kind.p, QG_KIND_NOROW, nc.kind.bytes, st))) ||
+        (rc = cuda_rc(cudaMemsetAsync(nc.num.p, 0, nc.num.bytes, st))) ||
+        (rc = cuda_rc(cudaMemsetAsync(nc.scode.p, 0xff, nc.scode.bytes, st))) ||
+        (rc = cuda_rc(cudaMemsetAsync(nc.fcode.p, 0xff, nc.fcode.bytes, st))))
+      return cleanup(rc);
+    if (nc.arr) {
+      if ((rc = nc.arr_cnt.ensure((size_t)ncap * 4)) || (rc = nc.arr_off.ensure((size_t)(ncap + 1) * 4)))
+        return cleanup(rc);
+      if ((rc = cuda_rc(cudaMemsetAsync(nc.arr_cnt.p, 0, (size_t)ncap * 4, st)))) return cleanup(rc);
+    }
+    CompactColArgs a{};
+    a.map = (const uint32_t*)map.p;
+    a.n = c.n;
+    a.kind = (const uint8_t*)c.kind.p; a.kind_out = (uint8_t*)nc.kind.p;
+    a.num = (const double*)c.num.p; a.num_out = (double*)nc.num.p;
+    a.scode = (const int32_t*)c.scode.p; a.scode_out = (int32_t*)nc.scode.p;
+    a.fcode = (const int32_t*)c.fcode.p; a.fcode_out = (int32_t*)nc.fcode.p;
+    a.arr_off = nc.arr ? (const int32_t*)c.arr_off.p : nullptr;
+    a.arr_cnt_out = nc.arr ? (uint32_t*)nc.arr_cnt.p : nullptr;
+    if ((rc = launch_compact_column(a, st))) return cleanup(rc);
+    if (nc.arr) {
+      // new offsets over all ncap rows (rows past nc.n own no elements, so their offsets equal the total:
+      // the padding rule of qg_facets_set_array_column), then the element lists themselves
+      if ((rc = launch_exclusive_scan_u32((const uint32_t*)nc.arr_cnt.p, (uint32_t*)nc.arr_off.p, ncap, (uint32_t*)tmp.p,
+                                          st)))
+        return cleanup(rc);
+      uint32_t n_elems = 0;
+      if ((rc = cuda_rc(cudaMemcpyAsync(&n_elems, (uint32_t*)nc.arr_off.p + ncap, 4, cudaMemcpyDeviceToHost, st))) ||
+          (rc = cuda_rc(cudaStreamSynchronize(st))))
+        return cleanup(rc);
+      if ((rc = nc.arr_code.ensure(std::max<size_t>(1, n_elems) * 4))) return cleanup(rc);
+      if ((rc = launch_compact_elems((const uint32_t*)map.p, c.n, (const int32_t*)c.arr_off.p,
+                                     (const int32_t*)c.arr_code.p, (const uint32_t*)nc.arr_off.p, (int32_t*)nc.arr_code.p,
+                                     idx->sm_count, st)))
+        return cleanup(rc);
+    }
+  }
+  if ((rc = cuda_rc(cudaStreamSynchronize(st)))) return cleanup(rc);
+  // ---- switch over ------------------------------------------------------------------------------------
+  cudaFree(idx->vec); cudaFree(idx->inv_norm); cudaFree(idx->norm2); cudaFree(idx->unit_bias); cudaFree(idx->live);
+  if (idx->vec16) cudaFree(idx->vec16);
+  idx->vec = (float*)nvec.p; nvec.p = nullptr; nvec.bytes = 0;
+  idx->inv_norm = (float*)ninv.p; ninv.p = nullptr; ninv.bytes = 0;
+  idx->norm2 = (float*)nn2.p; nn2.p = nullptr; nn2.bytes = 0;
+  idx->unit_bias = (float*)nub.p; nub.p = nullptr; nub.bytes = 0;
+  idx->live = (uint32_t*)nlive.p; nlive.p = nullptr; nlive.bytes = 0;
+  idx->vec16 = nv16.p; nv16.p = nullptr; nv16.bytes = 0;
+  for (size_t i = 0; i < idx->cols.size(); ++i) {
+    FacetColumn& c = idx->cols[i];
+    if (!c.set) continue;
+    c.kind.release(); c.num.release(); c.scode.release(); c.fcode.release();
+    c.arr_off.release(); c.arr_code.release();
+    if (c.synthetic) {  // recreated on demand by prepare_columns
+      c = FacetColumn();
+      continue;
+    }
+    NewCol& nc = ncols[i];
+    c.kind = nc.kind; c.num = nc.num; c.scode = nc.scode; c.fcode = nc.fcode;
+    nc.kind = DevBuf(); nc.num = DevBuf(); nc.scode = DevBuf(); nc.fcode = DevBuf();
+    c.n = nc.n;
+    if (nc.arr) {
+      c.arr_off = nc.arr_off; c.arr_code = nc.arr_code;
+      nc.arr_off = DevBuf(); nc.arr_code = DevBuf();
+      c.arr_rows = ncap;
+    } else {
+      c.arr_rows = -1;
+    }
+  }
+  idx->cap = ncap;
+  idx->n_rows = n_new;
+  idx->live_epoch++;
+  idx->facet_epoch++;
+  idx->col_table_dirty = true;
+  if (old_to_new)
+    for (long long r = 0; r < n_old; ++r)
+      old_to_new[r] = h_map[(size_t)r] == 0xFFFFFFFFu ? -1 : (int64_t)h_map[(size_t)r];
+  return cleanup(0);
+}
+
 int64_t qg_index_size(const qg_index* idx) { return idx ? idx->n_live : 0; }
 int64_t qg_index_rows(const qg_index* idx) { return idx ? idx->n_rows : 0; }
 int qg_index_dim(const qg_index* idx) { return idx ? idx->dim : 0; }
@@ -655,6 +831,7 @@ int qg_facets_set_column(qg_index* idx, int field, const uint8_t* kind, const do
   }
   QG_CUDA_OK(cudaStreamSynchronize(idx->up_stream));
   c.set = true;
+  c.synthetic = false;
   c.n = n;
   c.arr_rows = -1;  // a new column invalidates the element lists of the old one
   idx->facet_epoch++;
@@ -776,6 +953,7 @@ static int prepare_columns(qg_index* idx, const qg_filter* f) {
       }
       col.kind.release(); col.num.release(); col.scode.release(); col.fcode.release();
       col.kind = nk; col.num = nn; col.scode = ns; col.fcode = nf;
+      if (!col.set) col.synthetic = true;
       col.set = true;
       idx->col_table_dirty = true;
     }

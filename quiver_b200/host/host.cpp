@@ -332,6 +332,46 @@ int qh_index_delete(qh_index* idx, const char* id) {
   return 0;
 }
 
+namespace {
+
+// qg_index_compact + the id <-> row tables renumbered with its map (caller holds idx->mu exclusively).
+int index_compact_locked(qh_index* idx, std::vector<int64_t>* map_out, int64_t* out_removed) {
+  const int64_t n_old = qg_index_rows(idx->h);
+  std::vector<int64_t> map((size_t)n_old);
+  int64_t n_new = 0;
+  if (int rc = qg_index_compact(idx->h, map.data(), &n_new)) return gpu_fail(rc);
+  std::vector<std::string> ids((size_t)n_new);
+  for (int64_t r = 0; r < n_old; ++r)
+    if (map[(size_t)r] >= 0) ids[(size_t)map[(size_t)r]] = std::move(idx->ids[(size_t)r]);
+  idx->ids.swap(ids);
+  for (auto& kv : idx->rows) kv.second = map[(size_t)kv.second];
+  if (out_removed) *out_removed = n_old - n_new;
+  if (map_out) map_out->swap(map);
+  return 0;
+}
+
+}  // namespace
+
+int qh_index_compact(qh_index* idx, int64_t* out_removed) {
+  if (!idx) return fail(QG_ERR_INVALID, "null argument");
+  std::unique_lock<std::shared_mutex> lk(idx->mu);
+  return index_compact_locked(idx, nullptr, out_removed);
+}
+
+int qh_collection_compact(qh_collection* c, int64_t* out_removed) {
+  if (!c) return fail(QG_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> col_lock(c->col_mu);
+  std::unique_lock<std::shared_mutex> lk(c->index->mu);
+  std::vector<int64_t> map;
+  if (int rc = index_compact_locked(c->index, &map, out_removed)) return rc;
+  std::vector<qh::ValuePtr> md(c->index->ids.size());
+  for (size_t r = 0; r < map.size() && r < c->metadata.size(); ++r)
+    if (map[r] >= 0) md[(size_t)map[r]] = std::move(c->metadata[r]);
+  c->metadata.swap(md);
+  c->epoch++;  // host-side encoded columns follow the new numbering on their next use
+  return 0;
+}
+
 int64_t qh_index_size(const qh_index* idx) {
   if (!idx) return 0;
   std::shared_lock<std::shared_mutex> lk(idx->mu);

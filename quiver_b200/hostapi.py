@@ -23,7 +23,7 @@ _lib = None
 EXPORTED_SYMBOLS = [
     "qh_last_error", "qh_results_queries", "qh_results_count", "qh_results_id", "qh_results_distance",
     "qh_results_free", "qh_index_create", "qh_index_destroy", "qh_index_insert", "qh_index_insert_batch",
-    "qh_index_delete", "qh_index_size", "qh_index_search", "qh_index_batch_search", "qh_collection_create",
+    "qh_index_delete", "qh_index_compact", "qh_collection_compact", "qh_index_size", "qh_index_search", "qh_index_batch_search", "qh_collection_create",
     "qh_collection_destroy", "qh_collection_add", "qh_collection_add_batch", "qh_collection_delete",
     "qh_collection_count", "qh_collection_set_facet_fields", "qh_collection_search",
     "qh_collection_search_with_facets", "qh_collection_filter_mask", "qh_collection_rows", "qh_collection_row_id",
@@ -69,6 +69,8 @@ def load() -> C.CDLL:
     lib.qh_index_insert.argtypes = [vp, cp, vp, i32]
     lib.qh_index_insert_batch.argtypes = [vp, C.POINTER(cp), vp, i64, i32]
     lib.qh_index_delete.argtypes = [vp, cp]
+    lib.qh_index_compact.argtypes = [vp, C.POINTER(i64)]
+    lib.qh_collection_compact.argtypes = [vp, C.POINTER(i64)]
     lib.qh_index_size.argtypes = [vp]
     lib.qh_index_size.restype = i64
     lib.qh_index_search.argtypes = [vp, vp, i32, i32, C.POINTER(vp)]
@@ -182,6 +184,13 @@ class HybridIndex:
 
     def Delete(self, id: str) -> None:
         _check(self._lib.qh_index_delete(self.handle, id.encode()))
+
+    def Compact(self) -> int:
+        """Drop the rows of deleted vectors from HBM; returns how many rows went (not in the reference: its map
+        frees a vector on Delete, exact.go:61-70)."""
+        removed = C.c_int64(0)
+        _check(self._lib.qh_index_compact(self.handle, C.byref(removed)))
+        return removed.value
 
     def Size(self) -> int:
         return int(self._lib.qh_index_size(self.handle))
@@ -345,6 +354,11 @@ class Collection:
 
     def Delete(self, id: str) -> None:
         _check(self._lib.qh_collection_delete(self.handle, id.encode()))
+
+    def Compact(self) -> int:
+        removed = C.c_int64(0)
+        _check(self._lib.qh_collection_compact(self.handle, C.byref(removed)))
+        return removed.value
 
     def Count(self) -> int:
         return int(self._lib.qh_collection_count(self.handle))
