@@ -171,9 +171,13 @@ typedef enum qg_clause_op {
   QG_OP_NUM_IN_TOL = 12,  /* kind NUMBER and any |num - fset[ia+j]| <= fb, j < ic       */
   QG_OP_NUM_IN = 13,      /* kinds in mask ib and num == fset[ia+j] for some j < ic     */
   QG_OP_NUM_BITS_EQ = 14, /* kind NUMBER and bit pattern of num == bits(fa)             */
-  QG_OP_ELEM_IN = 15      /* kind OTHER and any element code of the row's array in
+  QG_OP_ELEM_IN = 15,     /* kind OTHER and any element code of the row's array in
                              set[ia .. ia+ic) (SetFilter over array facets, facets.go:308-320;
                              needs qg_facets_set_array_column)                           */
+  QG_OP_WHOLE_EQ = 16     /* kind OTHER and fcode == ia: the row's whole array / map value
+                             equals the filter's under reflect.DeepEqual (EqualityFilter,
+                             facets.go:85); for OTHER rows fcode is the id of the value in the
+                             column's whole-value dictionary                              */
 } qg_clause_op;
 
 typedef struct qg_clause {

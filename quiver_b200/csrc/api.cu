@@ -878,7 +878,7 @@ int qg_filter_compile(qg_index* idx, const qg_pred* preds, int n_preds, const qg
   }
   for (int i = 0; i < n_clauses; ++i) {
     const qg_clause& c = clauses[i];
-    if (c.op < QG_OP_FALSE || c.op > QG_OP_ELEM_IN) return fail(QG_ERR_UNSUPPORTED, "unknown clause op");
+    if (c.op < QG_OP_FALSE || c.op > QG_OP_WHOLE_EQ) return fail(QG_ERR_UNSUPPORTED, "unknown clause op");
     if (c.op >= QG_OP_KIND_IN) {
       if (c.field < 0 || c.field >= 4096) return fail(QG_ERR_INVALID, "clause field out of range");
     }

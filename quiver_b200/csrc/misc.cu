@@ -189,6 +189,9 @@ __device__ __forceinline__ bool eval_clause(const qg_clause& c, const FacetColDe
           }
         }
         break;
+      case QG_OP_WHOLE_EQ:
+        r = kind == QG_KIND_OTHER && col.fcode[row] == c.ia;
+        break;
       default:
         r = false;
     }

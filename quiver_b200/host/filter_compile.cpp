@@ -135,6 +135,12 @@ std::string nested_key(const Value& v) {
   return "?";
 }
 
+int whole_code(const Column& col, const std::string& key) {
+  auto it = std::lower_bound(col.whole_keys.begin(), col.whole_keys.end(), key);
+  if (it == col.whole_keys.end() || *it != key) return -1;
+  return (int)(it - col.whole_keys.begin());
+}
+
 int elem_code(const Column& col, const std::string& key) {
   auto it = std::lower_bound(col.elem_keys.begin(), col.elem_keys.end(), key);
   if (it == col.elem_keys.end() || *it != key) return -1;
@@ -160,6 +166,8 @@ void encode_column(const std::vector<CellRef>& cells, Column* out) {
   out->arr_off.assign(n + 1, 0);
   out->arr_code.clear();
   out->elem_keys.clear();
+  out->whole_keys.clear();
+  std::vector<std::string> whole(n);    // DeepEqual key of the array / map rows
   std::vector<std::string> elems;       // element keys in row order
   std::vector<int32_t> elem_count(n, 0);
   std::vector<std::string> text(n), fold(n);
@@ -180,6 +188,7 @@ void encode_column(const std::vector<CellRef>& cells, Column* out) {
       case Value::Array:
         out->kind[i] = (uint8_t)(K_OTHER | (v->arr.empty() ? 0 : 0x80));
         out->has_array_rows = true;
+        whole[i] = nested_key(*v);
         for (const ValuePtr& e : v->arr) {
           static const Value kNil;
           elems.push_back(element_key(e ? *e : kNil));
@@ -189,6 +198,7 @@ void encode_column(const std::vector<CellRef>& cells, Column* out) {
       case Value::Object:
         out->kind[i] = (uint8_t)(K_OTHER | (v->obj.empty() ? 0 : 0x80));
         out->has_array_rows = true;
+        whole[i] = nested_key(*v);
         elems.push_back(element_key(*v));  // a map is compared whole (facets.go:322-328)
         elem_count[i] = 1;
         break;
@@ -199,7 +209,10 @@ void encode_column(const std::vector<CellRef>& cells, Column* out) {
     if (k == K_MISSING || k == QG_KIND_NOROW) continue;
     out->texts.push_back(text[i]);
     if (k == K_STRING) out->folded.push_back(fold[i]);
+    if (k == K_OTHER) out->whole_keys.push_back(whole[i]);
   }
+  std::sort(out->whole_keys.begin(), out->whole_keys.end());
+  out->whole_keys.erase(std::unique(out->whole_keys.begin(), out->whole_keys.end()), out->whole_keys.end());
   std::sort(out->texts.begin(), out->texts.end());
   out->texts.erase(std::unique(out->texts.begin(), out->texts.end()), out->texts.end());
   std::sort(out->folded.begin(), out->folded.end());
@@ -215,6 +228,7 @@ void encode_column(const std::vector<CellRef>& cells, Column* out) {
     if (k == K_MISSING || k == QG_KIND_NOROW) continue;
     out->scode[i] = text_code(*out, text[i]);
     if (k == K_STRING) out->fcode[i] = folded_code(*out, fold[i]);
+    if (k == K_OTHER) out->fcode[i] = whole_code(*out, whole[i]);
   }
 }
 
@@ -289,9 +303,12 @@ int compile_facet_filters(const std::vector<FacetFilter>& filters, ColumnSource&
           c.fa = v.b ? 1.0 : 0.0;
           b.add(c);
         } else {
-          if (col.has_array_rows) {
-            if (err) *err = "equality on array / map facet values is not supported on the device path";
-            return QG_ERR_UNSUPPORTED;
+          // an array / map filter value: reflect.DeepEqual against the facet's own array / map (facets.go:85)
+          const int code = whole_code(col, nested_key(v));
+          if (code >= 0) {
+            qg_clause c = clause(QG_OP_WHOLE_EQ, field);
+            c.ia = code;
+            b.add(c);
           }
         }
         break;

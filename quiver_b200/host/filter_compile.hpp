@@ -19,7 +19,8 @@ struct Column {
   std::vector<uint8_t> kind;    // qg_value_kind (| 0x80 when a string / array / map is non-empty)
   std::vector<double> num;
   std::vector<int32_t> scode;   // rank of the value's "%v" text in `texts` (sorted, unique); -1 when absent
-  std::vector<int32_t> fcode;   // id of the case-folded string in `folded` (sorted, unique); -1 otherwise
+  std::vector<int32_t> fcode;   // strings: id of the case-folded string in `folded` (sorted, unique);
+                                // arrays / maps: id of the whole value in `whole_keys`; -1 otherwise
   std::vector<std::string> texts;
   std::vector<std::string> folded;
   bool has_array_rows = false;  // a row holds an array / map value
@@ -28,6 +29,8 @@ struct Column {
   // strings; arr_code holds indices into it.
   std::vector<int32_t> arr_off, arr_code;
   std::vector<std::string> elem_keys;
+  // reflect.DeepEqual keys of the array / map values themselves (EqualityFilter on such a facet, facets.go:85)
+  std::vector<std::string> whole_keys;
 };
 
 // Dictionary key of one value under facets.valuesEqual (facets.go:515-520): equal keys <=> valuesEqual.
@@ -71,7 +74,7 @@ struct ColumnSource {
   virtual const Column& column(const std::string& name) = 0;
 };
 
-// Returns 0, or QG_ERR_UNSUPPORTED with *err set when the predicate needs array elements.
+// Returns 0 (every predicate shape of the reference has a device form).
 int compile_core_filters(const std::vector<CoreFilter>& filters, ColumnSource& cols, Program* out, std::string* err);
 int compile_facet_filters(const std::vector<FacetFilter>& filters, ColumnSource& cols, Program* out, std::string* err);
 

@@ -354,6 +354,22 @@ def test_facet_masks_bit_exact(H):
         ([H.NewSetFilter("labels", [{"k": 1}])], [F.SetFilter("labels", [{"map": {"k": I(1)}}])]),
         ([H.NewSetFilter("labels", [{"k": 1.0}])], [F.SetFilter("labels", [{"map": {"k": Fl(1.0)}}])]),
         ([H.NewEqualityFilter("labels", "RED")], [F.EqualityFilter("labels", "RED")]),
+        # a filter value that is itself an array / map: reflect.DeepEqual with the facet's value (facets.go:85) —
+        # order- and type-sensitive (a Go int inside the literal never equals a decoded float64)
+        ([H.NewEqualityFilter("labels", ["red"])], [F.EqualityFilter("labels", {"list": ["red"]})]),
+        ([H.NewEqualityFilter("labels", ["Red"])], [F.EqualityFilter("labels", {"list": ["Red"]})]),
+        ([H.NewEqualityFilter("labels", [])], [F.EqualityFilter("labels", {"list": []})]),
+        ([H.NewEqualityFilter("labels", [1.0])], [F.EqualityFilter("labels", {"list": [Fl(1.0)]})]),
+        ([H.NewEqualityFilter("labels", [1])], [F.EqualityFilter("labels", {"list": [I(1)]})]),
+        ([H.NewEqualityFilter("labels", ["red", "blue"])], [F.EqualityFilter("labels", {"list": ["red", "blue"]})]),
+        ([H.NewEqualityFilter("labels", ["blue", "red"])], [F.EqualityFilter("labels", {"list": ["blue", "red"]})]),
+        ([H.NewEqualityFilter("labels", [None])], [F.EqualityFilter("labels", {"list": [None]})]),
+        ([H.NewEqualityFilter("labels", [True, 2.5])], [F.EqualityFilter("labels", {"list": [True, Fl(2.5)]})]),
+        ([H.NewEqualityFilter("labels", {"k": 1.0})], [F.EqualityFilter("labels", {"map": {"k": Fl(1.0)}})]),
+        ([H.NewEqualityFilter("labels", {"k": 1})], [F.EqualityFilter("labels", {"map": {"k": I(1)}})]),
+        ([H.NewEqualityFilter("labels", {"k": 0.0}), H.NewExistsFilter("category", True)],
+         [F.EqualityFilter("labels", {"map": {"k": Fl(0.0)}}), F.ExistsFilter("category", True)]),
+        ([H.NewEqualityFilter("category", ["cat3"])], [F.EqualityFilter("category", {"list": ["cat3"]})]),
         ([H.NewExistsFilter("labels", True)], [F.ExistsFilter("labels", True)]),
         ([H.NewRangeFilter("labels", 1, 3, True, True)], [F.RangeFilter("labels", I(1), I(3), True, True)]),
         ([H.NewSetFilter("labels", ["blue", 1]), H.NewEqualityFilter("category", "cat1")],
