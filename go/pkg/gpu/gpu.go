@@ -137,6 +137,40 @@ func (x *Index) Delete(id string) error {
 		return lastError(rc)
 	}
 	delete(x.rows, id)
+	// The reference's map frees a vector on Delete; here dead rows stay in HBM until they outnumber the
+	// live ones, then one qg_index_compact pass squeezes them out (the write lock is already held).
+	if dead := len(x.ids) - len(x.rows); dead >= compactMinDead && dead > len(x.rows) {
+		return x.compactLocked()
+	}
+	return nil
+}
+
+const compactMinDead = 4096
+
+// Compact drops tombstoned rows from the device arrays and renumbers the id <-> row tables.
+func (x *Index) Compact() error {
+	x.mu.Lock()
+	defer x.mu.Unlock()
+	return x.compactLocked()
+}
+
+func (x *Index) compactLocked() error {
+	if len(x.ids) == len(x.rows) {
+		return nil
+	}
+	oldToNew := make([]C.int64_t, len(x.ids))
+	var n C.int64_t
+	if rc := C.qg_index_compact(x.h, &oldToNew[0], &n); rc != 0 {
+		return lastError(rc)
+	}
+	ids := make([]string, int(n))
+	for r, j := range oldToNew {
+		if j >= 0 {
+			ids[j] = x.ids[r]
+			x.rows[x.ids[r]] = int64(j)
+		}
+	}
+	x.ids = ids
 	return nil
 }
 
