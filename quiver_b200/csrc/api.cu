@@ -631,7 +631,7 @@ int qg_index_compact(qg_index* idx, int64_t* old_to_new, int64_t* out_rows) {
   };
   DevBuf cnt, woff, tmp, map, nvec, ninv, nn2, nub, nv16, nlive;
   std::vector<NewCol> ncols(idx->cols.size());
-  std::vector<uint32_t> h_map;
+  std::unique_ptr<uint32_t[]> h_map;  // uninitialised on purpose: filled by the D2H copy
   auto cleanup = [&](int rc) {
     cnt.release(); woff.release(); tmp.release(); map.release();
     nvec.release(); ninv.release(); nn2.release(); nub.release(); nv16.release(); nlive.release();
@@ -660,8 +660,8 @@ int qg_index_compact(qg_index* idx, int64_t* old_to_new, int64_t* out_rows) {
   bool any_col = false;
   for (const FacetColumn& c : idx->cols) any_col = any_col || (c.set && !c.synthetic);
   if (old_to_new || any_col) {
-    h_map.resize((size_t)n_old);
-    if ((rc = cuda_rc(cudaMemcpyAsync(h_map.data(), map.p, (size_t)n_old * 4, cudaMemcpyDeviceToHost, st))) ||
+    h_map.reset(new uint32_t[(size_t)n_old]);
+    if ((rc = cuda_rc(cudaMemcpyAsync(h_map.get(), map.p, (size_t)n_old * 4, cudaMemcpyDeviceToHost, st))) ||
         (rc = cuda_rc(cudaStreamSynchronize(st))))
       return cleanup(rc);
   }

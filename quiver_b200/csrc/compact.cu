@@ -139,26 +139,64 @@ int launch_compact_map(const uint32_t* live, const uint32_t* word_off, long long
   return 0;
 }
 
-// One warp per old row, 128-bit loads and stores (dp % 4 == 0 floats, dp16 % 8 == 0 halves).
+// One warp per group of 32 consecutive old rows. The lanes read the group's 32 map entries in one coalesced
+// load and move the per-row scalars; the live rows of a group land on consecutive new rows, and their
+// vectors are moved four rows at a time (four independent 128-bit loads per lane in flight before the first
+// store) — a dead row costs nothing, and the latency of the map load is paid once per 32 rows.
+static constexpr int COMPACT_UNROLL = 4;
+
+template <typename V>
+__device__ __forceinline__ void move_rows(const V* __restrict__ src, V* __restrict__ dst, size_t pitch, int per_row,
+                                          const long long (&r)[COMPACT_UNROLL], const uint32_t (&j)[COMPACT_UNROLL],
+                                          int cnt, int lane) {
+  for (int i0 = 0; i0 < per_row; i0 += 32) {
+    const int i = i0 + lane;
+    V t[COMPACT_UNROLL];
+#pragma unroll
+    for (int u = 0; u < COMPACT_UNROLL; ++u)
+      if (u < cnt && i < per_row) t[u] = src[(size_t)r[u] * pitch + i];
+#pragma unroll
+    for (int u = 0; u < COMPACT_UNROLL; ++u)
+      if (u < cnt && i < per_row) dst[(size_t)j[u] * pitch + i] = t[u];
+  }
+}
+
 __global__ void __launch_bounds__(256) compact_rows_kernel(CompactRowsArgs a) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int v4 = a.dp >> 2, h8 = a.dp16 >> 3;
-  for (long long r = warp0; r < a.n_rows; r += (long long)gridDim.x * 8) {
-    const uint32_t j = a.map[r];
-    if (j == 0xFFFFFFFFu) continue;
-    const float4* src = reinterpret_cast<const float4*>(a.vec + (size_t)r * a.dp);
-    float4* dst = reinterpret_cast<float4*>(a.vec_out + (size_t)j * a.dp);
-    for (int i = lane; i < v4; i += 32) dst[i] = src[i];
-    if (a.vec16) {
-      const uint4* s16 = reinterpret_cast<const uint4*>((const uint16_t*)a.vec16 + (size_t)r * a.dp16);
-      uint4* d16 = reinterpret_cast<uint4*>((uint16_t*)a.vec16_out + (size_t)j * a.dp16);
-      for (int i = lane; i < h8; i += 32) d16[i] = s16[i];
+  const float4* src = reinterpret_cast<const float4*>(a.vec);
+  float4* dst = reinterpret_cast<float4*>(a.vec_out);
+  const uint4* src16 = reinterpret_cast<const uint4*>(a.vec16);
+  uint4* dst16 = reinterpret_cast<uint4*>(a.vec16_out);
+  for (long long base = warp0 * 32; base < a.n_rows; base += (long long)gridDim.x * 8 * 32) {
+    const long long mine = base + lane;
+    const uint32_t jm = mine < a.n_rows ? a.map[mine] : 0xFFFFFFFFu;
+    const bool alive = jm != 0xFFFFFFFFu;
+    if (alive) {
+      a.inv_norm_out[jm] = a.inv_norm[mine];
+      a.norm2_out[jm] = a.norm2[mine];
+      a.unit_bias_out[jm] = a.unit_bias[mine];
     }
-    if (lane == 0) {
-      a.inv_norm_out[j] = a.inv_norm[r];
-      a.norm2_out[j] = a.norm2[r];
-      a.unit_bias_out[j] = a.unit_bias[r];
+    unsigned m = __ballot_sync(0xffffffffu, alive);
+    while (m) {
+      long long r[COMPACT_UNROLL];
+      uint32_t j[COMPACT_UNROLL];
+      int cnt = 0;
+#pragma unroll
+      for (int u = 0; u < COMPACT_UNROLL; ++u) {
+        r[u] = 0;
+        j[u] = 0;
+        if (m) {
+          const int s = __ffs(m) - 1;
+          m &= m - 1;
+          r[u] = base + s;
+          j[u] = __shfl_sync(0xffffffffu, jm, s);
+          cnt = u + 1;
+        }
+      }
+      move_rows(src, dst, (size_t)v4, v4, r, j, cnt, lane);
+      if (a.vec16) move_rows(src16, dst16, (size_t)h8, h8, r, j, cnt, lane);
     }
   }
 }
@@ -166,7 +204,7 @@ __global__ void __launch_bounds__(256) compact_rows_kernel(CompactRowsArgs a) {
 int launch_compact_rows(const CompactRowsArgs& a, int sm_count, cudaStream_t st) {
   if (a.n_rows <= 0) return 0;
   if ((a.dp & 3) || (a.vec16 && (a.dp16 & 7))) return fail(1, "compact: row pitch is not 16-byte aligned");
-  long long blocks = (a.n_rows + 7) / 8;
+  long long blocks = (a.n_rows + 255) / 256;  // 8 warps x 32 rows per CTA pass
   const long long cap = (long long)sm_count * 8;  // 8 resident 256-thread CTAs per SM
   if (blocks > cap) blocks = cap;
   compact_rows_kernel<<<(int)blocks, 256, 0, st>>>(a);

@@ -27,7 +27,7 @@ struct CompactRowsArgs {
   const float* norm2;    float* norm2_out;
   const float* unit_bias; float* unit_bias_out;
 };
-// One warp per old row: live rows are copied to their new position in every array.
+// One warp per 32 old rows: live rows are copied to their new position in every array.
 int launch_compact_rows(const CompactRowsArgs& a, int sm_count, cudaStream_t st);
 
 struct CompactColArgs {
