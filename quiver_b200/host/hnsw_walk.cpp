@@ -204,7 +204,7 @@ extern "C" int qh_hnsw_search_batch(qh_index* idx, const qh_hnsw_graph* g, const
   *out = nullptr;
   qg_index* h = nullptr;
   int idim = 0;
-  qh_internal_index_handle(idx, &h, &idim);
+  if (int rc = qh_internal_index_handle(idx, &h, &idim)) return rc;  // also uploads write-combined Inserts
   if (nq <= 0 || !queries) return qh_internal_fail(QG_ERR_INVALID, "no queries provided");
   if (dim != idim) {
     const std::string msg = "query dimension mismatch: expected " + std::to_string(idim) + ", got " + std::to_string(dim);

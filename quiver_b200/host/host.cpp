@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -54,9 +55,40 @@ struct qh_index {
   mutable std::shared_mutex mu;          // hybrid_index.go:42: searches share, mutations exclude
   std::vector<std::string> ids;          // row -> id
   std::unordered_map<std::string, int64_t> rows;  // live id -> row
+  // Single-vector Inserts are write-combined: the vector is copied here (Insert copies, exact.go:53-54), its row
+  // number is fixed at once, and the H2D upload happens for the whole run of them — before the next call that
+  // reads device rows (search, delete, compact, a filter), or when the buffer holds `pending_cap` rows.
+  std::vector<float> pending;
+  int64_t pending_rows = 0;
+  int64_t pending_cap = 4096;  // 0 = upload every Insert on its own (QH_INSERT_BUFFER=0)
 };
 
 namespace {
+
+// Upload the write-combined Inserts (caller holds idx->mu exclusively). On failure the rows stay pending.
+int flush_locked(qh_index* idx) {
+  if (idx->pending_rows == 0) return 0;
+  int64_t first = 0;
+  if (int rc = qg_index_upload(idx->h, idx->pending.data(), idx->pending_rows, &first)) return gpu_fail(rc);
+  if (first + idx->pending_rows != (int64_t)idx->ids.size())
+    return fail(QG_ERR_CUDA, "insert buffer and device rows out of step");
+  idx->pending.clear();
+  idx->pending_rows = 0;
+  return 0;
+}
+
+// Shared lock for a reader of device rows: taken only once nothing is pending (the flush needs the exclusive
+// lock, so it is done in between; an Insert slipping in just repeats the round).
+std::shared_lock<std::shared_mutex> lock_flushed(qh_index* idx, int* rc) {
+  *rc = 0;
+  for (;;) {
+    std::shared_lock<std::shared_mutex> lk(idx->mu);
+    if (idx->pending_rows == 0) return lk;
+    lk.unlock();
+    std::unique_lock<std::shared_mutex> wl(idx->mu);
+    if ((*rc = flush_locked(idx))) return std::shared_lock<std::shared_mutex>();
+  }
+}
 
 int index_insert_locked(qh_index* idx, const char* const* ids, const float* vecs, int64_t n, int dim) {
   if (dim != idx->dim)
@@ -68,6 +100,14 @@ int index_insert_locked(qh_index* idx, const char* const* ids, const float* vecs
     if (idx->rows.count(id) || !batch.emplace(id, 1).second)
       return fail(QG_ERR_INVALID, "vector with ID " + id + " already exists");
   }
+  if (n == 1 && idx->pending_cap > 0) {
+    idx->pending.insert(idx->pending.end(), vecs, vecs + dim);
+    idx->pending_rows++;
+    idx->rows[ids[0]] = (int64_t)idx->ids.size();
+    idx->ids.push_back(ids[0]);
+    return idx->pending_rows >= idx->pending_cap ? flush_locked(idx) : 0;
+  }
+  if (int rc = flush_locked(idx)) return rc;  // rows keep their insertion order
   int64_t first = 0;
   if (int rc = qg_index_upload(idx->h, vecs, n, &first)) return gpu_fail(rc);
   for (int64_t i = 0; i < n; ++i) {
@@ -297,6 +337,7 @@ int qh_index_create(qh_index** out, int dim, const char* distance, int arith, in
   qh_index* idx = new qh_index();
   idx->h = h;
   idx->dim = dim;
+  if (const char* e = std::getenv("QH_INSERT_BUFFER")) idx->pending_cap = std::max(0, std::atoi(e));
   *out = idx;
   return 0;
 }
@@ -327,6 +368,7 @@ int qh_index_delete(qh_index* idx, const char* id) {
   auto it = idx->rows.find(id);
   if (it == idx->rows.end()) return fail(QG_ERR_INVALID, std::string("vector with ID ") + id + " not found");
   const int64_t row = it->second;
+  if (int rc = flush_locked(idx)) return rc;
   if (int rc = qg_index_tombstone(idx->h, &row, 1)) return gpu_fail(rc);
   idx->rows.erase(it);
   return 0;
@@ -336,6 +378,7 @@ namespace {
 
 // qg_index_compact + the id <-> row tables renumbered with its map (caller holds idx->mu exclusively).
 int index_compact_locked(qh_index* idx, std::vector<int64_t>* map_out, int64_t* out_removed) {
+  if (int rc = flush_locked(idx)) return rc;
   const int64_t n_old = qg_index_rows(idx->h);
   std::vector<int64_t> map((size_t)n_old);
   int64_t n_new = 0;
@@ -391,7 +434,9 @@ int qh_index_batch_search(qh_index* idx, const float* queries, int nq, int dim, 
   if (strategy == "hnsw")
     return fail(QG_ERR_UNSUPPORTED, "the GPU index serves the exact strategy; use the HNSW adapter for graph search");
   if (!strategy.empty() && strategy != "exact") return fail(QG_ERR_INVALID, "invalid search strategy: " + strategy);
-  std::shared_lock<std::shared_mutex> lk(idx->mu);
+  int flush_rc = 0;
+  std::shared_lock<std::shared_mutex> lk = lock_flushed(idx, &flush_rc);
+  if (flush_rc) return flush_rc;
   // SearchWithRequest order (hybrid_index.go:392-402): query dim, negative dim, k
   if (idx->dim > 0 && dim != idx->dim)
     return fail(QG_ERR_DIM, "query dimension mismatch: expected " + std::to_string(idx->dim) + ", got " +
@@ -505,7 +550,9 @@ static int collection_search(qh_collection* c, int which, const float* query, in
   }
   std::unique_ptr<qh_results> res(new qh_results());
   res->lists.assign(1, {});
-  std::shared_lock<std::shared_mutex> lk(c->index->mu);
+  int flush_rc = 0;
+  std::shared_lock<std::shared_mutex> lk = lock_flushed(c->index, &flush_rc);
+  if (flush_rc) return flush_rc;
   if (c->index->rows.empty()) {  // empty index: no results, no error (collection.go:666-677, 1179-1182)
     *out = res.release();
     return 0;
@@ -540,7 +587,9 @@ int qh_collection_filter_mask(qh_collection* c, int which, const qh_filter* filt
   if (!c || !mask_out) return fail(QG_ERR_INVALID, "null argument");
   const int64_t rows = (int64_t)c->metadata.size();
   if (n_rows < rows) return fail(QG_ERR_INVALID, "mask buffer too small");
-  std::shared_lock<std::shared_mutex> lk(c->index->mu);
+  int flush_rc = 0;
+  std::shared_lock<std::shared_mutex> lk = lock_flushed(c->index, &flush_rc);
+  if (flush_rc) return flush_rc;
   qh::Program prog;
   if (int rc = build_program(c, which, filters, ffilters, n_filters, &prog)) return rc;
   FilterHandle fh;
@@ -577,6 +626,10 @@ int qh_debug_equal_fold(const char* a, const char* b) {
 // ---- internals shared with hnsw_walk.cpp -------------------------------------------------------------
 extern "C" {
 int qh_internal_index_handle(qh_index* idx, qg_index** h, int* dim) {
+  {
+    std::unique_lock<std::shared_mutex> wl(idx->mu);
+    if (int rc = flush_locked(idx)) return rc;
+  }
   *h = idx->h;
   *dim = idx->dim;
   return 0;

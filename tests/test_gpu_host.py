@@ -440,3 +440,40 @@ def test_collection_search_with_filters(H, oracle):
     with pytest.raises(H.QuiverError, match="invalid vector dimension: expected 64, got 3"):
         c.Search([1, 2, 3], 5)
     c.close()
+
+
+def test_single_inserts_are_write_combined_and_visible_at_once(H, oracle):
+    """Insert one vector at a time (Collection.Add -> Index.Insert, collection.go:178): the host layer buffers the
+    rows and uploads them in one go before the next device read, so every Insert is visible to the very next
+    Search, Delete or filter — interleaved here — and the final index equals one built with InsertBatch."""
+    rng = np.random.default_rng(31)
+    n, d, k = 6000, 24, 7
+    corpus = rng.random((n, d), dtype=np.float32)
+    ids = [f"s{i:05d}" for i in range(n)]
+    idx = H.HybridIndex(d, "euclidean")
+    live = np.zeros(n, dtype=np.uint8)
+    for i in range(n):
+        idx.Insert(ids[i], corpus[i])
+        live[i] = 1
+        if i in (0, 1, 17, 4095, 4096, 4097, 5000):      # around the buffer capacity too
+            res = idx.Search(corpus[i], 1)
+            assert res[0][0] == ids[i] and res[0][1] == 0.0
+        if i in (100, 4500):                              # delete a buffered row; a buffered id is a duplicate
+            idx.Delete(ids[i - 1])
+            live[i - 1] = 0
+            assert idx.Size() == int(live.sum())
+            with pytest.raises(H.QuiverError, match="already exists"):
+                idx.Insert(ids[i], corpus[i])
+    assert idx.Size() == int(live.sum())
+    q = rng.random((5, d), dtype=np.float32)
+    batch = H.HybridIndex(d, "euclidean")
+    keep = np.nonzero(live)[0]
+    batch.InsertBatchArrays([ids[i] for i in keep], corpus[keep])
+    for qi in q:
+        got = idx.Search(qi, k)
+        od, orow = oracle.exact_search(corpus, qi, k, 1, 0, live)
+        assert [g[0] for g in got] == [ids[r] for r in orow]
+        assert [np.float32(g[1]).view(np.uint32) for g in got] == [x.view(np.uint32) for x in od]
+        assert got == batch.Search(qi, k)
+    idx.close()
+    batch.close()
