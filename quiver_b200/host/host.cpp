@@ -103,16 +103,18 @@ int index_insert_locked(qh_index* idx, const char* const* ids, const float* vecs
   if (n == 1 && idx->pending_cap > 0) {
     idx->pending.insert(idx->pending.end(), vecs, vecs + dim);
     idx->pending_rows++;
-    idx->rows[ids[0]] = (int64_t)idx->ids.size();
-    idx->ids.push_back(ids[0]);
+    const std::string id0 = ids[0] ? ids[0] : "";
+    idx->rows[id0] = (int64_t)idx->ids.size();
+    idx->ids.push_back(id0);
     return idx->pending_rows >= idx->pending_cap ? flush_locked(idx) : 0;
   }
   if (int rc = flush_locked(idx)) return rc;  // rows keep their insertion order
   int64_t first = 0;
   if (int rc = qg_index_upload(idx->h, vecs, n, &first)) return gpu_fail(rc);
   for (int64_t i = 0; i < n; ++i) {
-    idx->ids.push_back(ids[i]);
-    idx->rows[ids[i]] = first + i;
+    const std::string id = ids[i] ? ids[i] : "";
+    idx->ids.push_back(id);
+    idx->rows[id] = first + i;
   }
   return 0;
 }
