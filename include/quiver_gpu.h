@@ -106,8 +106,9 @@ int qg_index_tombstone(qg_index* idx, const int64_t* rows, int64_t n);
  * index the same property after a burst of deletes. old_to_new (nullable) receives, for each of
  * the qg_index_rows() rows before the call, its new row or -1; the caller renumbers its
  * id <-> row tables with it. Works out of place (the live part of the index must fit a second
- * time; QG_ERR_OOM leaves the index untouched). Needs the same external exclusion as upload /
- * tombstone; compiled filters stay valid and are re-evaluated on their next use. */
+ * time; an error leaves the index untouched and the contents of old_to_new undefined). Needs
+ * the same external exclusion as upload / tombstone; compiled filters stay valid and are
+ * re-evaluated on their next use. */
 int qg_index_compact(qg_index* idx, int64_t* old_to_new /*nullable*/, int64_t* out_rows /*nullable*/);
 int64_t qg_index_size(const qg_index* idx);  /* live rows                    */
 int64_t qg_index_rows(const qg_index* idx);  /* rows held (uploaded and not yet compacted away) */

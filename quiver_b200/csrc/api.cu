@@ -1,6 +1,7 @@
 // api.cu — the C ABI of libquivergpu.so (include/quiver_gpu.h): index lifecycle, upload through
 // pinned staging buffers, facet columns / filters, search orchestration.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -609,6 +610,17 @@ int qg_index_tombstone(qg_index* idx, const int64_t* rows, int64_t n) {
 int qg_index_compact(qg_index* idx, int64_t* old_to_new, int64_t* out_rows) {
   if (int rc = check_index(idx)) return rc;
   QG_CUDA_OK(cudaDeviceSynchronize());  // nothing may still read the arrays that are about to be replaced
+  // QG_COMPACT_TIMING=1: wall-clock stage times on stderr (development aid)
+  static const bool timing = std::getenv("QG_COMPACT_TIMING") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    cudaDeviceSynchronize();
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[qg_index_compact] %-28s %8.3f ms\n", what,
+                 std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
   const long long n_old = idx->n_rows, n_new = idx->n_live;
   if (out_rows) *out_rows = n_new;
   if (n_old == n_new) {
@@ -629,11 +641,11 @@ int qg_index_compact(qg_index* idx, int64_t* old_to_new, int64_t* out_rows) {
       arr_off.release(); arr_code.release(); arr_cnt.release();
     }
   };
-  DevBuf cnt, woff, tmp, map, nvec, ninv, nn2, nub, nv16, nlive;
+  DevBuf cnt, woff, tmp, map, map64, nvec, ninv, nn2, nub, nv16, nlive;
   std::vector<NewCol> ncols(idx->cols.size());
   std::unique_ptr<uint32_t[]> h_map;  // uninitialised on purpose: filled by the D2H copy
   auto cleanup = [&](int rc) {
-    cnt.release(); woff.release(); tmp.release(); map.release();
+    cnt.release(); woff.release(); tmp.release(); map.release(); map64.release();
     nvec.release(); ninv.release(); nn2.release(); nub.release(); nv16.release(); nlive.release();
     for (auto& c : ncols) c.drop();
     return rc;
@@ -657,19 +669,35 @@ int qg_index_compact(qg_index* idx, int64_t* old_to_new, int64_t* out_rows) {
   if ((long long)total != n_new)
     return cleanup(fail(QG_ERR_CUDA, "compact: live mask holds " + std::to_string(total) + " rows, expected " +
                                              std::to_string(n_new)));
+  lap("scan + map");
   bool any_col = false;
   for (const FacetColumn& c : idx->cols) any_col = any_col || (c.set && !c.synthetic);
-  if (old_to_new || any_col) {
+  if (old_to_new) {
+    // widened on the device and copied straight into the caller's buffer: one pass over it on the host side
+    // (a 10M-row map cost 78 ms as a uint32 download plus a widening loop, page faults included)
+    if ((rc = map64.ensure((size_t)n_old * 8)) ||
+        (rc = launch_widen_map((const uint32_t*)map.p, n_old, (long long*)map64.p, st)) ||
+        (rc = cuda_rc(cudaMemcpyAsync(old_to_new, map64.p, (size_t)n_old * 8, cudaMemcpyDeviceToHost, st))) ||
+        (rc = cuda_rc(cudaStreamSynchronize(st))))
+      return cleanup(rc);
+    map64.release();
+  } else if (any_col) {
     h_map.reset(new uint32_t[(size_t)n_old]);
     if ((rc = cuda_rc(cudaMemcpyAsync(h_map.get(), map.p, (size_t)n_old * 4, cudaMemcpyDeviceToHost, st))) ||
         (rc = cuda_rc(cudaStreamSynchronize(st))))
       return cleanup(rc);
   }
+  auto new_row = [&](long long r) -> long long {
+    if (old_to_new) return (long long)old_to_new[r];
+    return h_map[(size_t)r] == 0xFFFFFFFFu ? -1ll : (long long)h_map[(size_t)r];
+  };
+  lap("map D2H");
   // ---- vectors, bf16 copy, norms, live mask -------------------------------------------------------------
   if ((rc = nvec.ensure((size_t)ncap * idx->dp * 4)) || (rc = ninv.ensure((size_t)ncap * 4)) ||
       (rc = nn2.ensure((size_t)ncap * 4)) || (rc = nub.ensure((size_t)ncap * 4)) ||
       (idx->use_bf16 && (rc = nv16.ensure((size_t)ncap * idx->dp16 * 2))) || (rc = nlive.ensure((size_t)(ncap / 32) * 4)))
     return cleanup(rc);
+  lap("cudaMalloc new arrays");
   if ((rc = cuda_rc(cudaMemsetAsync(nlive.p, 0, (size_t)(ncap / 32) * 4, st))) ||
       (rc = launch_fill_f32((float*)nn2.p, ncap, INFINITY, st)) || (rc = launch_fill_f32((float*)nub.p, ncap, INFINITY, st)))
     return cleanup(rc);
@@ -685,6 +713,7 @@ int qg_index_compact(qg_index* idx, int64_t* old_to_new, int64_t* out_rows) {
     if ((rc = launch_compact_rows(a, idx->sm_count, st)) || (rc = launch_set_live((uint32_t*)nlive.p, 0, n_new, st)))
       return cleanup(rc);
   }
+  lap("fills + row move");
   // ---- facet columns ----------------------------------------------------------------------------------
   for (size_t i = 0; i < idx->cols.size(); ++i) {
     const FacetColumn& c = idx->cols[i];
@@ -693,7 +722,7 @@ int qg_index_compact(qg_index* idx, int64_t* old_to_new, int64_t* out_rows) {
     // rows the column covers after the move: the live ones among its first c.n rows
     nc.n = 0;
     for (long long r = c.n - 1; r >= 0; --r)
-      if (h_map[(size_t)r] != 0xFFFFFFFFu) { nc.n = (long long)h_map[(size_t)r] + 1; break; }
+      if (new_row(r) >= 0) { nc.n = new_row(r) + 1; break; }
     nc.arr = c.arr_rows >= 0;
     if ((rc = nc.kind.ensure((size_t)ncap)) || (rc = nc.num.ensure((size_t)ncap * 8)) ||
         (rc = nc.scode.ensure((size_t)ncap * 4)) || (rc = nc.fcode.ensure((size_t)ncap * 4)))
@@ -736,6 +765,7 @@ int qg_index_compact(qg_index* idx, int64_t* old_to_new, int64_t* out_rows) {
     }
   }
   if ((rc = cuda_rc(cudaStreamSynchronize(st)))) return cleanup(rc);
+  lap("facet columns");
   // ---- switch over ------------------------------------------------------------------------------------
   cudaFree(idx->vec); cudaFree(idx->inv_norm); cudaFree(idx->norm2); cudaFree(idx->unit_bias); cudaFree(idx->live);
   if (idx->vec16) cudaFree(idx->vec16);
@@ -771,10 +801,10 @@ int qg_index_compact(qg_index* idx, int64_t* old_to_new, int64_t* out_rows) {
   idx->live_epoch++;
   idx->facet_epoch++;
   idx->col_table_dirty = true;
-  if (old_to_new)
-    for (long long r = 0; r < n_old; ++r)
-      old_to_new[r] = h_map[(size_t)r] == 0xFFFFFFFFu ? -1 : (int64_t)h_map[(size_t)r];
-  return cleanup(0);
+  lap("cudaFree old arrays");
+  rc = cleanup(0);
+  lap("free scratch");
+  return rc;
 }
 
 int64_t qg_index_size(const qg_index* idx) { return idx ? idx->n_live : 0; }

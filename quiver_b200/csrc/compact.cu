@@ -139,6 +139,23 @@ int launch_compact_map(const uint32_t* live, const uint32_t* word_off, long long
   return 0;
 }
 
+// The map as the caller receives it: int64, -1 for a deleted row.
+__global__ void widen_map_kernel(const uint32_t* __restrict__ map, long long n, long long* __restrict__ out) {
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+    const uint32_t j = map[r];
+    out[r] = j == 0xFFFFFFFFu ? -1ll : (long long)j;
+  }
+}
+
+int launch_widen_map(const uint32_t* map, long long n, long long* out, cudaStream_t st) {
+  if (n <= 0) return 0;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  widen_map_kernel<<<(int)blocks, 256, 0, st>>>(map, n, out);
+  QG_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // One warp per group of 32 consecutive old rows. The lanes read the group's 32 map entries in one coalesced
 // load and move the per-row scalars; the live rows of a group land on consecutive new rows, and their
 // vectors are moved four rows at a time (four independent 128-bit loads per lane in flight before the first

@@ -18,6 +18,9 @@ int launch_word_popcount(const uint32_t* live, long long n_words, uint32_t* cnt,
 int launch_compact_map(const uint32_t* live, const uint32_t* word_off, long long n_rows, uint32_t* map,
                        cudaStream_t st);
 
+// out[r] = map[r] widened to int64, -1 for a dead row (the form qg_index_compact hands to its caller).
+int launch_widen_map(const uint32_t* map, long long n, long long* out, cudaStream_t st);
+
 struct CompactRowsArgs {
   const uint32_t* map;  // old row -> new row
   long long n_rows;     // old rows
