@@ -477,3 +477,54 @@ def test_single_inserts_are_write_combined_and_visible_at_once(H, oracle):
         assert got == batch.Search(qi, k)
     idx.close()
     batch.close()
+
+
+def test_concurrent_searches_while_inserting(H):
+    """hybrid_stress_test.go:29-74 shape: goroutines searching a bare HybridIndex while another inserts. Searches
+    share the lock, each Insert takes it exclusively and its buffered row is uploaded before the next search reads
+    the device; every answer must be a valid, sorted list whose first hit is the query's own vector (inserted
+    before the searchers start)."""
+    import threading
+    rng = np.random.default_rng(41)
+    d, n0, n_more = 32, 3000, 3000
+    base = rng.random((n0, d), dtype=np.float32)
+    more = rng.random((n_more, d), dtype=np.float32)
+    idx = H.HybridIndex(d, "euclidean")
+    idx.InsertBatchArrays([f"b{i}" for i in range(n0)], base)
+    errors = []
+    stop = threading.Event()
+
+    def searcher(seed):
+        r = np.random.default_rng(seed)
+        try:
+            while not stop.is_set():
+                i = int(r.integers(n0))
+                res = idx.Search(base[i], 5)
+                assert len(res) == 5 and res[0][0] == f"b{i}" and res[0][1] == 0.0
+                assert all(res[j][1] <= res[j + 1][1] for j in range(4))
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    def inserter():
+        try:
+            for i in range(n_more):
+                idx.Insert(f"m{i}", more[i])
+                if i % 500 == 499:
+                    idx.Delete(f"m{i - 1}")
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    ts = [threading.Thread(target=searcher, args=(s,)) for s in range(4)]
+    for t in ts:
+        t.start()
+    w = threading.Thread(target=inserter)
+    w.start()
+    w.join()
+    stop.set()
+    for t in ts:
+        t.join()
+    assert not errors, errors[:3]
+    assert idx.Size() == n0 + n_more - n_more // 500
+    res = idx.Search(more[-1], 1)
+    assert res[0][0] == f"m{n_more - 1}" and res[0][1] == 0.0
+    idx.close()
