@@ -23,7 +23,7 @@ def _parity(oracle, idx, corpus, queries, k, metric, which, label):
     return dist, row, cnt
 
 
-@pytest.mark.parametrize("metric,d", [(1, 96), (0, 128), (0, 50), (2, 7), (4, 33)])
+@pytest.mark.parametrize("metric,d", [(1, 96), (0, 128), (0, 50), (2, 7), (4, 33), (0, 768), (1, 516)])
 def test_compact_matches_fresh_index(capi, oracle, metric, d):
     rng = np.random.default_rng(100 + d)
     n = 70000
