@@ -46,6 +46,9 @@ int qh_index_insert(qh_index* idx, const char* id, const float* vec, int dim);
 int qh_index_insert_batch(qh_index* idx, const char* const* ids, const float* vecs, int64_t n, int dim);
 /* Delete (hybrid_index.go:241-290): a missing ID is an error (ExactIndex alone would not mind). */
 int qh_index_delete(qh_index* idx, const char* id);
+/* HybridIndex.DeleteBatch (hybrid_index.go:293-375): "some vectors not found: [a b]" and nothing deleted
+ * when an id is missing; otherwise one tombstone launch for the whole batch. */
+int qh_index_delete_batch(qh_index* idx, const char* const* ids, int64_t n);
 int64_t qh_index_size(const qh_index* idx);
 /* Drop the rows of deleted vectors from the device arrays (qg_index_compact) and renumber the
  * id <-> row tables. The reference frees a vector the moment it is deleted (exact.go:61-70,
@@ -70,6 +73,11 @@ int qh_collection_add(qh_collection* c, const char* id, const float* vec, int di
 int qh_collection_add_batch(qh_collection* c, const char* const* ids, const float* vecs, int64_t n, int dim,
                             const char* const* metadata_json /* n entries, each may be NULL */);
 int qh_collection_delete(qh_collection* c, const char* id);
+/* Collection.DeleteBatch (collection.go:375-414): "vector not found: <id>" for the first missing id. */
+int qh_collection_delete_batch(qh_collection* c, const char* const* ids, int64_t n);
+/* Collection.Update (collection.go:417-466): vec nullable (keep the vector), metadata_json nullable / empty
+ * (keep the metadata). A new vector is Delete + Insert under the same id. */
+int qh_collection_update(qh_collection* c, const char* id, const float* vec, int dim, const char* metadata_json);
 int64_t qh_collection_count(const qh_collection* c);
 /* qh_index_compact for the collection's index; the per-row metadata moves with the rows. */
 int qh_collection_compact(qh_collection* c, int64_t* out_removed);

@@ -376,6 +376,26 @@ int qh_index_delete(qh_index* idx, const char* id) {
   return 0;
 }
 
+// HybridIndex.DeleteBatch (hybrid_index.go:293-375): every id must exist, else nothing is deleted.
+int qh_index_delete_batch(qh_index* idx, const char* const* ids, int64_t n) {
+  if (!idx || (n > 0 && !ids)) return fail(QG_ERR_INVALID, "null argument");
+  if (n <= 0) return 0;
+  std::unique_lock<std::shared_mutex> lk(idx->mu);
+  std::string missing;
+  std::vector<int64_t> rows;
+  rows.reserve((size_t)n);
+  for (int64_t i = 0; i < n; ++i) {
+    auto it = idx->rows.find(ids[i] ? ids[i] : "");
+    if (it == idx->rows.end()) missing += (missing.empty() ? "" : " ") + std::string(ids[i] ? ids[i] : "");
+    else rows.push_back(it->second);
+  }
+  if (!missing.empty()) return fail(QG_ERR_INVALID, "some vectors not found: [" + missing + "]");  // %v of []string
+  if (int rc = flush_locked(idx)) return rc;
+  if (int rc = qg_index_tombstone(idx->h, rows.data(), (int64_t)rows.size())) return gpu_fail(rc);  // one launch
+  for (int64_t i = 0; i < n; ++i) idx->rows.erase(ids[i] ? ids[i] : "");
+  return 0;
+}
+
 namespace {
 
 // qg_index_compact + the id <-> row tables renumbered with its map (caller holds idx->mu exclusively).
@@ -405,8 +425,9 @@ int qh_index_compact(qh_index* idx, int64_t* out_removed) {
 
 int qh_collection_compact(qh_collection* c, int64_t* out_removed) {
   if (!c) return fail(QG_ERR_INVALID, "null argument");
-  std::lock_guard<std::mutex> col_lock(c->col_mu);
+  // lock order as in a search: the index lock, then the column mutex
   std::unique_lock<std::shared_mutex> lk(c->index->mu);
+  std::lock_guard<std::mutex> col_lock(c->col_mu);
   std::vector<int64_t> map;
   if (int rc = index_compact_locked(c->index, &map, out_removed)) return rc;
   std::vector<qh::ValuePtr> md(c->index->ids.size());
@@ -516,6 +537,54 @@ int qh_collection_delete(qh_collection* c, const char* id) {
   if (!c || !id) return fail(QG_ERR_INVALID, "null argument");
   if (!c->index->rows.count(id)) return fail(QG_ERR_INVALID, "vector not found");  // ErrVectorNotFound
   return qh_index_delete(c->index, id);
+}
+
+// Collection.DeleteBatch (collection.go:375-414): the first missing id is reported, nothing is deleted.
+int qh_collection_delete_batch(qh_collection* c, const char* const* ids, int64_t n) {
+  if (!c || (n > 0 && !ids)) return fail(QG_ERR_INVALID, "null argument");
+  for (int64_t i = 0; i < n; ++i)
+    if (!ids[i] || !c->index->rows.count(ids[i]))
+      return fail(QG_ERR_INVALID, std::string("vector not found: ") + (ids[i] ? ids[i] : ""));
+  return qh_index_delete_batch(c->index, ids, n);
+}
+
+// Collection.Update (collection.go:417-466): a new vector is Delete + Insert under the same id (the row moves
+// to the end, its metadata with it); new metadata replaces the old document.
+int qh_collection_update(qh_collection* c, const char* id, const float* vec, int dim, const char* metadata_json) {
+  if (!c || !id) return fail(QG_ERR_INVALID, "null argument");
+  auto it = c->index->rows.find(id);
+  if (it == c->index->rows.end()) return fail(QG_ERR_INVALID, "vector not found");
+  if (vec && dim != c->dim)
+    return fail(QG_ERR_DIM, "invalid vector dimension: expected " + std::to_string(c->dim) + ", got " +
+                                std::to_string(dim));
+  const bool has_md = metadata_json && metadata_json[0];
+  qh::ValuePtr parsed;
+  if (has_md) {
+    std::string err;
+    qh::ValuePtr v = qh::parse_json(metadata_json, false, &err);
+    if (!v || (v->type != qh::Value::Object && v->type != qh::Value::Null))
+      return fail(QG_ERR_INVALID, "invalid metadata format: " + (v ? std::string("not a JSON object") : err));
+    if (v->type == qh::Value::Object) parsed = v;
+  }
+  int64_t row = it->second;
+  if (vec) {
+    if (int rc = qh_index_delete(c->index, id)) return rc;
+    {
+      std::unique_lock<std::shared_mutex> lk(c->index->mu);
+      const char* ids1[1] = {id};
+      if (int rc = index_insert_locked(c->index, ids1, vec, 1, dim)) return rc;
+    }
+  }
+  std::lock_guard<std::mutex> col_lock(c->col_mu);
+  if (vec) {
+    qh::ValuePtr moved = (size_t)row < c->metadata.size() ? c->metadata[(size_t)row] : nullptr;
+    if ((size_t)row < c->metadata.size()) c->metadata[(size_t)row].reset();
+    c->metadata.push_back(moved);
+    row = (int64_t)c->metadata.size() - 1;
+  }
+  if (has_md) c->metadata[(size_t)row] = parsed;
+  c->epoch++;
+  return 0;
 }
 
 int64_t qh_collection_count(const qh_collection* c) { return c ? qh_index_size(c->index) : 0; }

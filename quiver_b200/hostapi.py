@@ -23,7 +23,8 @@ _lib = None
 EXPORTED_SYMBOLS = [
     "qh_last_error", "qh_results_queries", "qh_results_count", "qh_results_id", "qh_results_distance",
     "qh_results_free", "qh_index_create", "qh_index_destroy", "qh_index_insert", "qh_index_insert_batch",
-    "qh_index_delete", "qh_index_compact", "qh_collection_compact", "qh_index_size", "qh_index_search", "qh_index_batch_search", "qh_collection_create",
+    "qh_index_delete", "qh_index_delete_batch", "qh_collection_delete_batch", "qh_collection_update",
+    "qh_index_compact", "qh_collection_compact", "qh_index_size", "qh_index_search", "qh_index_batch_search", "qh_collection_create",
     "qh_collection_destroy", "qh_collection_add", "qh_collection_add_batch", "qh_collection_delete",
     "qh_collection_count", "qh_collection_set_facet_fields", "qh_collection_search",
     "qh_collection_search_with_facets", "qh_collection_filter_mask", "qh_collection_rows", "qh_collection_row_id",
@@ -69,6 +70,9 @@ def load() -> C.CDLL:
     lib.qh_index_insert.argtypes = [vp, cp, vp, i32]
     lib.qh_index_insert_batch.argtypes = [vp, C.POINTER(cp), vp, i64, i32]
     lib.qh_index_delete.argtypes = [vp, cp]
+    lib.qh_index_delete_batch.argtypes = [vp, C.POINTER(cp), i64]
+    lib.qh_collection_delete_batch.argtypes = [vp, C.POINTER(cp), i64]
+    lib.qh_collection_update.argtypes = [vp, cp, vp, i32, cp]
     lib.qh_index_compact.argtypes = [vp, C.POINTER(i64)]
     lib.qh_collection_compact.argtypes = [vp, C.POINTER(i64)]
     lib.qh_index_size.argtypes = [vp]
@@ -184,6 +188,10 @@ class HybridIndex:
 
     def Delete(self, id: str) -> None:
         _check(self._lib.qh_index_delete(self.handle, id.encode()))
+
+    def DeleteBatch(self, ids: Sequence[str]) -> None:
+        arr = (C.c_char_p * max(1, len(ids)))(*[i.encode() for i in ids])
+        _check(self._lib.qh_index_delete_batch(self.handle, arr, len(ids)))
 
     def Compact(self) -> int:
         """Drop the rows of deleted vectors from HBM; returns how many rows went (not in the reference: its map
@@ -354,6 +362,17 @@ class Collection:
 
     def Delete(self, id: str) -> None:
         _check(self._lib.qh_collection_delete(self.handle, id.encode()))
+
+    def DeleteBatch(self, ids: Sequence[str]) -> None:
+        arr = (C.c_char_p * max(1, len(ids)))(*[i.encode() for i in ids])
+        _check(self._lib.qh_collection_delete_batch(self.handle, arr, len(ids)))
+
+    def Update(self, id: str, vector=None, metadata=None) -> None:
+        v = None if vector is None else _f32(vector)
+        md = None if metadata is None else (metadata if isinstance(metadata, (bytes, str)) else json.dumps(metadata))
+        if isinstance(md, str):
+            md = md.encode()
+        _check(self._lib.qh_collection_update(self.handle, id.encode(), _ptr(v), 0 if v is None else v.size, md))
 
     def Compact(self) -> int:
         removed = C.c_int64(0)

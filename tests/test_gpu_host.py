@@ -528,3 +528,74 @@ def test_concurrent_searches_while_inserting(H):
     res = idx.Search(more[-1], 1)
     assert res[0][0] == f"m{n_more - 1}" and res[0][1] == 0.0
     idx.close()
+
+
+def test_delete_batch_and_update(H, oracle):
+    """HybridIndex.DeleteBatch (hybrid_index.go:293-375), Collection.DeleteBatch (collection.go:375-414) and
+    Collection.Update (collection.go:417-466) with the reference's error text and all-or-nothing checks."""
+    from oracle import filters as F
+    from oracle import rerank
+    rng = np.random.default_rng(51)
+    n, d, k = 4000, 20, 6
+    corpus = rng.random((n, d), dtype=np.float32)
+    ids = [f"u{i:04d}" for i in range(n)]
+    idx = H.HybridIndex(d, "cosine")
+    idx.InsertBatchArrays(ids, corpus)
+    with pytest.raises(H.QuiverError, match=r"some vectors not found: \[nope also-missing\]"):
+        idx.DeleteBatch([ids[0], "nope", ids[1], "also-missing"])
+    assert idx.Size() == n                               # nothing was deleted
+    idx.DeleteBatch([])                                  # no-op
+    gone = list(range(0, n, 3))
+    idx.DeleteBatch([ids[i] for i in gone])
+    live = np.ones(n, dtype=np.uint8)
+    live[gone] = 0
+    assert idx.Size() == int(live.sum())
+    q = rng.random(d, dtype=np.float32)
+    od, orow = oracle.exact_search(corpus, q, k, 0, 0, live)
+    got = idx.Search(q, k)
+    assert [g[0] for g in got] == [ids[r] for r in orow]
+    assert [np.float32(g[1]).view(np.uint32) for g in got] == [x.view(np.uint32) for x in od]
+    idx.close()
+
+    rows = [{"category": f"cat{i % 4}", "price": float(i)} for i in range(n)]
+    c = H.Collection("upd", d, "euclidean")
+    c.AddBatch(ids, corpus, rows)
+    with pytest.raises(H.QuiverError, match="vector not found: ghost"):
+        c.DeleteBatch([ids[5], "ghost"])
+    assert c.Count() == n
+    c.DeleteBatch([ids[i] for i in range(10)])
+    assert c.Count() == n - 10
+    with pytest.raises(H.QuiverError, match="vector not found"):
+        c.Update(ids[3], q)
+    with pytest.raises(H.QuiverError, match="invalid vector dimension: expected 20, got 3"):
+        c.Update(ids[100], [1, 2, 3])
+    with pytest.raises(H.QuiverError, match="invalid metadata format"):
+        c.Update(ids[100], None, "[1, 2]")
+    # new vector, metadata kept: the id now sits at distance 0 from q and still passes its old filter
+    c.Update(ids[100], q)
+    got = c.Search(q, 1, [("category", "=", "cat0")])
+    assert got[0][0] == ids[100] and got[0][1] == 0.0
+    # new metadata only: the vector stays, the filter answer changes
+    c.Update(ids[100], None, {"category": "moved", "price": -1.0})
+    assert c.Search(q, 1, [("category", "=", "moved")])[0][0] == ids[100]
+    assert c.Search(q, 1, [("category", "=", "cat0")])[0][0] != ids[100]
+    # both at once, then the whole ranking against the oracle
+    v2 = rng.random(d, dtype=np.float32)
+    c.Update(ids[200], v2, {"category": "cat1", "price": 200.5})
+    corpus2 = corpus.copy()
+    corpus2[100] = q
+    corpus2[200] = v2
+    rows2 = list(rows)
+    rows2[100] = {"category": "moved", "price": -1.0}
+    rows2[200] = {"category": "cat1", "price": 200.5}
+    live = np.ones(n, dtype=np.uint8)
+    live[:10] = 0
+    mask = np.array(F.metadata_mask([json.dumps(m) for m in rows2], [("category", "=", "cat1")]))
+    want = rerank.filtered_search(corpus2, ids, v2, k, 1, mask, live=live)
+    got = c.Search(v2, k, [("category", "=", "cat1")])
+    assert sorted(g[0] for g in got) == sorted(w[0] for w in want) and got[0][0] == ids[200]
+    assert [np.float32(g[1]).view(np.uint32) for g in got] == [np.float32(w[1]).view(np.uint32) for w in want]
+    assert c.Count() == n - 10
+    c.Compact()
+    assert [g[0] for g in c.Search(v2, k, [("category", "=", "cat1")])] == [g[0] for g in got]
+    c.close()
