@@ -78,6 +78,12 @@ int qh_collection_delete_batch(qh_collection* c, const char* const* ids, int64_t
 /* Collection.Update (collection.go:417-466): vec nullable (keep the vector), metadata_json nullable / empty
  * (keep the metadata). A new vector is Delete + Insert under the same id. */
 int qh_collection_update(qh_collection* c, const char* id, const float* vec, int dim, const char* metadata_json);
+/* Collection.UpdateBatch (collection.go:469-529): all vectors validated first ("no vectors provided for batch
+ * update", "vector ID cannot be empty", "vector not found: <id>", "invalid vector dimension for vector <id>:
+ * expected %d, got %d", "invalid metadata format for vector <id>: ..."), then one tombstone launch and one
+ * upload for the batch. metadata_json nullable; a null / empty entry keeps that vector's metadata. */
+int qh_collection_update_batch(qh_collection* c, const char* const* ids, const float* vecs, int64_t n, int dim,
+                               const char* const* metadata_json);
 int64_t qh_collection_count(const qh_collection* c);
 /* qh_index_compact for the collection's index; the per-row metadata moves with the rows. */
 int qh_collection_compact(qh_collection* c, int64_t* out_removed);

@@ -587,6 +587,59 @@ int qh_collection_update(qh_collection* c, const char* id, const float* vec, int
   return 0;
 }
 
+// Collection.UpdateBatch (collection.go:469-529): everything is validated first; then every vector is deleted
+// and re-inserted under its id — here as one tombstone launch and one upload for the whole batch.
+int qh_collection_update_batch(qh_collection* c, const char* const* ids, const float* vecs, int64_t n, int dim,
+                               const char* const* metadata_json) {
+  if (!c || (n > 0 && (!ids || !vecs))) return fail(QG_ERR_INVALID, "null argument");
+  if (n <= 0) return fail(QG_ERR_INVALID, "no vectors provided for batch update");
+  std::vector<qh::ValuePtr> parsed((size_t)n);
+  std::vector<char> has_md((size_t)n, 0);
+  std::unordered_map<std::string, int> seen;
+  bool duplicates = false;
+  for (int64_t i = 0; i < n; ++i) {
+    if (!ids[i] || !ids[i][0]) return fail(QG_ERR_INVALID, "vector ID cannot be empty");
+    const std::string id = ids[i];
+    if (!c->index->rows.count(id)) return fail(QG_ERR_INVALID, "vector not found: " + id);
+    if (dim != c->dim)
+      return fail(QG_ERR_DIM, "invalid vector dimension for vector " + id + ": expected " + std::to_string(c->dim) +
+                                  ", got " + std::to_string(dim));
+    const char* md = metadata_json ? metadata_json[i] : nullptr;
+    if (md && md[0]) {
+      std::string err;
+      qh::ValuePtr v = qh::parse_json(md, false, &err);
+      if (!v || (v->type != qh::Value::Object && v->type != qh::Value::Null))
+        return fail(QG_ERR_INVALID, "invalid metadata format for vector " + id + ": " +
+                                        (v ? std::string("not a JSON object") : err));
+      if (v->type == qh::Value::Object) parsed[(size_t)i] = v;
+      has_md[(size_t)i] = 1;
+    }
+    duplicates = duplicates || !seen.emplace(id, 1).second;
+  }
+  if (duplicates) {  // the reference applies them one after the other; so do we
+    for (int64_t i = 0; i < n; ++i)
+      if (int rc = qh_collection_update(c, ids[i], vecs + (size_t)i * dim, dim, metadata_json ? metadata_json[i] : nullptr))
+        return rc;
+    return 0;
+  }
+  std::vector<int64_t> old_rows((size_t)n);
+  for (int64_t i = 0; i < n; ++i) old_rows[(size_t)i] = c->index->rows[ids[i]];
+  if (int rc = qh_index_delete_batch(c->index, ids, n)) return rc;
+  {
+    std::unique_lock<std::shared_mutex> lk(c->index->mu);
+    if (int rc = index_insert_locked(c->index, ids, vecs, n, dim)) return rc;
+  }
+  std::lock_guard<std::mutex> col_lock(c->col_mu);
+  for (int64_t i = 0; i < n; ++i) {
+    const size_t r = (size_t)old_rows[(size_t)i];
+    qh::ValuePtr md = has_md[(size_t)i] ? parsed[(size_t)i] : (r < c->metadata.size() ? c->metadata[r] : nullptr);
+    if (r < c->metadata.size()) c->metadata[r].reset();
+    c->metadata.push_back(md);
+  }
+  c->epoch++;
+  return 0;
+}
+
 int64_t qh_collection_count(const qh_collection* c) { return c ? qh_index_size(c->index) : 0; }
 int64_t qh_collection_rows(const qh_collection* c) { return c ? (int64_t)c->metadata.size() : 0; }
 const char* qh_collection_row_id(const qh_collection* c, int64_t row) {

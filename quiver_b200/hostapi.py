@@ -24,6 +24,7 @@ EXPORTED_SYMBOLS = [
     "qh_last_error", "qh_results_queries", "qh_results_count", "qh_results_id", "qh_results_distance",
     "qh_results_free", "qh_index_create", "qh_index_destroy", "qh_index_insert", "qh_index_insert_batch",
     "qh_index_delete", "qh_index_delete_batch", "qh_collection_delete_batch", "qh_collection_update",
+    "qh_collection_update_batch",
     "qh_index_compact", "qh_collection_compact", "qh_index_size", "qh_index_search", "qh_index_batch_search", "qh_collection_create",
     "qh_collection_destroy", "qh_collection_add", "qh_collection_add_batch", "qh_collection_delete",
     "qh_collection_count", "qh_collection_set_facet_fields", "qh_collection_search",
@@ -73,6 +74,7 @@ def load() -> C.CDLL:
     lib.qh_index_delete_batch.argtypes = [vp, C.POINTER(cp), i64]
     lib.qh_collection_delete_batch.argtypes = [vp, C.POINTER(cp), i64]
     lib.qh_collection_update.argtypes = [vp, cp, vp, i32, cp]
+    lib.qh_collection_update_batch.argtypes = [vp, C.POINTER(cp), vp, i64, i32, C.POINTER(cp)]
     lib.qh_index_compact.argtypes = [vp, C.POINTER(i64)]
     lib.qh_collection_compact.argtypes = [vp, C.POINTER(i64)]
     lib.qh_index_size.argtypes = [vp]
@@ -373,6 +375,18 @@ class Collection:
         if isinstance(md, str):
             md = md.encode()
         _check(self._lib.qh_collection_update(self.handle, id.encode(), _ptr(v), 0 if v is None else v.size, md))
+
+    def UpdateBatch(self, ids: Sequence[str], vectors, metadata: Optional[Sequence] = None) -> None:
+        mat = _f32(vectors)
+        n = len(ids)
+        if n and mat.ndim == 1:
+            mat = mat.reshape(n, -1)
+        arr = (C.c_char_p * max(1, n))(*[i.encode() for i in ids])
+        mds = None
+        if metadata is not None:
+            enc = [None if m is None else (m if isinstance(m, (bytes, str)) else json.dumps(m)) for m in metadata]
+            mds = (C.c_char_p * max(1, n))(*[e.encode() if isinstance(e, str) else e for e in enc])
+        _check(self._lib.qh_collection_update_batch(self.handle, arr, _ptr(mat), n, mat.shape[1] if n else 0, mds))
 
     def Compact(self) -> int:
         removed = C.c_int64(0)

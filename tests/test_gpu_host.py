@@ -599,3 +599,46 @@ def test_delete_batch_and_update(H, oracle):
     c.Compact()
     assert [g[0] for g in c.Search(v2, k, [("category", "=", "cat1")])] == [g[0] for g in got]
     c.close()
+
+
+def test_update_batch(H, oracle):
+    """Collection.UpdateBatch (collection.go:469-529): validation first, then every vector replaced."""
+    rng = np.random.default_rng(61)
+    n, d, k = 3000, 16, 5
+    corpus = rng.random((n, d), dtype=np.float32)
+    ids = [f"w{i:04d}" for i in range(n)]
+    rows = [{"category": f"cat{i % 3}"} for i in range(n)]
+    c = H.Collection("ub", d, "euclidean")
+    c.AddBatch(ids, corpus, rows)
+    with pytest.raises(H.QuiverError, match="no vectors provided for batch update"):
+        c.UpdateBatch([], np.zeros((0, d), dtype=np.float32))
+    with pytest.raises(H.QuiverError, match="vector ID cannot be empty"):
+        c.UpdateBatch([ids[0], ""], corpus[:2])
+    with pytest.raises(H.QuiverError, match="vector not found: missing"):
+        c.UpdateBatch([ids[0], "missing"], corpus[:2])
+    with pytest.raises(H.QuiverError, match=f"invalid vector dimension for vector {ids[0]}: expected 16, got 4"):
+        c.UpdateBatch([ids[0]], np.zeros((1, 4), dtype=np.float32))
+    with pytest.raises(H.QuiverError, match=f"invalid metadata format for vector {ids[1]}"):
+        c.UpdateBatch([ids[0], ids[1]], corpus[:2], [None, "[]"])
+    assert c.Count() == n
+    upd = list(range(0, n, 7))
+    new = rng.random((len(upd), d), dtype=np.float32)
+    mds = [None if j % 2 else {"category": "fresh"} for j in range(len(upd))]
+    c.UpdateBatch([ids[i] for i in upd], new, mds)
+    assert c.Count() == n
+    corpus2 = corpus.copy()
+    corpus2[upd] = new
+    q = rng.random(d, dtype=np.float32)
+    od, orow = oracle.exact_search(corpus2, q, k, 1, 0, None)
+    got = c.Search(q, k)
+    assert sorted(g[0] for g in got) == sorted(ids[r] for r in orow)
+    assert [np.float32(g[1]).view(np.uint32) for g in got] == [x.view(np.uint32) for x in od]
+    fresh = {ids[upd[j]] for j in range(len(upd)) if j % 2 == 0}
+    got = c.Search(q, len(fresh) + 5, [("category", "=", "fresh")])
+    assert {g[0] for g in got} == fresh
+    kept = c.Search(new[1], 1, [("category", "=", rows[upd[1]]["category"])])   # metadata kept for odd entries
+    assert kept[0][0] == ids[upd[1]] and kept[0][1] == 0.0
+    # the same id twice in one batch: applied in order, the last vector wins
+    c.UpdateBatch([ids[1], ids[1]], np.stack([corpus[2], q]))
+    assert c.Search(q, 1)[0][0] == ids[1] and c.Count() == n
+    c.close()
