@@ -174,11 +174,28 @@ func (x *Index) compactLocked() error {
 	return nil
 }
 
+// DeleteBatch — core.BatchIndex (collection.go:91-96): one tombstone launch for the whole batch.
+// Missing ids are skipped like ExactIndex.Delete does (exact.go:61-70).
 func (x *Index) DeleteBatch(ids []string) error {
+	x.mu.Lock()
+	defer x.mu.Unlock()
+	rows := make([]C.int64_t, 0, len(ids))
 	for _, id := range ids {
-		if err := x.Delete(id); err != nil {
-			return err
+		if row, ok := x.rows[id]; ok {
+			rows = append(rows, C.int64_t(row))
 		}
+	}
+	if len(rows) == 0 {
+		return nil
+	}
+	if rc := C.qg_index_tombstone(x.h, &rows[0], C.int64_t(len(rows))); rc != 0 {
+		return lastError(rc)
+	}
+	for _, id := range ids {
+		delete(x.rows, id)
+	}
+	if dead := len(x.ids) - len(x.rows); dead >= compactMinDead && dead > len(x.rows) {
+		return x.compactLocked()
 	}
 	return nil
 }
