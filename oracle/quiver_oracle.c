@@ -10,7 +10,7 @@
  * absent). This file restates the algorithm line by line; every
  * function cites the reference file:line it follows. It is pinned against every
  * known-answer vector the reference's own tests hold for this path
- * (tests/golden/*.json, extracted from the Go test sources by
+ * (the JSON files under tests/golden, extracted from the Go test sources by
  * tests/golden/make_golden.py; checked in tests/test_oracle_golden.py).
  *
  * Build: gcc -O2 -ffp-contract=off -fno-fast-math  (Go on amd64 never fuses
