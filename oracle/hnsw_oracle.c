@@ -121,7 +121,6 @@ typedef struct {
   uint64_t trace_hash;  /* order-sensitive hash of the rows whose distance was computed */
 } qo_hnsw;
 
-static int list_cap(const qo_hnsw* h, int l) { return (l == 0 ? h->max_m0 : h->M) + 1; }
 static uint32_t* list_ptr(const qo_hnsw* h, int64_t i, int l) {
   /* lists of node i are stored back to back: level 0 (max_m0+1 slots), then M+1 slots per level */
   uint32_t* base = h->conn[i];
