@@ -55,3 +55,25 @@ def test_host_library_reports_reference_errors_without_a_device(hostapi, capi):
     with pytest.raises(hostapi.QuiverError) as e:
         hostapi.HybridIndex(8, "cosine")
     assert "no CPU fallback" in str(e.value)
+
+
+def test_reference_arm_line_contract():
+    """bench.py --impl reference: the JSON line the driver parses — same metric / unit as the native arm,
+    --steps / --warmup honoured, every host core busy, e2e repeating the line's own value with zero copies."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--rows", "20000",
+                        "--steps", "4", "--warmup", "3"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, "stdout carries the JSON line and nothing else"
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"].startswith("exact k-NN QPS") and line["unit"] == "queries/s"
+    assert line["steps"] == 4 and line["warmup"] == 3 and line["higher_is_better"] is True and line["n_gpus"] == 1
+    cores = len(os.sched_getaffinity(0))
+    assert line["cpu_baseline"]["cores"] == cores and line["cpu_baseline"]["kind"] == "port"
+    assert line["cpu_baseline"]["value"] == line["value"] > 0
+    assert line["e2e"] == {"value": line["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0
