@@ -232,6 +232,15 @@ int qg_search_batch_device(qg_index* idx, const void* d_queries, int q, int dim,
                            void* d_out_negdist, void* d_out_row, void* d_out_count,
                            void* stream);
 
+/* The reference algorithm verbatim on the device (exact.go:114-129): the exact distance of EVERY live
+ * row that passes `filter`, a full sort by (distance, row), the first k. Same arguments and results as
+ * qg_search_batch; no candidate selection, no certificate, q full passes over the corpus. This is the
+ * library's own last-resort path, exported so that full-size parity tests can use it as the GPU-side
+ * oracle: it is checked against the CPU oracle on corpora the CPU finishes, and the fast regimes are
+ * checked against it on the 10M / 100M-row configurations ("parity chain"). */
+int qg_search_exhaustive(qg_index* idx, const float* queries, int q, int dim, int k, qg_filter* filter,
+                         float* out_dist, int64_t* out_row, int* out_count);
+
 /* ---- row-sharded search across GPUs (no reference counterpart) -----------
  * Per-shard top-k as packed 64-bit keys: high 32 bits = order-preserving image of the
  * exact float32 distance, low 32 bits = global row (row_base + local row). Missing

@@ -61,7 +61,7 @@ EXPORTED_SYMBOLS = [
     "qg_index_destroy", "qg_index_upload", "qg_index_upload_device", "qg_index_upload_synthetic",
     "qg_index_tombstone", "qg_index_compact", "qg_index_size", "qg_index_rows", "qg_index_dim", "qg_index_metric",
     "qg_index_fetch", "qg_facets_set_column", "qg_facets_set_array_column", "qg_filter_compile", "qg_filter_eval", "qg_filter_destroy",
-    "qg_search_batch", "qg_search_batch_device", "qg_search_shard_keys_device", "qg_merge_shard_keys_device",
+    "qg_search_batch", "qg_search_exhaustive", "qg_search_batch_device", "qg_search_shard_keys_device", "qg_merge_shard_keys_device",
     "qg_batch_distance", "qg_batch_distance_multi", "qg_last_scan_stats", "qg_index_set_profiling",
     "qg_index_read_profile", "qg_debug_tc_pass", "qg_queries_upload", "qg_queries_destroy",
     "qg_batch_distance_queries",
@@ -75,9 +75,11 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise ImportError(f"{LIB_PATH} is missing: run `make -j8 lib` (there is no CPU fallback)")
-    lib = C.CDLL(LIB_PATH)
+    # QG_LIB: development aid (an instrumented build of the same library, see tools/tc_timing.py)
+    path = os.environ.get("QG_LIB") or LIB_PATH
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: run `make -j8 lib` (there is no CPU fallback)")
+    lib = C.CDLL(path)
     vp, i32, i64, f32p = C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_float)
     lib.qg_abi_version.restype = i32
     lib.qg_last_error.restype = C.c_char_p
@@ -103,6 +105,7 @@ def load() -> C.CDLL:
     lib.qg_filter_eval.argtypes = [vp, vp, vp, C.POINTER(i64)]
     lib.qg_filter_destroy.argtypes = [vp]
     lib.qg_search_batch.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    lib.qg_search_exhaustive.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
     lib.qg_search_batch_device.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.qg_search_shard_keys_device.argtypes = [vp, vp, i32, i32, i32, vp, i64, vp, vp]
     lib.qg_merge_shard_keys_device.argtypes = [i32, vp, i32, i32, i32, vp, vp, vp, vp]
@@ -292,6 +295,21 @@ class Index:
                                          filter.handle if filter is not None else None, _ptr(neg), _ptr(dist),
                                          _ptr(negd), _ptr(row), _ptr(cnt)))
         return dist, row, cnt, negd
+
+    def search_exhaustive(self, queries: np.ndarray, k: int, filter: Optional[Filter] = None):
+        """The reference algorithm on the device (every row's exact distance + full sort): the GPU-side
+        oracle of the full-size parity tests. Returns (dist [q,k], row [q,k], count [q])."""
+        queries = np.ascontiguousarray(queries, dtype=np.float32)
+        if queries.ndim == 1:
+            queries = queries[None, :]
+        q, dim = queries.shape
+        dist = np.full((q, max(k, 0)), np.inf, dtype=np.float32)
+        row = np.full((q, max(k, 0)), -1, dtype=np.int64)
+        cnt = np.zeros(q, dtype=np.int32)
+        _check(self._lib.qg_search_exhaustive(self.handle, _ptr(queries), q, dim, k,
+                                              filter.handle if filter is not None else None, _ptr(dist), _ptr(row),
+                                              _ptr(cnt)))
+        return dist, row, cnt
 
     def search_device(self, d_queries: int, q: int, k: int, d_dist: int, d_row: int, d_count: int,
                       stream: int = 0, filter: Optional[Filter] = None, d_negatives: int = 0, d_negdist: int = 0):

@@ -1780,6 +1780,61 @@ int qg_search_batch(qg_index* idx, const float* queries, int q, int dim, int k, 
   return rc;
 }
 
+int qg_search_exhaustive(qg_index* idx, const float* queries, int q, int dim, int k, qg_filter* filter,
+                         float* out_dist, int64_t* out_row, int* out_count) {
+  if (int rc = check_index(idx)) return rc;
+  int err = 0;
+  const int empty = validate_search(idx, q, dim, k, &err);
+  if (err) return err;
+  if (q == 0) return 0;
+  if (!out_count) return fail(QG_ERR_INVALID, "out_count is null");
+  if (empty) {
+    for (int i = 0; i < q; ++i) out_count[i] = 0;
+    for (long long i = 0; k > 0 && i < (long long)q * k; ++i) {
+      if (out_dist) out_dist[i] = INFINITY;
+      if (out_row) out_row[i] = -1;
+    }
+    return 0;
+  }
+  if (!queries || !out_dist || !out_row) return fail(QG_ERR_INVALID, "null buffer");
+  if (filter && filter->owner != idx) return fail(QG_ERR_INVALID, "filter does not belong to this index");
+  Workspace* w = ws_acquire(idx);
+  if (!w) return fail(QG_ERR_CUDA, "could not create a stream");
+  int rc = 0;
+  do {
+    cudaStream_t st = w->stream;
+    const size_t rowb = (size_t)idx->dp * 4;
+    if ((rc = w->qpad.ensure(rowb))) break;
+    if ((rc = w->d_dist.ensure((size_t)k * 4))) break;
+    if ((rc = w->d_row.ensure((size_t)k * 8))) break;
+    if ((rc = w->d_count.ensure(4))) break;
+    const uint32_t* mask = nullptr;
+    if (filter) {
+      if ((rc = filter_refresh(idx, filter, st))) break;
+      mask = (const uint32_t*)filter->comb_mask.p;
+    } else if (idx->n_live < idx->n_rows) {
+      mask = idx->live;
+    }
+    for (int i = 0; i < q && !rc; ++i) {
+      cudaError_t e = cudaMemsetAsync(w->qpad.p, 0, rowb, st);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(w->qpad.p, queries + (size_t)i * dim, (size_t)dim * 4, cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, cudaGetErrorString(e)); break; }
+      if ((rc = exhaustive_search(w->ex, idx->vec, idx->n_rows, idx->dp, idx->dim, mask, (const float*)w->qpad.p,
+                                  nullptr, idx->metric, idx->arith, k, (float*)w->d_dist.p, nullptr,
+                                  (long long*)w->d_row.p, (int*)w->d_count.p, nullptr, 0, st)))
+        break;
+      e = cudaMemcpyAsync(out_dist + (size_t)i * k, w->d_dist.p, (size_t)k * 4, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(out_row + (size_t)i * k, w->d_row.p, (size_t)k * 8, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(out_count + i, w->d_count.p, 4, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) rc = fail(QG_ERR_CUDA, std::string("exhaustive search: ") + cudaGetErrorString(e));
+    }
+  } while (0);
+  ws_release(idx, w);
+  return rc;
+}
+
 int qg_batch_distance_multi(qg_index* idx, const float* queries, int b, int dim, const uint32_t* rows, int m,
                             float* out) {
   if (int rc = check_index(idx)) return rc;
@@ -1993,11 +2048,23 @@ int qg_debug_tc_pass(qg_index* idx, const float* queries, int nq, int k, float* 
     ta.raw = dbg_raw;
     ta.work_counter = (int*)w->tc_cnt.p + TC_MAX_COLS;
     int launches = 0;
-    if ((rc = w->counters.ensure(64 * 8))) break;
-    cudaMemsetAsync(w->counters.p, 0, 64 * 8, st);
+    constexpr size_t kTraceWords = 64 + 5 * 2048;  // tc_scan.cu: TS_TRACE_ROLES x TS_TRACE_CAP events behind the counters
+    if ((rc = w->counters.ensure(kTraceWords * 8))) break;
+    cudaMemsetAsync(w->counters.p, 0, kTraceWords * 8, st);
     ta.dbg = (unsigned long long*)w->counters.p;
     if ((rc = launch_tc_pass(plan, ta, idx->sm_count, st, &launches))) break;
     e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess && std::getenv("QG_TC_TRACE")) {
+      // event trace of CTA 0 (instrumented build): one line per event, "role index clock code"
+      std::vector<unsigned long long> tr(kTraceWords);
+      cudaMemcpy(tr.data(), w->counters.p, kTraceWords * 8, cudaMemcpyDeviceToHost);
+      if (FILE* f = std::fopen(std::getenv("QG_TC_TRACE"), "w")) {
+        for (int role = 0; role < 5; ++role)
+          for (int i = 0; i < 2048 && tr[64 + role * 2048 + i] != 0; ++i)
+            std::fprintf(f, "%d %d %llu %d\n", role, i, tr[64 + role * 2048 + i] >> 4, (int)(tr[64 + role * 2048 + i] & 15));
+        std::fclose(f);
+      }
+    }
     if (e == cudaSuccess && std::getenv("QG_TC_TIMING")) {
       unsigned long long h[64];
       cudaMemcpy(h, w->counters.p, sizeof(h), cudaMemcpyDeviceToHost);

@@ -6,7 +6,8 @@ os.environ["QG_TC_TIMING"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from quiver_b200 import capi
 n, d, nq = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
-idx = capi.Index(d, 1, reserve_rows=n)
+metric = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+idx = capi.Index(d, metric, reserve_rows=n)
 idx.upload_synthetic(1, 42, 0, n)
 q = np.floor(np.random.default_rng(0).random((nq, d), dtype=np.float32) * 218)
 for _ in range(3):
