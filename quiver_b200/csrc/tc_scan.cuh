@@ -45,18 +45,14 @@ struct TcPlan {
 
 // Columns the bf16 copy of a row carries after the d vector elements: for L2 the three bf16 pieces of
 // -|x|^2 / 2 (hi + mid + lo is exact to 24 bits), so that the MMA itself produces q.x - |x|^2 / 2 and the
-// epilogue of an unmasked scan is a bare max tree ("raw" scan: no row-term ring, no FFMA, no shared-memory
-// loads per score). They are added where they fit the padding of the last 128-byte k-block (d = 96, 100,
-// 200 ...). Where they do not (d = 128, 256 ...) they would cost a ninth k-step, 16 more bytes per row and
-// — the query blocks then take 160 of the 512 tensor-memory columns — the third accumulator buffer:
-// measured 74-76 us against 68 us per 256-query pass over 1M x 128 (round 2; QG_TC_RAWK=1 switches the
-// extended layout on for experiments). Dot / cosine rows need no extra columns (cosine rows are stored
+// epilogue of an unmasked scan is a bare max tree ("raw" scan). They are only added where they fit the
+// padding of the last 128-byte k-block (d = 96, 100, 200 ...): a whole extra k-block for three columns
+// (d = 128) costs more shared-memory traffic than the lighter epilogue returns (measured: 126 us against
+// 120 us per 256-query pass over 1M x 128). Dot / cosine rows need none (cosine rows are stored
 // normalised), so their unmasked scans are always raw.
-bool tc_rawk_enabled();
 inline int tc_extra_cols(int d, int mode_l2) {
   if (!mode_l2) return 0;
-  if ((d + 3 + 63) / 64 == (d + 63) / 64) return 3;  // fits the padding of the last 128-byte k-block
-  return (tc_rawk_enabled() && d + 3 <= 512) ? 3 : 0;
+  return (d + 3 + 63) / 64 == (d + 63) / 64 ? 3 : 0;
 }
 inline bool tc_raw_supported(int d, int mode_l2) { return !mode_l2 || tc_extra_cols(d, mode_l2) == 3; }
 inline int tc_dp16(int d, int mode_l2) { return (d + tc_extra_cols(d, mode_l2) + 7) & ~7; }
