@@ -38,7 +38,7 @@ $(BUILD)/%.o: $(CSRC)/%.cu $(CU_HDRS)
 
 $(LIBDIR)/libquivergpu.so: $(CU_OBJS)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) $(ARCH) -shared -cudart static -o $@ $(CU_OBJS)
+	$(NVCC) $(ARCH) -shared -cudart static -o $@ $(CU_OBJS) -ldl
 
 # Host side above the C ABI (C++ because the reference host is compiled Go and no Go toolchain
 # exists in this image). -ffp-contract=off: the rerank arithmetic must not fuse (hybrid_index.go:552).

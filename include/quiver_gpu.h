@@ -256,6 +256,67 @@ int qg_merge_shard_keys_device(int device, const void* d_keys_gathered, int worl
                                void* d_out_dist, void* d_out_row, void* d_out_count,
                                void* stream);
 
+/* ---- several GPUs of one box behind the C ABI (no reference counterpart: Quiver is one
+ *      process with one in-memory index, pkg/core/db.go:707-845 -> hybrid_index.go:677-811) --------
+ * The collective is NCCL over NVLink / NVSwitch, loaded at run time (libnccl.so.2) the first time one
+ * of these entry points is used; the rest of the library has no NCCL dependency. Two shapes:
+ *
+ *  (1) one process per GPU (the launch shape of bench.py / torchrun): every rank holds a qg_comm made
+ *      from a shared 128-byte id (qg_comm_unique_id on rank 0, handed to the others by the caller) and
+ *      its own qg_index (shard or replica); qg_comm_search_* runs this rank's part of a batch, the
+ *      exchange and the merge, all enqueued on the caller's stream.
+ *  (2) one host process driving all GPUs (the shape a Go host has): qg_group_* owns one index, one
+ *      stream, one NCCL communicator (ncclCommInitAll) and one worker thread per device.
+ *
+ * Layouts (qg_layout): QG_LAYOUT_ROWS — the corpus is row-sharded in contiguous blocks, every GPU
+ * scans its shard for the whole batch, the per-shard top-k keys travel through one all-gather of
+ * q*k*8 bytes per rank and are merged (north_star); QG_LAYOUT_QUERIES — every GPU holds the whole corpus
+ * and answers a contiguous block of the batch (the reference's own structure: BatchSearch runs one
+ * goroutine per query over one shared index). Both are exact, results equal the single-GPU run bit for bit. */
+typedef enum qg_layout { QG_LAYOUT_ROWS = 0, QG_LAYOUT_QUERIES = 1, QG_LAYOUT_AUTO = 2 } qg_layout;
+typedef struct qg_comm qg_comm;
+#define QG_COMM_ID_BYTES 128
+int qg_comm_unique_id(void* id_out /* QG_COMM_ID_BYTES */);
+int qg_comm_create_rank(const void* id /* QG_COMM_ID_BYTES */, int world, int rank, int device, qg_comm** out);
+int qg_comm_destroy(qg_comm* c);
+int qg_comm_world(const qg_comm* c);
+int qg_comm_rank(const qg_comm* c);
+/* Row-sharded batch: `shard` holds rows [row_base, row_base + qg_index_rows) of the corpus; all buffers on
+ * this rank's device; every rank receives the merged q x k result (global rows). Collective: every rank
+ * of the communicator must call with the same q, dim, k. */
+int qg_comm_search_rows_device(qg_comm* c, qg_index* shard, const void* d_queries, int q, int dim, int k,
+                               qg_filter* filter, int64_t row_base, void* d_out_dist, void* d_out_row,
+                               void* d_out_count, void* stream);
+/* Query-split batch over replicas: d_queries holds all q queries on every rank, rank r answers the block
+ * [r*ceil(q/world), ...). gather != 0: the result blocks are all-gathered and every rank ends with all q
+ * results; gather == 0: no collective at all, the rank's block lands at its place of the q x k outputs
+ * (the other rows are left untouched) — the caller copies only its own block to the host. */
+int qg_comm_search_queries_device(qg_comm* c, qg_index* replica, const void* d_queries, int q, int dim, int k,
+                                  qg_filter* filter, int gather, void* d_out_dist, void* d_out_row,
+                                  void* d_out_count, void* stream);
+
+typedef struct qg_group qg_group;
+int qg_group_create(const int* devices, int n_devices, int dim, int metric, const qg_config* cfg /*nullable; .device ignored*/,
+                    qg_group** out);
+int qg_group_destroy(qg_group* g);
+int qg_group_devices(const qg_group* g);
+/* The per-device index (facet columns, tombstones, introspection); row numbering of a row-sharded group:
+ * device i holds global rows [qg_group_row_base(g, i), + qg_index_rows). */
+qg_index* qg_group_index(qg_group* g, int i);
+int64_t qg_group_row_base(const qg_group* g, int i);
+int64_t qg_group_rows(const qg_group* g);   /* rows of the corpus (not counting replicas) */
+int qg_group_layout(const qg_group* g);     /* QG_LAYOUT_ROWS / QG_LAYOUT_QUERIES */
+/* Load the corpus once (a group is filled by one upload call; `layout` AUTO: replicate when the fp32 rows
+ * plus the bf16 copy stay under a quarter of one GPU's memory, else shard by rows). Host rows go through
+ * each device's pinned staging, all devices in parallel. */
+int qg_group_upload(qg_group* g, const float* rows, int64_t n, int layout);
+int qg_group_upload_synthetic(qg_group* g, int kind, uint64_t seed, int64_t n, int layout);
+/* qg_search_batch over the group: host buffers in, host buffers out, global rows. Row-sharded: every
+ * device scans its shard, all-gather of the keys, device 0 merges and copies out. Replicated: every
+ * device answers a block of the batch and copies it straight into the caller's buffers (no collective). */
+int qg_group_search_batch(qg_group* g, const float* queries, int q, int dim, int k, float* out_dist,
+                          int64_t* out_row, int* out_count);
+
 /* ---- neighbour-distance batches for HNSW (replaces the per-pair computeDistance call
  *      in searchLayer, pkg/hnsw/hnsw.go:536-563 / :547) ------------------------------
  * out[i] = distance(query, row rows[i]) in the index metric and arithmetic;

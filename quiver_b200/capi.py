@@ -65,6 +65,10 @@ EXPORTED_SYMBOLS = [
     "qg_batch_distance", "qg_batch_distance_multi", "qg_last_scan_stats", "qg_index_set_profiling",
     "qg_index_read_profile", "qg_debug_tc_pass", "qg_queries_upload", "qg_queries_destroy",
     "qg_batch_distance_queries",
+    "qg_comm_unique_id", "qg_comm_create_rank", "qg_comm_destroy", "qg_comm_world", "qg_comm_rank",
+    "qg_comm_search_rows_device", "qg_comm_search_queries_device",
+    "qg_group_create", "qg_group_destroy", "qg_group_devices", "qg_group_index", "qg_group_row_base",
+    "qg_group_rows", "qg_group_layout", "qg_group_upload", "qg_group_upload_synthetic", "qg_group_search_batch",
 ]
 
 _lib = None
@@ -118,6 +122,26 @@ def load() -> C.CDLL:
     lib.qg_queries_upload.argtypes = [vp, vp, i32, i32, C.POINTER(vp)]
     lib.qg_queries_destroy.argtypes = [vp]
     lib.qg_batch_distance_queries.argtypes = [vp, vp, vp, i32, vp]
+    lib.qg_comm_unique_id.argtypes = [vp]
+    lib.qg_comm_create_rank.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
+    lib.qg_comm_destroy.argtypes = [vp]
+    lib.qg_comm_world.argtypes = [vp]
+    lib.qg_comm_rank.argtypes = [vp]
+    lib.qg_comm_search_rows_device.argtypes = [vp, vp, vp, i32, i32, i32, vp, i64, vp, vp, vp, vp]
+    lib.qg_comm_search_queries_device.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32, vp, vp, vp, vp]
+    lib.qg_group_create.argtypes = [vp, i32, i32, i32, C.POINTER(qg_config), C.POINTER(vp)]
+    lib.qg_group_destroy.argtypes = [vp]
+    lib.qg_group_devices.argtypes = [vp]
+    lib.qg_group_index.argtypes = [vp, i32]
+    lib.qg_group_index.restype = vp
+    lib.qg_group_row_base.argtypes = [vp, i32]
+    lib.qg_group_row_base.restype = i64
+    lib.qg_group_rows.argtypes = [vp]
+    lib.qg_group_rows.restype = i64
+    lib.qg_group_layout.argtypes = [vp]
+    lib.qg_group_upload.argtypes = [vp, vp, i64, i32]
+    lib.qg_group_upload_synthetic.argtypes = [vp, i32, C.c_uint64, i64, i32]
+    lib.qg_group_search_batch.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -367,3 +391,103 @@ def merge_shard_keys_device(device: int, d_keys: int, world: int, q: int, k: int
     _check(load().qg_merge_shard_keys_device(device, C.c_void_p(d_keys), world, q, k, C.c_void_p(d_dist),
                                              C.c_void_p(d_row), C.c_void_p(d_count),
                                              C.c_void_p(stream) if stream else None))
+
+
+LAYOUT_ROWS, LAYOUT_QUERIES, LAYOUT_AUTO = 0, 1, 2
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """128-byte id rank 0 creates and hands to the other ranks (qg_comm_unique_id)."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    _check(load().qg_comm_unique_id(buf))
+    return buf.raw
+
+
+class Comm:
+    """One rank's NCCL communicator inside libquivergpu (qg_comm): the one-process-per-GPU shape."""
+
+    def __init__(self, uid: bytes, world: int, rank: int, device: int):
+        self._lib = load()
+        h = C.c_void_p()
+        _check(self._lib.qg_comm_create_rank(C.c_char_p(uid), world, rank, device, C.byref(h)))
+        self.handle, self.world, self.rank, self.device = h, world, rank, device
+
+    def search_rows_device(self, shard: "Index", d_queries: int, q: int, k: int, row_base: int, d_dist: int, d_row: int,
+                           d_count: int, stream: int = 0, filter: Optional[Filter] = None) -> None:
+        _check(self._lib.qg_comm_search_rows_device(self.handle, shard.handle, C.c_void_p(d_queries), q, shard.dim, k,
+                                                    filter.handle if filter is not None else None, row_base,
+                                                    C.c_void_p(d_dist), C.c_void_p(d_row), C.c_void_p(d_count),
+                                                    C.c_void_p(stream) if stream else None))
+
+    def search_queries_device(self, replica: "Index", d_queries: int, q: int, k: int, d_dist: int, d_row: int,
+                              d_count: int, stream: int = 0, gather: bool = True,
+                              filter: Optional[Filter] = None) -> None:
+        _check(self._lib.qg_comm_search_queries_device(self.handle, replica.handle, C.c_void_p(d_queries), q,
+                                                       replica.dim, k, filter.handle if filter is not None else None,
+                                                       1 if gather else 0, C.c_void_p(d_dist), C.c_void_p(d_row),
+                                                       C.c_void_p(d_count), C.c_void_p(stream) if stream else None))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.qg_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Group:
+    """All GPUs of one box driven by one host process (qg_group): the shape a Go host has."""
+
+    def __init__(self, devices: Sequence[int], dim: int, metric: int, arith: int = ARITH_VECTORTYPES):
+        self._lib = load()
+        devs = (C.c_int * len(devices))(*devices)
+        cfg = qg_config(0, arith, 0, 0, 0)
+        h = C.c_void_p()
+        _check(self._lib.qg_group_create(C.cast(devs, C.c_void_p), len(devices), dim, metric, C.byref(cfg), C.byref(h)))
+        self.handle, self.dim, self.metric, self.n = h, dim, metric, len(devices)
+
+    def upload(self, rows: np.ndarray, layout: int = LAYOUT_AUTO) -> None:
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        _check(self._lib.qg_group_upload(self.handle, _ptr(rows), rows.shape[0], layout))
+
+    def upload_synthetic(self, kind: int, seed: int, n: int, layout: int = LAYOUT_AUTO) -> None:
+        _check(self._lib.qg_group_upload_synthetic(self.handle, kind, seed, n, layout))
+
+    @property
+    def layout(self) -> int:
+        return int(self._lib.qg_group_layout(self.handle))
+
+    @property
+    def rows(self) -> int:
+        return int(self._lib.qg_group_rows(self.handle))
+
+    def row_base(self, i: int) -> int:
+        return int(self._lib.qg_group_row_base(self.handle, i))
+
+    def search(self, queries: np.ndarray, k: int):
+        queries = np.ascontiguousarray(queries, dtype=np.float32)
+        if queries.ndim == 1:
+            queries = queries[None, :]
+        q, dim = queries.shape
+        kk = max(k, 0)
+        dist = np.full((q, kk), np.inf, dtype=np.float32)
+        row = np.full((q, kk), -1, dtype=np.int64)
+        cnt = np.zeros(q, dtype=np.int32)
+        _check(self._lib.qg_group_search_batch(self.handle, _ptr(queries), q, dim, k, _ptr(dist), _ptr(row), _ptr(cnt)))
+        return dist, row, cnt
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.qg_group_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

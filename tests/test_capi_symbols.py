@@ -8,7 +8,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-DECL = re.compile(r"^\s*(?:const\s+)?(?:int|int64_t|void|double|const char\*|char\*)\s*\*?\s*(q[gh]_[a-z0-9_]+)\s*\(", re.M)
+DECL = re.compile(r"^\s*(?:const\s+)?(?:int|int64_t|void|double|const char\*|char\*|qg_index\*)\s*\*?\s*(q[gh]_[a-z0-9_]+)\s*\(", re.M)
 
 
 def declared(header):
