@@ -11,9 +11,13 @@ the top of the config's "query batch 1-10k" range; the library serves it as pass
 through the tensor-core regime; --queries 1 exercises the flat-scan regime).
   value   queries/s with the query batch already resident in HBM (device API, CUDA events)
   e2e     queries/s through qg_search_batch with HOST buffers (pinned staging, H2D + D2H inside)
-  N > 1   the corpus is row-sharded across the ranks (contiguous blocks), every rank scans its
-          shard for the replicated query batch, the per-shard top-k keys are exchanged with one
-          NCCL all-gather and merged on every rank (strong scaling: the corpus is fixed).
+  N > 1   one process per GPU; the data-path collective is NCCL inside libquivergpu (qg_comm_*). The
+          headline corpus (0.5 GB) is replicated and the batch split (quiver_b200/sharded.choose_layout;
+          --shard rows forces the row-sharded layout); the `row_sharded` sub-record measures north_star's
+          layout — per-shard top-k + all-gather of the keys + merge — on C4-shaped shards of 12.5M x 96
+          rows per GPU (100M x 96 at 8 GPUs) for batches of 1 / 32 / 1024 queries.
+  real_valued (N = 1): the same 1M x 128 / 10 000-query step on real-valued corpora (U[0,1), N(0,1)),
+          where every element is rounded in the bf16 copy.
 The oracle (oracle/) is used only as the checker and for the cpu_baseline / --impl reference legs.
 """
 import argparse
@@ -23,6 +27,8 @@ import subprocess
 import sys
 import threading
 import time
+
+import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -46,6 +52,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--no-subrecords", action="store_true",
+                    help="skip the real_valued / row_sharded sub-records and the ncu traffic step")
     ap.add_argument("--shard", default="auto", choices=["auto", "rows", "queries"],
                     help="multi-GPU layout (quiver_b200/sharded.py choose_layout): row-sharded corpus + all-gather "
                          "merge, or replicated corpus + query-split batch")
@@ -172,8 +180,179 @@ def run_reference(args):
     emit(line)
 
 
+def measure_traffic(args, kernel_regex, skip):
+    """dram__bytes_read + write of ONE launch of the dominant kernel, from a short ncu run of the same
+    library on the same workload (tools/prof_once.py), outside every timed region. None when ncu cannot
+    profile on this box."""
+    import csv
+    import io
+    cmd = ["ncu", "--csv", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none",
+           "-k", f"regex:{kernel_regex}", "-s", str(skip), "-c", "1", sys.executable,
+           os.path.join(ROOT, "tools", "prof_once.py"), str(args.rows), str(args.dim), str(METRIC_ID[args.metric]),
+           str(min(args.queries, 256)), str(args.k), "3"]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=240).stdout
+        rows = [r for r in csv.reader(io.StringIO(out)) if len(r) > 5]
+        hdr = next(r for r in rows if "Metric Name" in r)
+        i_name, i_unit, i_val = hdr.index("Metric Name"), hdr.index("Metric Unit"), hdr.index("Metric Value")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        n = 0
+        for r in rows:
+            if r is hdr or len(r) <= i_val or not r[i_name].startswith("dram__bytes_"):
+                continue
+            tot += float(r[i_val].replace(",", "")) * scale.get(r[i_unit], 1.0)
+            n += 1
+        return int(tot) if n >= 2 else None
+    except Exception:
+        return None
+
+
+def check_against_oracle(oracle, corpus, q_host, ids, k, mid, got_d, got_r, cnt_host):
+    """Bit-identical rows and float32 distances for the listed queries (threaded oracle, one query per core)."""
+    ids = [i for i in ids if cnt_host[i] >= 0]
+    if not ids:
+        return 0
+    od, orow, ocnt = oracle.exact_search_batch(corpus, q_host[ids], k, mid, threads=host_cores())
+    for j, i in enumerate(ids):
+        n = int(ocnt[j])
+        assert np.array_equal(got_r[i, :n], orow[j, :n]), (i, got_r[i], orow[j])
+        assert np.array_equal(got_d[i, :n].view(np.uint32), od[j, :n].view(np.uint32)), (i, got_d[i], od[j])
+    return len(ids)
+
+
+def real_valued_record(capi, oracle, torch, args, dev, peaks):
+    """SURVEY 8d's real-valued variants of the headline corpus (kind 0 = U[0,1), kind 2 = approx N(0,1)): every
+    element is rounded when it becomes bf16, so the certificate's error bound is exercised at full size
+    (kind 1's integers 0..217 are exact in bf16)."""
+    out = []
+    Q, k, d, mid = args.queries, args.k, args.dim, METRIC_ID[args.metric]
+    st = torch.cuda.current_stream().cuda_stream
+    for kind in (0, 2):
+        idx = capi.Index(d, mid, device=dev.index or 0, reserve_rows=args.rows)
+        idx.upload_synthetic(kind, args.seed, 0, args.rows)
+        qh = oracle.synth(kind, 9999, 0, Q, d, threads=min(8, host_cores()))
+        dq = torch.from_numpy(qh).to(dev)
+        dd = torch.empty((Q, k), dtype=torch.float32, device=dev)
+        dr = torch.empty((Q, k), dtype=torch.int64, device=dev)
+        dc = torch.empty((Q,), dtype=torch.int32, device=dev)
+        for _ in range(3):
+            idx.search_device(dq.data_ptr(), Q, k, dd.data_ptr(), dr.data_ptr(), dc.data_ptr(), stream=st)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_it = 10
+        e0.record()
+        for _ in range(n_it):
+            idx.search_device(dq.data_ptr(), Q, k, dd.data_ptr(), dr.data_ptr(), dc.data_ptr(), stream=st)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n_it
+        cnt = dc.cpu().numpy()
+        unc = int((cnt < 0).sum())
+        # the host entry point repeats uncertified queries (flat scan, then the exhaustive path)
+        hd, hr, hc, _ = idx.search(qh, k)
+        esc = idx.stats()["escalations"]
+        assert (hc == min(k, args.rows)).all()
+        corpus = oracle.synth(kind, args.seed, 0, args.rows, d, threads=min(16, host_cores()))
+        ids = sorted(set(int(x) for x in np.linspace(0, Q - 1, 64)) | set(np.nonzero(cnt < 0)[0][:32].tolist()))
+        n_chk = check_against_oracle(oracle, corpus, qh, ids, k, mid, hd, hr, hc)
+        out.append({"kind": kind, "data": {0: "uniform [0,1)", 2: "approx normal (sum of 4 uniforms)"}[kind],
+                    "rows": args.rows, "dim": d, "queries_per_step": Q, "k": k, "ms_per_step": ms,
+                    "qps_device_api": (Q - unc) / (ms * 1e-3), "uncertified_device_api": unc,
+                    "escalations_host_api": int(esc),
+                    "parity": f"{n_chk} queries (spread + every uncertified one, through qg_search_batch) bit-identical "
+                              f"to the oracle over all {args.rows} rows"})
+        idx.close()
+        del corpus
+    return out
+
+
+def row_sharded_record(capi, oracle, torch, dist, comm, world, rank, local_rank, dev, peaks):
+    """north_star's layout on C4-shaped shards: 12.5M x 96 L2-normalised rows (synthetic kind 3) per GPU —
+    100M x 96 at 8 GPUs — per-shard top-k, one NCCL all-gather of the keys inside libquivergpu
+    (qg_comm_search_rows_device), merge. Weak scaling: the shard size is fixed, the corpus grows with N."""
+    per, d, k, mid = 12_500_000, 96, 10, METRIC_ID["l2"]
+    row0 = rank * per
+    shard = capi.Index(d, mid, device=local_rank, reserve_rows=per)
+    shard.upload_synthetic(3, 42, row0, per)
+    st = torch.cuda.current_stream().cuda_stream
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    recs = []
+    for Q in (1, 32, 1024):
+        qh = oracle.synth(3, 9999, 0, Q, d, threads=min(8, host_cores()))
+        dq = torch.from_numpy(qh).to(dev)
+        dd = torch.empty((Q, k), dtype=torch.float32, device=dev)
+        dr = torch.empty((Q, k), dtype=torch.int64, device=dev)
+        dc = torch.empty((Q,), dtype=torch.int32, device=dev)
+        keys = torch.empty((Q, k), dtype=torch.int64, device=dev)
+
+        def step():
+            comm.search_rows_device(shard, dq.data_ptr(), Q, k, row0, dd.data_ptr(), dr.data_ptr(), dc.data_ptr(), stream=st)
+        for _ in range(3):
+            step()
+        dist.barrier()
+        torch.cuda.synchronize()
+        n_it = 20 if Q < 1024 else 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        e0.record()
+        for _ in range(n_it):
+            step()
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / n_it], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        stats = shard.stats()
+        # the shard scan alone (no exchange), for the share of the all-gather + merge
+        e0.record()
+        for _ in range(n_it):
+            shard.search_shard_keys_device(dq.data_ptr(), Q, k, row0, keys.data_ptr(), stream=st)
+        e1.record()
+        torch.cuda.synchronize()
+        t2 = torch.tensor([e0.elapsed_time(e1) / n_it], dtype=torch.float64, device=dev)
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        scan_ms = float(t2.item())
+        # parity at full size: this rank's shard through the fast path == the exhaustive GPU oracle
+        # (qg_search_exhaustive: every row's exact distance + full sort), then the merged list == the
+        # merge of the per-rank oracle lists
+        n_par = min(Q, 4)
+        xd, xr, xc = shard.search_exhaustive(qh[:n_par], k)
+        mine = torch.from_numpy(np.where(np.arange(k)[None, :] < xc[:, None],
+                                         (capi_ordered(xd).astype(np.uint64) << np.uint64(32)) |
+                                         (xr + row0).astype(np.uint64), np.uint64(0xFFFFFFFFFFFFFFFF)).view(np.int64)).to(dev)
+        allk = torch.empty((world, n_par, k), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allk.view(world * n_par, k), mine)
+        from quiver_b200 import sharded
+        md, mr, mc = sharded.merge_keys(allk.cpu().numpy().view(np.uint64), k)
+        gd, gr, gc = dd.cpu().numpy(), dr.cpu().numpy(), dc.cpu().numpy()
+        unc = int((gc < 0).sum())
+        assert np.array_equal(gr[:n_par], mr) and np.array_equal(gd[:n_par].view(np.uint32), md.view(np.uint32)), \
+            (gr[:n_par], mr)
+        bytes_rank = stats["bytes_algorithmic"] * stats["passes"]
+        recs.append({"queries_per_step": Q, "ms_per_step": ms, "qps": Q / (ms * 1e-3),
+                     "shard_scan_ms": scan_ms, "allgather_merge_us": max(0.0, (ms - scan_ms) * 1e3),
+                     "path": {0: "exhaustive", 1: "flat scan", 2: "gather scan", 3: "tensor-core"}[stats["path"]],
+                     "passes": stats["passes"],
+                     "aggregate_GBps": world * bytes_rank / (ms * 1e-3) / 1e9,
+                     "frac_of_aggregate_measured_hbm": bytes_rank / (ms * 1e-3) / 1e9 / hbm,
+                     "uncertified": unc,
+                     "parity": f"{n_par} queries: merged result == merge of the per-shard exhaustive GPU oracle lists "
+                               f"(every row's exact distance + full sort on each rank), bit-identical"})
+    shard.close()
+    return {"layout": "rows (north_star): per-shard top-k + NCCL all-gather of the keys + merge, all inside libquivergpu",
+            "rows_per_gpu": per, "rows_total": per * world, "dim": d, "k": k, "metric": "l2",
+            "data": "synthetic kind 3 (approx normal, L2-normalised: Deep-shaped)", "scaling": "weak",
+            "hbm_peak_per_gpu_GBps": hbm, "batches": recs}
+
+
+def capi_ordered(d):
+    b = np.ascontiguousarray(d, dtype=np.float32).view(np.uint32)
+    return np.where(b & np.uint32(0x80000000), ~b, b | np.uint32(0x80000000)).astype(np.uint32)
+
+
 def run_native(args):
-    import numpy as np
     import torch
     import torch.distributed as dist
     from quiver_b200 import capi
@@ -188,12 +367,18 @@ def run_native(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    comm = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL prints its version banner (and anything NCCL_DEBUG asks for) to stdout by default; stdout
         # carries exactly one JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
+        # the data-path collective lives inside libquivergpu (qg_comm_*); torch.distributed only carries the
+        # communicator id, the barriers and the max-over-ranks of the timings
+        uid = [capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        comm = capi.Comm(uid[0], world, rank, local_rank)
 
     import oracle  # checker + cpu_baseline only
     oracle.build()
@@ -204,6 +389,8 @@ def run_native(args):
     layout = "rows" if world == 1 else (args.shard if args.shard != "auto" else
                                         sharded.choose_layout(args.rows, d, Q, world))
     by_queries = layout == "queries"
+    q0, q1 = 0, Q
+    qper = Q
     if by_queries:
         # replicated corpus, this rank answers a contiguous slice of the batch
         row0, nloc = 0, args.rows
@@ -224,28 +411,16 @@ def run_native(args):
     d_dist = torch.empty((Q, k), dtype=torch.float32, device=dev)
     d_row = torch.empty((Q, k), dtype=torch.int64, device=dev)
     d_cnt = torch.empty((Q,), dtype=torch.int32, device=dev)
-    if world > 1 and by_queries:
-        blk = torch.zeros(sharded.ReplicatedIndex.block_bytes(qper, k), dtype=torch.uint8, device=dev)
-        b_row, b_dist, b_cnt = sharded.unpack_block(blk, qper, k)
-        d_allb = torch.empty(world * blk.numel(), dtype=torch.uint8, device=dev)  # rank-major result blocks
-    elif world > 1:
-        d_keys = torch.empty((Q, k), dtype=torch.int64, device=dev)  # packed u64 keys
-        d_all = torch.empty((world * Q, k), dtype=torch.int64, device=dev)  # rank-major concatenation
 
-    def step_device():
+    def step_device(gather=True):
         if world == 1:
             idx.search_device(dq.data_ptr(), Q, k, d_dist.data_ptr(), d_row.data_ptr(), d_cnt.data_ptr(), stream=st)
         elif by_queries:
-            # the results stay in block layout (per rank: rows | distances | counts); every rank gets all
-            if q1 > q0:
-                idx.search_device(dq[q0:q1].data_ptr(), q1 - q0, k, b_dist.data_ptr(), b_row.data_ptr(),
-                                  b_cnt.data_ptr(), stream=st)
-            dist.all_gather_into_tensor(d_allb, blk)
+            comm.search_queries_device(idx, dq.data_ptr(), Q, k, d_dist.data_ptr(), d_row.data_ptr(), d_cnt.data_ptr(),
+                                       stream=st, gather=gather)
         else:
-            idx.search_shard_keys_device(dq.data_ptr(), Q, k, row0, d_keys.data_ptr(), stream=st)
-            dist.all_gather_into_tensor(d_all, d_keys)
-            capi.merge_shard_keys_device(local_rank, d_all.data_ptr(), world, Q, k, d_dist.data_ptr(),
-                                         d_row.data_ptr(), d_cnt.data_ptr(), stream=st)
+            comm.search_rows_device(idx, dq.data_ptr(), Q, k, row0, d_dist.data_ptr(), d_row.data_ptr(),
+                                    d_cnt.data_ptr(), stream=st)
 
     def barrier():
         if world > 1:
@@ -255,54 +430,37 @@ def run_native(args):
     # ---- parity gate before any timing is reported ------------------------------------------------
     step_device()
     torch.cuda.synchronize()
-    if world > 1 and by_queries:
-        sharded.scatter_blocks(d_allb, world, qper, Q, k, d_dist, d_row, d_cnt)
-        torch.cuda.synchronize()
     checked = None
     host_corpus = None
     uncertified = 0  # queries the device API returned with count -1 (not counted as served)
     if not args.no_check and rank == 0:
-        nchk = min(Q, 8)
+        nchk = min(Q, 256)
         chk_ids = sorted(set(int(x) for x in np.linspace(0, Q - 1, nchk)))
-        # full oracle check when the corpus fits comfortably in host memory, else a 200k-row prefix
-        sub_rows = args.rows if args.rows * d <= 300_000_000 else 200_000
-        if sub_rows == args.rows:
-            corpus_chk = oracle.synth(args.kind, args.seed, 0, sub_rows, d, threads=min(16, host_cores()))
+        got_d, got_r = d_dist.cpu().numpy(), d_row.cpu().numpy()
+        cnt_host = d_cnt.cpu().numpy()
+        uncertified = int((cnt_host < 0).sum())
+        # the device API marks a query whose selection could not be proven with count -1 (the host API
+        # re-runs it through the flat scan); a sampled threshold makes that rare, not impossible
+        assert uncertified <= max(1, Q // 2000), f"{uncertified} uncertified queries in the device-API run"
+        # full oracle check when the corpus fits comfortably in host memory, else the GPU-side oracle
+        if args.rows * d <= 300_000_000:
+            corpus_chk = oracle.synth(args.kind, args.seed, 0, args.rows, d, threads=min(16, host_cores()))
             host_corpus = corpus_chk
-            got_d, got_r = d_dist.cpu().numpy(), d_row.cpu().numpy()
-            cnt_host = d_cnt.cpu().numpy()
-            uncertified = int((cnt_host < 0).sum())
-            # the device API marks a query whose selection could not be proven with count -1 (the host API
-            # re-runs it through the flat scan); a sampled threshold makes that rare, not impossible
-            assert uncertified <= max(1, Q // 2000), f"{uncertified} uncertified queries in the device-API run"
             assert ((cnt_host == min(k, args.rows)) | (cnt_host < 0)).all()
-            chk_ids = [i for i in chk_ids if cnt_host[i] >= 0]
-            for i in chk_ids:
-                od, orow = oracle.exact_search(corpus_chk, q_host[i], k, mid)
-                assert np.array_equal(got_r[i, :len(orow)], orow), (i, got_r[i], orow)
-                assert np.array_equal(got_d[i, :len(od)].view(np.uint32), od.view(np.uint32))
-            checked = (f"{len(chk_ids)} queries spread over the batch bit-identical to the oracle over all "
-                       f"{sub_rows} rows; {Q - uncertified} of {Q} queries certified in the device-API run")
+            n_ok = check_against_oracle(oracle, corpus_chk, q_host, chk_ids, k, mid, got_d, got_r, cnt_host)
+            checked = (f"{n_ok} queries spread over the batch bit-identical (rows and float32 distances) to the "
+                       f"CPU oracle over all {args.rows} rows; {Q - uncertified} of {Q} queries certified in the "
+                       f"device-API run")
+        elif world == 1:
+            # full-size membership: the exhaustive GPU oracle (qg_search_exhaustive: every row's exact distance
+            # in the reference's arithmetic + full sort; itself checked against the CPU oracle in tests/)
+            ids = [i for i in chk_ids[:32] if cnt_host[i] >= 0]
+            xd, xr, xc = idx.search_exhaustive(q_host[ids], k)
+            assert np.array_equal(got_r[ids], xr) and np.array_equal(got_d[ids].view(np.uint32), xd.view(np.uint32))
+            checked = (f"{len(ids)} queries bit-identical to the exhaustive GPU oracle over all {args.rows} rows "
+                       f"(every row's exact distance + full sort)")
         else:
-            # full-size property: distances of the returned rows equal the oracle's pairwise arithmetic,
-            # ascending, and no row of a 200k-row prefix beats the k-th result
-            corpus_chk = oracle.synth(args.kind, args.seed, 0, sub_rows, d, threads=min(16, host_cores()))
-            got_d, got_r = d_dist.cpu().numpy(), d_row.cpu().numpy()
-            cnt_host = d_cnt.cpu().numpy()
-            uncertified = int((cnt_host < 0).sum())
-            assert uncertified <= max(1, Q // 2000), f"{uncertified} uncertified queries in the device-API run"
-            chk_ids = [i for i in chk_ids if cnt_host[i] >= 0]
-            for i in chk_ids:
-                rows_i = got_r[i]
-                vecs = np.stack([oracle.synth(args.kind, args.seed, int(r), 1, d, threads=1)[0] for r in rows_i])
-                want = np.array([oracle.distance(mid, q_host[i], v) for v in vecs], dtype=np.float32)
-                assert np.array_equal(want.view(np.uint32), got_d[i].view(np.uint32)), (want, got_d[i])
-                assert np.all(np.diff(got_d[i]) >= 0)
-                od, orow = oracle.exact_search(corpus_chk, q_host[i], k, mid)
-                inside = rows_i < sub_rows
-                assert od[0] >= got_d[i][0] and set(orow[od < got_d[i][-1]]).issubset(set(rows_i[inside]))
-            checked = (f"{nchk} queries: returned distances bit-identical to the oracle's pairwise arithmetic, "
-                       f"ascending, and consistent with the oracle's exact top-{k} over a {sub_rows}-row prefix")
+            checked = "see row_sharded.batches[].parity (per-shard exhaustive GPU oracle)"
 
     # ---- value: device-resident, CUDA events on the launching stream ----------------------------------
     for _ in range(max(3, args.warmup)):
@@ -349,29 +507,40 @@ def run_native(args):
         def step_e2e():
             e2e_out[0] = idx.search(q_host, k, out=e2e_out[0])  # result buffers reused from step to step
             return e2e_out[0]
+        h2d, d2h = Q * d * 4, Q * k * 12 + Q * 4
+        e2e_api = "qg_search_batch (host buffers, pinned staging)"
     else:
-        # results land in pinned host buffers (a pageable .cpu() would add a staging copy per step)
-        if by_queries:
-            h_allb = torch.empty(d_allb.numel(), dtype=torch.uint8).pin_memory()
-        else:
-            h_dist = torch.empty((Q, k), dtype=torch.float32).pin_memory()
-            h_row = torch.empty((Q, k), dtype=torch.int64).pin_memory()
-            h_cnt = torch.empty((Q,), dtype=torch.int32).pin_memory()
+        # results land in pinned host buffers (a pageable .cpu() would add a staging copy per step); every
+        # query's result reaches host memory exactly once: on the rank that answered it (replicas) or on
+        # rank 0 (row shards, after the merge)
+        nq_out = (q1 - q0) if by_queries else (Q if rank == 0 else 0)
+        h_dist = torch.empty((max(nq_out, 1), k), dtype=torch.float32).pin_memory()
+        h_row = torch.empty((max(nq_out, 1), k), dtype=torch.int64).pin_memory()
+        h_cnt = torch.empty((max(nq_out, 1),), dtype=torch.int32).pin_memory()
 
         def step_e2e():
             if by_queries:
-                dq[q0:q1].copy_(q_pin[q0:q1], non_blocking=True)
+                if q1 > q0:
+                    dq[q0:q1].copy_(q_pin[q0:q1], non_blocking=True)
+                step_device(gather=False)  # no collective: the rank's block stays where it was computed
+                if q1 > q0:
+                    h_dist[:q1 - q0].copy_(d_dist[q0:q1], non_blocking=True)
+                    h_row[:q1 - q0].copy_(d_row[q0:q1], non_blocking=True)
+                    h_cnt[:q1 - q0].copy_(d_cnt[q0:q1], non_blocking=True)
+            else:
+                dq.copy_(q_pin, non_blocking=True)
                 step_device()
-                h_allb.copy_(d_allb, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-                return h_allb
-            dq.copy_(q_pin, non_blocking=True)
-            step_device()
-            h_dist.copy_(d_dist, non_blocking=True)
-            h_row.copy_(d_row, non_blocking=True)
-            h_cnt.copy_(d_cnt, non_blocking=True)
+                if rank == 0:
+                    h_dist.copy_(d_dist, non_blocking=True)
+                    h_row.copy_(d_row, non_blocking=True)
+                    h_cnt.copy_(d_cnt, non_blocking=True)
             torch.cuda.current_stream().synchronize()
-            return h_dist, h_row, h_cnt
+        h2d = Q * d * 4 if by_queries else world * Q * d * 4
+        d2h = Q * k * 12 + Q * 4
+        e2e_api = ("per rank: pinned H2D of its query block + qg_comm_search_queries_device(gather=0) + D2H of its "
+                   "result block (no collective)" if by_queries else
+                   "per rank: pinned H2D of the batch + qg_comm_search_rows_device (shard scan, NCCL all-gather, "
+                   "merge); rank 0 copies the merged result to the host")
     for _ in range(3):
         step_e2e()
     barrier()
@@ -385,17 +554,26 @@ def run_native(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_qps = Q * e2e_steps / float(t.item())
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---- roofline of the dominant kernel (the scan), timed live by events inside the timed region ----
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+
+    # ---- north_star's layout in the driver's record: C4-shaped row shards (every rank takes part) ----
+    row_sharded = None
+    if world > 1 and not args.no_subrecords:
+        idx_keep = idx
+        row_sharded = row_sharded_record(capi, oracle, torch, dist, comm, world, rank, local_rank, dev, peaks)
+        idx = idx_keep
+
+    if rank != 0:
+        if world > 1:
+            comm.close()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the scan), timed live by events inside the timed region ----
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     scan_launch_ms = prof["scan_ms"] / max(1, prof["scan_launches"])
@@ -419,28 +597,40 @@ def run_native(args):
                 "prep_launch_ms": prof["prep_ms"] / max(1, prof["prep_launches"]) if prof["prep_launches"] else None}
     if tc:
         # a [rows x d] x [d x queries] contraction per pass: the binding roof is whichever floor is higher,
-        # the corpus stream (HBM) or the MMA work (tensor pipe; tf32 runs at half the bf16 rate)
+        # the corpus stream (HBM) or the MMA work (tensor pipe; tf32 runs at half the bf16 rate). The step is
+        # tens of milliseconds at full clocks, not a seconds-long power-limited loop, so the tensor ceiling is
+        # the BURST figure of MEASURED_PEAKS.json.
         qpp = min(Q_gpu, stats["queries_per_pass"])
         flops = 2.0 * qpp * nloc * d
         tfl = flops / (scan_launch_ms * 1e-3) / 1e12 if scan_launch_ms > 0 else 0.0
-        bf16 = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        bf16 = float(peaks.get("bf16_tflops", 1590.0))
         tpeak = bf16 if bf16_stream else bf16 / 2
         t_hbm, t_tensor = bytes_per_launch / (peak * 1e9), flops / (tpeak * 1e12)
         tensor = {"achieved": tfl, "peak": tpeak, "unit": "TFLOP/s", "frac": tfl / tpeak, "queries_per_pass": qpp,
                   "flops_per_launch": flops,
-                  "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained%s)" % ("" if bf16_stream else " / 2 for tf32")
-                                 if "bf16_tflops_sustained" in peaks else "fallback 1400 TFLOP/s"}
+                  "frac_of_sustained": tfl / float(peaks.get("bf16_tflops_sustained", 1400.0)) / (1 if bf16_stream else 0.5),
+                  "peak_source": "measured burst (MEASURED_PEAKS.json bf16_tflops%s)" % ("" if bf16_stream else " / 2 for tf32")
+                                 if "bf16_tflops" in peaks else "fallback 1590 TFLOP/s (B200_PROFILING.md)"}
         if t_tensor > t_hbm:
             roofline.update({"bound": "tensor", "achieved": tfl, "peak": tpeak, "unit": "TFLOP/s", "frac": tfl / tpeak,
-                             "peak_source": tensor["peak_source"], "flops_per_launch": flops, "hbm": hbm})
+                             "peak_source": tensor["peak_source"], "flops_per_launch": flops,
+                             "frac_of_sustained": tensor["frac_of_sustained"], "hbm": hbm})
         else:
             roofline["tensor"] = tensor
         roofline["floors_us"] = {"hbm": t_hbm * 1e6, "tensor": t_tensor * 1e6}
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        roofline["traffic"] = tr.get("tc_ts_kernel_bytes_per_launch" if tc else "scan_fast_kernel_bytes_per_launch")
-    except Exception:
-        pass
+    if world == 1 and not args.no_subrecords:
+        # one ncu launch of the same kernel on the same workload, outside the timed regions
+        tr = measure_traffic(args, "tc_ts_kernel" if tc else "scan_fast_kernel", 3 if tc else 2)
+        roofline["traffic"] = tr
+        roofline["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu run of "
+                                      "tools/prof_once.py inside this bench run" if tr else None)
+    if roofline["traffic"] is None:
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            roofline["traffic"] = tr.get("tc_ts_kernel_bytes_per_launch" if tc else "scan_fast_kernel_bytes_per_launch")
+            roofline["traffic_source"] = "profiles/traffic.json (an earlier ncu --set full capture; ncu could not run here)"
+        except Exception:
+            pass
 
     # ---- the small-batch regime (flat scan, one query per pass) for the HBM roofline it is judged on ----
     small = None
@@ -463,8 +653,13 @@ def run_native(args):
         st1 = idx.stats()
         l_ms = pr1["scan_ms"] / max(1, pr1["scan_launches"])
         small = {"queries_per_step": 1, "qps": nsm / (s0.elapsed_time(s1) * 1e-3), "kernel": "scan_fast_kernel",
-                 "launch_ms": l_ms, "achieved_GBps": st1["bytes_algorithmic"] / (l_ms * 1e-3) / 1e9 if l_ms > 0 else None,
+                 "launch_ms": l_ms, "bytes_per_launch": st1["bytes_algorithmic"],
+                 "achieved_GBps": st1["bytes_algorithmic"] / (l_ms * 1e-3) / 1e9 if l_ms > 0 else None,
                  "frac_of_measured_hbm": st1["bytes_algorithmic"] / (l_ms * 1e-3) / 1e9 / peak if l_ms > 0 else None}
+
+    real_valued = None
+    if world == 1 and not args.no_subrecords and args.rows * d <= 300_000_000:
+        real_valued = real_valued_record(capi, oracle, torch, args, dev, peaks)
 
     cpu_base = None
     if not args.no_cpu_baseline:
@@ -482,16 +677,16 @@ def run_native(args):
                    "rows": args.rows, "dim": d, "k": k, "queries_per_step": Q,
                    "parallelism": "single GPU" if world == 1 else (
                        f"corpus replicated x{world} ({args.rows*d*6/1e9:.2f} GB per GPU with the bf16 copy), batch split "
-                       f"in contiguous blocks of {qper} queries, one NCCL all-gather of the result blocks"
-                       if by_queries else f"row-sharded x{world}, NCCL all-gather of per-shard top-k"),
+                       f"in contiguous blocks of {qper} queries, one NCCL all-gather of the result blocks inside "
+                       f"libquivergpu (qg_comm_search_queries_device); the row-sharded north_star layout is measured "
+                       f"in row_sharded" if by_queries else
+                       f"row-sharded x{world}, NCCL all-gather of per-shard top-k inside libquivergpu "
+                       f"(qg_comm_search_rows_device)"),
                    "l2_policy": f"inputs larger than L2: every step streams the {args.rows*d*4/1e6:.0f} MB corpus "
                                 f"({nloc*d*4/1e6:.0f} MB per GPU)",
                    "parity_check": checked},
-        "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": Q * d * 4,
-                "d2h_bytes_per_step": Q * k * 12 + Q * 4, "steps": e2e_steps,
-                "api": "qg_search_batch (host buffers, pinned staging)" if world == 1 else (
-                       "pinned H2D of the rank's query block + search + all-gather + D2H of all results" if by_queries
-                       else "pinned H2D + shard search + all-gather + merge + D2H")},
+        "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": e2e_api},
         "gpu_launches": launches_per_step * args.steps,
         "kernels_per_step": {"passes": stats["passes"], "launches": stats["kernel_launches"],
                              "path": {0: "exhaustive", 1: "flat scan", 2: "gather scan", 3: "tensor-core"}[stats["path"]],
@@ -499,11 +694,14 @@ def run_native(args):
                              "merge": 1 if (world > 1 and not by_queries) else 0},
         "uncertified_queries_device_api": uncertified,
         "small_batch_regime": small,
+        "real_valued": real_valued,
+        "row_sharded": row_sharded,
         "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_base,
         "host_cores": host_cores(), "device": capi.device_info(local_rank)["name"],
     }
     emit(line)
     if world > 1:
+        comm.close()
         dist.destroy_process_group()
 
 

@@ -56,6 +56,19 @@ def check_rows(kind, seed, dim, metric, q_host, dist, row, cnt, k, normalize_row
     return "ok" if ok else "MISMATCH"
 
 
+def check_membership(idx, q_host, dist, row, cnt, k, flt=None, n_check=32):
+    """Full-size membership parity: the fast path's rows and float32 distances equal the exhaustive
+    GPU path's (qg_search_exhaustive: every row's exact distance + full sort; validated against the CPU oracle
+    in tests/test_gpu_parity_chain.py) for n_check queries."""
+    ids = [i for i in range(min(len(cnt), n_check)) if cnt[i] >= 0]
+    if not ids:
+        return "UNCERTIFIED"
+    xd, xr, xc = idx.search_exhaustive(q_host[ids], k, filter=flt)
+    ok = np.array_equal(row[ids], xr) and np.array_equal(dist[ids].view(np.uint32), xd.view(np.uint32)) and \
+        np.array_equal(cnt[ids], xc)
+    return f"{len(ids)} queries == exhaustive GPU oracle" if ok else "MEMBERSHIP MISMATCH"
+
+
 def emit(out, **rec):
     print(json.dumps(rec), flush=True)
     out.append(rec)
@@ -110,11 +123,13 @@ def c3(out, scale):
         par = check_rows(2, 42, d, 0, qh, dist, row, cnt, kk)
         if use_f and par == "ok":
             par = "ok" if bool(np.all(want_bits[row[:min(q, 3)].ravel()])) else "FILTER VIOLATED"
+        member = check_membership(idx, qh, dist, row, cnt, kk, flt=flt if use_f else None)
         emit(out, config="C3 cosine 10M x 768" + (" + facet prefilter" if use_f else "") +
              (" + negative examples (window max(2k,30))" if use_neg else ""), rows=n, q=q, k=kk, ms=round(ms, 3),
              qps=round(q / ms * 1e3, 1), path=stt["path"], passes=stt["passes"],
              algorithmic_GB=round(stt["bytes_algorithmic"] / 1e9, 3),
-             GBps=round(stt["bytes_algorithmic"] * stt["passes"] / (ms * 1e-3) / 1e9, 1), parity=par)
+             GBps=round(stt["bytes_algorithmic"] * stt["passes"] / (ms * 1e-3) / 1e9, 1), parity=par,
+             membership=member)
     flt.close()
     idx.close()
 
@@ -133,7 +148,8 @@ def c4(out, scale):
         emit(out, config="C4 L2 100M x 96 (Deep-shaped), all rows on ONE GPU", rows=n, q=q, k=k, ms=round(ms, 3),
              qps=round(q / ms * 1e3, 1), path=stt["path"], passes=stt["passes"],
              GBps=round(stt["bytes_algorithmic"] * stt["passes"] / (ms * 1e-3) / 1e9, 1),
-             uncertified=int((cnt < 0).sum()), parity=check_rows(3, 42, d, 1, qh, dist, row, cnt, k), fill_s=round(fill_s, 1))
+             uncertified=int((cnt < 0).sum()), parity=check_rows(3, 42, d, 1, qh, dist, row, cnt, k),
+             membership=check_membership(idx, qh, dist, row, cnt, k), fill_s=round(fill_s, 1))
     idx.close()
 
 
