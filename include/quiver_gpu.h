@@ -335,6 +335,26 @@ int qg_queries_upload(qg_index* idx, const float* queries, int b, int dim, qg_qu
 int qg_queries_destroy(qg_queries* qs);
 int qg_batch_distance_queries(qg_index* idx, const qg_queries* qs, const uint32_t* rows, int m, float* out);
 
+/* ---- hnsw.Search on the device (replaces the whole walk of pkg/hnsw/hnsw.go:471-580, 602-672) -----
+ * The reference's graph as flat arrays, resident on the index's device; node id = row of the index
+ * (insertion order): level[n] (-1 = deleted node), adj0[n x max_m0] level-0
+ * connections in list order padded with 0xFFFFFFFF, upper_off[n + 1] / upper_adj = per node level[i]
+ * blocks of m entries for the levels 1..level[i]. The arrays are copied. */
+typedef struct qg_hnsw qg_hnsw;
+int qg_hnsw_upload(qg_index* idx, int64_t n_nodes, int m, int max_m0, int entry_point, int current_level,
+                   const int32_t* level, const uint32_t* adj0, const int64_t* upper_off, const uint32_t* upper_adj,
+                   qg_hnsw** out);
+int qg_hnsw_destroy(qg_hnsw* g);
+/* One persistent kernel, a warp per query: ef = 1 descent through the upper layers, base layer with
+ * ef = max(ef_search, k), the reference's heaps / visit order / stop and admit rules, distances in the
+ * index's metric and arithmetic — step-identical to the reference's walk. out_idx / out_dist are q x k
+ * (k already clamped to the node count by the caller, hnsw.go:615-617; unused entries 0xFFFFFFFF / +inf),
+ * out_count[i] = results of the graph walk (may be < k: the caller runs the under-fill exact pass,
+ * hnsw.go:676-710) or -1 when the query's candidate heap outgrew the kernel's shared-memory slice (the
+ * caller repeats it with the host walk); out_evals (nullable) = distance evaluations per query. */
+int qg_hnsw_search_batch(qg_index* idx, const qg_hnsw* g, const float* queries, int q, int dim, int k, int ef_search,
+                         uint32_t* out_idx, float* out_dist, int* out_count, int64_t* out_evals);
+
 /* ---- introspection for benchmarks and tests -----------------------------------------*/
 typedef struct qg_scan_stats {
   int64_t rows_scanned;     /* rows whose vector bytes the last scan read            */

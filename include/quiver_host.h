@@ -145,6 +145,18 @@ typedef struct qh_hnsw_graph {
 int qh_hnsw_search_batch(qh_index* idx, const qh_hnsw_graph* g, const float* queries, int nq, int dim, int k,
                          qh_results** out, int64_t* out_evals, int64_t* out_steps);
 
+/* The same search with the whole walk on the device: the graph is uploaded once (qh_hnsw_upload; the
+ * caller keeps the host arrays of `g` alive for the lifetime of the handle), every search is one launch of
+ * the persistent kernel behind qg_hnsw_search_batch (a warp per query, heaps in shared memory, the
+ * reference's sift rules — step-identical), the under-fill exact pass of all affected queries is ONE
+ * batched exact search. out_fallbacks (nullable): queries repeated by the lock-step walk above because
+ * their candidate heap outgrew the kernel's shared-memory slice. */
+typedef struct qh_hnsw_dev qh_hnsw_dev;
+int qh_hnsw_upload(qh_index* idx, const qh_hnsw_graph* g, qh_hnsw_dev** out);
+int qh_hnsw_dev_free(qh_hnsw_dev* d);
+int qh_hnsw_search_device(qh_index* idx, qh_hnsw_dev* d, const float* queries, int nq, int dim, int k,
+                          qh_results** out, int64_t* out_evals, int* out_fallbacks);
+
 /* ---- development aids (CPU-only; no device needed) --------------------------------------------- */
 /* fmt.Sprintf("%v", json value) into buf; returns the length or -1 on a JSON error. */
 int qh_debug_sprint_v(const char* value_json, int typed_literals, char* buf, int buf_len);

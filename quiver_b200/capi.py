@@ -65,6 +65,7 @@ EXPORTED_SYMBOLS = [
     "qg_batch_distance", "qg_batch_distance_multi", "qg_last_scan_stats", "qg_index_set_profiling",
     "qg_index_read_profile", "qg_debug_tc_pass", "qg_queries_upload", "qg_queries_destroy",
     "qg_batch_distance_queries",
+    "qg_hnsw_upload", "qg_hnsw_destroy", "qg_hnsw_search_batch",
     "qg_comm_unique_id", "qg_comm_create_rank", "qg_comm_destroy", "qg_comm_world", "qg_comm_rank",
     "qg_comm_search_rows_device", "qg_comm_search_queries_device",
     "qg_group_create", "qg_group_destroy", "qg_group_devices", "qg_group_index", "qg_group_row_base",
@@ -122,6 +123,9 @@ def load() -> C.CDLL:
     lib.qg_queries_upload.argtypes = [vp, vp, i32, i32, C.POINTER(vp)]
     lib.qg_queries_destroy.argtypes = [vp]
     lib.qg_batch_distance_queries.argtypes = [vp, vp, vp, i32, vp]
+    lib.qg_hnsw_upload.argtypes = [vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, C.POINTER(vp)]
+    lib.qg_hnsw_destroy.argtypes = [vp]
+    lib.qg_hnsw_search_batch.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
     lib.qg_comm_unique_id.argtypes = [vp]
     lib.qg_comm_create_rank.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
     lib.qg_comm_destroy.argtypes = [vp]

@@ -16,6 +16,7 @@
 #include "compact.cuh"
 #include "exact.cuh"
 #include "finalize.cuh"
+#include "hnsw.cuh"
 #include "misc.cuh"
 #include "scan.cuh"
 #include "tc_scan.cuh"
@@ -1941,6 +1942,111 @@ int qg_batch_distance_queries(qg_index* idx, const qg_queries* qs, const uint32_
 
 int qg_batch_distance(qg_index* idx, const float* query, int dim, const uint32_t* rows, int n, float* out) {
   return qg_batch_distance_multi(idx, query, 1, dim, rows, n, out);
+}
+
+struct qg_hnsw {
+  qg_index* owner = nullptr;
+  HnswDevGraph g{};
+  DevBuf level, adj0, upper_off, upper_adj, work;
+  std::mutex mu;  // one search at a time uses the workspace
+};
+
+int qg_hnsw_upload(qg_index* idx, int64_t n_nodes, int m, int max_m0, int entry_point, int current_level,
+                   const int32_t* level, const uint32_t* adj0, const int64_t* upper_off, const uint32_t* upper_adj,
+                   qg_hnsw** out) {
+  if (int rc = check_index(idx)) return rc;
+  if (!out) return fail(QG_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (n_nodes < 0 || m <= 0 || max_m0 <= 0) return fail(QG_ERR_INVALID, "bad graph shape");
+  if (n_nodes > 0 && (!level || !adj0 || !upper_off)) return fail(QG_ERR_INVALID, "null graph array");
+  if (n_nodes > idx->n_rows) return fail(QG_ERR_RANGE, "the graph has more nodes than the index has rows");
+  std::unique_ptr<qg_hnsw> g(new qg_hnsw());
+  g->owner = idx;
+  g->g.n_nodes = n_nodes;
+  g->g.m = m;
+  g->g.max_m0 = max_m0;
+  g->g.entry_point = entry_point;
+  g->g.current_level = current_level;
+  if (n_nodes > 0) {
+    const size_t n = (size_t)n_nodes;
+    const size_t ulen = (size_t)upper_off[n];
+    if (ulen > 0 && !upper_adj) return fail(QG_ERR_INVALID, "null graph array");
+    if (int rc = g->level.ensure(n * 4)) return rc;
+    if (int rc = g->adj0.ensure(n * (size_t)max_m0 * 4)) return rc;
+    if (int rc = g->upper_off.ensure((n + 1) * 8)) return rc;
+    if (int rc = g->upper_adj.ensure(std::max<size_t>(ulen, 1) * 4)) return rc;
+    QG_CUDA_OK(cudaMemcpy(g->level.p, level, n * 4, cudaMemcpyHostToDevice));
+    QG_CUDA_OK(cudaMemcpy(g->adj0.p, adj0, n * (size_t)max_m0 * 4, cudaMemcpyHostToDevice));
+    QG_CUDA_OK(cudaMemcpy(g->upper_off.p, upper_off, (n + 1) * 8, cudaMemcpyHostToDevice));
+    if (ulen > 0) QG_CUDA_OK(cudaMemcpy(g->upper_adj.p, upper_adj, ulen * 4, cudaMemcpyHostToDevice));
+    const size_t wb = hnsw_workspace_bytes(n_nodes, idx->sm_count);
+    if (int rc = g->work.ensure(wb)) return rc;
+    QG_CUDA_OK(cudaMemset(g->work.p, 0, wb));  // the kernel leaves the visited bitsets clean
+  }
+  g->g.level = (const int32_t*)g->level.p;
+  g->g.adj0 = (const uint32_t*)g->adj0.p;
+  g->g.upper_off = (const long long*)g->upper_off.p;
+  g->g.upper_adj = (const uint32_t*)g->upper_adj.p;
+  *out = g.release();
+  return 0;
+}
+
+int qg_hnsw_destroy(qg_hnsw* g) {
+  if (!g) return 0;
+  if (g->owner) cudaSetDevice(g->owner->device);
+  g->level.release(); g->adj0.release(); g->upper_off.release(); g->upper_adj.release(); g->work.release();
+  delete g;
+  return 0;
+}
+
+int qg_hnsw_search_batch(qg_index* idx, const qg_hnsw* gc, const float* queries, int q, int dim, int k, int ef_search,
+                         uint32_t* out_idx, float* out_dist, int* out_count, int64_t* out_evals) {
+  if (int rc = check_index(idx)) return rc;
+  qg_hnsw* g = const_cast<qg_hnsw*>(gc);
+  if (!g || g->owner != idx) return fail(QG_ERR_INVALID, "graph does not belong to this index");
+  if (q < 0) return fail(QG_ERR_INVALID, "negative query count");
+  if (q == 0) return 0;
+  if (!out_count) return fail(QG_ERR_INVALID, "out_count is null");
+  if (g->g.n_nodes == 0) {  // hnsw.go:606-608: empty graph => no results, no error
+    for (int i = 0; i < q; ++i) out_count[i] = 0;
+    return 0;
+  }
+  if (dim != idx->dim)
+    return fail(QG_ERR_DIM, "query dimension mismatch: expected " + std::to_string(idx->dim) + ", got " +
+                                std::to_string(dim));
+  if (k <= 0) return fail(QG_ERR_K, "k must be positive");
+  if ((long long)k > g->g.n_nodes) return fail(QG_ERR_INVALID, "k must be clamped to the node count by the caller");
+  if (!queries || !out_idx || !out_dist) return fail(QG_ERR_INVALID, "null buffer");
+  if (g->g.entry_point < 0 || g->g.entry_point >= g->g.n_nodes)
+    return fail(QG_ERR_RANGE, "entry point out of range (validate it first, hnsw.go:620-634)");
+  std::lock_guard<std::mutex> lk(g->mu);
+  Workspace* w = ws_acquire(idx);
+  if (!w) return fail(QG_ERR_CUDA, "could not create a stream");
+  int rc = 0;
+  do {
+    cudaStream_t st = w->stream;
+    const size_t qbytes = (size_t)q * dim * 4, on = (size_t)q * k;
+    if ((rc = w->d_q.ensure(qbytes))) break;
+    if ((rc = w->d_rows32.ensure(on * 4))) break;
+    if ((rc = w->d_dist.ensure(on * 4))) break;
+    if ((rc = w->d_count.ensure((size_t)q * 4))) break;
+    if ((rc = w->d_rows64.ensure((size_t)q * 8))) break;
+    cudaError_t e = cudaMemcpyAsync(w->d_q.p, queries, qbytes, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, cudaGetErrorString(e)); break; }
+    const int ef0 = std::max(ef_search, k);  // hnsw.go:660-663
+    if ((rc = launch_hnsw_search(g->g, idx->vec, idx->dp, idx->dim, idx->metric, idx->arith, (const float*)w->d_q.p, q, k,
+                                 ef0, g->work.p, idx->sm_count, (uint32_t*)w->d_rows32.p, (float*)w->d_dist.p,
+                                 (int*)w->d_count.p, out_evals ? (long long*)w->d_rows64.p : nullptr, st)))
+      break;
+    e = cudaMemcpyAsync(out_idx, w->d_rows32.p, on * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_dist, w->d_dist.p, on * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_count, w->d_count.p, (size_t)q * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && out_evals) e = cudaMemcpyAsync(out_evals, w->d_rows64.p, (size_t)q * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fail(QG_ERR_CUDA, std::string("hnsw search: ") + cudaGetErrorString(e));
+  } while (0);
+  ws_release(idx, w);
+  return rc;
 }
 
 int qg_index_set_profiling(qg_index* idx, int on) {

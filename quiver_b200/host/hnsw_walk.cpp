@@ -393,3 +393,143 @@ extern "C" int qh_hnsw_search_batch(qh_index* idx, const qh_hnsw_graph* g, const
   *out = res.release();
   return 0;
 }
+
+
+// ================================================================================================
+// The same search with the WHOLE walk on the device (qg_hnsw_search_batch: one persistent kernel, a
+// warp per query, csrc/hnsw.cu). The host keeps what needs string ids: the under-fill exact pass
+// ordered by (Distance, VectorID) (hnsw.go:676-710) and the id lookup of the results.
+// ================================================================================================
+struct qh_hnsw_dev {
+  qh_index* owner = nullptr;
+  qg_hnsw* dev = nullptr;
+  qh_hnsw_graph host{};          // the caller's arrays (kept alive by the caller): the lock-step fallback uses them
+  int64_t n_nodes = 0;
+  int ef_search = 0;
+  bool has_entry = false;
+};
+
+extern "C" int qh_hnsw_upload(qh_index* idx, const qh_hnsw_graph* g, qh_hnsw_dev** out) {
+  if (!idx || !g || !out) return qh_internal_fail(QG_ERR_INVALID, "null argument");
+  *out = nullptr;
+  qg_index* h = nullptr;
+  int idim = 0;
+  if (int rc = qh_internal_index_handle(idx, &h, &idim)) return rc;
+  std::unique_ptr<qh_hnsw_dev> d(new qh_hnsw_dev());
+  d->owner = idx;
+  d->host = *g;
+  d->n_nodes = g->n_nodes;
+  d->ef_search = g->ef_search;
+  // entry point validation (hnsw.go:620-634): a stale entry is replaced by the first live node
+  int64_t entry = g->entry_point;
+  if (g->n_nodes > 0 && (entry < 0 || entry >= g->n_nodes || g->level[entry] < 0)) {
+    entry = -1;
+    for (int64_t i = 0; i < g->n_nodes; ++i)
+      if (g->level[i] >= 0) { entry = i; break; }
+  }
+  d->has_entry = g->n_nodes > 0 && entry >= 0;
+  if (d->has_entry) {
+    if (int rc = qg_hnsw_upload(h, g->n_nodes, g->m, g->max_m0, (int)entry, g->current_level, g->level, g->adj0,
+                                g->upper_off, g->upper_adj, &d->dev))
+      return qh_internal_fail(rc, qg_last_error());
+  }
+  *out = d.release();
+  return 0;
+}
+
+extern "C" int qh_hnsw_dev_free(qh_hnsw_dev* d) {
+  if (!d) return 0;
+  if (d->dev) qg_hnsw_destroy(d->dev);
+  delete d;
+  return 0;
+}
+
+extern "C" int qh_hnsw_search_device(qh_index* idx, qh_hnsw_dev* d, const float* queries, int nq, int dim, int k,
+                                     qh_results** out, int64_t* out_evals, int* out_fallbacks) {
+  if (!idx || !d || !out) return qh_internal_fail(QG_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (out_fallbacks) *out_fallbacks = 0;
+  if (d->owner != idx) return qh_internal_fail(QG_ERR_INVALID, "graph does not belong to this index");
+  qg_index* h = nullptr;
+  int idim = 0;
+  if (int rc = qh_internal_index_handle(idx, &h, &idim)) return rc;
+  if (nq <= 0 || !queries) return qh_internal_fail(QG_ERR_INVALID, "no queries provided");
+  if (dim != idim) {
+    const std::string msg = "query dimension mismatch: expected " + std::to_string(idim) + ", got " + std::to_string(dim);
+    return qh_internal_fail(QG_ERR_DIM, msg.c_str());
+  }
+  std::unique_ptr<qh_results, int (*)(qh_results*)> res(qh_internal_results_new(nq), qh_results_free);
+  if (d->n_nodes == 0 || !d->has_entry) {  // hnsw.go:606-608, 628-631: nothing to search
+    *out = res.release();
+    return 0;
+  }
+  if (k <= 0) return qh_internal_fail(QG_ERR_K, "k must be positive");
+  const int kk = (int)std::min<int64_t>(k, d->n_nodes);
+  std::vector<uint32_t> ridx((size_t)nq * kk);
+  std::vector<float> rdist((size_t)nq * kk);
+  std::vector<int> rcnt((size_t)nq);
+  std::vector<int64_t> evals((size_t)nq, 0);
+  if (int rc = qg_hnsw_search_batch(h, d->dev, queries, nq, dim, kk, d->ef_search, ridx.data(), rdist.data(), rcnt.data(),
+                                    evals.data()))
+    return qh_internal_fail(rc, qg_last_error());
+  // queries whose candidate heap outgrew the kernel's shared-memory slice: the lock-step host walk
+  std::vector<int> redo;
+  for (int i = 0; i < nq; ++i)
+    if (rcnt[(size_t)i] < 0) redo.push_back(i);
+  std::vector<std::vector<std::pair<std::string, float>>> redone(redo.size());
+  if (!redo.empty()) {
+    std::vector<float> rq(redo.size() * (size_t)dim);
+    for (size_t u = 0; u < redo.size(); ++u)
+      std::memcpy(rq.data() + u * dim, queries + (size_t)redo[u] * dim, (size_t)dim * 4);
+    qh_results* rr = nullptr;
+    std::vector<int64_t> rev(redo.size());
+    if (int rc = qh_hnsw_search_batch(idx, &d->host, rq.data(), (int)redo.size(), dim, k, &rr, rev.data(), nullptr)) return rc;
+    for (size_t u = 0; u < redo.size(); ++u) {
+      const int cnt = qh_results_count(rr, (int)u);
+      for (int j = 0; j < cnt; ++j) redone[u].emplace_back(qh_results_id(rr, (int)u, j), qh_results_distance(rr, (int)u, j));
+      evals[(size_t)redo[u]] = rev[u];
+    }
+    qh_results_free(rr);
+    if (out_fallbacks) *out_fallbacks = (int)redo.size();
+  }
+  // under-filled walks get the exact pass (hnsw.go:676-710), all of them in one batched search
+  std::vector<int> underfilled;
+  for (int i = 0; i < nq; ++i)
+    if (rcnt[(size_t)i] >= 0 && rcnt[(size_t)i] < kk) underfilled.push_back(i);
+  std::vector<float> ud;
+  std::vector<int64_t> ur;
+  std::vector<int> uc;
+  if (!underfilled.empty()) {
+    const int nu = (int)underfilled.size();
+    std::vector<float> uq((size_t)nu * dim);
+    ud.resize((size_t)nu * kk);
+    ur.resize((size_t)nu * kk);
+    uc.resize((size_t)nu);
+    for (int u = 0; u < nu; ++u)
+      std::memcpy(uq.data() + (size_t)u * dim, queries + (size_t)underfilled[(size_t)u] * dim, (size_t)dim * 4);
+    if (int erc = qg_search_batch(h, uq.data(), nu, dim, kk, nullptr, nullptr, ud.data(), nullptr, ur.data(), uc.data()))
+      return qh_internal_fail(erc, qg_last_error());
+  }
+  size_t next_redo = 0, next_under = 0;
+  for (int i = 0; i < nq; ++i) {
+    if (rcnt[(size_t)i] < 0) {
+      for (const auto& e : redone[next_redo]) qh_internal_results_push(res.get(), i, e.first.c_str(), e.second);
+      ++next_redo;
+    } else if (rcnt[(size_t)i] < kk) {
+      const size_t u = next_under++;
+      std::vector<std::pair<float, std::string>> lst;  // (Distance, VectorID) order, hnsw.go:699-704
+      for (int j = 0; j < uc[u]; ++j) lst.emplace_back(ud[u * kk + j], qh_internal_row_id(idx, ur[u * kk + j]));
+      std::stable_sort(lst.begin(), lst.end(), [](const auto& a, const auto& b) {
+        if (a.first == b.first) return a.second < b.second;
+        return a.first < b.first;
+      });
+      for (const auto& e : lst) qh_internal_results_push(res.get(), i, e.second.c_str(), e.first);
+    } else {
+      for (int j = 0; j < kk; ++j)
+        qh_internal_results_push(res.get(), i, qh_internal_row_id(idx, ridx[(size_t)i * kk + j]), rdist[(size_t)i * kk + j]);
+    }
+  }
+  if (out_evals) std::memcpy(out_evals, evals.data(), (size_t)nq * 8);
+  *out = res.release();
+  return 0;
+}

@@ -29,7 +29,8 @@ EXPORTED_SYMBOLS = [
     "qh_collection_destroy", "qh_collection_add", "qh_collection_add_batch", "qh_collection_delete",
     "qh_collection_count", "qh_collection_set_facet_fields", "qh_collection_search",
     "qh_collection_search_with_facets", "qh_collection_filter_mask", "qh_collection_rows", "qh_collection_row_id",
-    "qh_debug_sprint_v", "qh_debug_equal_fold", "qh_hnsw_search_batch",
+    "qh_debug_sprint_v", "qh_debug_equal_fold", "qh_hnsw_search_batch", "qh_hnsw_upload", "qh_hnsw_dev_free",
+    "qh_hnsw_search_device",
 ]
 
 
@@ -96,6 +97,9 @@ def load() -> C.CDLL:
     lib.qh_collection_rows.restype = i64
     lib.qh_collection_row_id.argtypes = [vp, i64]
     lib.qh_collection_row_id.restype = cp
+    lib.qh_hnsw_upload.argtypes = [vp, C.POINTER(qh_hnsw_graph), C.POINTER(vp)]
+    lib.qh_hnsw_dev_free.argtypes = [vp]
+    lib.qh_hnsw_search_device.argtypes = [vp, vp, vp, i32, i32, i32, C.POINTER(vp), vp, C.POINTER(i32)]
     lib.qh_hnsw_search_batch.argtypes = [vp, C.POINTER(qh_hnsw_graph), vp, i32, i32, i32, C.POINTER(vp), vp,
                                          C.POINTER(i64)]
     lib.qh_debug_sprint_v.argtypes = [cp, i32, C.c_char_p, i32]
@@ -253,6 +257,52 @@ class HybridIndex:
         _check(self._lib.qh_hnsw_search_batch(self.handle, C.byref(g), _ptr(qs), qs.shape[0], qs.shape[1], k,
                                               C.byref(res), _ptr(evals), C.byref(steps)))
         return _take(res), evals, steps.value
+
+    def HNSWUpload(self, graph: dict) -> "DeviceGraph":
+        """The graph made resident on the device for HNSW searches that run entirely there."""
+        return DeviceGraph(self, graph)
+
+
+class DeviceGraph:
+    """An HNSW graph resident on the index's device (qh_hnsw_upload). Keeps the host arrays alive: the
+    lock-step fallback of qh_hnsw_search_device reads them."""
+
+    def __init__(self, index: "HybridIndex", graph: dict):
+        self._lib = index._lib
+        self.index = index
+        self._keep = (np.ascontiguousarray(graph["level"], dtype=np.int32),
+                      np.ascontiguousarray(graph["adj0"], dtype=np.uint32),
+                      np.ascontiguousarray(graph["upper_off"], dtype=np.int64),
+                      np.ascontiguousarray(graph["upper_adj"], dtype=np.uint32))
+        level, adj0, uoff, uadj = self._keep
+        self._g = qh_hnsw_graph(int(graph["n"]), int(graph["M"]), int(graph["MaxM0"]), int(graph["entry"]),
+                                int(graph["current_level"]), int(graph["EfSearch"]), level.ctypes.data,
+                                adj0.ctypes.data, uoff.ctypes.data, uadj.ctypes.data)
+        h = C.c_void_p()
+        _check(self._lib.qh_hnsw_upload(index.handle, C.byref(self._g), C.byref(h)))
+        self.handle = h
+
+    def search(self, queries, k: int):
+        """hnsw.Search for a batch, the whole walk on the device. Returns (results per query, distance
+        evaluations per query, queries that fell back to the lock-step host walk)."""
+        qs = _f32(queries)
+        evals = np.zeros(qs.shape[0], dtype=np.int64)
+        fb = C.c_int(0)
+        res = C.c_void_p()
+        _check(self._lib.qh_hnsw_search_device(self.index.handle, self.handle, _ptr(qs), qs.shape[0], qs.shape[1], k,
+                                               C.byref(res), _ptr(evals), C.byref(fb)))
+        return _take(res), evals, fb.value
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.qh_hnsw_dev_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class FluentHybridSearch:

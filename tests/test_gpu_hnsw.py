@@ -67,3 +67,64 @@ def test_walk_edge_cases(H, oracle):
     res, evals, steps = idx.HNSWSearchBatch(graph.export(), q, 100)  # k > n clamps (hnsw.go:615-617)
     assert all(len(r) == 40 for r in res)
     idx.close()
+
+
+@pytest.mark.parametrize("distance,metric,arith", [("euclidean", 1, 0), ("cosine", 0, 0), ("dot_product", 2, 0),
+                                                   ("euclidean", 1, 1), ("cosine", 0, 1)])
+def test_device_walk_is_step_identical(H, oracle, distance, metric, arith):
+    """The whole walk on the device (hnsw_search_kernel: a warp per query, heaps in shared memory): same
+    results, same float32 distances, same number of distance evaluations as the oracle's restatement of
+    hnsw.Search — on the reference's own graph and on the textbook variant (long base-layer walks)."""
+    import os
+    from oracle import hnsw
+    rng = np.random.default_rng(11 + metric + 7 * arith)
+    n, d, k, nq = 6000, 40, 10, 160
+    corpus = rng.standard_normal((n, d)).astype(np.float32)
+    ids = [f"n{i:05d}" for i in range(n)]
+    queries = np.concatenate([rng.standard_normal((nq - 8, d)).astype(np.float32), corpus[:8]])
+    for standard in ("0", "1"):
+        os.environ["QO_HNSW_STANDARD"] = standard
+        graph = hnsw.Graph(corpus, metric, arith=arith, M=16, MaxM0=32, EfConstruction=100, EfSearch=64, seed=5)
+        os.environ["QO_HNSW_STANDARD"] = "0"
+        idx = H.HybridIndex(d, distance, arith=arith)
+        idx.InsertBatch({ids[i]: corpus[i] for i in range(n)})
+        dg = idx.HNSWUpload(graph.export())
+        res, evals, fallbacks = dg.search(queries, k)
+        assert fallbacks == 0
+        full = 0
+        for i in range(nq):
+            od, oidx, oev, _ = graph.search(queries[i], k)
+            assert evals[i] == oev, (standard, i, evals[i], oev)
+            if len(oidx) < k:
+                want = _underfill_oracle(oracle, corpus, ids, queries[i], k, metric) if arith == 0 else None
+                if want is not None:
+                    assert [r[0] for r in res[i]] == [w[0] for w in want]
+                continue
+            full += 1
+            assert [r[0] for r in res[i]] == [ids[j] for j in oidx], (standard, i)
+            assert [np.float32(r[1]).view(np.uint32) for r in res[i]] == [np.float32(x).view(np.uint32) for x in od]
+        if standard == "1":
+            assert full > nq // 2 and evals.mean() > 200  # the textbook graph gives real base-layer walks
+        dg.close()
+        idx.close()
+
+
+def test_device_walk_edge_cases(H, oracle):
+    from oracle import hnsw
+    rng = np.random.default_rng(9)
+    corpus = rng.random((40, 8), dtype=np.float32)
+    graph = hnsw.Graph(corpus, 1, EfSearch=16, seed=2)
+    idx = H.HybridIndex(8, "euclidean")
+    idx.InsertBatch({f"v{i:02d}": corpus[i] for i in range(40)})
+    dg = idx.HNSWUpload(graph.export())
+    q = rng.random((3, 8), dtype=np.float32)
+    with pytest.raises(H.QuiverError, match="k must be positive"):
+        dg.search(q, 0)
+    with pytest.raises(H.QuiverError, match="query dimension mismatch: expected 8, got 7"):
+        dg.search(q[:, :7], 3)
+    res, evals, fb = dg.search(q, 100)  # k > n clamps (hnsw.go:615-617)
+    assert all(len(r) == 40 for r in res)
+    ref, _, _ = idx.HNSWSearchBatch(graph.export(), q, 100)
+    assert res == ref
+    dg.close()
+    idx.close()
