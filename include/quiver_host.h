@@ -32,6 +32,12 @@ int qh_results_queries(const qh_results* r);
 int qh_results_count(const qh_results* r, int query);
 const char* qh_results_id(const qh_results* r, int query, int j);
 float qh_results_distance(const qh_results* r, int query, int j);
+/* types.SearchResultItem (pkg/types/search.go:31-42): Score = 1 - Distance (collection.go:763); Vector and
+ * Metadata are present only in the results of qh_collection_search_request when its options asked for them
+ * (NULL / length 0 otherwise, like the `omitempty` fields). */
+float qh_results_score(const qh_results* r, int query, int j);
+const float* qh_results_vector(const qh_results* r, int query, int j, int* out_len);
+const char* qh_results_metadata(const qh_results* r, int query, int j);
 int qh_results_free(qh_results* r);
 
 /* ---- hybrid index, exact strategy ------------------------------------------------------------
@@ -103,6 +109,23 @@ typedef struct qh_filter {
 int qh_collection_search(qh_collection* c, const float* query, int dim, int k, const qh_filter* filters, int n_filters,
                          qh_results** out);
 
+/* types.SearchOptions + SearchRequest.NamespaceID (pkg/types/search.go:45-52, 84-85) as FluentSearch sets
+ * them (IncludeVectors / IncludeMetadata / UseExactSearch / WithNamespace, collection.go:946-985). */
+typedef struct qh_search_options {
+  int include_vectors;
+  int include_metadata;
+  int exact_search;          /* carried, not consulted: this index is always exact (see host.cpp) */
+  const char* namespace_id;  /* carried, not consulted by Collection.Search (nullable) */
+} qh_search_options;
+/* Collection.Search(types.SearchRequest) (collection.go:637-807): qh_collection_search + the decoration of
+ * every result with its stored vector / metadata document (collection.go:758-779). opt nullable. */
+int qh_collection_search_request(qh_collection* c, const float* query, int dim, int k, const qh_filter* filters,
+                                 int n_filters, const qh_search_options* opt, qh_results** out);
+/* persistence.Collection.Search / SearchWithFacets (pkg/persistence/collection.go:226-261, 327-378): the
+ * prefilter path under that type's argument checks (limit <= 0 = every row). */
+int qh_collection_persistence_search(qh_collection* c, const float* query, int dim, int limit,
+                                     const struct qh_facet_filter* filters, int n_filters, qh_results** out);
+
 /* facets.Filter implementations (pkg/facets/facets.go). type: 0 equality (value_json), 1 range
  * (min_json / max_json, NULL or "null" = open; include flags), 2 set (value_json = JSON array),
  * 3 exists (should_exist). */
@@ -156,6 +179,12 @@ int qh_hnsw_upload(qh_index* idx, const qh_hnsw_graph* g, qh_hnsw_dev** out);
 int qh_hnsw_dev_free(qh_hnsw_dev* d);
 int qh_hnsw_search_device(qh_index* idx, qh_hnsw_dev* d, const float* queries, int nq, int dim, int k,
                           qh_results** out, int64_t* out_evals, int* out_fallbacks);
+/* HNSWAdapter.SearchWithNegativeExample (pkg/hnsw/adapter.go:345-437): max(2k, 30) candidates from the graph
+ * search (clamped to the index size), Distance - w * negDistance in float32 with w clamped to at most 1
+ * (:375-377), stable (Distance, ID) order, the first k — the returned Distance is the adjusted score, as in
+ * the reference. No negative example / w <= 0 / no more than k candidates: the plain search truncated to k. */
+int qh_hnsw_search_negative(qh_index* idx, qh_hnsw_dev* d, const float* query, int dim, const float* negative,
+                            int neg_dim, float negative_weight, int k, qh_results** out);
 
 /* ---- development aids (CPU-only; no device needed) --------------------------------------------- */
 /* fmt.Sprintf("%v", json value) into buf; returns the length or -1 on a JSON error. */

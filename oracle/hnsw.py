@@ -10,9 +10,14 @@ from . import cref
 
 class Graph:
     def __init__(self, corpus: np.ndarray, metric: int, arith: int = 0, M: int = 16, MaxM0: int = 32,
-                 EfConstruction: int = 200, EfSearch: int = 100, MaxLevel: int = 16, seed: int = 1):
+                 EfConstruction: int = 200, EfSearch: int = 100, MaxLevel: int = 16, seed: int = 1, flat: dict = None):
+        """Builds the graph by inserting the rows of `corpus` one by one (hnsw.Insert), or — `flat` given —
+        adopts a graph stored as the flat arrays export() returns."""
         lib = cref._load()
         vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+        lib.qo_hnsw_import.argtypes = [vp, i64, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]
+        lib.qo_hnsw_import.restype = vp
+        lib.qo_hnsw_search_batch_mt.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, vp]
         lib.qo_hnsw_build.argtypes = [vp, i64, i32, i32, i32, i32, i32, i32, i32, i32, C.c_uint64]
         lib.qo_hnsw_build.restype = vp
         lib.qo_hnsw_free.argtypes = [vp]
@@ -23,8 +28,18 @@ class Graph:
         self.corpus = np.ascontiguousarray(corpus, dtype=np.float32)  # the graph borrows this buffer
         self.metric, self.arith, self.M, self.MaxM0, self.EfSearch = metric, arith, M, MaxM0, EfSearch
         n, d = self.corpus.shape
-        self.h = lib.qo_hnsw_build(self.corpus.ctypes.data_as(vp), n, d, metric, arith, M, MaxM0, EfConstruction,
-                                   EfSearch, MaxLevel, seed)
+        if flat is not None:
+            self._flat = {k: np.ascontiguousarray(flat[k]) for k in ("level", "adj0", "upper_off", "upper_adj")}
+            f = self._flat
+            self.h = lib.qo_hnsw_import(self.corpus.ctypes.data_as(vp), n, d, metric, arith, M, MaxM0, EfSearch,
+                                        int(flat["entry"]), int(flat["current_level"]),
+                                        f["level"].astype(np.int32).ctypes.data_as(vp),
+                                        f["adj0"].astype(np.uint32).ctypes.data_as(vp),
+                                        f["upper_off"].astype(np.int64).ctypes.data_as(vp),
+                                        f["upper_adj"].astype(np.uint32).ctypes.data_as(vp))
+        else:
+            self.h = lib.qo_hnsw_build(self.corpus.ctypes.data_as(vp), n, d, metric, arith, M, MaxM0, EfConstruction,
+                                       EfSearch, MaxLevel, seed)
 
     def __del__(self):
         try:
@@ -43,6 +58,19 @@ class Graph:
         if m < 0:
             raise ValueError("k must be positive")
         return dist[:m].copy(), idx[:m].copy(), ev.value, tr.value
+
+    def search_batch(self, queries, k: int, threads: int = 1):
+        """hnsw.Search for every query on `threads` host threads -> (dist [nq,k], idx [nq,k], count, evals)."""
+        qs = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = qs.shape[0]
+        dist = np.full((nq, k), np.inf, dtype=np.float32)
+        idx = np.full((nq, k), 0xFFFFFFFF, dtype=np.uint32)
+        cnt = np.zeros(nq, dtype=np.int32)
+        ev = np.zeros(nq, dtype=np.int64)
+        vp = C.c_void_p
+        self._lib.qo_hnsw_search_batch_mt(self.h, qs.ctypes.data_as(vp), nq, k, threads, dist.ctypes.data_as(vp),
+                                          idx.ctypes.data_as(vp), cnt.ctypes.data_as(vp), ev.ctypes.data_as(vp))
+        return dist, idx, cnt, ev
 
     def export(self):
         """Flat arrays for the GPU-batched walk (see qh_hnsw_graph in include/quiver_host.h)."""

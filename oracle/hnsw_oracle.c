@@ -18,6 +18,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <pthread.h>
+
 #include "synth.h"
 
 float qo_distance(int metric, int arith, const float* a, const float* b, int d);
@@ -323,4 +325,83 @@ void qo_hnsw_export(const qo_hnsw* h, int32_t* level, uint32_t* adj0, int64_t* u
       for (int c = 0; c < h->M; ++c) upper_adj[u++] = c < h->conn_n[i][l] ? list_ptr(h, i, l)[c] : 0xFFFFFFFFu;
   }
   upper_off[h->n] = u;
+}
+
+
+/* A graph from its flat arrays (the layout qo_hnsw_export writes): lets a stored graph be walked on the host
+ * without rebuilding it (tests/bench_hnsw_c5.py at 1M nodes). */
+qo_hnsw* qo_hnsw_import(const float* vec, int64_t n, int d, int metric, int arith, int M, int max_m0, int ef_search,
+                        int entry, int cur_level, const int32_t* level, const uint32_t* adj0, const int64_t* upper_off,
+                        const uint32_t* upper_adj) {
+  qo_hnsw* h = (qo_hnsw*)calloc(1, sizeof(qo_hnsw));
+  h->d = d; h->metric = metric; h->arith = arith; h->M = M; h->max_m0 = max_m0;
+  h->ef_construction = 0; h->ef_search = ef_search; h->max_level = 16;
+  h->vec = vec;
+  h->n = n;
+  h->entry = (uint32_t)entry;
+  h->cur_level = cur_level;
+  h->level = (int32_t*)calloc((size_t)n + 1, sizeof(int32_t));
+  h->conn = (uint32_t**)calloc((size_t)n + 1, sizeof(uint32_t*));
+  h->conn_n = (int32_t**)calloc((size_t)n + 1, sizeof(int32_t*));
+  h->visited = (uint8_t*)calloc((size_t)n + 1, 1);
+  for (int64_t i = 0; i < n; ++i) {
+    const int lv = level[i] < 0 ? 0 : level[i];
+    h->level[i] = level[i];
+    h->conn[i] = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)((max_m0 + 1) + lv * (M + 1)));
+    h->conn_n[i] = (int32_t*)calloc((size_t)lv + 1, sizeof(int32_t));
+    uint32_t* l0 = list_ptr(h, i, 0);
+    for (int c = 0; c < max_m0 && adj0[i * max_m0 + c] != 0xFFFFFFFFu; ++c) l0[h->conn_n[i][0]++] = adj0[i * max_m0 + c];
+    for (int l = 1; l <= lv; ++l) {
+      uint32_t* ll = list_ptr(h, i, l);
+      const uint32_t* src = upper_adj + upper_off[i] + (size_t)(l - 1) * M;
+      for (int c = 0; c < M && src[c] != 0xFFFFFFFFu; ++c) ll[h->conn_n[i][l]++] = src[c];
+    }
+  }
+  return h;
+}
+
+/* hnsw.Search for a batch on `threads` host threads (one goroutine per query in the reference's BatchSearch):
+ * every thread walks with its own visited array and heaps over the shared, read-only graph. */
+typedef struct {
+  const qo_hnsw* h;
+  const float* queries;
+  int64_t nq;
+  int k, tid, threads;
+  float* out_dist;
+  uint32_t* out_idx;
+  int32_t* out_cnt;
+  int64_t* out_evals;
+} qo_walk_job;
+
+static void* walk_thread(void* arg) {
+  qo_walk_job* j = (qo_walk_job*)arg;
+  qo_hnsw local = *j->h; /* shallow copy: graph arrays shared, scratch private */
+  local.visited = (uint8_t*)calloc((size_t)local.n + 1, 1);
+  memset(&local.cand, 0, sizeof(local.cand));
+  memset(&local.res, 0, sizeof(local.res));
+  for (int64_t i = j->tid; i < j->nq; i += j->threads) {
+    int64_t ev = 0;
+    const int m = qo_hnsw_search(&local, j->queries + (size_t)i * local.d, j->k, j->out_dist + (size_t)i * j->k,
+                                 j->out_idx + (size_t)i * j->k, &ev, NULL);
+    j->out_cnt[i] = m;
+    if (j->out_evals) j->out_evals[i] = ev;
+  }
+  free(local.visited);
+  free(local.cand.a);
+  free(local.res.a);
+  return NULL;
+}
+
+void qo_hnsw_search_batch_mt(const qo_hnsw* h, const float* queries, int64_t nq, int k, int threads, float* out_dist,
+                             uint32_t* out_idx, int32_t* out_cnt, int64_t* out_evals) {
+  if (threads < 1) threads = 1;
+  if (threads > 256) threads = 256;
+  pthread_t th[256];
+  qo_walk_job jobs[256];
+  for (int t = 0; t < threads; ++t) {
+    qo_walk_job jb = {h, queries, nq, k, t, threads, out_dist, out_idx, out_cnt, out_evals};
+    jobs[t] = jb;
+    pthread_create(&th[t], NULL, walk_thread, &jobs[t]);
+  }
+  for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
 }

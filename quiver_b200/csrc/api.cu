@@ -24,6 +24,7 @@
 namespace qg {
 
 static thread_local std::string g_error;
+static thread_local qg_scan_stats g_my_stats{};  // stats of THIS thread's last search_enqueue (qg_search_batch reads them back)
 void set_error(const std::string& msg) { g_error = msg; }
 int fail(int code, const std::string& msg) {
   g_error = msg;
@@ -222,6 +223,11 @@ struct qg_index {
   std::vector<FacetColumn> cols;
   DevBuf col_table;  // FacetColDev[]
   bool col_table_dirty = true;
+  // Facet columns and their device pointer table: qg_facets_set_* and the (re)evaluation of a predicate mask
+  // (prepare_columns + the eval launch + its sync) exclude each other, so concurrent filtered searches — which
+  // only hold the caller's SHARED lock — never see a column half rebuilt.
+  std::mutex cols_mu;
+  std::mutex stats_mu;  // idx->stats is introspection shared by concurrent searches
   std::mutex ws_mu;
   std::vector<std::unique_ptr<Workspace>> ws_free;
   std::vector<std::unique_ptr<Workspace>> ws_async;  // in flight on caller streams
@@ -845,6 +851,7 @@ int qg_facets_set_column(qg_index* idx, int field, const uint8_t* kind, const do
   if (field < 0 || field >= 4096) return fail(QG_ERR_INVALID, "field index out of range");
   if (n < 0 || n > idx->n_rows) return fail(QG_ERR_RANGE, "column longer than the index");
   if (n > 0 && (!kind || !num || !scode || !fcode)) return fail(QG_ERR_INVALID, "null column buffer");
+  std::lock_guard<std::mutex> cols_lock(idx->cols_mu);
   if ((size_t)field >= idx->cols.size()) idx->cols.resize(field + 1);
   FacetColumn& c = idx->cols[field];
   const size_t cap = (size_t)std::max<long long>(idx->cap, 1);
@@ -873,6 +880,7 @@ int qg_facets_set_column(qg_index* idx, int field, const uint8_t* kind, const do
 int qg_facets_set_array_column(qg_index* idx, int field, const int32_t* offsets, const int32_t* elem_codes, int64_t n,
                                int64_t n_elems) {
   if (int rc = check_index(idx)) return rc;
+  std::lock_guard<std::mutex> cols_lock(idx->cols_mu);
   if (field < 0 || (size_t)field >= idx->cols.size() || !idx->cols[field].set)
     return fail(QG_ERR_INVALID, "set the column with qg_facets_set_column first");
   FacetColumn& c = idx->cols[field];
@@ -1016,6 +1024,8 @@ static int filter_refresh(qg_index* idx, qg_filter* f, cudaStream_t st) {
   const size_t words = (size_t)((n + 31) / 32) + 1;
   DevBuf cnt;
   if (f->raw_rows != n || f->raw_facet_epoch != idx->facet_epoch) {
+    // columns may be (re)built by another search's host layer: excluded until this mask has been evaluated
+    std::lock_guard<std::mutex> cols_lock(idx->cols_mu);
     if (int rc = prepare_columns(idx, f)) return rc;
     if (int rc = f->raw_mask.ensure(words * 4)) return rc;
     if (int rc = cnt.ensure(8)) return rc;
@@ -1097,6 +1107,12 @@ struct SearchArgs {
   long long row_base;
 };
 
+static void publish_stats(qg_index* idx, const qg_scan_stats& st) {
+  g_my_stats = st;
+  std::lock_guard<std::mutex> lk(idx->stats_mu);
+  idx->stats = st;
+}
+
 // Enqueue the whole search on `st` using workspace `w`. Validation already done.
 static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cudaStream_t st) {
   const int q = a.q, k = a.k, d = idx->dim, dp = idx->dp;
@@ -1122,7 +1138,7 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
     fill_empty_kernel<<<64, 256, 0, st>>>(a.d_dist, a.d_negdist, a.d_row, a.d_count, a.d_keys,
                                           std::max<long long>(out_n, q), q);
     QG_CUDA_OK(cudaGetLastError());
-    idx->stats = stats;
+    publish_stats(idx, stats);
     return 0;
   }
 
@@ -1165,7 +1181,7 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
     stats.queries_per_pass = 1;
     stats.rows_scanned = idx->n_rows;
     stats.bytes_algorithmic = n_pass * (long long)d * 4;
-    idx->stats = stats;
+    publish_stats(idx, stats);
     return 0;
   }
 
@@ -1326,7 +1342,7 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
     stats.bytes_algorithmic = idx->n_rows * (long long)(plan.bf16 ? idx->dp16 * 2 : d * 4) +
                               (tc_raw ? 0 : idx->n_rows * 4) + (mask ? idx->n_rows / 8 : 0);
     stats.reserved = plan.bf16;
-    idx->stats = stats;
+    publish_stats(idx, stats);
     return 0;
   }
 
@@ -1424,7 +1440,7 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
   stats.rows_scanned = n_items;
   stats.bytes_algorithmic = n_items * (long long)d * 4 + (mask && !gather ? idx->n_rows / 8 : 0) +
                             (sp.inv_norm ? n_items * 4 : 0) + (gather ? n_items * 4 : 0);
-  idx->stats = stats;
+  publish_stats(idx, stats);
   return 0;
 }
 
@@ -1551,7 +1567,10 @@ int qg_search_shard_keys_device(qg_index* idx, const void* d_queries, int q, int
       rc = exhaustive_search(w->ex, idx->vec, idx->n_rows, idx->dp, idx->dim, mask, (const float*)w->qpad.p, nullptr,
                              idx->metric, idx->arith, k, nullptr, nullptr, nullptr, (int*)w->d_count.p + i,
                              (uint64_t*)d_out_keys + (size_t)i * k, row_base, st);
-      idx->stats.escalations++;
+      {
+        std::lock_guard<std::mutex> slk(idx->stats_mu);
+        idx->stats.escalations++;
+      }
     }
   }
   ws_release_async(idx, w, st);
@@ -1648,10 +1667,10 @@ int qg_search_batch(qg_index* idx, const float* queries, int q, int dim, int k, 
                    (long long*)w->d_row.p + (size_t)q0 * k, (int*)w->d_count.p + q0, nullptr, 0};
       if ((rc = search_enqueue(idx, w, a, st))) break;
       if (c == 0) {
-        total = idx->stats;
+        total = g_my_stats;
       } else {
-        total.passes += idx->stats.passes;
-        total.kernel_launches += idx->stats.kernel_launches;
+        total.passes += g_my_stats.passes;
+        total.kernel_launches += g_my_stats.kernel_launches;
       }
       if (n_chunks > 1) {
         // this chunk's results travel to the host (second copy stream) while the next chunks are scanned
@@ -1670,7 +1689,7 @@ int qg_search_batch(qg_index* idx, const float* queries, int q, int dim, int k, 
       }
     }
     if (rc) break;
-    idx->stats = total;
+    publish_stats(idx, total);
     bool copied_out = false;
     if (n_chunks > 1) {
       // hand every chunk to the caller's buffers as soon as it has landed (later chunks are still in flight)
@@ -1698,8 +1717,8 @@ int qg_search_batch(qg_index* idx, const float* queries, int q, int dim, int k, 
     }
     int escalations = 0;
     // queries the tensor-core regime could not certify: redo one by one with the flat scan
-    if (idx->stats.path == 3) {
-      const qg_scan_stats first = idx->stats;
+    if (total.path == 3) {
+      const qg_scan_stats first = total;
       for (int i = 0; i < q && !rc; ++i) {
         if (h_cnt[i] >= 0) continue;
         ++escalations;
@@ -1722,7 +1741,7 @@ int qg_search_batch(qg_index* idx, const float* queries, int q, int dim, int k, 
         if (e != cudaSuccess) rc = fail(QG_ERR_CUDA, std::string("flat re-scan: ") + cudaGetErrorString(e));
       }
       if (rc) break;
-      idx->stats = first;
+      publish_stats(idx, first);
     }
     // queries the flat scan could not certify either: redo with the exhaustive path
     for (int i = 0; i < q && !rc; ++i) {
@@ -1769,7 +1788,8 @@ int qg_search_batch(qg_index* idx, const float* queries, int q, int dim, int k, 
       if (e != cudaSuccess) rc = fail(QG_ERR_CUDA, std::string("exhaustive search: ") + cudaGetErrorString(e));
     }
     if (rc) break;
-    idx->stats.escalations = escalations;
+    total.escalations = escalations;
+    publish_stats(idx, total);
     if (!copied_out || escalations > 0) {  // (re-run queries changed their rows in the staging buffers)
       std::memcpy(out_dist, h_dist, obytes * 4);
       if (negatives) std::memcpy(out_negdist, h_neg, obytes * 4);
@@ -2232,6 +2252,7 @@ int qg_debug_tc_pass(qg_index* idx, const float* queries, int nq, int k, float* 
 
 int qg_last_scan_stats(const qg_index* idx, qg_scan_stats* out) {
   if (!idx || !out) return fail(QG_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(const_cast<qg_index*>(idx)->stats_mu);
   *out = idx->stats;
   return 0;
 }

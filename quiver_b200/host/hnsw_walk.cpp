@@ -193,6 +193,7 @@ struct Walk {
 // qh_index internals needed here (defined in host.cpp)
 extern "C" int qh_internal_index_handle(qh_index* idx, qg_index** h, int* dim);
 extern "C" const char* qh_internal_row_id(qh_index* idx, int64_t row);
+extern "C" int64_t qh_internal_id_row(qh_index* idx, const char* id);
 extern "C" int qh_internal_fail(int code, const char* msg);
 extern "C" qh_results* qh_internal_results_new(int nq);
 extern "C" void qh_internal_results_push(qh_results* r, int q, const char* id, float dist);
@@ -530,6 +531,66 @@ extern "C" int qh_hnsw_search_device(qh_index* idx, qh_hnsw_dev* d, const float*
     }
   }
   if (out_evals) std::memcpy(out_evals, evals.data(), (size_t)nq * 8);
+  *out = res.release();
+  return 0;
+}
+
+
+extern "C" int64_t qh_index_size(const qh_index* idx);
+
+// HNSWAdapter.SearchWithNegativeExample (pkg/hnsw/adapter.go:345-437).
+extern "C" int qh_hnsw_search_negative(qh_index* idx, qh_hnsw_dev* d, const float* query, int dim, const float* negative,
+                                       int neg_dim, float negative_weight, int k, qh_results** out) {
+  if (!idx || !d || !out) return qh_internal_fail(QG_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (k <= 0) return qh_internal_fail(QG_ERR_K, "k must be positive");  // adapter.go:347-349
+  int64_t retrieve = std::max(2 * (int64_t)k, (int64_t)30);               // :353-356
+  const int64_t size = qh_index_size(idx);
+  if (retrieve > size) retrieve = size;
+  qh_results* initial = nullptr;
+  if (retrieve <= 0) {  // empty index: Search returns no results
+    *out = qh_internal_results_new(1);
+    return 0;
+  }
+  if (int rc = qh_hnsw_search_device(idx, d, query, 1, dim, (int)retrieve, &initial, nullptr, nullptr)) {
+    const std::string msg = std::string("initial search failed: ") + qh_last_error();  // :360-362
+    return qh_internal_fail(rc, msg.c_str());
+  }
+  std::unique_ptr<qh_results, int (*)(qh_results*)> init(initial, qh_results_free);
+  const int n0 = qh_results_count(initial, 0);
+  std::unique_ptr<qh_results, int (*)(qh_results*)> res(qh_internal_results_new(1), qh_results_free);
+  if (!negative || neg_dim == 0 || negative_weight <= 0.f || n0 <= k) {  // :366-372
+    for (int j = 0; j < std::min(n0, k); ++j)
+      qh_internal_results_push(res.get(), 0, qh_results_id(initial, 0, j), qh_results_distance(initial, 0, j));
+    *out = res.release();
+    return 0;
+  }
+  if (negative_weight > 1.0f) negative_weight = 1.0f;  // :375-377
+  struct Ext { std::string id; float dist; };
+  std::vector<Ext> ext;
+  if (neg_dim == dim) {  // a dimension mismatch makes DistanceFunc fail for every candidate: all are skipped (:404-406)
+    qg_index* h = nullptr;
+    int idim = 0;
+    if (int rc = qh_internal_index_handle(idx, &h, &idim)) return rc;
+    std::vector<uint32_t> rows((size_t)n0);
+    for (int j = 0; j < n0; ++j) {
+      const int64_t r = qh_internal_id_row(idx, qh_results_id(initial, 0, j));
+      rows[(size_t)j] = r < 0 ? 0xFFFFFFFFu : (uint32_t)r;
+    }
+    std::vector<float> nd((size_t)n0);
+    if (int rc = qg_batch_distance(h, negative, dim, rows.data(), n0, nd.data())) return qh_internal_fail(rc, qg_last_error());
+    for (int j = 0; j < n0; ++j) {
+      if (rows[(size_t)j] == 0xFFFFFFFFu) continue;  // id no longer in the index (:386-390)
+      // Distance - (negativeWeight * negDistance) in float32 (:415); this file is compiled with -ffp-contract=off
+      const float prod = negative_weight * nd[(size_t)j];
+      ext.push_back(Ext{qh_results_id(initial, 0, j), qh_results_distance(initial, 0, j) - prod});
+    }
+  }
+  std::stable_sort(ext.begin(), ext.end(), [](const Ext& a, const Ext& b) {  // :418-423
+    if (a.dist == b.dist) return a.id < b.id;
+    return a.dist < b.dist;
+  });
+  for (int j = 0; j < std::min<int>(k, (int)ext.size()); ++j) qh_internal_results_push(res.get(), 0, ext[(size_t)j].id.c_str(), ext[(size_t)j].dist);
   *out = res.release();
   return 0;
 }

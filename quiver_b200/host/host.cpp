@@ -40,6 +40,10 @@ int metric_of(const char* name) {
 struct Hit {
   std::string id;
   float distance;
+  // types.SearchResultItem (pkg/types/search.go:31-42): filled by qh_collection_search_request
+  std::vector<float> vector;  // Options.IncludeVectors
+  std::string metadata;       // Options.IncludeMetadata: the stored json.RawMessage
+  bool has_metadata = false;
 };
 
 }  // namespace
@@ -150,7 +154,7 @@ int index_search_locked(qh_index* idx, const float* queries, int nq, int dim, in
         const float prod = neg_weight * negd[(size_t)i * kk + j];
         d = d - prod;
       }
-      list.push_back(Hit{idx->ids[(size_t)row[(size_t)i * kk + j]], d});
+      list.push_back(Hit{idx->ids[(size_t)row[(size_t)i * kk + j]], d, {}, {}, false});
     }
     if (has_neg) {
       // sort.SliceStable by (Distance, ID) (:555-560), then the first k (:567-569)
@@ -172,6 +176,7 @@ struct qh_collection : qh::ColumnSource {
   int dim = 0;
   qh_index* index = nullptr;
   std::vector<qh::ValuePtr> metadata;      // per row: parsed metadata object, or nullptr
+  std::vector<std::string> metadata_raw;   // per row: the document as stored (json.RawMessage, collection.go:160-168); "" = none
   std::vector<std::string> facet_fields;
   // device columns: one per (family, field); rebuilt lazily after a mutation
   struct DevCol {
@@ -183,6 +188,10 @@ struct qh_collection : qh::ColumnSource {
   uint64_t epoch = 1;
   int family = 0;  // 0 = metadata columns, 1 = facet columns (set before compiling)
   std::mutex col_mu;  // column (re)builds touch device state: one search at a time compiles predicates
+  // Collection.mu (collection.go:100): Add / Update / Delete / compact / SetFacetFields hold it exclusively for
+  // their whole span — id lookups, the index mutation and the metadata edit are one step for every reader —
+  // Search / FluentSearch / SearchWithFacets / Get share it. Lock order: cmu, then index->mu, then col_mu.
+  mutable std::shared_mutex cmu;
 
   const qh::Value* facet_value(const qh::Value& md, const std::string& path) const {
     // ExtractFacets dot-path walk (facets.go:405-421); nil values are dropped (:423)
@@ -323,6 +332,16 @@ int qh_results_count(const qh_results* r, int q) {
 }
 const char* qh_results_id(const qh_results* r, int q, int j) { return r->lists[(size_t)q][(size_t)j].id.c_str(); }
 float qh_results_distance(const qh_results* r, int q, int j) { return r->lists[(size_t)q][(size_t)j].distance; }
+float qh_results_score(const qh_results* r, int q, int j) { return 1.0f - r->lists[(size_t)q][(size_t)j].distance; }
+const float* qh_results_vector(const qh_results* r, int q, int j, int* out_len) {
+  const Hit& h = r->lists[(size_t)q][(size_t)j];
+  if (out_len) *out_len = (int)h.vector.size();
+  return h.vector.empty() ? nullptr : h.vector.data();
+}
+const char* qh_results_metadata(const qh_results* r, int q, int j) {
+  const Hit& h = r->lists[(size_t)q][(size_t)j];
+  return h.has_metadata ? h.metadata.c_str() : nullptr;
+}
 int qh_results_free(qh_results* r) {
   delete r;
   return 0;
@@ -426,14 +445,20 @@ int qh_index_compact(qh_index* idx, int64_t* out_removed) {
 int qh_collection_compact(qh_collection* c, int64_t* out_removed) {
   if (!c) return fail(QG_ERR_INVALID, "null argument");
   // lock order as in a search: the index lock, then the column mutex
+  std::unique_lock<std::shared_mutex> clk(c->cmu);
   std::unique_lock<std::shared_mutex> lk(c->index->mu);
   std::lock_guard<std::mutex> col_lock(c->col_mu);
   std::vector<int64_t> map;
   if (int rc = index_compact_locked(c->index, &map, out_removed)) return rc;
   std::vector<qh::ValuePtr> md(c->index->ids.size());
+  std::vector<std::string> raw(c->index->ids.size());
   for (size_t r = 0; r < map.size() && r < c->metadata.size(); ++r)
-    if (map[r] >= 0) md[(size_t)map[r]] = std::move(c->metadata[r]);
+    if (map[r] >= 0) {
+      md[(size_t)map[r]] = std::move(c->metadata[r]);
+      if (r < c->metadata_raw.size()) raw[(size_t)map[r]] = std::move(c->metadata_raw[r]);
+    }
   c->metadata.swap(md);
+  c->metadata_raw.swap(raw);
   c->epoch++;  // host-side encoded columns follow the new numbering on their next use
   return 0;
 }
@@ -501,6 +526,7 @@ int qh_collection_destroy(qh_collection* c) {
 int qh_collection_add_batch(qh_collection* c, const char* const* ids, const float* vecs, int64_t n, int dim,
                             const char* const* metadata_json) {
   if (!c || (n > 0 && (!ids || !vecs))) return fail(QG_ERR_INVALID, "null argument");
+  std::unique_lock<std::shared_mutex> clk(c->cmu);
   std::vector<qh::ValuePtr> parsed((size_t)n);
   for (int64_t i = 0; i < n; ++i) {
     if (!ids[i] || !ids[i][0]) return fail(QG_ERR_INVALID, "vector ID cannot be empty");  // collection.go:143-148
@@ -522,7 +548,11 @@ int qh_collection_add_batch(qh_collection* c, const char* const* ids, const floa
     std::unique_lock<std::shared_mutex> lk(c->index->mu);
     if (int rc = index_insert_locked(c->index, ids, vecs, n, dim)) return rc;
   }
-  for (int64_t i = 0; i < n; ++i) c->metadata.push_back(parsed[(size_t)i]);
+  for (int64_t i = 0; i < n; ++i) {
+    c->metadata.push_back(parsed[(size_t)i]);
+    const char* md = metadata_json ? metadata_json[i] : nullptr;
+    c->metadata_raw.push_back(md ? md : "");
+  }
   c->epoch++;
   return 0;
 }
@@ -535,6 +565,7 @@ int qh_collection_add(qh_collection* c, const char* id, const float* vec, int di
 
 int qh_collection_delete(qh_collection* c, const char* id) {
   if (!c || !id) return fail(QG_ERR_INVALID, "null argument");
+  std::unique_lock<std::shared_mutex> clk(c->cmu);
   if (!c->index->rows.count(id)) return fail(QG_ERR_INVALID, "vector not found");  // ErrVectorNotFound
   return qh_index_delete(c->index, id);
 }
@@ -542,6 +573,7 @@ int qh_collection_delete(qh_collection* c, const char* id) {
 // Collection.DeleteBatch (collection.go:375-414): the first missing id is reported, nothing is deleted.
 int qh_collection_delete_batch(qh_collection* c, const char* const* ids, int64_t n) {
   if (!c || (n > 0 && !ids)) return fail(QG_ERR_INVALID, "null argument");
+  std::unique_lock<std::shared_mutex> clk(c->cmu);
   for (int64_t i = 0; i < n; ++i)
     if (!ids[i] || !c->index->rows.count(ids[i]))
       return fail(QG_ERR_INVALID, std::string("vector not found: ") + (ids[i] ? ids[i] : ""));
@@ -550,8 +582,14 @@ int qh_collection_delete_batch(qh_collection* c, const char* const* ids, int64_t
 
 // Collection.Update (collection.go:417-466): a new vector is Delete + Insert under the same id (the row moves
 // to the end, its metadata with it); new metadata replaces the old document.
+static int collection_update_locked(qh_collection* c, const char* id, const float* vec, int dim, const char* metadata_json);
 int qh_collection_update(qh_collection* c, const char* id, const float* vec, int dim, const char* metadata_json) {
   if (!c || !id) return fail(QG_ERR_INVALID, "null argument");
+  std::unique_lock<std::shared_mutex> clk(c->cmu);
+  return collection_update_locked(c, id, vec, dim, metadata_json);
+}
+// (caller holds c->cmu exclusively)
+static int collection_update_locked(qh_collection* c, const char* id, const float* vec, int dim, const char* metadata_json) {
   auto it = c->index->rows.find(id);
   if (it == c->index->rows.end()) return fail(QG_ERR_INVALID, "vector not found");
   if (vec && dim != c->dim)
@@ -578,11 +616,17 @@ int qh_collection_update(qh_collection* c, const char* id, const float* vec, int
   std::lock_guard<std::mutex> col_lock(c->col_mu);
   if (vec) {
     qh::ValuePtr moved = (size_t)row < c->metadata.size() ? c->metadata[(size_t)row] : nullptr;
+    std::string moved_raw = (size_t)row < c->metadata_raw.size() ? c->metadata_raw[(size_t)row] : std::string();
     if ((size_t)row < c->metadata.size()) c->metadata[(size_t)row].reset();
+    if ((size_t)row < c->metadata_raw.size()) c->metadata_raw[(size_t)row].clear();
     c->metadata.push_back(moved);
+    c->metadata_raw.push_back(moved_raw);
     row = (int64_t)c->metadata.size() - 1;
   }
-  if (has_md) c->metadata[(size_t)row] = parsed;
+  if (has_md) {
+    c->metadata[(size_t)row] = parsed;
+    c->metadata_raw[(size_t)row] = metadata_json;
+  }
   c->epoch++;
   return 0;
 }
@@ -593,6 +637,7 @@ int qh_collection_update_batch(qh_collection* c, const char* const* ids, const f
                                const char* const* metadata_json) {
   if (!c || (n > 0 && (!ids || !vecs))) return fail(QG_ERR_INVALID, "null argument");
   if (n <= 0) return fail(QG_ERR_INVALID, "no vectors provided for batch update");
+  std::unique_lock<std::shared_mutex> clk(c->cmu);
   std::vector<qh::ValuePtr> parsed((size_t)n);
   std::vector<char> has_md((size_t)n, 0);
   std::unordered_map<std::string, int> seen;
@@ -618,7 +663,7 @@ int qh_collection_update_batch(qh_collection* c, const char* const* ids, const f
   }
   if (duplicates) {  // the reference applies them one after the other; so do we
     for (int64_t i = 0; i < n; ++i)
-      if (int rc = qh_collection_update(c, ids[i], vecs + (size_t)i * dim, dim, metadata_json ? metadata_json[i] : nullptr))
+      if (int rc = collection_update_locked(c, ids[i], vecs + (size_t)i * dim, dim, metadata_json ? metadata_json[i] : nullptr))
         return rc;
     return 0;
   }
@@ -633,22 +678,33 @@ int qh_collection_update_batch(qh_collection* c, const char* const* ids, const f
   for (int64_t i = 0; i < n; ++i) {
     const size_t r = (size_t)old_rows[(size_t)i];
     qh::ValuePtr md = has_md[(size_t)i] ? parsed[(size_t)i] : (r < c->metadata.size() ? c->metadata[r] : nullptr);
+    std::string raw = has_md[(size_t)i] ? std::string(metadata_json[i])
+                                         : (r < c->metadata_raw.size() ? c->metadata_raw[r] : std::string());
     if (r < c->metadata.size()) c->metadata[r].reset();
+    if (r < c->metadata_raw.size()) c->metadata_raw[r].clear();
     c->metadata.push_back(md);
+    c->metadata_raw.push_back(raw);
   }
   c->epoch++;
   return 0;
 }
 
 int64_t qh_collection_count(const qh_collection* c) { return c ? qh_index_size(c->index) : 0; }
-int64_t qh_collection_rows(const qh_collection* c) { return c ? (int64_t)c->metadata.size() : 0; }
+int64_t qh_collection_rows(const qh_collection* c) {
+  if (!c) return 0;
+  std::shared_lock<std::shared_mutex> clk(c->cmu);
+  return (int64_t)c->metadata.size();
+}
 const char* qh_collection_row_id(const qh_collection* c, int64_t row) {
-  if (!c || row < 0 || row >= (int64_t)c->index->ids.size()) return "";
+  if (!c) return "";
+  std::shared_lock<std::shared_mutex> clk(c->cmu);
+  if (row < 0 || row >= (int64_t)c->index->ids.size()) return "";
   return c->index->ids[(size_t)row].c_str();
 }
 
 int qh_collection_set_facet_fields(qh_collection* c, const char* const* fields, int n) {
   if (!c) return fail(QG_ERR_INVALID, "null argument");
+  std::unique_lock<std::shared_mutex> clk(c->cmu);
   c->facet_fields.clear();
   for (int i = 0; i < n; ++i) c->facet_fields.push_back(fields[i] ? fields[i] : "");
   c->epoch++;  // SetFacetFields re-indexes every row (collection.go:1111-1130)
@@ -674,6 +730,7 @@ static int collection_search(qh_collection* c, int which, const float* query, in
   }
   std::unique_ptr<qh_results> res(new qh_results());
   res->lists.assign(1, {});
+  std::shared_lock<std::shared_mutex> clk(c->cmu);
   int flush_rc = 0;
   std::shared_lock<std::shared_mutex> lk = lock_flushed(c->index, &flush_rc);
   if (flush_rc) return flush_rc;
@@ -701,6 +758,68 @@ int qh_collection_search(qh_collection* c, const float* query, int dim, int k, c
   return collection_search(c, 0, query, dim, k, filters, nullptr, n_filters, out);
 }
 
+// Collection.Search(types.SearchRequest) (collection.go:637-807): the filtered search above plus the
+// SearchOptions decoration of every result (collection.go:758-779). Options.ExactSearch and NamespaceID are
+// carried by the reference's request but not consulted by Collection.Search (only DB.BatchSearch groups by
+// them, db.go:856-862); this index is always exact.
+int qh_collection_search_request(qh_collection* c, const float* query, int dim, int k, const qh_filter* filters,
+                                 int n_filters, const qh_search_options* opt, qh_results** out) {
+  if (int rc = collection_search(c, 0, query, dim, k, filters, nullptr, n_filters, out)) return rc;
+  if (!opt || (!opt->include_vectors && !opt->include_metadata)) return 0;
+  qh_results* res = *out;
+  std::shared_lock<std::shared_mutex> clk(c->cmu);
+  int flush_rc = 0;
+  std::shared_lock<std::shared_mutex> lk = lock_flushed(c->index, &flush_rc);
+  if (flush_rc) return flush_rc;
+  std::vector<Hit>& list = res->lists[0];
+  std::vector<int64_t> rows;
+  std::vector<size_t> which;
+  for (size_t j = 0; j < list.size(); ++j) {
+    auto it = c->index->rows.find(list[j].id);
+    if (it == c->index->rows.end()) continue;  // deleted since the search: the reference's map lookup would miss too
+    if (opt->include_metadata && (size_t)it->second < c->metadata_raw.size() && !c->metadata_raw[(size_t)it->second].empty()) {
+      list[j].metadata = c->metadata_raw[(size_t)it->second];
+      list[j].has_metadata = true;
+    }
+    if (opt->include_vectors) {
+      rows.push_back(it->second);
+      which.push_back(j);
+    }
+  }
+  if (!rows.empty()) {
+    std::vector<float> buf(rows.size() * (size_t)c->dim);
+    if (int rc = qg_index_fetch(c->index->h, rows.data(), (int64_t)rows.size(), buf.data())) return gpu_fail(rc);
+    for (size_t t = 0; t < rows.size(); ++t)
+      list[which[t]].vector.assign(buf.begin() + (long)(t * (size_t)c->dim), buf.begin() + (long)((t + 1) * (size_t)c->dim));
+  }
+  return 0;
+}
+
+// persistence.Collection.Search / SearchWithFacets (pkg/persistence/collection.go:226-261, 327-378): the same
+// prefilter path under that type's argument checks — "query vector is nil", "query vector dimension mismatch:
+// got %d, expected %d" (got first), limit <= 0 returns every row, vectors without facet values never pass a
+// filter. The reference orders by Distance only (an O(n^2) selection sort over Go's map order, so ties come in
+// any order); here ties are ordered by row.
+int qh_collection_persistence_search(qh_collection* c, const float* query, int dim, int limit,
+                                     const qh_facet_filter* filters, int n_filters, qh_results** out) {
+  if (!c || !out) return fail(QG_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (!query) return fail(QG_ERR_INVALID, "query vector is nil");
+  if (dim != c->dim)
+    return fail(QG_ERR_DIM, "query vector dimension mismatch: got " + std::to_string(dim) + ", expected " +
+                                std::to_string(c->dim));
+  int64_t count = qh_collection_count(c);
+  if (count == 0) {
+    std::unique_ptr<qh_results> res(new qh_results());
+    res->lists.assign(1, {});
+    *out = res.release();
+    return 0;
+  }
+  const int k = (limit > 0 && (int64_t)limit < count) ? limit : (int)std::min<int64_t>(count, 0x7fffffff);
+  if (n_filters <= 0) return collection_search(c, 0, query, dim, k, nullptr, nullptr, 0, out);
+  return collection_search(c, 1, query, dim, k, nullptr, filters, n_filters, out);
+}
+
 int qh_collection_search_with_facets(qh_collection* c, const float* query, int dim, int k,
                                      const qh_facet_filter* filters, int n_filters, qh_results** out) {
   return collection_search(c, 1, query, dim, k, nullptr, filters, n_filters, out);
@@ -709,6 +828,7 @@ int qh_collection_search_with_facets(qh_collection* c, const float* query, int d
 int qh_collection_filter_mask(qh_collection* c, int which, const qh_filter* filters, const qh_facet_filter* ffilters,
                               int n_filters, uint8_t* mask_out, int64_t n_rows) {
   if (!c || !mask_out) return fail(QG_ERR_INVALID, "null argument");
+  std::shared_lock<std::shared_mutex> clk(c->cmu);
   const int64_t rows = (int64_t)c->metadata.size();
   if (n_rows < rows) return fail(QG_ERR_INVALID, "mask buffer too small");
   int flush_rc = 0;
@@ -761,6 +881,11 @@ int qh_internal_index_handle(qh_index* idx, qg_index** h, int* dim) {
 const char* qh_internal_row_id(qh_index* idx, int64_t row) {
   return (row >= 0 && row < (int64_t)idx->ids.size()) ? idx->ids[(size_t)row].c_str() : "";
 }
+int64_t qh_internal_id_row(qh_index* idx, const char* id) {
+  std::shared_lock<std::shared_mutex> lk(idx->mu);
+  auto it = idx->rows.find(id ? id : "");
+  return it == idx->rows.end() ? -1 : it->second;
+}
 int qh_internal_fail(int code, const char* msg) { return fail(code, msg ? msg : ""); }
 qh_results* qh_internal_results_new(int nq) {
   qh_results* r = new qh_results();
@@ -768,6 +893,6 @@ qh_results* qh_internal_results_new(int nq) {
   return r;
 }
 void qh_internal_results_push(qh_results* r, int q, const char* id, float dist) {
-  r->lists[(size_t)q].push_back(Hit{id, dist});
+  r->lists[(size_t)q].push_back(Hit{id, dist, {}, {}, false});
 }
 }

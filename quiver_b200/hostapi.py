@@ -8,6 +8,7 @@ compiler) is in the C++ library; this file only marshals arguments. No CPU fallb
 from __future__ import annotations
 
 import ctypes as C
+import time
 import json
 import os
 from typing import List, Optional, Sequence, Tuple
@@ -30,7 +31,8 @@ EXPORTED_SYMBOLS = [
     "qh_collection_count", "qh_collection_set_facet_fields", "qh_collection_search",
     "qh_collection_search_with_facets", "qh_collection_filter_mask", "qh_collection_rows", "qh_collection_row_id",
     "qh_debug_sprint_v", "qh_debug_equal_fold", "qh_hnsw_search_batch", "qh_hnsw_upload", "qh_hnsw_dev_free",
-    "qh_hnsw_search_device",
+    "qh_hnsw_search_device", "qh_hnsw_search_negative", "qh_results_score", "qh_results_vector",
+    "qh_results_metadata", "qh_collection_search_request", "qh_collection_persistence_search",
 ]
 
 
@@ -42,6 +44,11 @@ class qh_facet_filter(C.Structure):
     _fields_ = [("type", C.c_int), ("field", C.c_char_p), ("value_json", C.c_char_p), ("min_json", C.c_char_p),
                 ("max_json", C.c_char_p), ("include_min", C.c_int), ("include_max", C.c_int),
                 ("should_exist", C.c_int)]
+
+
+class qh_search_options(C.Structure):
+    _fields_ = [("include_vectors", C.c_int), ("include_metadata", C.c_int), ("exact_search", C.c_int),
+                ("namespace_id", C.c_char_p)]
 
 
 class qh_hnsw_graph(C.Structure):
@@ -66,6 +73,16 @@ def load() -> C.CDLL:
     lib.qh_results_id.restype = cp
     lib.qh_results_distance.argtypes = [vp, i32, i32]
     lib.qh_results_distance.restype = C.c_float
+    lib.qh_results_score.argtypes = [vp, i32, i32]
+    lib.qh_results_score.restype = C.c_float
+    lib.qh_results_vector.argtypes = [vp, i32, i32, C.POINTER(i32)]
+    lib.qh_results_vector.restype = C.POINTER(C.c_float)
+    lib.qh_results_metadata.argtypes = [vp, i32, i32]
+    lib.qh_results_metadata.restype = cp
+    lib.qh_collection_search_request.argtypes = [vp, vp, i32, i32, C.POINTER(qh_filter), i32,
+                                                 C.POINTER(qh_search_options), C.POINTER(vp)]
+    lib.qh_collection_persistence_search.argtypes = [vp, vp, i32, i32, C.POINTER(qh_facet_filter), i32, C.POINTER(vp)]
+    lib.qh_hnsw_search_negative.argtypes = [vp, vp, vp, i32, vp, i32, C.c_float, i32, C.POINTER(vp)]
     lib.qh_results_free.argtypes = [vp]
     lib.qh_index_create.argtypes = [C.POINTER(vp), i32, cp, i32, i32]
     lib.qh_index_destroy.argtypes = [vp]
@@ -136,6 +153,26 @@ def _take(res: C.c_void_p) -> List[List[Tuple[str, np.float32]]]:
     for q in range(lib.qh_results_queries(res)):
         out.append([(lib.qh_results_id(res, q, j).decode(), np.float32(lib.qh_results_distance(res, q, j)))
                     for j in range(lib.qh_results_count(res, q))])
+    lib.qh_results_free(res)
+    return out
+
+
+def _take_items(res: C.c_void_p) -> List[dict]:
+    """types.SearchResultItem per result of query 0 (pkg/types/search.go:31-42): ID, Distance, Score and — when
+    the request's options asked for them — Vector and Metadata (absent keys = the reference's omitempty)."""
+    lib = load()
+    out = []
+    for j in range(lib.qh_results_count(res, 0)):
+        item = {"ID": lib.qh_results_id(res, 0, j).decode(), "Distance": np.float32(lib.qh_results_distance(res, 0, j)),
+                "Score": np.float32(lib.qh_results_score(res, 0, j))}
+        n = C.c_int(0)
+        vp_ = lib.qh_results_vector(res, 0, j, C.byref(n))
+        if n.value > 0:
+            item["Vector"] = np.ctypeslib.as_array(vp_, shape=(n.value,)).copy()
+        md = lib.qh_results_metadata(res, 0, j)
+        if md is not None:
+            item["Metadata"] = md.decode()
+        out.append(item)
     lib.qh_results_free(res)
     return out
 
@@ -254,8 +291,10 @@ class HybridIndex:
         evals = np.zeros(qs.shape[0], dtype=np.int64)
         steps = C.c_int64(0)
         res = C.c_void_p()
+        t0 = time.perf_counter()
         _check(self._lib.qh_hnsw_search_batch(self.handle, C.byref(g), _ptr(qs), qs.shape[0], qs.shape[1], k,
                                               C.byref(res), _ptr(evals), C.byref(steps)))
+        self.last_call_s = time.perf_counter() - t0
         return _take(res), evals, steps.value
 
     def HNSWUpload(self, graph: dict) -> "DeviceGraph":
@@ -289,9 +328,20 @@ class DeviceGraph:
         evals = np.zeros(qs.shape[0], dtype=np.int64)
         fb = C.c_int(0)
         res = C.c_void_p()
+        t0 = time.perf_counter()
         _check(self._lib.qh_hnsw_search_device(self.index.handle, self.handle, _ptr(qs), qs.shape[0], qs.shape[1], k,
                                                C.byref(res), _ptr(evals), C.byref(fb)))
+        self.last_call_s = time.perf_counter() - t0  # the C call alone (the list conversion below is Python's)
         return _take(res), evals, fb.value
+
+    def search_with_negative_example(self, query, negative, negative_weight: float, k: int):
+        """HNSWAdapter.SearchWithNegativeExample (pkg/hnsw/adapter.go:345-437) -> [(ID, adjusted Distance)]."""
+        q = _f32(query)
+        neg = None if negative is None or len(negative) == 0 else _f32(negative)
+        res = C.c_void_p()
+        _check(self._lib.qh_hnsw_search_negative(self.index.handle, self.handle, _ptr(q), q.size, _ptr(neg),
+                                                 0 if neg is None else neg.size, float(negative_weight), k, C.byref(res)))
+        return _take(res)[0]
 
     def close(self):
         if getattr(self, "handle", None):
@@ -463,6 +513,27 @@ class Collection:
         _check(self._lib.qh_collection_search(self.handle, _ptr(q), q.size, TopK, arr, n, C.byref(res)))
         return _take(res)[0]
 
+    def SearchRequest(self, Vector, TopK: int, Filters: Sequence[Tuple[str, str, object]] = (),
+                      IncludeVectors: bool = False, IncludeMetadata: bool = False, ExactSearch: bool = False,
+                      NamespaceID: str = ""):
+        """Collection.Search(types.SearchRequest) -> types.SearchResponse.Results (collection.go:637-807)."""
+        q = _f32(Vector)
+        arr, n = self._filters(Filters)
+        opt = qh_search_options(int(IncludeVectors), int(IncludeMetadata), int(ExactSearch), NamespaceID.encode())
+        res = C.c_void_p()
+        _check(self._lib.qh_collection_search_request(self.handle, _ptr(q), q.size, TopK, arr, n, C.byref(opt),
+                                                      C.byref(res)))
+        return _take_items(res)
+
+    def PersistenceSearch(self, query, limit: int, filters: Sequence[qh_facet_filter] = ()):
+        """persistence.Collection.Search / SearchWithFacets (pkg/persistence/collection.go:226-261, 327-378)."""
+        q = None if query is None else _f32(query)
+        arr = (qh_facet_filter * max(1, len(filters)))(*filters)
+        res = C.c_void_p()
+        _check(self._lib.qh_collection_persistence_search(self.handle, _ptr(q), 0 if q is None else q.size, limit, arr,
+                                                          len(filters), C.byref(res)))
+        return _take(res)[0]
+
     def SearchWithFacets(self, query, k: int, filters: Sequence[qh_facet_filter] = ()):
         q = _f32(query)
         arr = (qh_facet_filter * max(1, len(filters)))(*filters)
@@ -487,13 +558,36 @@ class Collection:
 
 
 class FluentSearch:
-    """core.FluentSearch (collection.go:874-1108): WithK, Filter, FilterNotEquals, FilterGreaterThan,
-    FilterLessThan, FilterIn, Execute. Default k = 10; k is clamped to Count() (:924-926)."""
+    """core.FluentSearch (collection.go:874-1108): WithK, WithNamespace, IncludeVectors, IncludeMetadata,
+    UseExactSearch, Filter, FilterNotEquals, FilterGreaterThan, FilterLessThan, FilterIn, Execute. Defaults:
+    k = 10, IncludeMetadata = true (:887-895); k is clamped to Count() (:924-926). Once a builder call has
+    failed the later ones are ignored and Execute returns that first error (the `valid` flag)."""
 
     def __init__(self, collection: Collection, vector):
         self.c, self.vector, self.k, self.filters, self.err = collection, vector, 10, [], None
+        self.include_vectors, self.include_metadata, self.exact, self.namespace = False, True, False, ""
         if len(vector) != collection.Dimension:
             self.err = QuiverError(2, f"invalid vector dimension: expected {collection.Dimension}, got {len(vector)}")
+
+    def WithNamespace(self, namespace: str):
+        if self.err is None:
+            self.namespace = namespace
+        return self
+
+    def IncludeVectors(self, include: bool):
+        if self.err is None:
+            self.include_vectors = bool(include)
+        return self
+
+    def IncludeMetadata(self, include: bool):
+        if self.err is None:
+            self.include_metadata = bool(include)
+        return self
+
+    def UseExactSearch(self):
+        if self.err is None:
+            self.exact = True
+        return self
 
     def WithK(self, k):
         if k <= 0:
@@ -530,3 +624,13 @@ class FluentSearch:
             raise QuiverError(3, "k must be greater than 0")
         k = min(self.k, max(self.c.Count(), 1))
         return self.c.Search(self.vector, k, self.filters)
+
+    def ExecuteResponse(self):
+        """Execute() with the full types.SearchResultItem list (Score, and Vector / Metadata per the options)."""
+        if self.err is not None:
+            raise self.err
+        if self.k <= 0:
+            raise QuiverError(3, "k must be greater than 0")
+        k = min(self.k, max(self.c.Count(), 1))
+        return self.c.SearchRequest(self.vector, k, self.filters, self.include_vectors, self.include_metadata,
+                                    self.exact, self.namespace)
