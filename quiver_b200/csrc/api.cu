@@ -201,6 +201,11 @@ struct qg_filter {
   DevBuf comb_mask, gather_list;
   long long comb_matches = 0;
   bool gather_valid = false;
+  // Dense copy of the passing rows for batched searches (build_filter_view): fp32 rows, bf16 copy, norms, in
+  // ascending row order, plus the new -> old row list. Valid for (view_live_epoch, view_facet_epoch, view_rows).
+  DevBuf v_vec, v_vec16, v_inv, v_n2, v_ub, v_new2old, v_map, v_cnt, v_woff, v_tmp;
+  long long view_n = -1, view_rows = -1;
+  uint64_t view_live_epoch = ~0ull, view_facet_epoch = ~0ull;
 };
 
 struct qg_index {
@@ -952,6 +957,8 @@ int qg_filter_destroy(qg_filter* f) {
   if (f->owner) cudaSetDevice(f->owner->device);
   f->d_preds.release(); f->d_clauses.release(); f->d_iset.release(); f->d_fset.release();
   f->raw_mask.release(); f->comb_mask.release(); f->gather_list.release();
+  f->v_vec.release(); f->v_vec16.release(); f->v_inv.release(); f->v_n2.release(); f->v_ub.release();
+  f->v_new2old.release(); f->v_map.release(); f->v_cnt.release(); f->v_woff.release(); f->v_tmp.release();
   delete f;
   return 0;
 }
@@ -1083,6 +1090,83 @@ static int filter_refresh(qg_index* idx, qg_filter* f, cudaStream_t st) {
   return 0;
 }
 
+// new2old[map[r]] = r for every passing row r
+__global__ void __launch_bounds__(256) invert_map_kernel(const uint32_t* __restrict__ map, long long n,
+                                                         uint32_t* __restrict__ new2old) {
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+    const uint32_t m = map[r];
+    if (m != 0xFFFFFFFFu) new2old[m] = (uint32_t)r;
+  }
+}
+// results of a search over a filter view carry view rows: back to index rows (+ the shard's row base)
+__global__ void __launch_bounds__(256) translate_rows_kernel(long long* __restrict__ rows, uint64_t* __restrict__ keys,
+                                                             long long n, const uint32_t* __restrict__ new2old,
+                                                             long long row_base) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (rows != nullptr) {
+      const long long r = rows[i];
+      if (r >= 0) rows[i] = (long long)new2old[r] + row_base;
+    }
+    if (keys != nullptr) {
+      const uint64_t k = keys[i];
+      if (k != KEY_NONE) keys[i] = (k & 0xFFFFFFFF00000000ull) | (uint64_t)(uint32_t)((long long)new2old[(uint32_t)k] + row_base);
+    }
+  }
+}
+
+// Dense copy of the rows that pass `f` (filter AND live), in ascending row order — so ties between equal
+// distances resolve exactly as over the whole index. A batch that would need many gather passes of the flat
+// scan (each re-reading the passing rows through row-sized gathers) instead pays one ordered gather (every
+// passing row read once, written once: the row move of qg_index_compact with the filter's mask in place of the
+// live mask) and then runs the tensor-core scan over a dense, unmasked corpus. C3 (10M x 768, 10 % pass, 32
+// queries): 8 gather passes = 9.4 ms before; copy ~1 ms + one dense pass ~0.5 ms. The copy is cached in the
+// filter handle and reused until rows, tombstones or facet columns change. Caller holds f->mu.
+static int build_filter_view(qg_index* idx, qg_filter* f, cudaStream_t st) {
+  if (f->view_n >= 0 && f->view_rows == idx->n_rows && f->view_live_epoch == idx->live_epoch &&
+      f->view_facet_epoch == idx->facet_epoch)
+    return 0;
+  f->view_n = -1;
+  const long long n_old = idx->n_rows, n_new = f->comb_matches;
+  const long long n_words = (n_old + 31) / 32;
+  const long long ncap = (std::max<long long>(n_new, 1024) + 1023) & ~1023ll;
+  int rc = 0;
+  if ((rc = f->v_cnt.ensure((size_t)n_words * 4)) || (rc = f->v_woff.ensure((size_t)(n_words + 1) * 4)) ||
+      (rc = f->v_tmp.ensure((size_t)scan_tmp_words(std::max(n_words, ncap)) * 4)) ||
+      (rc = f->v_map.ensure((size_t)n_old * 4)) || (rc = f->v_new2old.ensure((size_t)ncap * 4)) ||
+      (rc = f->v_vec.ensure((size_t)ncap * idx->dp * 4)) || (rc = f->v_inv.ensure((size_t)ncap * 4)) ||
+      (rc = f->v_n2.ensure((size_t)ncap * 4)) || (rc = f->v_ub.ensure((size_t)ncap * 4)) ||
+      (idx->use_bf16 && (rc = f->v_vec16.ensure((size_t)ncap * idx->dp16 * 2))))
+    return rc;
+  const uint32_t* mask = (const uint32_t*)f->comb_mask.p;
+  if ((rc = launch_word_popcount(mask, n_words, (uint32_t*)f->v_cnt.p, st)) ||
+      (rc = launch_exclusive_scan_u32((const uint32_t*)f->v_cnt.p, (uint32_t*)f->v_woff.p, n_words, (uint32_t*)f->v_tmp.p, st)) ||
+      (rc = launch_compact_map(mask, (const uint32_t*)f->v_woff.p, n_old, (uint32_t*)f->v_map.p, st)) ||
+      (rc = launch_fill_f32((float*)f->v_n2.p, ncap, INFINITY, st)) ||
+      (rc = launch_fill_f32((float*)f->v_ub.p, ncap, INFINITY, st)))
+    return rc;
+  QG_CUDA_OK(cudaMemsetAsync(f->v_inv.p, 0, (size_t)ncap * 4, st));
+  CompactRowsArgs a{};
+  a.map = (const uint32_t*)f->v_map.p;
+  a.n_rows = n_old;
+  a.vec = idx->vec; a.vec_out = (float*)f->v_vec.p; a.dp = idx->dp;
+  a.vec16 = idx->use_bf16 ? idx->vec16 : nullptr; a.vec16_out = f->v_vec16.p; a.dp16 = idx->dp16;
+  a.inv_norm = idx->inv_norm; a.inv_norm_out = (float*)f->v_inv.p;
+  a.norm2 = idx->norm2; a.norm2_out = (float*)f->v_n2.p;
+  a.unit_bias = idx->unit_bias; a.unit_bias_out = (float*)f->v_ub.p;
+  if ((rc = launch_compact_rows(a, idx->sm_count, st))) return rc;
+  {
+    long long blocks = std::min<long long>((n_old + 255) / 256, 148 * 8);
+    invert_map_kernel<<<(int)std::max<long long>(blocks, 1), 256, 0, st>>>((const uint32_t*)f->v_map.p, n_old,
+                                                                          (uint32_t*)f->v_new2old.p);
+    QG_CUDA_OK(cudaGetLastError());
+  }
+  f->view_n = n_new;
+  f->view_rows = idx->n_rows;
+  f->view_live_epoch = idx->live_epoch;
+  f->view_facet_epoch = idx->facet_epoch;
+  return 0;
+}
+
 __global__ void fill_empty_kernel(float* dist, float* negdist, long long* row, int* count, uint64_t* keys,
                                   long long n, int nq) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -1192,21 +1276,49 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
   const bool tc_possible = q >= idx->tc_min_q && mode != MODE_L1 && kp <= 128 && idx->n_rows >= idx->tc_min_rows &&
                            n_pass >= idx->tc_min_rows && tc_available() == 0 &&
                            tc_plan(dp, d + tc_extra_cols(d, mode == MODE_L2), q, idx->use_bf16, &plan) == 0;
+  // the arrays the tensor-core scan and its finalize read: the index's own, or the filter's dense view
+  struct RowArrays {
+    const float* vec;
+    const float* inv_norm;
+    const float* norm2;
+    const float* unit_bias;
+    const void* vec16;
+    long long n_rows;
+  } R{idx->vec, idx->inv_norm, idx->norm2, idx->unit_bias, idx->vec16, idx->n_rows};
+  const uint32_t* view_new2old = nullptr;
   if (tc_possible && gather != nullptr) {
-    // a selective filter has a compacted row list: the flat scan then reads only the matching rows, but
-    // serves at most max_qb queries per pass; the tensor-core scan reads every row (masked) once per
-    // plan.n_cols queries. Take whichever moves fewer bytes, the row-gather stream counted at 1.5x
-    // (measured on 10M x 768: 2.6-4.0 TB/s for gathered rows against 7 TB/s for the dense stream).
+    // A selective filter has a compacted row list. Three ways to serve the batch, costed in row reads:
+    //  - flat gather scan: only the matching rows, but at most max_qb queries per pass and through row-sized
+    //    gathers (counted at 1.5x: 2.6-4.0 TB/s measured on 10M x 768 against 7 TB/s for a dense stream);
+    //  - masked tensor-core scan: every row of the index once per plan.n_cols queries;
+    //  - dense VIEW of the matching rows (build_filter_view: read + write once, cached in the filter) and the
+    //    tensor-core scan over it.
     const int flat_qb = scan_fast_supported(dp) ? scan_fast_max_qb(dp) : 8;
+    const double tc_passes = (double)((q + plan.n_cols - 1) / plan.n_cols);
     const double flat_cost = 1.5 * (double)((q + flat_qb - 1) / flat_qb) * (double)n_pass;
-    const double tc_cost = (double)((q + plan.n_cols - 1) / plan.n_cols) * (double)idx->n_rows;
-    if (tc_cost < flat_cost) {
+    const double tc_cost = tc_passes * (double)idx->n_rows;
+    const bool view_cached = a.filter->view_n >= 0 && a.filter->view_rows == idx->n_rows &&
+                             a.filter->view_live_epoch == idx->live_epoch && a.filter->view_facet_epoch == idx->facet_epoch;
+    const double view_cost = (view_cached ? 0.0 : 2.5 * (double)n_pass) + tc_passes * (double)n_pass;
+    static const bool view_on = [] { const char* e = std::getenv("QG_FILTER_VIEW"); return e == nullptr || std::atoi(e) != 0; }();
+    if (view_on && view_cost < flat_cost && view_cost < tc_cost && n_pass >= idx->tc_min_rows) {
+      {
+        std::lock_guard<std::mutex> flk(a.filter->mu);
+        if (int rc = build_filter_view(idx, a.filter, st)) return rc;
+      }
+      R = RowArrays{(const float*)a.filter->v_vec.p, (const float*)a.filter->v_inv.p, (const float*)a.filter->v_n2.p,
+                    (const float*)a.filter->v_ub.p, idx->use_bf16 ? a.filter->v_vec16.p : nullptr, n_pass};
+      view_new2old = (const uint32_t*)a.filter->v_new2old.p;
+      gather = nullptr;
+      mask = nullptr;
+      n_items = n_pass;
+    } else if (tc_cost < flat_cost) {
       gather = nullptr;
       n_items = idx->n_rows;
     }
   }
   if (tc_possible && !gather) {
-    const long long n_sample = tc_sample_tiles(plan, idx->n_rows, k);
+    const long long n_sample = tc_sample_tiles(plan, R.n_rows, k);
     // TS variant: the sample + threshold stage runs once for all passes of the search
     const int n_pass_tc = (q + plan.n_cols - 1) / plan.n_cols;
     const bool hoist = plan.variant == 1 && n_pass_tc > 1;
@@ -1220,7 +1332,7 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
     if (int rc = w->tc_cand.ensure((size_t)group * plan.n_cols * TC_CAND_CAP * 8)) return rc;
     if (int rc = w->tc_cnt.ensure((cnt_slots + 8) * 4)) return rc;
     // raw scan: bf16 stream without a mask — the norm columns of the bf16 rows make the MMA output the score
-    const bool tc_raw = plan.variant == 1 && plan.bf16 && mask == nullptr && idx->n_rows >= plan.tile_rows &&
+    const bool tc_raw = plan.variant == 1 && plan.bf16 && mask == nullptr && R.n_rows >= plan.tile_rows &&
                         tc_raw_supported(d, mode == MODE_L2);
     if (plan.variant == 1) {
       // all queries of the search in tensor-memory order, one block per pass
@@ -1233,11 +1345,11 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
       stats.kernel_launches++;
     }
     // TS variant: additive row term with the mask folded in (+inf = excluded)
-    const float* tc_bias = mode == MODE_L2 ? idx->norm2 : idx->unit_bias;
+    const float* tc_bias = mode == MODE_L2 ? R.norm2 : R.unit_bias;
     if (plan.variant == 1 && mask != nullptr) {
-      const long long n_pad = (idx->n_rows + 127) & ~127ll;
+      const long long n_pad = (R.n_rows + 127) & ~127ll;
       if (int rc = w->tc_bias.ensure((size_t)n_pad * 4)) return rc;
-      if (int rc = launch_tc_bias(mask, mode == MODE_L2 ? idx->norm2 : nullptr, idx->n_rows, n_pad,
+      if (int rc = launch_tc_bias(mask, mode == MODE_L2 ? R.norm2 : nullptr, R.n_rows, n_pad,
                                   (float*)w->tc_bias.p, st))
         return rc;
       stats.kernel_launches++;
@@ -1254,7 +1366,7 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
     cp.tc_gamma = (plan.bf16 ? 1.02 / 256.0 : 1.02 / 512.0) + (double)d / 4194304.0;
     cp.tc_norm_gamma = (tc_raw && mode == MODE_L2) ? (double)(d + 16) / 4194304.0 : 0.0;
     FinalizeParams& fb = cp.base;
-    fb.vec = idx->vec;
+    fb.vec = R.vec;
     fb.dp = dp;
     fb.d = d;
     fb.metric = idx->metric;
@@ -1264,7 +1376,7 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
     fb.k = k;
     fb.gamma = (float)((d + 16) * 5.9604645e-8);
     fb.max_norm2 = idx->max_norm2;
-    fb.row_base = a.row_base;
+    fb.row_base = view_new2old ? 0 : a.row_base;  // view rows are translated (and based) after the finalize
     // profiling: kind 2 = sample + threshold kernels, kind 0 = main scan kernel
     TcStageHook hook{[](void* ctx, int stage, int begin, cudaStream_t s) {
                        Workspace* ws = static_cast<Workspace*>(ctx);
@@ -1286,13 +1398,13 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
       TcArgs ta{};
       ta.sample_only = all ? 1 : 0;
       ta.presampled = hoist ? 1 : 0;
-      ta.vec = idx->vec;
-      ta.vec16 = idx->vec16;
+      ta.vec = R.vec;
+      ta.vec16 = R.vec16;
       ta.dp16 = idx->dp16;
-      ta.n_rows = idx->n_rows;
+      ta.n_rows = R.n_rows;
       ta.dp = dp;
-      ta.row_norm2 = idx->norm2;
-      ta.inv_norm = idx->metric == METRIC_COSINE ? idx->inv_norm : nullptr;
+      ta.row_norm2 = R.norm2;
+      ta.inv_norm = idx->metric == METRIC_COSINE ? R.inv_norm : nullptr;
       ta.mask = mask;
       ta.bias = tc_bias;
       ta.queries = qpad + (size_t)q0 * dp;
@@ -1336,11 +1448,18 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
       if (frc) return frc;
       stats.kernel_launches++;
     }
+    if (view_new2old != nullptr) {
+      const long long total = (long long)q * k;
+      const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 4);
+      translate_rows_kernel<<<blocks, 256, 0, st>>>(a.d_row, a.d_keys, total, view_new2old, a.row_base);
+      QG_CUDA_OK(cudaGetLastError());
+      stats.kernel_launches++;
+    }
     stats.path = 3;
     stats.queries_per_pass = plan.n_cols;
-    stats.rows_scanned = idx->n_rows;
-    stats.bytes_algorithmic = idx->n_rows * (long long)(plan.bf16 ? idx->dp16 * 2 : d * 4) +
-                              (tc_raw ? 0 : idx->n_rows * 4) + (mask ? idx->n_rows / 8 : 0);
+    stats.rows_scanned = R.n_rows;
+    stats.bytes_algorithmic = R.n_rows * (long long)(plan.bf16 ? idx->dp16 * 2 : d * 4) +
+                              (tc_raw ? 0 : R.n_rows * 4) + (mask ? R.n_rows / 8 : 0);
     stats.reserved = plan.bf16;
     publish_stats(idx, stats);
     return 0;

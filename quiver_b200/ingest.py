@@ -144,15 +144,32 @@ def load_parquet(path: str, collection, dim: Optional[int] = None, batch_rows: i
     return total
 
 
-def save_parquet(path: str, ids: Sequence[str], vectors: Sequence, metadata: Sequence[Optional[dict]]) -> None:
-    """Write the layout writeVectorsToParquet produces (id, vector LIST<FLOAT>, metadata JSON; SNAPPY)."""
+def save_parquet(path: str, ids: Sequence[str], vectors: Sequence, metadata: Sequence[Optional[dict]],
+                 parquet_go_layout: bool = False) -> None:
+    """Write the layout writeVectorsToParquet produces (id, vector LIST<FLOAT>, metadata JSON; SNAPPY).
+
+    parquet_go_layout: reproduce what xitongsys/parquet-go derives from the struct tags of
+    ParquetVectorRecord (parquet.go:16-20) instead of pyarrow's defaults — every field REQUIRED (Go value
+    types, not pointers), the LIST as the three-level `required group vector (LIST) { repeated group list
+    { required float element } }`, dictionary encoding on `id` only (PLAIN_DICTIONARY there, PLAIN on
+    `metadata`), data page v1, SNAPPY. (A file written by parquet-go itself cannot be produced in this image:
+    there is no Go toolchain.)"""
     pa = _pa()
-    vec = pa.array([None if v is None else [float(np.float32(x)) for x in v] for v in vectors],
-                   type=pa.list_(pa.float32()))
     md = pa.array([json.dumps(m if m is not None else {}) if not isinstance(m, str) else m for m in metadata],
                   type=pa.string())
-    table = pa.table({"id": pa.array(list(ids), type=pa.string()), "vector": vec, "metadata": md})
-    pa.parquet.write_table(table, path, compression="snappy")
+    if not parquet_go_layout:
+        vec = pa.array([None if v is None else [float(np.float32(x)) for x in v] for v in vectors],
+                       type=pa.list_(pa.float32()))
+        table = pa.table({"id": pa.array(list(ids), type=pa.string()), "vector": vec, "metadata": md})
+        pa.parquet.write_table(table, path, compression="snappy")
+        return
+    ltype = pa.list_(pa.field("element", pa.float32(), nullable=False))
+    schema = pa.schema([pa.field("id", pa.string(), nullable=False), pa.field("vector", ltype, nullable=False),
+                        pa.field("metadata", pa.string(), nullable=False)])
+    vec = pa.array([[] if v is None else [float(np.float32(x)) for x in v] for v in vectors], type=ltype)
+    table = pa.Table.from_arrays([pa.array(list(ids), type=pa.string()), vec, md], schema=schema)
+    pa.parquet.write_table(table, path, compression="snappy", use_dictionary=["id"], data_page_version="1.0",
+                           version="1.0", use_compliant_nested_type=True, write_statistics=False)
 
 
 def _insert(target, ids, mat, md) -> None:

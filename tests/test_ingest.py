@@ -64,6 +64,87 @@ def test_parquet_batches_of_1000(tmp_path):
     assert all_ids == ids and max(sizes) <= ingest.BATCH_ROWS and sum(sizes) == 2300
 
 
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _fixture():
+    rows = json.load(open(os.path.join(GOLDEN, "storage_fixture_rows.json")))
+    return rows["ids"], np.load(os.path.join(GOLDEN, "storage_fixture_vectors.npy")), rows["metadata"], rows
+
+
+def test_parquet_go_layout_fixture():
+    """tests/golden/vectors_parquetgo.parquet carries the physical layout xitongsys/parquet-go derives from
+    ParquetVectorRecord (parquet.go:16-20): REQUIRED fields, three-level LIST named list / element, dictionary
+    on `id` only, SNAPPY. The reader applies parquet.go:133-166 to it."""
+    import pyarrow.parquet as pq
+    path = os.path.join(GOLDEN, "vectors_parquetgo.parquet")
+    pf = pq.ParquetFile(path)
+    text = str(pf.schema)
+    for line in ("required binary field_id=-1 id (String);", "required group field_id=-1 vector (List) {",
+                 "repeated group field_id=-1 list {", "required float field_id=-1 element;",
+                 "required binary field_id=-1 metadata (String);"):
+        assert line in text, text
+    rg = pf.metadata.row_group(0)
+    enc = {rg.column(i).path_in_schema: (set(rg.column(i).encodings), rg.column(i).compression) for i in range(rg.num_columns)}
+    assert "PLAIN_DICTIONARY" in enc["id"][0] and "PLAIN_DICTIONARY" not in enc["metadata"][0]
+    assert all(c == "SNAPPY" for _, c in enc.values())
+    ids, vec, md, rows = _fixture()
+    got_ids, mats, got_md = [], [], []
+    for b_ids, mat, b_md in ingest.iter_parquet(path, dim=vec.shape[1]):
+        got_ids += b_ids
+        mats.append(mat)
+        got_md += b_md
+    assert got_ids == ids  # the empty-id row and the empty-vector row are gone
+    assert np.array_equal(np.concatenate(mats).view(np.uint32), vec.view(np.uint32))
+    want_md = [dict(m) for m in md]
+    want_md[rows["unparsable_metadata_row"]] = {}
+    assert [json.loads(m) for m in got_md] == want_md
+
+
+def test_arrow_hnsw_fixture():
+    """tests/golden/index_arrow_hnsw.arrow: the file ArrowHNSWIndex.Save writes (arrow_hnsw.go:153-197)."""
+    ids, vec, _, _ = _fixture()
+    got_ids, mats = [], []
+    for b_ids, mat in ingest.iter_arrow_ipc(os.path.join(GOLDEN, "index_arrow_hnsw.arrow"), dim=vec.shape[1]):
+        assert not mat.flags["OWNDATA"]  # the child buffer IS the row-major matrix
+        got_ids += b_ids
+        mats.append(mat.copy())
+    assert got_ids == ids and len(mats) == 3
+    assert np.array_equal(np.concatenate(mats).view(np.uint32), vec.view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_fixture_files_loaded_to_hbm_answer_like_the_oracle(oracle):
+    """Upload path end to end: the two fixture files -> pinned staging -> HBM; the searches over the loaded
+    indexes equal the CPU oracle over the fixture's vectors (not a second GPU index)."""
+    from oracle import filters as F
+    from oracle import rerank
+    from quiver_b200 import hostapi
+    ids, vec, md, rows = _fixture()
+    d = vec.shape[1]
+    rng = np.random.default_rng(2)
+    idx = hostapi.HybridIndex(d, "euclidean")
+    assert ingest.load_arrow_ipc(os.path.join(GOLDEN, "index_arrow_hnsw.arrow"), idx, dim=d) == len(ids)
+    col = hostapi.Collection("loaded", d, "cosine")
+    assert ingest.load_parquet(os.path.join(GOLDEN, "vectors_parquetgo.parquet"), col, dim=d) == len(ids)
+    md_loaded = [dict(m) for m in md]
+    md_loaded[rows["unparsable_metadata_row"]] = {}
+    raw = [json.dumps(m) for m in md_loaded]
+    for _ in range(5):
+        q = rng.standard_normal(d).astype(np.float32)
+        od, orow = oracle.exact_search(vec, q, 10, 1)
+        got = idx.Search(q, 10)
+        assert [g[0] for g in got] == [ids[r] for r in orow]
+        assert [np.float32(g[1]).view(np.uint32) for g in got] == [x.view(np.uint32) for x in od]
+        mask = np.array(F.metadata_mask(raw, [("category", "=", "cat2"), ("lang", "=", "en")]))
+        want = rerank.filtered_search(vec, ids, q, 6, 0, mask)
+        got = col.Search(q, 6, Filters=[("category", "=", "cat2"), ("lang", "=", "en")])
+        assert [g[0] for g in got] == [w[0] for w in want]
+        assert [np.float32(g[1]).view(np.uint32) for g in got] == [np.float32(w[1]).view(np.uint32) for w in want]
+    idx.close()
+    col.close()
+
+
 @pytest.mark.gpu
 def test_arrow_ipc_load_matches_direct_insert(tmp_path):
     from quiver_b200 import hostapi
