@@ -17,6 +17,7 @@ import "C"
 import (
 	"errors"
 	"fmt"
+	"runtime"
 	"sync"
 	"unsafe"
 
@@ -49,8 +50,17 @@ func MetricOf(t vectortypes.DistanceType) Metric {
 	}
 }
 
-func lastError(rc C.int) error {
-	return fmt.Errorf("%s (qg_status %d)", C.GoString(C.qg_last_error()), int(rc))
+// call runs one qg_* call and, when it fails, reads the library's thread-local error text ON THE SAME OS
+// THREAD: the Go scheduler may move a goroutine to another thread between two cgo calls, and the message
+// ("k must be positive", "query dimension mismatch: expected %d, got %d", ...) would then come back empty or
+// stale. The pair is therefore pinned with LockOSThread.
+func call(f func() C.int) error {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	if rc := f(); rc != 0 {
+		return fmt.Errorf("%s (qg_status %d)", C.GoString(C.qg_last_error()), int(rc))
+	}
+	return nil
 }
 
 // Index satisfies core.Index and core.BatchIndex (pkg/core/collection.go:78-96) and
@@ -67,8 +77,8 @@ type Index struct {
 func New(dim int, metric Metric, device int) (*Index, error) {
 	cfg := C.qg_config{device: C.int(device)}
 	var h *C.qg_index
-	if rc := C.qg_index_create(&h, C.int(dim), C.int(metric), &cfg); rc != 0 {
-		return nil, lastError(rc)
+	if err := call(func() C.int { return C.qg_index_create(&h, C.int(dim), C.int(metric), &cfg) }); err != nil {
+		return nil, err
 	}
 	return &Index{h: h, dim: dim, rows: map[string]int64{}, metric: metric}, nil
 }
@@ -86,8 +96,8 @@ func (x *Index) Insert(id string, v vectortypes.F32) error {
 		return fmt.Errorf("vector with ID %s already exists", id)
 	}
 	var first C.int64_t
-	if rc := C.qg_index_upload(x.h, (*C.float)(unsafe.Pointer(&v[0])), 1, &first); rc != 0 {
-		return lastError(rc)
+	if err := call(func() C.int { return C.qg_index_upload(x.h, (*C.float)(unsafe.Pointer(&v[0])), 1, &first) }); err != nil {
+		return err
 	}
 	x.ids = append(x.ids, id)
 	x.rows[id] = int64(first)
@@ -114,8 +124,10 @@ func (x *Index) InsertBatch(vs map[string]vectortypes.F32) error {
 		return nil
 	}
 	var first C.int64_t
-	if rc := C.qg_index_upload(x.h, (*C.float)(unsafe.Pointer(&flat[0])), C.int64_t(len(ids)), &first); rc != 0 {
-		return lastError(rc)
+	if err := call(func() C.int {
+		return C.qg_index_upload(x.h, (*C.float)(unsafe.Pointer(&flat[0])), C.int64_t(len(ids)), &first)
+	}); err != nil {
+		return err
 	}
 	for i, id := range ids {
 		x.ids = append(x.ids, id)
@@ -133,8 +145,8 @@ func (x *Index) Delete(id string) error {
 		return nil
 	}
 	r := C.int64_t(row)
-	if rc := C.qg_index_tombstone(x.h, &r, 1); rc != 0 {
-		return lastError(rc)
+	if err := call(func() C.int { return C.qg_index_tombstone(x.h, &r, 1) }); err != nil {
+		return err
 	}
 	delete(x.rows, id)
 	// The reference's map frees a vector on Delete; here dead rows stay in HBM until they outnumber the
@@ -160,8 +172,8 @@ func (x *Index) compactLocked() error {
 	}
 	oldToNew := make([]C.int64_t, len(x.ids))
 	var n C.int64_t
-	if rc := C.qg_index_compact(x.h, &oldToNew[0], &n); rc != 0 {
-		return lastError(rc)
+	if err := call(func() C.int { return C.qg_index_compact(x.h, &oldToNew[0], &n) }); err != nil {
+		return err
 	}
 	ids := make([]string, int(n))
 	for r, j := range oldToNew {
@@ -188,8 +200,8 @@ func (x *Index) DeleteBatch(ids []string) error {
 	if len(rows) == 0 {
 		return nil
 	}
-	if rc := C.qg_index_tombstone(x.h, &rows[0], C.int64_t(len(rows))); rc != 0 {
-		return lastError(rc)
+	if err := call(func() C.int { return C.qg_index_tombstone(x.h, &rows[0], C.int64_t(len(rows))) }); err != nil {
+		return err
 	}
 	for _, id := range ids {
 		delete(x.rows, id)
@@ -234,10 +246,11 @@ func (x *Index) BatchSearch(qs []vectortypes.F32, k int) ([][]types.BasicSearchR
 	dist := make([]float32, n*kk)
 	rows := make([]int64, n*kk)
 	cnt := make([]int32, n)
-	rc := C.qg_search_batch(x.h, (*C.float)(unsafe.Pointer(&flat[0])), C.int(n), C.int(dim), C.int(k), nil, nil,
-		(*C.float)(unsafe.Pointer(&dist[0])), nil, (*C.int64_t)(unsafe.Pointer(&rows[0])), (*C.int)(unsafe.Pointer(&cnt[0])))
-	if rc != 0 {
-		return nil, errors.New(C.GoString(C.qg_last_error())) // "k must be positive", "query dimension mismatch: ..."
+	if err := call(func() C.int {
+		return C.qg_search_batch(x.h, (*C.float)(unsafe.Pointer(&flat[0])), C.int(n), C.int(dim), C.int(k), nil, nil,
+			(*C.float)(unsafe.Pointer(&dist[0])), nil, (*C.int64_t)(unsafe.Pointer(&rows[0])), (*C.int)(unsafe.Pointer(&cnt[0])))
+	}); err != nil {
+		return nil, err // "k must be positive", "query dimension mismatch: ..."
 	}
 	out := make([][]types.BasicSearchResult, n)
 	for i := range out {
@@ -255,10 +268,80 @@ func (x *Index) BatchDistance(q []float32, rows []uint32, out []float32) error {
 	if len(rows) == 0 {
 		return nil
 	}
-	rc := C.qg_batch_distance(x.h, (*C.float)(unsafe.Pointer(&q[0])), C.int(len(q)),
-		(*C.uint32_t)(unsafe.Pointer(&rows[0])), C.int(len(rows)), (*C.float)(unsafe.Pointer(&out[0])))
-	if rc != 0 {
-		return lastError(rc)
+	return call(func() C.int {
+		return C.qg_batch_distance(x.h, (*C.float)(unsafe.Pointer(&q[0])), C.int(len(q)),
+			(*C.uint32_t)(unsafe.Pointer(&rows[0])), C.int(len(rows)), (*C.float)(unsafe.Pointer(&out[0])))
+	})
+}
+
+// Group drives every GPU of the box from this one process (qg_group_*: one worker thread, stream, index and
+// NCCL communicator per device inside libquivergpu). It is what DB.BatchSearch (pkg/core/db.go:707-845) hands a
+// batch to when the collection spans GPUs: row-sharded (every GPU scans its shard, one all-gather of the
+// per-shard top-k keys, merge) or replicated with the batch split — the library picks by corpus size.
+type Group struct {
+	mu  sync.RWMutex
+	h   *C.qg_group
+	ids []string // global row -> id
+	dim int
+}
+
+func NewGroup(devices []int, dim int, metric Metric) (*Group, error) {
+	devs := make([]C.int, len(devices))
+	for i, d := range devices {
+		devs[i] = C.int(d)
 	}
+	var h *C.qg_group
+	if err := call(func() C.int { return C.qg_group_create(&devs[0], C.int(len(devs)), C.int(dim), C.int(metric), nil, &h) }); err != nil {
+		return nil, err
+	}
+	return &Group{h: h, dim: dim}, nil
+}
+
+// Load uploads the corpus once (rows in id order); layout 2 = QG_LAYOUT_AUTO.
+func (g *Group) Load(ids []string, flat []float32) error {
+	g.mu.Lock()
+	defer g.mu.Unlock()
+	if err := call(func() C.int {
+		return C.qg_group_upload(g.h, (*C.float)(unsafe.Pointer(&flat[0])), C.int64_t(len(ids)), C.QG_LAYOUT_AUTO)
+	}); err != nil {
+		return err
+	}
+	g.ids = append([]string(nil), ids...)
 	return nil
 }
+
+func (g *Group) BatchSearch(qs []vectortypes.F32, k int) ([][]types.BasicSearchResult, error) {
+	g.mu.RLock()
+	defer g.mu.RUnlock()
+	n := len(qs)
+	if n == 0 {
+		return nil, nil
+	}
+	flat := make([]float32, 0, n*g.dim)
+	for _, q := range qs {
+		flat = append(flat, q...)
+	}
+	kk := k
+	if kk < 1 {
+		kk = 1
+	}
+	dist := make([]float32, n*kk)
+	rows := make([]int64, n*kk)
+	cnt := make([]int32, n)
+	if err := call(func() C.int {
+		return C.qg_group_search_batch(g.h, (*C.float)(unsafe.Pointer(&flat[0])), C.int(n), C.int(len(qs[0])), C.int(k),
+			(*C.float)(unsafe.Pointer(&dist[0])), (*C.int64_t)(unsafe.Pointer(&rows[0])), (*C.int)(unsafe.Pointer(&cnt[0])))
+	}); err != nil {
+		return nil, err
+	}
+	out := make([][]types.BasicSearchResult, n)
+	for i := range out {
+		out[i] = make([]types.BasicSearchResult, cnt[i])
+		for j := 0; j < int(cnt[i]); j++ {
+			out[i][j] = types.BasicSearchResult{ID: g.ids[rows[i*kk+j]], Distance: dist[i*kk+j]}
+		}
+	}
+	return out, nil
+}
+
+func (g *Group) Close() { C.qg_group_destroy(g.h) }

@@ -171,6 +171,10 @@ int index_search_locked(qh_index* idx, const float* queries, int nq, int dim, in
 }  // namespace
 
 // ---- collection -------------------------------------------------------------------------------------
+struct SharedFilter {
+  qg_filter* f = nullptr;
+  ~SharedFilter() { if (f) qg_filter_destroy(f); }
+};
 struct qh_collection : qh::ColumnSource {
   std::string name;
   int dim = 0;
@@ -192,6 +196,10 @@ struct qh_collection : qh::ColumnSource {
   // their whole span — id lookups, the index mutation and the metadata edit are one step for every reader —
   // Search / FluentSearch / SearchWithFacets / Get share it. Lock order: cmu, then index->mu, then col_mu.
   mutable std::shared_mutex cmu;
+  // compiled predicate programs of the current collection state (see make_filter)
+  std::mutex filter_cache_mu;
+  std::vector<std::pair<std::string, std::shared_ptr<SharedFilter>>> filter_cache;
+  uint64_t filter_cache_epoch = 0;
 
   const qh::Value* facet_value(const qh::Value& md, const std::string& path) const {
     // ExtractFacets dot-path walk (facets.go:405-421); nil values are dropped (:423)
@@ -303,16 +311,47 @@ int build_program(qh_collection* c, int which, const qh_filter* filters, const q
   return 0;
 }
 
+// A compiled predicate program on the device. Handles are shared through the collection's small cache
+// (filter_cache below): the library keeps the evaluated mask — and, for batched searches, the dense view of
+// the passing rows — inside the handle, so a predicate that comes back (the same category filter on every
+// request) is evaluated and gathered once per collection state, not once per search.
 struct FilterHandle {
+  std::shared_ptr<SharedFilter> h;
   qg_filter* f = nullptr;
-  ~FilterHandle() { if (f) qg_filter_destroy(f); }
 };
 
 int make_filter(qh_collection* c, const qh::Program& prog, FilterHandle* out, int64_t* matches) {
-  if (int rc = qg_filter_compile(c->index->h, prog.preds.data(), (int)prog.preds.size(), prog.clauses.data(),
-                                 (int)prog.clauses.size(), prog.iset.data(), (int)prog.iset.size(), prog.fset.data(),
-                                 (int)prog.fset.size(), &out->f))
-    return gpu_fail(rc);
+  // cache key: the program's bytes; valid for the collection state (epoch) it was compiled in — column
+  // indices and dictionary codes inside the clauses belong to that state
+  std::string key;
+  auto add = [&](const void* p, size_t n) { key.append(reinterpret_cast<const char*>(p), n); key.push_back('|'); };
+  add(prog.preds.data(), prog.preds.size() * sizeof(qg_pred));
+  add(prog.clauses.data(), prog.clauses.size() * sizeof(qg_clause));
+  add(prog.iset.data(), prog.iset.size() * 4);
+  add(prog.fset.data(), prog.fset.size() * 8);
+  {
+    std::lock_guard<std::mutex> lk(c->filter_cache_mu);
+    if (c->filter_cache_epoch != c->epoch) {
+      c->filter_cache.clear();
+      c->filter_cache_epoch = c->epoch;
+    }
+    for (auto& e : c->filter_cache)
+      if (e.first == key) out->h = e.second;
+  }
+  if (!out->h) {
+    auto sh = std::make_shared<SharedFilter>();
+    if (int rc = qg_filter_compile(c->index->h, prog.preds.data(), (int)prog.preds.size(), prog.clauses.data(),
+                                   (int)prog.clauses.size(), prog.iset.data(), (int)prog.iset.size(), prog.fset.data(),
+                                   (int)prog.fset.size(), &sh->f))
+      return gpu_fail(rc);
+    out->h = sh;
+    std::lock_guard<std::mutex> lk(c->filter_cache_mu);
+    if (c->filter_cache_epoch == c->epoch) {
+      if (c->filter_cache.size() >= 4) c->filter_cache.erase(c->filter_cache.begin());  // oldest out
+      c->filter_cache.emplace_back(key, sh);
+    }
+  }
+  out->f = out->h->f;
   if (matches) {
     if (int rc = qg_filter_eval(c->index->h, out->f, nullptr, matches)) return gpu_fail(rc);
   }
@@ -518,6 +557,7 @@ int qh_collection_create(qh_collection** out, const char* name, int dim, const c
 
 int qh_collection_destroy(qh_collection* c) {
   if (!c) return 0;
+  c->filter_cache.clear();  // the handles belong to the index: gone before it
   qh_index_destroy(c->index);
   delete c;
   return 0;

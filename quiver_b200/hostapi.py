@@ -61,10 +61,11 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise ImportError(f"{LIB_PATH} is missing: run `make -j8 all`")
+    path = os.environ.get("QH_LIB") or LIB_PATH  # QH_LIB: development aid (the ThreadSanitizer build)
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: run `make -j8 all`")
     capi.load()  # libquivergpu.so first (resolved through $ORIGIN rpath as well)
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp, i32, i64, cp = C.c_void_p, C.c_int, C.c_int64, C.c_char_p
     lib.qh_last_error.restype = cp
     lib.qh_results_queries.argtypes = [vp]

@@ -9,7 +9,7 @@ quirk fragments layer 0 — short walks; the under-fill exact pass answers most 
 (QO_HNSW_STANDARD=1, a measurement aid) that shows the regime the neighbour batches are meant for.
 Checked: device results == host walk results (ids, float32 distances, evaluation counts) on a sample.
 
-usage: python tests/bench_hnsw_c5.py [rows] [queries]"""
+usage: python tests/bench_hnsw_c5.py [rows] [queries] [both|faithful|textbook]"""
 import json
 import os
 import sys
@@ -111,5 +111,10 @@ def run(standard: bool, n: int, nq: int, d: int = 128, k: int = 10):
 if __name__ == "__main__":
     rows = int(sys.argv[1]) if len(sys.argv) > 1 else 50000
     nq = int(sys.argv[2]) if len(sys.argv) > 2 else 10000
-    out = [run(False, rows, nq), run(True, rows, nq)]
+    which = sys.argv[3] if len(sys.argv) > 3 else "both"
+    out = []
+    if which in ("both", "faithful"):
+        out.append(run(False, rows, nq))
+    if which in ("both", "textbook"):
+        out.append(run(True, rows, nq))
     print(json.dumps({"metric": "HNSW search on the device vs the reference's walk on the host (C5)", "runs": out}))
