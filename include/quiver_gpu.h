@@ -345,6 +345,21 @@ int qg_hnsw_upload(qg_index* idx, int64_t n_nodes, int m, int max_m0, int entry_
                    const int32_t* level, const uint32_t* adj0, const int64_t* upper_off, const uint32_t* upper_adj,
                    qg_hnsw** out);
 int qg_hnsw_destroy(qg_hnsw* g);
+/* Graph construction on the device for the rows the index holds (replaces the loop of hnsw.Insert /
+ * connectNode calls, hnsw.go:266-468, that builds the reference's graph). Nodes are
+ * inserted in batches: each node of a batch searches the graph of the committed nodes with
+ * ef = ef_construction, links to its closest m (max_m0 on level 0) results — selectNeighbors' plain
+ * closest-k, hnsw.go:583-599 — and the reverse links are merged afterwards with the reference's prune rule.
+ * Levels follow randomLevel's law (p = 0.25 per level, at most min(max_level, 10) promotions, hnsw.go:716-738)
+ * from the counter-based hash of (seed, node). A batched build is not step-identical to sequential inserts;
+ * its bar is recall at equal efSearch against the host-built graph. max_batch <= 0 = default (8192). */
+int qg_hnsw_build(qg_index* idx, int m, int max_m0, int ef_construction, int max_level, uint64_t seed, int max_batch,
+                  qg_hnsw** out);
+/* The graph as flat host arrays (the layout qg_hnsw_upload takes). upper_adj has qg_hnsw_upper_len entries. */
+int64_t qg_hnsw_nodes(const qg_hnsw* g);
+int64_t qg_hnsw_upper_len(const qg_hnsw* g);
+int qg_hnsw_export(const qg_hnsw* g, int32_t* level, uint32_t* adj0, int64_t* upper_off, uint32_t* upper_adj,
+                   int* entry_point, int* current_level);
 /* One persistent kernel, a warp per query: ef = 1 descent through the upper layers, base layer with
  * ef = max(ef_search, k), the reference's heaps / visit order / stop and admit rules, distances in the
  * index's metric and arithmetic — step-identical to the reference's walk. out_idx / out_dist are q x k

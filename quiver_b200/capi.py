@@ -65,7 +65,8 @@ EXPORTED_SYMBOLS = [
     "qg_batch_distance", "qg_batch_distance_multi", "qg_last_scan_stats", "qg_index_set_profiling",
     "qg_index_read_profile", "qg_debug_tc_pass", "qg_queries_upload", "qg_queries_destroy",
     "qg_batch_distance_queries",
-    "qg_hnsw_upload", "qg_hnsw_destroy", "qg_hnsw_search_batch",
+    "qg_hnsw_upload", "qg_hnsw_destroy", "qg_hnsw_search_batch", "qg_hnsw_build", "qg_hnsw_nodes",
+    "qg_hnsw_upper_len", "qg_hnsw_export",
     "qg_comm_unique_id", "qg_comm_create_rank", "qg_comm_destroy", "qg_comm_world", "qg_comm_rank",
     "qg_comm_search_rows_device", "qg_comm_search_queries_device",
     "qg_group_create", "qg_group_destroy", "qg_group_devices", "qg_group_index", "qg_group_row_base",
@@ -125,6 +126,12 @@ def load() -> C.CDLL:
     lib.qg_batch_distance_queries.argtypes = [vp, vp, vp, i32, vp]
     lib.qg_hnsw_upload.argtypes = [vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, C.POINTER(vp)]
     lib.qg_hnsw_destroy.argtypes = [vp]
+    lib.qg_hnsw_build.argtypes = [vp, i32, i32, i32, i32, C.c_uint64, i32, C.POINTER(vp)]
+    lib.qg_hnsw_nodes.argtypes = [vp]
+    lib.qg_hnsw_nodes.restype = i64
+    lib.qg_hnsw_upper_len.argtypes = [vp]
+    lib.qg_hnsw_upper_len.restype = i64
+    lib.qg_hnsw_export.argtypes = [vp, vp, vp, vp, vp, C.POINTER(i32), C.POINTER(i32)]
     lib.qg_hnsw_search_batch.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
     lib.qg_comm_unique_id.argtypes = [vp]
     lib.qg_comm_create_rank.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
@@ -488,6 +495,72 @@ class Group:
     def close(self):
         if getattr(self, "handle", None):
             self._lib.qg_group_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class HnswGraph:
+    """An HNSW graph on the index's device (qg_hnsw): built there (qg_hnsw_build) or uploaded (qg_hnsw_upload)."""
+
+    def __init__(self, index: Index, handle):
+        self._lib, self.index, self.handle = load(), index, handle
+
+    @classmethod
+    def build(cls, index: Index, M: int = 16, MaxM0: int = 32, EfConstruction: int = 200, MaxLevel: int = 16,
+              seed: int = 1, max_batch: int = 0) -> "HnswGraph":
+        h = C.c_void_p()
+        _check(load().qg_hnsw_build(index.handle, M, MaxM0, EfConstruction, MaxLevel, seed, max_batch, C.byref(h)))
+        g = cls(index, h)
+        g.M, g.MaxM0 = M, MaxM0
+        return g
+
+    @classmethod
+    def upload(cls, index: Index, graph: dict) -> "HnswGraph":
+        level = np.ascontiguousarray(graph["level"], dtype=np.int32)
+        adj0 = np.ascontiguousarray(graph["adj0"], dtype=np.uint32)
+        uoff = np.ascontiguousarray(graph["upper_off"], dtype=np.int64)
+        uadj = np.ascontiguousarray(graph["upper_adj"], dtype=np.uint32)
+        h = C.c_void_p()
+        _check(load().qg_hnsw_upload(index.handle, int(graph["n"]), int(graph["M"]), int(graph["MaxM0"]),
+                                     int(graph["entry"]), int(graph["current_level"]), _ptr(level), _ptr(adj0),
+                                     _ptr(uoff), _ptr(uadj), C.byref(h)))
+        g = cls(index, h)
+        g.M, g.MaxM0 = int(graph["M"]), int(graph["MaxM0"])
+        return g
+
+    def export(self, EfSearch: int = 128) -> dict:
+        n = int(self._lib.qg_hnsw_nodes(self.handle))
+        ulen = int(self._lib.qg_hnsw_upper_len(self.handle))
+        level = np.empty(n, dtype=np.int32)
+        adj0 = np.empty((n, self.MaxM0), dtype=np.uint32)
+        uoff = np.empty(n + 1, dtype=np.int64)
+        uadj = np.empty(max(ulen, 1), dtype=np.uint32)
+        entry, cur = C.c_int(0), C.c_int(0)
+        _check(self._lib.qg_hnsw_export(self.handle, _ptr(level), _ptr(adj0), _ptr(uoff), _ptr(uadj), C.byref(entry),
+                                        C.byref(cur)))
+        return {"n": n, "entry": entry.value, "current_level": cur.value, "level": level, "adj0": adj0,
+                "upper_off": uoff, "upper_adj": uadj, "M": self.M, "MaxM0": self.MaxM0, "EfSearch": EfSearch}
+
+    def search(self, queries: np.ndarray, k: int, ef_search: int = 128):
+        """qg_hnsw_search_batch -> (idx [q,k] uint32, dist [q,k], count [q], evals [q])."""
+        qs = np.ascontiguousarray(queries, dtype=np.float32)
+        q = qs.shape[0]
+        idx = np.full((q, k), 0xFFFFFFFF, dtype=np.uint32)
+        dist = np.full((q, k), np.inf, dtype=np.float32)
+        cnt = np.zeros(q, dtype=np.int32)
+        ev = np.zeros(q, dtype=np.int64)
+        _check(self._lib.qg_hnsw_search_batch(self.index.handle, self.handle, _ptr(qs), q, qs.shape[1], k, ef_search,
+                                              _ptr(idx), _ptr(dist), _ptr(cnt), _ptr(ev)))
+        return idx, dist, cnt, ev
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.qg_hnsw_destroy(self.handle)
             self.handle = None
 
     def __del__(self):

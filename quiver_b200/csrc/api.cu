@@ -19,6 +19,7 @@
 #include "hnsw.cuh"
 #include "misc.cuh"
 #include "scan.cuh"
+#include "synth.cuh"
 #include "tc_scan.cuh"
 
 namespace qg {
@@ -2127,6 +2128,147 @@ int qg_hnsw_upload(qg_index* idx, int64_t n_nodes, int m, int max_m0, int entry_
   g->g.upper_off = (const long long*)g->upper_off.p;
   g->g.upper_adj = (const uint32_t*)g->upper_adj.p;
   *out = g.release();
+  return 0;
+}
+
+int qg_hnsw_build(qg_index* idx, int m, int max_m0, int ef_construction, int max_level, uint64_t seed, int max_batch,
+                  qg_hnsw** out) {
+  if (int rc = check_index(idx)) return rc;
+  if (!out) return fail(QG_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (m <= 0 || m > 32 || max_m0 <= 0 || max_m0 > 32 || ef_construction <= 0 || max_level <= 0)
+    return fail(QG_ERR_INVALID, "hnsw build: need 0 < m, max_m0 <= 32, ef_construction > 0, max_level > 0");
+  if (idx->n_live != idx->n_rows) return fail(QG_ERR_UNSUPPORTED, "hnsw build: compact the index first (tombstoned rows)");
+  const long long n = idx->n_rows;
+  if (n >= (1ll << 30)) return fail(QG_ERR_RANGE, "hnsw build: at most 2^30 - 1 nodes");
+  if (max_batch <= 0) max_batch = 8192;
+  std::unique_ptr<qg_hnsw> g(new qg_hnsw());
+  g->owner = idx;
+  g->g.n_nodes = n;
+  g->g.m = m;
+  g->g.max_m0 = max_m0;
+  if (n == 0) {
+    *out = g.release();
+    return 0;
+  }
+  // levels (randomLevel, hnsw.go:716-738) and the offsets of the upper-level blocks
+  std::vector<int32_t> level((size_t)n);
+  std::vector<int64_t> uoff((size_t)n + 1);
+  const int attempts = std::min(max_level, 10);
+  int64_t u = 0;
+  for (long long i = 0; i < n; ++i) {
+    int lv = 0;
+    for (int a = 0; a < attempts; ++a) {
+      if (synth_uniform(seed, (uint64_t)i, (uint32_t)a, 7) < 0.25f) lv++;
+      else break;
+    }
+    if (lv >= max_level) lv = max_level - 1;
+    level[(size_t)i] = lv;
+    uoff[(size_t)i] = u;
+    u += (int64_t)lv * m;
+  }
+  uoff[(size_t)n] = u;
+  int rc = 0;
+  if ((rc = g->level.ensure((size_t)n * 4)) || (rc = g->adj0.ensure((size_t)n * max_m0 * 4)) ||
+      (rc = g->upper_off.ensure(((size_t)n + 1) * 8)) || (rc = g->upper_adj.ensure(std::max<size_t>((size_t)u, 1) * 4)))
+    return rc;
+  QG_CUDA_OK(cudaMemcpy(g->level.p, level.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+  QG_CUDA_OK(cudaMemcpy(g->upper_off.p, uoff.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice));
+  QG_CUDA_OK(cudaMemset(g->adj0.p, 0xff, (size_t)n * max_m0 * 4));
+  QG_CUDA_OK(cudaMemset(g->upper_adj.p, 0xff, std::max<size_t>((size_t)u, 1) * 4));
+  const size_t wb = hnsw_workspace_bytes(n, idx->sm_count);
+  if ((rc = g->work.ensure(wb))) return rc;
+  QG_CUDA_OK(cudaMemset(g->work.p, 0, wb));
+  g->g.level = (const int32_t*)g->level.p;
+  g->g.adj0 = (const uint32_t*)g->adj0.p;
+  g->g.upper_off = (const long long*)g->upper_off.p;
+  g->g.upper_adj = (const uint32_t*)g->upper_adj.p;
+  g->g.entry_point = 0;                 // the first node: entry point of its level (hnsw.go:317-323)
+  g->g.current_level = level[0];
+  // reverse-link records of a batch: at most max_m0 + levels * m per node
+  const unsigned int rev_cap = (unsigned int)std::min<long long>((long long)max_batch * (max_m0 + 4 * m), 1ll << 31);
+  DevBuf rev_key, rev_key2, rev_dist, rev_cnt, perm_a, perm_b;
+  void* sort_tmp = nullptr;
+  size_t sort_tmp_bytes = 0;
+  auto cleanup = [&](int code) {
+    rev_key.release(); rev_key2.release(); rev_dist.release(); rev_cnt.release(); perm_a.release(); perm_b.release();
+    if (sort_tmp) cudaFree(sort_tmp);
+    return code;
+  };
+  if ((rc = rev_key.ensure((size_t)rev_cap * 8)) || (rc = rev_key2.ensure((size_t)rev_cap * 8)) ||
+      (rc = rev_dist.ensure((size_t)rev_cap * 4)) || (rc = rev_cnt.ensure(4)) || (rc = perm_a.ensure((size_t)rev_cap * 4)) ||
+      (rc = perm_b.ensure((size_t)rev_cap * 4)))
+    return cleanup(rc);
+  Workspace* w = ws_acquire(idx);
+  if (!w) return cleanup(fail(QG_ERR_CUDA, "could not create a stream"));
+  cudaStream_t st = w->stream;
+  long long committed = 1;
+  while (committed < n && !rc) {
+    // a batch never exceeds an eighth of the committed graph: the nodes of a batch do not see each other
+    const int count = (int)std::min<long long>({(long long)max_batch, std::max<long long>(1, committed / 8), n - committed});
+    if ((rc = launch_hnsw_insert_batch(g->g, (uint32_t*)g->adj0.p, (uint32_t*)g->upper_adj.p, idx->vec, idx->dp, idx->dim,
+                                       idx->metric, idx->arith, ef_construction, committed, count, g->work.p, idx->sm_count,
+                                       (unsigned long long*)rev_key.p, (float*)rev_dist.p, (unsigned int*)rev_cnt.p, rev_cap,
+                                       st)))
+      break;
+    unsigned int n_rec = 0;
+    cudaError_t e = cudaMemcpyAsync(&n_rec, rev_cnt.p, 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, std::string("hnsw build: ") + cudaGetErrorString(e)); break; }
+    if (n_rec > rev_cap) { rc = fail(QG_ERR_CUDA, "hnsw build: reverse-link buffer overflow"); break; }
+    if ((rc = hnsw_sort_records((const unsigned long long*)rev_key.p, (unsigned long long*)rev_key2.p,
+                                (unsigned int*)perm_a.p, (unsigned int*)perm_b.p, n_rec, &sort_tmp, &sort_tmp_bytes, st)))
+      break;
+    if ((rc = launch_hnsw_link_batch(g->g, (uint32_t*)g->adj0.p, (uint32_t*)g->upper_adj.p, idx->vec, idx->dp, idx->dim,
+                                     idx->metric, idx->arith, (const unsigned long long*)rev_key2.p,
+                                     (const unsigned int*)perm_b.p, (const float*)rev_dist.p, n_rec, st)))
+      break;
+    // entry point / current level: the first node of the batch that reaches a new top level (hnsw.go:463-466)
+    for (long long i = committed; i < committed + count; ++i)
+      if (level[(size_t)i] > g->g.current_level) {
+        g->g.current_level = level[(size_t)i];
+        g->g.entry_point = (int)i;
+      }
+    committed += count;
+  }
+  if (!rc) {
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fail(QG_ERR_CUDA, std::string("hnsw build: ") + cudaGetErrorString(e));
+  }
+  ws_release(idx, w);
+  if (rc) return cleanup(rc);
+  cleanup(0);
+  *out = g.release();
+  return 0;
+}
+
+int64_t qg_hnsw_nodes(const qg_hnsw* g) { return g ? g->g.n_nodes : 0; }
+
+int64_t qg_hnsw_upper_len(const qg_hnsw* g) {
+  if (!g || g->g.n_nodes == 0) return 0;
+  long long last = 0;
+  cudaSetDevice(g->owner->device);
+  if (cudaMemcpy(&last, (const long long*)g->upper_off.p + g->g.n_nodes, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return last;
+}
+
+int qg_hnsw_export(const qg_hnsw* g, int32_t* level, uint32_t* adj0, int64_t* upper_off, uint32_t* upper_adj,
+                   int* entry_point, int* current_level) {
+  if (!g) return fail(QG_ERR_INVALID, "graph handle is null");
+  if (entry_point) *entry_point = g->g.entry_point;
+  if (current_level) *current_level = g->g.current_level;
+  const size_t n = (size_t)g->g.n_nodes;
+  if (n == 0) return 0;
+  if (!level || !adj0 || !upper_off) return fail(QG_ERR_INVALID, "null buffer");
+  QG_CUDA_OK(cudaSetDevice(g->owner->device));
+  QG_CUDA_OK(cudaMemcpy(level, g->level.p, n * 4, cudaMemcpyDeviceToHost));
+  QG_CUDA_OK(cudaMemcpy(adj0, g->adj0.p, n * (size_t)g->g.max_m0 * 4, cudaMemcpyDeviceToHost));
+  QG_CUDA_OK(cudaMemcpy(upper_off, g->upper_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost));
+  const size_t ulen = (size_t)upper_off[n];
+  if (ulen > 0) {
+    if (!upper_adj) return fail(QG_ERR_INVALID, "null buffer");
+    QG_CUDA_OK(cudaMemcpy(upper_adj, g->upper_adj.p, ulen * 4, cudaMemcpyDeviceToHost));
+  }
   return 0;
 }
 
