@@ -180,4 +180,94 @@ __device__ __forceinline__ void exact_distance_warp3(int metric, int arith, cons
   }
 }
 
+// ---- one (query, row) distance by ONE thread, reference arithmetic and order ----------------------
+// q: the query (shared memory, all lanes read the same element: broadcast), x: the stored row.
+// Same value as exact_distance_warp(metric, arith, q, x, d): the terms are formed with the same
+// roundings and added in index order.
+__device__ __forceinline__ float exact_distance_lane(int metric, int arith, const float* __restrict__ q,
+                                                     const float* __restrict__ x, int d, int dp) {
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  const int n4 = dp >> 2;  // rows are zero padded to a multiple of 4 floats; zero terms do not change a sum
+  if (arith == ARITH_HNSW_F32 && (metric == METRIC_COSINE || metric == METRIC_L2 || metric == METRIC_DOT)) {
+    // pkg/hnsw/adapter.go:105-167 — everything float32, sequential, no fused multiply-add
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < n4; ++i) {
+      const float4 v = __ldg(x4 + i);
+      const float xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (i * 4 + j >= d) break;
+        const float a = q[i * 4 + j], b = xs[j];
+        if (metric == METRIC_L2) {
+          const float df = __fsub_rn(a, b);
+          s0 = __fadd_rn(s0, __fmul_rn(df, df));
+        } else {
+          s0 = __fadd_rn(s0, __fmul_rn(a, b));
+          if (metric == METRIC_COSINE) {
+            s1 = __fadd_rn(s1, __fmul_rn(a, a));
+            s2 = __fadd_rn(s2, __fmul_rn(b, b));
+          }
+        }
+      }
+    }
+    if (metric == METRIC_L2) return (float)sqrt((double)s0);
+    if (metric == METRIC_DOT) return __fsub_rn(1.0f, s0);
+    if (s1 == 0.f || s2 == 0.f) return 1.0f;
+    const float sa = (float)sqrt((double)s1), sb = (float)sqrt((double)s2);
+    float sim = __fdiv_rn(s0, __fmul_rn(sa, sb));
+    if (sim > 1.0f) sim = 1.0f;
+    else if (sim < -1.0f) sim = -1.0f;
+    return __fsub_rn(1.0f, sim);
+  }
+  if (metric == METRIC_SQL2) {  // distances.go:60-72
+    float s = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < n4; ++i) {
+      const float4 v = __ldg(x4 + i);
+      const float xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (i * 4 + j >= d) break;
+        const float df = __fsub_rn(q[i * 4 + j], xs[j]);
+        s = __fadd_rn(s, __fmul_rn(df, df));
+      }
+    }
+    return s;
+  }
+  // float64 accumulators (distances.go:17-22, 48-52, 82-85, 99-101); a float32 product is exact in float64
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll 4
+  for (int i = 0; i < n4; ++i) {
+    const float4 v = __ldg(x4 + i);
+    const float xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (i * 4 + j >= d) break;
+      const float a = q[i * 4 + j], b = xs[j];
+      if (metric == METRIC_L2) {
+        const double df = (double)__fsub_rn(a, b);
+        s0 = __dadd_rn(s0, __dmul_rn(df, df));
+      } else if (metric == METRIC_L1) {
+        s0 = __dadd_rn(s0, fabs((double)__fsub_rn(a, b)));
+      } else {
+        s0 = __dadd_rn(s0, __dmul_rn((double)a, (double)b));
+        if (metric == METRIC_COSINE) {
+          s1 = __dadd_rn(s1, __dmul_rn((double)a, (double)a));
+          s2 = __dadd_rn(s2, __dmul_rn((double)b, (double)b));
+        }
+      }
+    }
+  }
+  if (metric == METRIC_L2) return (float)sqrt(s0);
+  if (metric == METRIC_L1) return (float)s0;
+  if (metric == METRIC_DOT) return (float)(1.0 - s0);
+  if (s1 == 0.0 || s2 == 0.0) return 1.0f;
+  double sim = s0 / (sqrt(s1) * sqrt(s2));
+  if (sim > 1.0) sim = 1.0;
+  else if (sim < -1.0) sim = -1.0;
+  return (float)(1.0 - sim);
+}
+
+
 }  // namespace qg

@@ -10,6 +10,8 @@
 // and certifies the result only if every scan CTA whose list was full dropped nothing with
 // score <= T. An uncertified query is reported with count -1 and redone by the exhaustive
 // path, so recall is 1.0 by construction, not by a margin heuristic.
+#include <cstdlib>
+
 #include "exact.cuh"
 #include "finalize.cuh"
 #include "scan.cuh"
@@ -741,9 +743,265 @@ __global__ void __launch_bounds__(FC_THREADS, 2) finalize_cand_kernel(const Fina
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same stage with ONE WARP per query (round 2). The CTA-per-query kernel above is a chain of
+// block-wide barriers (eight radix rounds, rank counting, two re-rank phases): 14 us of latency per query at
+// two resident CTAs per SM, 98 us for the 2 048 queries of a pass group — 14 % of the headline step. A
+// warp needs no block barrier at all and sixteen to twenty-four queries are in flight per SM:
+//   1. radix-256 select over the 32-bit score images (four rounds; the warp's 256 shared-memory counters),
+//      keys re-read from global memory each round (they sit in L1 / L2: ~2 KB per query);
+//   2. the selected candidates are re-ranked exactly, ONE LANE per candidate (exact_distance_lane: the
+//      reference's sequential sum is a chain anyway — 32 chains run side by side);
+//   3. E = k-th smallest exact distance (warp bitonic sort in shared memory), T from the same error bound,
+//      every further candidate with score <= T is re-ranked too, certificate as above;
+//   4. the exact keys are sorted and the first k emitted.
+// Any selection of >= k candidates followed by steps 3-4 yields the exact top-k when the certificate holds,
+// so the results equal the CTA kernel's bit for bit (tests: every tensor-core parity test runs through it).
+// ------------------------------------------------------------------------------------------------
+constexpr int FW_WARPS = 8;          // queries per CTA
+constexpr int FW_SEL_MAX = 64;       // selected candidates per query (kp <= 32 plus ties on the score image)
+constexpr int FW_EX_MAX = 512;       // exact keys per query: selected + extras (more extras => not certified).
+// For k <= 16 (kp = 32) the scan admits ~256 candidates per query, so 512 holds every list the sampled
+// threshold produces; larger k (kp = 64 / 128: ~750 admitted, most of them below T) stay on the CTA kernel.
+
+// ascending bitonic sort of n2 (power of two <= FW_EX_MAX) keys in the warp's shared memory
+__device__ __forceinline__ void warp_bitonic_sort_smem(uint64_t* a, int n2) {
+  const int lane = threadIdx.x & 31;
+  for (int k = 2; k <= n2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < (n2 >> 1); t += 32) {
+        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // index with bit j clear
+        const int hi = lo | j;
+        const bool up = (lo & k) == 0;
+        const uint64_t x = a[lo], y = a[hi];
+        if ((x > y) == up) {
+          a[lo] = y;
+          a[hi] = x;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(FW_WARPS * 32) finalize_cand_warp_kernel(const FinalizeCandParams cp, int nq) {
+  __shared__ int s_hist[FW_WARPS][256];
+  __shared__ uint64_t s_ex[FW_WARPS][FW_EX_MAX];
+  const FinalizeParams& p = cp.base;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const int q = blockIdx.x * FW_WARPS + warp;
+  // (no early griddepcontrol.launch_dependents here: all CTAs of this small grid are resident at once, so the
+  //  next scan's persistent CTAs — 61 K registers each — would be launched at once too and take every SM a
+  //  finished CTA of this kernel frees, leaving the CTAs still queued nowhere to run: measured 3.36 ms per
+  //  10 000-query step with the early trigger against 2.99 ms without.)
+  pdl_wait();  // candidate lists, counts and thresholds come from the scan / threshold kernels just before
+  if (q >= nq) return;
+  int* hist = s_hist[warp];
+  uint64_t* ex = s_ex[warp];
+  const int cap = cp.cap, k = p.k;
+  const int n_raw = cp.cand_cnt[q];
+  const bool overflow = n_raw > cap;
+  const int n = overflow ? cap : n_raw;
+  const float tau = cp.tau[q];
+  const bool all_admitted = tau == __int_as_float(0x7f800000);
+  const float* qv = p.queries + (size_t)q * p.dp;
+  const uint64_t* src = cp.cand + (size_t)q * cap;
+
+  // |q|^2 in float64 (same reduction order as the CTA kernel: lane-strided partial sums, xor butterfly)
+  double qn2 = 0.0;
+  for (int i = lane; i < p.d; i += 32) qn2 += (double)qv[i] * (double)qv[i];
+  for (int o = 16; o >= 1; o >>= 1) qn2 += __shfl_xor_sync(0xffffffffu, qn2, o);
+
+  // ---- 1. pivot = smallest score image P with at least `want` keys <= P (radix 256, four rounds) ----
+  const int want = n < cp.kp ? n : cp.kp;
+  uint32_t prefix = 0;
+  int below = 0;
+  if (want > 0) {
+    for (int r = 0; r < 4; ++r) {
+      const int shift = 24 - 8 * r;
+      for (int i = lane; i < 256; i += 32) hist[i] = 0;
+      __syncwarp();
+      for (int i = lane; i < n; i += 32) {
+        const uint32_t img = (uint32_t)(__ldcg(src + i) >> 32);
+        if (r == 0 || (img >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&hist[(img >> shift) & 255u], 1);
+      }
+      __syncwarp();
+      // lane l owns counters 8l .. 8l+7: inclusive scan across lanes, then inside the lane
+      int c[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        c[j] = hist[lane * 8 + j];
+        sum += c[j];
+      }
+      int inc = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += up;
+      }
+      const int before_lane = inc - sum;  // keys in the digits of lower lanes
+      const unsigned reach = __ballot_sync(0xffffffffu, below + inc >= want);
+      const int pick_lane = reach ? __ffs((int)reach) - 1 : 31;
+      int digit = 0, before = 0;
+      if (lane == pick_lane) {
+        int run = before_lane;
+        digit = 7;
+        before = run;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (below + run + c[j] >= want) {
+            digit = j;
+            before = run;
+            break;
+          }
+          run += c[j];
+          before = run;
+        }
+        digit += lane * 8;
+      }
+      digit = __shfl_sync(0xffffffffu, digit, pick_lane);
+      before = __shfl_sync(0xffffffffu, before, pick_lane);
+      prefix |= (uint32_t)digit << shift;
+      below += before;
+      __syncwarp();
+    }
+  }
+  const uint32_t pivot = prefix;
+
+  // ---- 2. selected candidates (image <= pivot, the first FW_SEL_MAX in list order) -> exact keys ----
+  int nsel = 0;
+  if (want > 0) {
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      const int i = i0 + lane;
+      const uint64_t key = i < n ? __ldcg(src + i) : KEY_NONE;
+      const bool sel = i < n && (uint32_t)(key >> 32) <= pivot;
+      const unsigned m = __ballot_sync(0xffffffffu, sel);
+      const int pos = nsel + __popc(m & lt);
+      if (sel && pos < FW_SEL_MAX) ex[pos] = key;  // scan key for now
+      nsel += __popc(m);
+    }
+  }
+  const int nsel_all = nsel;  // how many images are <= pivot (those beyond FW_SEL_MAX are treated as extras)
+  if (nsel > FW_SEL_MAX) nsel = FW_SEL_MAX;
+  __syncwarp();
+  for (int c0 = 0; c0 < nsel; c0 += 32) {
+    const int c = c0 + lane;
+    if (c < nsel) {
+      const uint32_t rid = key_row(ex[c]);
+      const float dist = exact_distance_lane(p.metric, p.arith, qv, p.vec + (size_t)rid * p.dp, p.d, p.dp);
+      ex[c] = make_key(dist, rid);
+    }
+  }
+  __syncwarp();
+
+  // ---- 3. certificate ----
+  bool certified = !overflow;
+  int nex = nsel;
+  if (nsel >= k) {
+    // E = k-th smallest exact distance of the selected candidates
+    int n2 = 32;
+    while (n2 < nsel) n2 <<= 1;
+    for (int i = nsel + lane; i < n2; i += 32) ex[i] = KEY_NONE;
+    __syncwarp();
+    warp_bitonic_sort_smem(ex, n2);
+    const float E = key_score(ex[k - 1]);
+    const double mx = (double)(p.max_norm2 ? *p.max_norm2 : 0.f);
+    float T = tc_score_upper_bound(p.metric, p.mode, p.cosine, E, cp.tc_gamma, (double)p.gamma, qn2, mx);
+    if (cp.tc_norm_gamma > 0.0) {  // raw L2 scan: the norm term is accumulated by the tensor core as well
+      const double t2 = (double)T + cp.tc_norm_gamma * mx;
+      T = (float)t2;
+      if ((double)T < t2) T = nextafterf(T, __int_as_float(0x7f800000));
+    }
+    if (!(T <= tau) && !all_admitted) certified = false;
+    // every further candidate whose scan score is <= T may still belong to the exact top-k
+    int ordinal = 0;  // position among the keys with image <= pivot (list order, as in step 2)
+    const int nex0 = nex;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      const int i = i0 + lane;
+      const uint64_t key = i < n ? __ldcg(src + i) : KEY_NONE;
+      const bool in_piv = i < n && (uint32_t)(key >> 32) <= pivot;
+      const unsigned mp = __ballot_sync(0xffffffffu, in_piv);
+      const int my_ord = ordinal + __popc(mp & lt);
+      ordinal += __popc(mp);
+      const bool extra = i < n && key_score(key) <= T && (in_piv ? my_ord >= FW_SEL_MAX : true);
+      const unsigned me = __ballot_sync(0xffffffffu, extra);
+      const int pos = nex + __popc(me & lt);
+      if (extra && pos < FW_EX_MAX) ex[pos] = key;
+      nex += __popc(me);
+    }
+    if (nex > FW_EX_MAX) {
+      nex = FW_EX_MAX;
+      certified = false;
+    }
+    __syncwarp();
+    for (int c0 = nex0; c0 < nex; c0 += 32) {
+      const int c = c0 + lane;
+      if (c < nex) {
+        const uint32_t rid = key_row(ex[c]);
+        const float dist = exact_distance_lane(p.metric, p.arith, qv, p.vec + (size_t)rid * p.dp, p.d, p.dp);
+        ex[c] = make_key(dist, rid);
+      }
+    }
+    __syncwarp();
+  } else {
+    // fewer than k candidates: complete only if the scan admitted every row
+    if (!all_admitted) certified = false;
+    (void)nsel_all;
+  }
+
+  // ---- 4. order the exact keys and emit the first k ----
+  pdl_launch_dependents();  // the next kernel's CTAs may take the SMs this kernel's tail leaves idle
+  {
+    int n2 = 32;
+    while (n2 < nex) n2 <<= 1;
+    for (int i = nex + lane; i < n2; i += 32) ex[i] = KEY_NONE;
+    __syncwarp();
+    warp_bitonic_sort_smem(ex, n2);
+  }
+  const int kk = nex < k ? nex : k;
+  if (p.out_keys != nullptr) {
+    for (int j = lane; j < k; j += 32) {
+      uint64_t o = KEY_NONE;
+      if (j < kk && certified) o = (ex[j] & 0xFFFFFFFF00000000ull) | (uint64_t)(uint32_t)(p.row_base + key_row(ex[j]));
+      p.out_keys[(size_t)q * k + j] = o;
+    }
+    if (lane == 0 && p.out_count) p.out_count[q] = certified ? kk : -1;
+  } else {
+    for (int j = lane; j < k; j += 32) {
+      const bool ok = j < kk;
+      p.out_dist[(size_t)q * k + j] = ok ? key_score(ex[j]) : __int_as_float(0x7f800000);
+      p.out_row[(size_t)q * k + j] = ok ? (long long)key_row(ex[j]) + p.row_base : -1ll;
+      if (p.out_negdist != nullptr) {
+        float nd = __int_as_float(0x7f800000);
+        if (ok) nd = exact_distance_lane(p.metric, p.arith, p.vec + (size_t)key_row(ex[j]) * p.dp,
+                                         p.negatives + (size_t)q * p.dp, p.d, p.dp);
+        p.out_negdist[(size_t)q * k + j] = nd;
+      }
+    }
+    if (lane == 0) p.out_count[q] = certified ? kk : -1;
+  }
+  if (lane == 0 && cp.reset_cnt != nullptr) {
+    cp.reset_cnt[q] = 0;
+    if (q < cp.n_reset_work && cp.reset_work != nullptr) cp.reset_work[q] = 0;
+  }
+}
+
 int launch_finalize_cand(const FinalizeCandParams& p, int nq, cudaStream_t st) {
   if (nq <= 0) return 0;
   if (p.cap > 4 * FC_THREADS) return fail(1, "finalize_cand: candidate capacity must be at most 2048");
+  static const bool warp_on = [] {
+    // opt-in: 80 us instead of 99 us per 2 048 queries on its own, but the step is slower with it (the next
+    // pass's threshold kernel no longer hides under the finalize)
+    const char* e = std::getenv("QG_FINALIZE_WARP");
+    return e != nullptr && std::atoi(e) != 0;
+  }();
+  // rows must be 16-byte aligned for the per-lane row loads (dp % 4 == 0)
+  if (warp_on && p.dbg == nullptr && p.kp <= 32 && (p.base.dp & 3) == 0) {
+    QG_CUDA_OK(launch_chained(finalize_cand_warp_kernel, dim3((nq + FW_WARPS - 1) / FW_WARPS), dim3(FW_WARPS * 32),
+                              (size_t)0, st, p, nq));
+    return 0;
+  }
   QG_CUDA_OK(launch_chained(finalize_cand_kernel, dim3(nq), dim3(FC_THREADS), finalize_cand_smem(p.cap), st, p));
   return 0;
 }

@@ -9,7 +9,7 @@ quirk fragments layer 0 — short walks; the under-fill exact pass answers most 
 (QO_HNSW_STANDARD=1, a measurement aid) that shows the regime the neighbour batches are meant for.
 Checked: device results == host walk results (ids, float32 distances, evaluation counts) on a sample.
 
-usage: python tests/bench_hnsw_c5.py [rows] [queries] [both|faithful|textbook]"""
+usage: python tests/bench_hnsw_c5.py [rows] [queries] [both|faithful|textbook|device]"""
 import json
 import os
 import sys
@@ -28,14 +28,25 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def run(standard: bool, n: int, nq: int, d: int = 128, k: int = 10):
+def run(standard: bool, n: int, nq: int, d: int = 128, k: int = 10, device_built: bool = False):
     import oracle
     from oracle import hnsw
-    from quiver_b200 import hostapi
+    from quiver_b200 import capi, hostapi
     corpus = oracle.synth(0, 42, 0, n, d, threads=8)
     queries = oracle.synth(0, 9999, 0, nq, d, threads=1)
     stored = os.path.join(ROOT, "tools", "data", f"hnsw_{n // 1000000}m_{'textbook' if standard else 'faithful'}.npz")
-    if n % 1000000 == 0 and os.path.exists(stored):
+    if device_built:
+        # the graph is built on the device (qg_hnsw_build, batched inserts) and exported
+        bidx = capi.Index(d, capi.L2, reserve_rows=n)
+        bidx.upload(corpus)
+        t = time.perf_counter()
+        bg = capi.HnswGraph.build(bidx, M=16, MaxM0=32, EfConstruction=200, seed=1)
+        t_build = time.perf_counter() - t
+        g = bg.export(EfSearch=128)
+        bg.close()
+        bidx.close()
+        graph = hnsw.Graph(corpus, 1, M=16, MaxM0=32, EfSearch=128, flat=g)
+    elif n % 1000000 == 0 and os.path.exists(stored):
         z = np.load(stored)
         flat = {kk: z[kk] for kk in ("level", "adj0", "upper_off", "upper_adj")}
         flat.update(n=int(z["n"]), entry=int(z["entry"]), current_level=int(z["current_level"]), M=16, MaxM0=32, EfSearch=128)
@@ -95,8 +106,10 @@ def run(standard: bool, n: int, nq: int, d: int = 128, k: int = 10):
         hit += len({r[0] for r in ex[i]} & {r[0] for r in res[i]})
     dg.close()
     idx.close()
-    return {"graph": "textbook entry-point descent (QO_HNSW_STANDARD=1)" if standard else "reference connectNode (faithful)",
-            "rows": n, "dim": d, "queries": nq, "k": k, "efSearch": 128, "M": 16, "build_s_host_one_thread": round(t_build, 1),
+    return {"graph": "built on the device (qg_hnsw_build, batched inserts, textbook descent)" if device_built else (
+                "textbook entry-point descent (QO_HNSW_STANDARD=1)" if standard else "reference connectNode (faithful)"),
+            "rows": n, "dim": d, "queries": nq, "k": k, "efSearch": 128, "M": 16,
+            ("build_s_device" if device_built else "build_s_host_one_thread"): round(t_build, 1),
             "distance_evals_per_query": float(np.mean(evals)),
             "graph_walk_filled_k": full / n_host, "fallbacks_to_host_walk": int(fallbacks),
             "device_walk_qps": nq / t_dev, "device_walk_ms": t_dev * 1e3,
@@ -117,4 +130,6 @@ if __name__ == "__main__":
         out.append(run(False, rows, nq))
     if which in ("both", "textbook"):
         out.append(run(True, rows, nq))
+    if which in ("both", "device"):
+        out.append(run(True, rows, nq, device_built=True))
     print(json.dumps({"metric": "HNSW search on the device vs the reference's walk on the host (C5)", "runs": out}))

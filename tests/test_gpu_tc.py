@@ -180,3 +180,35 @@ def test_concurrent_searches_share_one_index(capi):
         th.join(120)
     assert not errors, errors[:5]
     idx.close()
+
+
+_WARP_FINALIZE_SCRIPT = r"""
+import numpy as np
+from quiver_b200 import capi
+rng = np.random.default_rng(5)
+for metric, d in ((1, 128), (0, 64), (2, 96)):
+    corpus = rng.standard_normal((150_000, d)).astype(np.float32)
+    corpus[7000:7020] = corpus[11]
+    queries = np.concatenate([rng.standard_normal((299, d)).astype(np.float32), corpus[11:12]])
+    idx = capi.Index(d, metric)
+    idx.upload(corpus)
+    for k in (1, 10, 16):
+        dist, row, cnt, _ = idx.search(queries, k)
+        assert idx.stats()["path"] == 3, idx.stats()
+        xd, xr, xc = idx.search_exhaustive(queries, k)
+        assert np.array_equal(row, xr) and np.array_equal(dist.view(np.uint32), xd.view(np.uint32)), (metric, d, k)
+print("ok")
+"""
+
+
+def test_warp_per_query_finalize_is_bit_identical():
+    """finalize.cu: finalize_cand_warp_kernel is opt-in (QG_FINALIZE_WARP=1, read once per process): the same
+    batches must equal the exhaustive GPU oracle bit for bit, duplicates and ties included."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, QG_FINALIZE_WARP="1", PYTHONPATH=root)
+    out = subprocess.run([sys.executable, "-c", _WARP_FINALIZE_SCRIPT], env=env, cwd=root, capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout + out.stderr
