@@ -11,6 +11,8 @@ NVFLAGS   := -std=c++17 -O3 $(ARCH) -lineinfo -Xcompiler -fPIC -Xcompiler -Wall 
 ifeq ($(TC_INSTRUMENT),1)
 NVFLAGS   += -DQG_TC_INSTRUMENT
 endif
+# make EXTRA_NVFLAGS=-D...: experiment switches of single kernels
+NVFLAGS   += $(EXTRA_NVFLAGS)
 CSRC      := quiver_b200/csrc
 BUILD     := build/csrc
 LIBDIR    := quiver_b200/lib

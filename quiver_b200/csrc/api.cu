@@ -151,12 +151,14 @@ struct Workspace {
   cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
   std::vector<cudaEvent_t> chunk_ev;  // per chunk: queries staged, chunk computed, results on the host
   DevBuf qpad, negpad, partial, mask, counters;
+  DevBuf xchg;              // dense flat scan: threshold exchange words (scan.cuh), zeroed once
+  uint32_t xchg_epoch = 0;  // bumped per scan launch; words of older launches do not count
   DevBuf tc_sample, tc_tau, tc_cand, tc_cnt, tc_bias, tc_apack;
   DevBuf d_q, d_neg, d_dist, d_negdist, d_row, d_count, d_rows32, d_rows64, d_fetch;
   PinBuf h_in, h_out;
   ExhaustiveWork ex;
   void destroy() {
-    qpad.release(); negpad.release(); partial.release(); mask.release(); counters.release();
+    qpad.release(); negpad.release(); partial.release(); mask.release(); counters.release(); xchg.release();
     tc_sample.release(); tc_tau.release(); tc_cand.release(); tc_cnt.release(); tc_bias.release(); tc_apack.release();
     d_q.release(); d_neg.release(); d_dist.release(); d_negdist.release(); d_row.release(); d_count.release();
     d_rows32.release(); d_rows64.release(); d_fetch.release();
@@ -1467,6 +1469,9 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
   }
 
   const bool fast = scan_fast_supported(dp) && mode != MODE_L1;
+  // consecutive rows (no row list) take the dense kernel; QG_SCAN_DENSE=0 keeps the round-1 fast kernel
+  static const bool dense_on = [] { const char* e = std::getenv("QG_SCAN_DENSE"); return e == nullptr || std::atoi(e) != 0; }();
+  const bool dense = fast && gather == nullptr && dense_on;
   int tile_rows, nw = SCAN_NW, stages = 4, max_qb;
   if (fast) {
     tile_rows = scan_fast_tile_rows(dp);
@@ -1482,15 +1487,24 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
     max_qb = 8;
     while (max_qb > 1 && (size_t)max_qb * dp * 4 > 32 * 1024) max_qb >>= 1;
   }
-  // pools must fit next to the ring
-  {
+  int qb = 1;
+  if (dense) {
+    // ring and warps depend on the query block: the largest block (<= the batch) whose pools fit
+    int want = 1;
+    while (want < max_qb && want < q) want <<= 1;
+    size_t smem = 0;
+    for (qb = want; qb >= 1; qb >>= 1) {
+      if (scan_dense_geometry(dp, qb, kp, &tile_rows, &nw, &smem) == 0 && smem <= 227 * 1024) break;
+    }
+    if (qb < 1) return fail(QG_ERR_UNSUPPORTED, "scan: candidate pools do not fit shared memory");
+  } else {
+    // pools must fit next to the ring
     const size_t ring = fast ? (size_t)0 : (size_t)nw * stages * tile_rows * dp * 4;
     const size_t ring_fast = fast ? (size_t)scan_fast_ring_bytes(dp) : 0;
     const size_t avail = 225 * 1024 - (fast ? ring_fast : ring) - (fast ? 0 : (size_t)max_qb * dp * 4);
     while (max_qb > 1 && (size_t)max_qb * pool_slots(kp) * 8 > avail) max_qb >>= 1;
+    while (qb < max_qb && qb < q) qb <<= 1;
   }
-  int qb = 1;
-  while (qb < max_qb && qb < q) qb <<= 1;
 
   const long long n_tiles = (n_items + tile_rows - 1) / tile_rows;
   int nb = (int)std::min<long long>(idx->sm_count, (n_tiles + nw - 1) / nw);
@@ -1512,6 +1526,24 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
   sp.dp = dp;
   sp.tile_rows = tile_rows;
   sp.stages = stages;
+  // pacing load of the dense kernel (scan.cuh); QG_SCAN_PACE=0 turns it off
+  static const bool scan_pace = [] { const char* e = std::getenv("QG_SCAN_PACE"); return e == nullptr || std::atoi(e) != 0; }();
+  sp.pace = (scan_pace && dense && sp.inv_norm == nullptr) ? idx->norm2 : nullptr;
+  static const int scan_dbg = [] { const char* e = std::getenv("QG_SCAN_DBG"); return e ? std::atoi(e) : 0; }();
+  sp.dbg = scan_dbg;
+  // QG_SCAN_TRACE=1: per-CTA time stamps of the dense kernel, summarised on stderr after every launch (diagnostic)
+  static const bool scan_trace = [] { const char* e = std::getenv("QG_SCAN_TRACE"); return e && std::atoi(e) != 0; }();
+  static unsigned long long* trace_buf = nullptr;
+  if (scan_trace && trace_buf == nullptr) cudaMalloc(&trace_buf, 1024 * 32 * sizeof(unsigned long long));
+  sp.trace = scan_trace ? trace_buf : nullptr;
+  // threshold exchange between the CTAs of a dense launch (QG_SCAN_XCHG=0 turns it off)
+  static const bool xchg_on = [] { const char* e = std::getenv("QG_SCAN_XCHG"); return e == nullptr || std::atoi(e) != 0; }();
+  constexpr size_t kXchgBytes = (size_t)XCHG_MAX_QB * XCHG_MAX_CTAS * 16 * sizeof(unsigned long long);
+  const bool use_xchg = dense && xchg_on && kp <= XCHG_MAX_KP && qb <= XCHG_MAX_QB && nb <= XCHG_MAX_CTAS && nw == 16;
+  if (use_xchg && w->xchg.p == nullptr) {
+    if (int rc = w->xchg.ensure(kXchgBytes)) return rc;
+    QG_CUDA_OK(cudaMemsetAsync(w->xchg.p, 0, kXchgBytes, st));
+  }
 
   FinalizeParams fp{};
   fp.nb = nb;
@@ -1534,10 +1566,81 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
       sp.queries = qpad + (size_t)(q0 + p0) * dp;
       sp.nq = std::min(qb, qn - p0);
       sp.partial = (uint64_t*)w->partial.p + (size_t)p0 * nb * kp;
+      if (sp.trace) {
+        std::vector<unsigned long long> init((size_t)nb * 32, 0ull);
+        for (int c = 0; c < nb; ++c) init[(size_t)c * 32 + 5] = ~0ull;
+        cudaMemcpyAsync(sp.trace, init.data(), init.size() * 8, cudaMemcpyHostToDevice, st);
+        cudaStreamSynchronize(st);
+      }
+      if (use_xchg) {
+        if (++w->xchg_epoch == 0) w->xchg_epoch = 1;
+        sp.xchg = (unsigned long long*)w->xchg.p;
+        sp.epoch = w->xchg_epoch;
+      }
       const bool prof = idx->profiling && w->prof_begin(0, st) == 0;
-      int rc = fast ? launch_scan_fast(dp, qb, mode, sp, nb, st) : launch_scan_generic(qb, mode, sp, nb, nw, st);
+      int rc = dense ? launch_scan_dense(dp, qb, mode, sp, nb, st)
+                     : fast ? launch_scan_fast(dp, qb, mode, sp, nb, st) : launch_scan_generic(qb, mode, sp, nb, nw, st);
       if (prof) w->prof_end(st);
       if (rc) return rc;
+      if (sp.trace && dense) {
+        std::vector<unsigned long long> tr((size_t)nb * 32);
+        cudaStreamSynchronize(st);
+        cudaMemcpy(tr.data(), sp.trace, tr.size() * 8, cudaMemcpyDeviceToHost);
+        unsigned long long t0 = ~0ull, t_end = 0, pro = 0, first = 0, loop_last = 0, loop_first = ~0ull, start_last = 0;
+        for (int c = 0; c < nb; ++c) {
+          const unsigned long long* r = &tr[(size_t)c * 32];
+          t0 = std::min(t0, r[0]);
+          start_last = std::max(start_last, r[0]);
+          t_end = std::max(t_end, r[4]);
+          pro = std::max(pro, r[1] - r[0]);
+          first = std::max(first, r[2] - r[1]);
+          loop_last = std::max(loop_last, r[3]);
+          loop_first = std::min(loop_first, r[5]);
+        }
+        {
+          float ext_lo = INFINITY, ext_hi = -INFINITY, tau_lo = INFINITY, tau_hi = -INFINITY;
+          int pr_max = 0, cnt_max = 0;
+          long long cnt_sum = 0;
+          for (int c = 0; c < nb; ++c) {
+            const unsigned long long a6 = tr[(size_t)c * 32 + 6], a7 = tr[(size_t)c * 32 + 7];
+            float e, t;
+            const uint32_t eb = (uint32_t)a6, tb = (uint32_t)a7;
+            std::memcpy(&e, &eb, 4);
+            std::memcpy(&t, &tb, 4);
+            ext_lo = std::min(ext_lo, e); ext_hi = std::max(ext_hi, e);
+            tau_lo = std::min(tau_lo, t); tau_hi = std::max(tau_hi, t);
+            pr_max = std::max(pr_max, (int)(a6 >> 32));
+            cnt_max = std::max(cnt_max, (int)(a7 >> 32));
+            cnt_sum += (int)(a7 >> 32);
+          }
+          double intra = 0;
+          unsigned long long cta_first = ~0ull;
+          for (int c = 0; c < nb; ++c) {
+            intra += (double)(tr[(size_t)c * 32 + 3] - tr[(size_t)c * 32 + 5]);
+            cta_first = std::min(cta_first, tr[(size_t)c * 32 + 3]);
+          }
+          for (int c = 0; c < nb; c += 37) {
+            const unsigned long long* r = &tr[(size_t)c * 32];
+            std::fprintf(stderr, "scan trace: CTA %3d warps (tiles @ us):", c);
+            for (int wi = 0; wi < 16; ++wi)
+              if (r[16 + wi]) std::fprintf(stderr, " %llu@%.0f", r[16 + wi] >> 48, (double)((r[16 + wi] & 0xffffffffffffull) - (t0 & 0xffffffffffffull)) * 1e-3);
+            std::fprintf(stderr, "\n");
+            std::fprintf(stderr, "scan trace: CTA %3d fetches (tile, pool, seen):", c);
+            for (int f = 0; f < 4; ++f)
+              std::fprintf(stderr, " (%llu, %llu, %llu)", r[8 + f] >> 48, (r[8 + f] >> 24) & 0xffffff, r[8 + f] & 0xffffff);
+            std::fprintf(stderr, " threshold at %.1f us, prunes %llu, pool %llu\n", r[12] ? (r[12] - t0) * 1e-3 : -1.0, r[6] >> 32, r[7] >> 32);
+          }
+          std::fprintf(stderr, "scan trace: first..last warp within a CTA %.1f us on average | first CTA done at %.1f us\n",
+                       intra / nb * 1e-3, (cta_first - t0) * 1e-3);
+          std::fprintf(stderr, "scan trace: tau_ext %g..%g | own tau %g..%g | prunes max %d | pool at the end max %d, mean %.0f\n",
+                       ext_lo, ext_hi, tau_lo, tau_hi, pr_max, cnt_max, (double)cnt_sum / nb);
+        }
+        std::fprintf(stderr,
+                     "scan trace: span %.1f us | CTA starts spread %.1f | prologue max %.1f | first tile max %.1f | "
+                     "first warp done at %.1f, last at %.1f | finish after last warp %.1f\n",
+                     (t_end - t0) * 1e-3, (start_last - t0) * 1e-3, pro * 1e-3, first * 1e-3, (loop_first - t0) * 1e-3,
+                     (loop_last - t0) * 1e-3, (t_end - loop_last) * 1e-3);
+      }
       stats.kernel_launches++;
       stats.passes++;
     }
@@ -1559,7 +1662,7 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
   stats.queries_per_pass = qb;
   stats.rows_scanned = n_items;
   stats.bytes_algorithmic = n_items * (long long)d * 4 + (mask && !gather ? idx->n_rows / 8 : 0) +
-                            (sp.inv_norm ? n_items * 4 : 0) + (gather ? n_items * 4 : 0);
+                            ((sp.inv_norm || sp.pace) ? n_items * 4 : 0) + (gather ? n_items * 4 : 0);
   publish_stats(idx, stats);
   return 0;
 }

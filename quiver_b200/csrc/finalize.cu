@@ -61,7 +61,8 @@ __device__ __forceinline__ void generic_select(const uint64_t* part, int total, 
   const int tid = threadIdx.x;
   const int highwater = slots - FIN_THREADS;
   auto load_key = [&](int i) -> uint64_t {
-    return i < total ? __ldcg(part + (size_t)(i % nb) * kp + (i / nb)) : KEY_NONE;
+    const uint64_t key = i < total ? __ldcg(part + (size_t)(i % nb) * kp + (i / nb)) : KEY_NONE;
+    return key_row(key) == XCHG_ROW ? KEY_NONE : key;  // the threshold marker of a cut list is not a candidate
   };
   uint64_t next_key = load_key(tid);
   __syncthreads();
@@ -145,10 +146,11 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) finalize_kernel(const Finalize
     for (int b = tid; b < nb; b += FIN_THREADS) {
       const uint64_t* lst = part + (size_t)b * kp;
       const uint64_t lastk = __ldcg(lst + kp - 1);
-      if (lastk != KEY_NONE && key_score(lastk) <= T) s_bad = 1;  // a full list may have dropped rows <= T
+      // a full list — or one cut by an exchanged threshold, whose marker sits here — may have dropped rows <= T
+      if (lastk != KEY_NONE && key_score(lastk) <= T) s_bad = 1;
       for (int j = 0; j < kp; ++j) {
         const uint64_t key = __ldcg(lst + j);
-        if (key == KEY_NONE || key_score(key) > T) break;
+        if (key_row(key) == XCHG_ROW || key_score(key) > T) break;  // end of list, or its threshold marker
         if (key > last_key) {
           const int pos = atomicAdd(&s_extra, 1);
           if (ncand + pos < slots) pool[ncand + pos] = key;
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) finalize_fast_kernel(const Fin
     if (lane == 0) s_qn2 = s;
   }
   if (tid < FF_SAMPLE) {
-    samp[tid] = keys[0];
+    samp[tid] = key_row(keys[0]) == XCHG_ROW ? KEY_NONE : keys[0];
     rank[tid] = 0;
   }
   __syncthreads();
@@ -311,7 +313,7 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) finalize_fast_kernel(const Fin
   // ---- 2. candidates = keys <= threshold ---------------------------------------------------------
 #pragma unroll
   for (int r = 0; r < FF_R; ++r) {
-    if (keys[r] != KEY_NONE && keys[r] <= taukey) {
+    if (key_row(keys[r]) != XCHG_ROW && keys[r] <= taukey) {  // neither padding nor a threshold marker
       const int pos = atomicAdd(&s_ncand, 1);
       if (pos < FF_CAP) cand[pos] = keys[r];
     }
@@ -356,8 +358,8 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) finalize_fast_kernel(const Fin
       const uint64_t key = keys[r];
       if (key != KEY_NONE && key_score(key) <= T) {
         const int i = r * FIN_THREADS + tid;
-        if (i / nb == kp - 1) s_bad = 1;  // a full list may have dropped rows with score <= T
-        if (key > last_key) {
+        if (i / nb == kp - 1) s_bad = 1;  // a full (or threshold-cut) list may have dropped rows with score <= T
+        if (key > last_key && key_row(key) != XCHG_ROW) {
           const int pos = atomicAdd(&s_extra, 1);
           if (nsel + pos < FF_CAP) sel[nsel + pos] = key;
         }

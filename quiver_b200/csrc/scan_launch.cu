@@ -8,6 +8,8 @@ namespace qg {
 #define QG_DECL(DIM)                                                                           \
   int launch_scan_fast_##DIM(int qb, int mode, const ScanParams& p, int grid, cudaStream_t st); \
   int scan_fast_attr_##DIM();                                                                   \
+  int launch_scan_dense_##DIM(int qb, int mode, const ScanParams& p, int grid, cudaStream_t st); \
+  int scan_dense_geom_##DIM(int qb, int kp, int* tile_rows, int* warps, size_t* smem);           \
   int scan_fast_tile_rows_##DIM();                                                              \
   int scan_fast_max_qb_##DIM();                                                                 \
   int scan_fast_ring_##DIM();
@@ -58,6 +60,26 @@ int launch_scan_fast(int dp, int qb, int mode, const ScanParams& p, int grid, cu
   switch (dp) {
 #define QG_CASE(DIM) \
   case DIM: return launch_scan_fast_##DIM(qb, mode, p, grid, st);
+    QG_FAST_DIMS(QG_CASE)
+#undef QG_CASE
+    default: return -1;
+  }
+}
+
+int launch_scan_dense(int dp, int qb, int mode, const ScanParams& p, int grid, cudaStream_t st) {
+  switch (dp) {
+#define QG_CASE(DIM) \
+  case DIM: return launch_scan_dense_##DIM(qb, mode, p, grid, st);
+    QG_FAST_DIMS(QG_CASE)
+#undef QG_CASE
+    default: return -1;
+  }
+}
+
+int scan_dense_geometry(int dp, int qb, int kp, int* tile_rows, int* warps, size_t* smem) {
+  switch (dp) {
+#define QG_CASE(DIM) \
+  case DIM: return scan_dense_geom_##DIM(qb, kp, tile_rows, warps, smem);
     QG_FAST_DIMS(QG_CASE)
 #undef QG_CASE
     default: return -1;
