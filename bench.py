@@ -581,7 +581,7 @@ def run_native(args):
     achieved = bytes_per_launch / (scan_launch_ms * 1e-3) / 1e9 if scan_launch_ms > 0 else 0.0
     tc = stats["path"] == 3
     bf16_stream = tc and stats.get("reserved", 0) == 1
-    kernel_name = ("tc_ts_kernel (main scan, tcgen05.mma kind::%s, queries resident in TMEM)" % ("f16 on a bf16 copy of the corpus" if bf16_stream else "tf32")) if tc else "scan_fast_kernel"
+    kernel_name = ("tc_ts_kernel (main scan, tcgen05.mma kind::%s, queries resident in TMEM)" % ("f16 on a bf16 copy of the corpus" if bf16_stream else "tf32")) if tc else "scan_dense_kernel"
     total_ms = ms_profiled
     hbm = {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
            "frac_of_nominal_8TBs": achieved / 8000.0}
@@ -620,14 +620,14 @@ def run_native(args):
         roofline["floors_us"] = {"hbm": t_hbm * 1e6, "tensor": t_tensor * 1e6}
     if world == 1 and not args.no_subrecords:
         # one ncu launch of the same kernel on the same workload, outside the timed regions
-        tr = measure_traffic(args, "tc_ts_kernel" if tc else "scan_fast_kernel", 3 if tc else 2)
+        tr = measure_traffic(args, "tc_ts_kernel" if tc else "scan_dense_kernel", 3 if tc else 2)
         roofline["traffic"] = tr
         roofline["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu run of "
                                       "tools/prof_once.py inside this bench run" if tr else None)
     if roofline["traffic"] is None:
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            roofline["traffic"] = tr.get("tc_ts_kernel_bytes_per_launch" if tc else "scan_fast_kernel_bytes_per_launch")
+            roofline["traffic"] = tr.get("tc_ts_kernel_bytes_per_launch" if tc else "scan_dense_kernel_bytes_per_launch")
             roofline["traffic_source"] = "profiles/traffic.json (an earlier ncu --set full capture; ncu could not run here)"
         except Exception:
             pass
@@ -652,7 +652,7 @@ def run_native(args):
         pr1 = idx.read_profile()
         st1 = idx.stats()
         l_ms = pr1["scan_ms"] / max(1, pr1["scan_launches"])
-        small = {"queries_per_step": 1, "qps": nsm / (s0.elapsed_time(s1) * 1e-3), "kernel": "scan_fast_kernel",
+        small = {"queries_per_step": 1, "qps": nsm / (s0.elapsed_time(s1) * 1e-3), "kernel": "scan_dense_kernel",
                  "launch_ms": l_ms, "bytes_per_launch": st1["bytes_algorithmic"],
                  "achieved_GBps": st1["bytes_algorithmic"] / (l_ms * 1e-3) / 1e9 if l_ms > 0 else None,
                  "frac_of_measured_hbm": st1["bytes_algorithmic"] / (l_ms * 1e-3) / 1e9 / peak if l_ms > 0 else None}

@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(SCAN_NW * 32, 1) scan_fast_kernel(const ScanPa
 #pragma unroll
     for (int qi = 0; qi < QB; ++qi) tau_r[qi] = *reinterpret_cast<volatile float*>(&tau[qi]);
 
-    mbar_wait(&mybar[stage], parity);
+    mbar_poll(&mybar[stage], parity);  // polling: a thread parked by try_wait comes back late (see the dense kernel)
     const float4* tile = reinterpret_cast<const float4*>(ring + (size_t)stage * TILE_BYTES);
 
 #pragma unroll
@@ -1086,7 +1086,7 @@ __global__ void __launch_bounds__(SCAN_NW * 32, 1) scan_generic_kernel(const Sca
 #pragma unroll
     for (int qi = 0; qi < QB; ++qi) tau_r[qi] = *reinterpret_cast<volatile float*>(&tau[qi]);
 
-    mbar_wait(&mybar[stage], parity);
+    mbar_poll(&mybar[stage], parity);  // polling: a thread parked by try_wait comes back late (see the dense kernel)
     const float4* tb = reinterpret_cast<const float4*>(ring + (size_t)stage * tile_bytes);
     const float4* q4 = reinterpret_cast<const float4*>(qs);
 
