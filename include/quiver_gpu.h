@@ -67,8 +67,12 @@ typedef struct qg_config {
   int arith;             /* qg_arith                                                    */
   int64_t reserve_rows;  /* capacity hint; 0 = grow on demand                           */
   int select_margin;     /* extra fp32-scan candidates re-ranked exactly; 0 = default   */
-  int flags;             /* reserved, must be 0                                         */
+  int flags;             /* QG_FLAG_* bits, 0 = defaults                                */
 } qg_config;
+/* Do not keep the bf16 copy of the corpus (+50 % device memory for dim <= 512): batches of 8 and more then
+ * stream the fp32 rows through the tensor cores as tf32, smaller ones take the flat fp32 scan. Results are
+ * the same either way — every returned distance is recomputed from the fp32 rows. */
+#define QG_FLAG_NO_BF16_COPY 1
 
 typedef struct qg_index qg_index;
 typedef struct qg_filter qg_filter;

@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libquivergpu.so")
 
 COSINE, L2, DOT, SQL2, L1 = 0, 1, 2, 3, 4
 ARITH_VECTORTYPES, ARITH_HNSW_F32 = 0, 1
+FLAG_NO_BF16_COPY = 1  # qg_config.flags: no bf16 copy of the corpus (quiver_gpu.h)
 METRIC_NAMES = {"cosine": COSINE, "euclidean": L2, "l2": L2, "dot_product": DOT, "dot": DOT,
                 "squared_euclidean": SQL2, "manhattan": L1}
 
@@ -222,9 +223,9 @@ class Index:
     """Thin handle wrapper: rows are int64 indices; see quiver_b200.hybrid for the string-ID mirror."""
 
     def __init__(self, dim: int, metric: int, device: int = 0, arith: int = ARITH_VECTORTYPES,
-                 reserve_rows: int = 0, select_margin: int = 0):
+                 reserve_rows: int = 0, select_margin: int = 0, flags: int = 0):
         self._lib = load()
-        cfg = qg_config(device, arith, reserve_rows, select_margin, 0)
+        cfg = qg_config(device, arith, reserve_rows, select_margin, flags)
         h = C.c_void_p()
         _check(self._lib.qg_index_create(C.byref(h), dim, metric, C.byref(cfg)))
         self.handle = h

@@ -189,6 +189,7 @@ using namespace qg;
 
 struct qg_filter {
   qg_index* owner = nullptr;
+  int device = 0;  // the owner's device, for qg_filter_destroy (which may run after the index is gone)
   std::vector<qg_pred> preds;
   std::vector<qg_clause> clauses;
   std::vector<int32_t> iset;
@@ -450,7 +451,7 @@ int qg_index_create(qg_index** out, int dim, int metric, const qg_config* cfg) {
   if (dim <= 0) return fail(QG_ERR_DIM, "dimension must be positive");
   if (metric < 0 || metric > 4) return fail(QG_ERR_INVALID, "unknown metric");
   const int device = cfg ? cfg->device : 0;
-  if (cfg && cfg->flags != 0) return fail(QG_ERR_INVALID, "qg_config.flags must be 0");
+  if (cfg && (cfg->flags & ~QG_FLAG_NO_BF16_COPY) != 0) return fail(QG_ERR_INVALID, "unknown bit in qg_config.flags");
   if (int rc = ensure_device(device)) return rc;
   std::unique_ptr<qg_index> idx(new qg_index());
   idx->device = device;
@@ -467,12 +468,13 @@ int qg_index_create(qg_index** out, int dim, int metric, const qg_config* cfg) {
   // bf16 copy for the tensor-core stream (+50 % memory): every distance that is RETURNED is still
   // recomputed from the fp32 rows, the copy only feeds candidate selection. QG_TC_BF16=0 disables it.
   idx->dp16 = tc_dp16(dim, scan_mode_of(metric) == MODE_L2);
-  idx->use_bf16 = dim <= 512 && metric != QG_L1;
+  idx->use_bf16 = dim <= 512 && metric != QG_L1 && !(cfg && (cfg->flags & QG_FLAG_NO_BF16_COPY));
   if (const char* e = std::getenv("QG_TC_BF16")) idx->use_bf16 = idx->use_bf16 && std::atoi(e) != 0;
-  // With the bf16 copy a tensor-core pass streams half the bytes of the flat fp32 scan, so it wins from two
-  // queries on (1M x 128: 77 us for 2..8 queries against 134 / 220 us for 2 / 4 queries on the flat scan).
-  // A single query stays on the flat scan: it is also the re-run path of an uncertified tensor-core query.
-  if (idx->use_bf16 && std::getenv("QG_TC_MIN_Q") == nullptr) idx->tc_min_q = 2;
+  // With the bf16 copy a tensor-core pass streams half the bytes of the flat fp32 scan, so it wins from the
+  // first query on (1M x 128, whole call: 72 us for one query and 75 us for 2..8, against 100 us for one query
+  // and 134 / 220 us for 2 / 4 queries on the flat scan). The flat scan remains the regime of indexes without
+  // the copy, of filtered scans over row lists, and the re-run of a query the copy could not certify.
+  if (idx->use_bf16 && std::getenv("QG_TC_MIN_Q") == nullptr) idx->tc_min_q = 1;
   {
     std::lock_guard<std::mutex> lk(g_dev_mu);
     idx->sm_count = g_dev[device].sm_count;
@@ -938,6 +940,7 @@ int qg_filter_compile(qg_index* idx, const qg_pred* preds, int n_preds, const qg
   }
   std::unique_ptr<qg_filter> f(new qg_filter());
   f->owner = idx;
+  f->device = idx->device;
   f->preds.assign(preds, preds + n_preds);
   f->clauses.assign(clauses, clauses + n_clauses);
   f->iset.assign(iset, iset + n_iset);
@@ -957,7 +960,8 @@ int qg_filter_compile(qg_index* idx, const qg_pred* preds, int n_preds, const qg
 
 int qg_filter_destroy(qg_filter* f) {
   if (!f) return 0;
-  if (f->owner) cudaSetDevice(f->owner->device);
+  // the owner may already be destroyed (bindings release handles in any order): never look at it here
+  if (cudaSetDevice(f->device) != cudaSuccess) (void)cudaGetLastError();
   f->d_preds.release(); f->d_clauses.release(); f->d_iset.release(); f->d_fset.release();
   f->raw_mask.release(); f->comb_mask.release(); f->gather_list.release();
   f->v_vec.release(); f->v_vec16.release(); f->v_inv.release(); f->v_n2.release(); f->v_ub.release();
@@ -1192,6 +1196,7 @@ struct SearchArgs {
   int* d_count;
   uint64_t* d_keys;  // shard mode
   long long row_base;
+  bool no_tc = false;  // the flat re-run of a query the tensor-core regime could not certify
 };
 
 static void publish_stats(qg_index* idx, const qg_scan_stats& st) {
@@ -1276,7 +1281,7 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
 
   // ---- tensor-core regime: large query batches over a dense (possibly masked) corpus ----------------
   TcPlan plan{};
-  const bool tc_possible = q >= idx->tc_min_q && mode != MODE_L1 && kp <= 128 && idx->n_rows >= idx->tc_min_rows &&
+  const bool tc_possible = !a.no_tc && q >= idx->tc_min_q && mode != MODE_L1 && kp <= 128 && idx->n_rows >= idx->tc_min_rows &&
                            n_pass >= idx->tc_min_rows && tc_available() == 0 &&
                            tc_plan(dp, d + tc_extra_cols(d, mode == MODE_L2), q, idx->use_bf16, &plan) == 0;
   // the arrays the tensor-core scan and its finalize read: the index's own, or the filter's dense view
@@ -1949,7 +1954,7 @@ int qg_search_batch(qg_index* idx, const float* queries, int q, int dim, int k, 
                       negatives ? (const float*)w->d_neg.p + (size_t)i * dim : nullptr,
                       (float*)w->d_dist.p + (size_t)i * k,
                       negatives ? (float*)w->d_negdist.p + (size_t)i * k : nullptr,
-                      (long long*)w->d_row.p + (size_t)i * k, (int*)w->d_count.p + i, nullptr, 0};
+                      (long long*)w->d_row.p + (size_t)i * k, (int*)w->d_count.p + i, nullptr, 0, /*no_tc=*/true};
         if ((rc = search_enqueue(idx, w, a1, st))) break;
         e = cudaMemcpyAsync(h_dist + (size_t)i * k, (float*)w->d_dist.p + (size_t)i * k, (size_t)k * 4,
                             cudaMemcpyDeviceToHost, st);
@@ -2123,6 +2128,7 @@ struct qg_queries {
   qg_index* owner = nullptr;
   int b = 0, dim = 0;
   DevBuf d_q;
+  int device = 0;  // the owner's device, for qg_queries_destroy
 };
 
 int qg_queries_upload(qg_index* idx, const float* queries, int b, int dim, qg_queries** out) {
@@ -2135,6 +2141,7 @@ int qg_queries_upload(qg_index* idx, const float* queries, int b, int dim, qg_qu
                                 std::to_string(dim));
   std::unique_ptr<qg_queries> qs(new qg_queries());
   qs->owner = idx;
+  qs->device = idx->device;
   qs->b = b;
   qs->dim = dim;
   if (int rc = qs->d_q.ensure((size_t)b * dim * 4)) return rc;
@@ -2145,7 +2152,7 @@ int qg_queries_upload(qg_index* idx, const float* queries, int b, int dim, qg_qu
 
 int qg_queries_destroy(qg_queries* qs) {
   if (!qs) return 0;
-  if (qs->owner) cudaSetDevice(qs->owner->device);
+  if (cudaSetDevice(qs->device) != cudaSuccess) (void)cudaGetLastError();  // the index may be gone already
   qs->d_q.release();
   delete qs;
   return 0;
@@ -2189,6 +2196,7 @@ int qg_batch_distance(qg_index* idx, const float* query, int dim, const uint32_t
 
 struct qg_hnsw {
   qg_index* owner = nullptr;
+  int device = 0;  // the owner's device, for qg_hnsw_destroy (which may run after the index is gone)
   HnswDevGraph g{};
   DevBuf level, adj0, upper_off, upper_adj, work;
   std::mutex mu;  // one search at a time uses the workspace
@@ -2205,6 +2213,7 @@ int qg_hnsw_upload(qg_index* idx, int64_t n_nodes, int m, int max_m0, int entry_
   if (n_nodes > idx->n_rows) return fail(QG_ERR_RANGE, "the graph has more nodes than the index has rows");
   std::unique_ptr<qg_hnsw> g(new qg_hnsw());
   g->owner = idx;
+  g->device = idx->device;
   g->g.n_nodes = n_nodes;
   g->g.m = m;
   g->g.max_m0 = max_m0;
@@ -2247,6 +2256,7 @@ int qg_hnsw_build(qg_index* idx, int m, int max_m0, int ef_construction, int max
   if (max_batch <= 0) max_batch = 8192;
   std::unique_ptr<qg_hnsw> g(new qg_hnsw());
   g->owner = idx;
+  g->device = idx->device;
   g->g.n_nodes = n;
   g->g.m = m;
   g->g.max_m0 = max_m0;
@@ -2377,7 +2387,7 @@ int qg_hnsw_export(const qg_hnsw* g, int32_t* level, uint32_t* adj0, int64_t* up
 
 int qg_hnsw_destroy(qg_hnsw* g) {
   if (!g) return 0;
-  if (g->owner) cudaSetDevice(g->owner->device);
+  if (cudaSetDevice(g->device) != cudaSuccess) (void)cudaGetLastError();
   g->level.release(); g->adj0.release(); g->upper_off.release(); g->upper_adj.release(); g->work.release();
   delete g;
   return 0;

@@ -438,6 +438,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 //   TMEM columns: [0, nblk*kb*32) query blocks | then (blk*2 + acc) * 64 accumulators
 //   warps: 0 TMA (corpus tiles + the tile's per-row terms), 1 MMA + TMEM alloc, 2..9 epilogue
 // ================================================================================================
+// How the roles of the TS kernel wait on their barriers. mbarrier.try_wait may park a thread for a while before it
+// looks again; test_wait in a loop notices the phase flip at once but spends issue slots. QG_TC_POLL: bit 0 = the
+// control warps (TMA producer, MMA issuer) poll, bit 1 = the epilogue warps poll.
+#ifndef QG_TC_POLL
+#define QG_TC_POLL 0
+#endif
+__device__ __forceinline__ void ts_wait_ctrl(uint64_t* bar, uint32_t parity) {
+  if (QG_TC_POLL & 1) mbar_poll(bar, parity);
+  else mbar_wait(bar, parity);
+}
+__device__ __forceinline__ void ts_wait_epi(uint64_t* bar, uint32_t parity) {
+  if (QG_TC_POLL & 2) mbar_poll(bar, parity);
+  else mbar_wait(bar, parity);
+}
 constexpr int TS_KSTEP_BYTES = 128;               // one swizzle row: 32 floats
 constexpr int TS_EPI_WARPS = 16;                 // epilogue warps: four per TMEM lane quarter
 constexpr int TS_THREADS = 128 + TS_EPI_WARPS * 32;  // warp group 0: TMA producer, MMA issuer, two idle warps
@@ -646,7 +660,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
         const int xb = (int)(it % TS_XS);
         const uint32_t xphase = (uint32_t)((it / TS_XS) & 1);
         clk.start();
-        mbar_wait(&xs_empty[xb], xphase ^ 1u);
+        ts_wait_ctrl(&xs_empty[xb], xphase ^ 1u);
         clk.lap(1);
         if (elect_one()) {
           xs_work[xb] = live ? (int)w : -1;
@@ -662,7 +676,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
       }
       if (to_ring) {
         clk.start();
-        mbar_wait(&empty[stage], phase ^ 1u);
+        ts_wait_ctrl(&empty[stage], phase ^ 1u);
         clk.lap(2);
         if (elect_one()) {
           ring_tag[stage] = live ? (int)w : -1;
@@ -710,7 +724,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
     // ===== MMA issuer (converged warp, one elected lane issues) =====
     DbgClock clk{(p.dbg != nullptr && blockIdx.x == 0 && lane == 0) ? p.dbg : nullptr, 0};
     const long long t_mma_begin = TS_INSTRUMENT ? clock64() : 0;
-    mbar_wait(a_ready, 0);
+    ts_wait_ctrl(a_ready, 0);
     tc_fence_after();
     if (lane == 0) dbg_stamp(p.dbg, 3);
     const uint64_t desc0 = make_sdesc(smem_u32(ring));
@@ -722,14 +736,14 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
     uint32_t acc_phase = 0;
     for (;; ++it) {
       clk.start();
-      mbar_wait(&full[stage], phase);
+      ts_wait_ctrl(&full[stage], phase);
       clk.lap(5);
       const int wtag = lds_s32(&ring_tag[stage]);
       if (wtag < 0) break;  // end of work
       const uint64_t bdesc = desc0 + (uint64_t)((uint32_t)stage * (uint32_t)(tile_bytes >> 4));
 #pragma unroll
       for (int blk = 0; blk < NBLK; ++blk) {  // one accumulator unit per resident query block
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        ts_wait_ctrl(&tmem_empty[acc], acc_phase ^ 1u);
         clk.lap(4);
         tc_fence_after();
         if (elect_one()) {
@@ -782,7 +796,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
     if (RAW) {
       // end of work for the two epilogue halves: the next two accumulator buffers carry the tag
       for (int e = 0; e < 2; ++e) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        ts_wait_ctrl(&tmem_empty[acc], acc_phase ^ 1u);
         if (elect_one()) {
           acc_work[acc] = -1;
           __threadfence_block();
@@ -877,16 +891,16 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
       clk.start();
       long long w;
       if (RAW) {
-        mbar_wait(&tmem_full[acc], acc_phase);
+        ts_wait_epi(&tmem_full[acc], acc_phase);
         w = lds_s32(&acc_work[acc]);
         if (w < 0) break;  // end of work
         clk.lap(2);
       } else {
-        mbar_wait(&xs_full[xb], xphase);
+        ts_wait_epi(&xs_full[xb], xphase);
         w = lds_s32(&xs_work[xb]);
         if (w < 0) break;  // end of work
         clk.lap(1);
-        mbar_wait(&tmem_full[acc], acc_phase);
+        ts_wait_epi(&tmem_full[acc], acc_phase);
         clk.lap(2);
       }
       const long long tile = tile_of(w);

@@ -55,9 +55,18 @@ def test_filtered_batches_over_the_view(capi, oracle, metric, d):
     # exhaustive GPU oracle agrees for every query of the batch
     xd, xr, xc = idx.search_exhaustive(queries, k, filter=flt)
     assert np.array_equal(r3, xr) and np.array_equal(d3.view(np.uint32), xd.view(np.uint32))
-    # a single query still takes the flat gather scan
-    idx.search(queries[:1], k, filter=flt)
+    # a single query rides the cached view; behind a filter that has none yet it takes the flat gather scan
+    # (building a view for one query costs more than gathering the passing rows once)
+    d1, r1, c1, _ = idx.search(queries[:1], k, filter=flt)
+    assert idx.stats()["path"] == (3 if d <= 512 else 2)  # the bf16 copy (d <= 512) serves single queries too
+    assert np.array_equal(r1[0], r3[0]) and np.array_equal(d1[0].view(np.uint32), d3[0].view(np.uint32))
+    flt2 = _eq(capi, idx, 4)
+    d4, r4, c4, _ = idx.search(queries[:1], k, filter=flt2)
     assert idx.stats()["path"] == 2
+    live4 = (cat == 4).astype(np.uint8)
+    live4[dead] = 0
+    od, orow = oracle.exact_search(corpus, queries[0], k, metric, 0, live4)
+    assert np.array_equal(r4[0, :len(orow)], orow) and np.array_equal(d4[0, :len(od)].view(np.uint32), od.view(np.uint32))
     flt.close()
     idx.close()
 

@@ -60,9 +60,21 @@ def test_fast_regimes_equal_the_exhaustive_gpu_path_at_1m_rows(capi, oracle, kin
     assert (cnt == k).all() and (xc == k).all()
     assert np.array_equal(row[ids], xr), st
     assert np.array_equal(dist[ids].view(np.uint32), xd.view(np.uint32))
-    # flat fp32 scan: single queries
+    # single queries ride the bf16 copy too
     for j, i in enumerate(ids[:6]):
         d1, r1, c1, _ = idx.search(queries[i:i + 1], k)
-        assert idx.stats()["path"] == 1
+        assert idx.stats()["path"] == 3
         assert np.array_equal(r1[0], xr[j]) and np.array_equal(d1[0].view(np.uint32), xd[j].view(np.uint32))
     idx.close()
+    # flat fp32 scan (dense kernel): single queries and blocks of two on an index without the bf16 copy
+    flat = capi.Index(dim, metric, reserve_rows=n, flags=capi.FLAG_NO_BF16_COPY)
+    flat.upload_synthetic(kind, 42, 0, n)
+    for j, i in enumerate(ids[:6]):
+        d1, r1, c1, _ = flat.search(queries[i:i + 1], k)
+        assert flat.stats()["path"] == 1
+        assert np.array_equal(r1[0], xr[j]) and np.array_equal(d1[0].view(np.uint32), xd[j].view(np.uint32))
+    pair = [ids[0], ids[1]]
+    d2, r2, c2, _ = flat.search(queries[pair], k)
+    assert flat.stats()["path"] == 1 and flat.stats()["queries_per_pass"] == 2
+    assert np.array_equal(r2, xr[:2]) and np.array_equal(d2.view(np.uint32), xd[:2].view(np.uint32))
+    flat.close()

@@ -112,11 +112,14 @@ def test_tc_device_api_matches_flat_path(capi):
     torch.cuda.synchronize()
     assert idx.stats()["path"] == 3
     r1, d1 = [], []
-    for i in range(4):  # one query at a time: flat scan
-        di, ri, _, _ = idx.search(q[i:i + 1].cpu().numpy(), k)
-        assert idx.stats()["path"] == 1
+    flat = capi.Index(d, 1, flags=capi.FLAG_NO_BF16_COPY)  # without the bf16 copy single queries take the flat scan
+    flat.upload_synthetic(0, 7, 0, n)
+    for i in range(4):  # one query at a time
+        di, ri, _, _ = flat.search(q[i:i + 1].cpu().numpy(), k)
+        assert flat.stats()["path"] == 1
         r1.append(ri[0])
         d1.append(di[0])
+    flat.close()
     r1, d1 = np.stack(r1), np.stack(d1)
     ok = cnt[:4].cpu().numpy() >= 0
     assert ok.all()
