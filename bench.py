@@ -337,10 +337,49 @@ def row_sharded_record(capi, oracle, torch, dist, comm, world, rank, local_rank,
                      "passes": stats["passes"],
                      "aggregate_GBps": world * bytes_rank / (ms * 1e-3) / 1e9,
                      "frac_of_aggregate_measured_hbm": bytes_rank / (ms * 1e-3) / 1e9 / hbm,
-                     "uncertified": unc,
+                     "uncertified": unc, "_rows": gr[0].copy(), "_dist": gd[0].copy(),
                      "parity": f"{n_par} queries: merged result == merge of the per-shard exhaustive GPU oracle lists "
                                f"(every row's exact distance + full sort on each rank), bit-identical"})
     shard.close()
+    # The same single query over shards WITHOUT the bf16 copy (qg_config.flags = QG_FLAG_NO_BF16_COPY): the flat
+    # fp32 stream of north_star's regime (a) — every GPU reads its 4.8 GB of fp32 rows once — as HBM evidence.
+    # (With the copy, the default above, a single query streams half the bytes and is faster, see ms_per_step.)
+    flat = capi.Index(d, mid, device=local_rank, reserve_rows=per, flags=capi.FLAG_NO_BF16_COPY)
+    flat.upload_synthetic(3, 42, row0, per)
+    qh = oracle.synth(3, 9999, 0, 1, d, threads=1)
+    dq = torch.from_numpy(qh).to(dev)
+    dd = torch.empty((1, k), dtype=torch.float32, device=dev)
+    dr = torch.empty((1, k), dtype=torch.int64, device=dev)
+    dc = torch.empty((1,), dtype=torch.int32, device=dev)
+    for _ in range(3):
+        comm.search_rows_device(flat, dq.data_ptr(), 1, k, row0, dd.data_ptr(), dr.data_ptr(), dc.data_ptr(), stream=st)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    e0.record()
+    for _ in range(20):
+        comm.search_rows_device(flat, dq.data_ptr(), 1, k, row0, dd.data_ptr(), dr.data_ptr(), dc.data_ptr(), stream=st)
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / 20], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    fms = float(t.item())
+    fst = flat.stats()
+    fbytes = fst["bytes_algorithmic"] * fst["passes"]
+    same = bool(np.array_equal(dr.cpu().numpy()[0], recs[0]["_rows"]) and
+                np.array_equal(dd.cpu().numpy()[0].view(np.uint32), recs[0]["_dist"].view(np.uint32)))
+    assert same, "flat fp32 stream and bf16 stream disagree"
+    recs[0]["fp32_flat_stream"] = {"ms_per_step": fms, "path": {1: "flat scan", 3: "tensor-core"}.get(fst["path"], str(fst["path"])),
+                                   "bytes_per_gpu": fbytes, "aggregate_GBps": world * fbytes / (fms * 1e-3) / 1e9,
+                                   "frac_of_aggregate_measured_hbm": fbytes / (fms * 1e-3) / 1e9 / hbm,
+                                   "uncertified": int((dc.cpu().numpy() < 0).sum()),
+                                   "parity": "bit-identical to the default index's result for this query"}
+    for r in recs:
+        r.pop("_rows", None)
+        r.pop("_dist", None)
+    flat.close()
     return {"layout": "rows (north_star): per-shard top-k + NCCL all-gather of the keys + merge, all inside libquivergpu",
             "rows_per_gpu": per, "rows_total": per * world, "dim": d, "k": k, "metric": "l2",
             "data": "synthetic kind 3 (approx normal, L2-normalised: Deep-shaped)", "scaling": "weak",

@@ -31,7 +31,7 @@ def time_search(idx, dq, q, k, iters=20, warm=3):
 
 def main():
     out = []
-    configs = [(1_000_000, 128, 1, 1), (1_000_000, 96, 1, 3), (200_000, 768, 0, 2), (4_000_000, 128, 1, 1), (1_000_000, 128, 2, 1), (1_000_000, 128, 0, 0), (1_000_000, 128, 1, 0), (1_000_000, 128, 0, 1), (1_000_000, 128, 2, 0)]
+    configs = [(1_000_000, 128, 1, 1), (1_000_000, 96, 1, 3), (200_000, 768, 0, 2), (4_000_000, 128, 1, 1), (1_000_000, 128, 2, 1), (1_000_000, 128, 0, 0), (1_000_000, 128, 1, 0), (1_000_000, 128, 0, 1), (1_000_000, 128, 2, 0), (12_500_000, 96, 1, 3), (4_000_000, 256, 1, 2), (2_000_000, 768, 0, 2), (4_000_000, 192, 1, 2)]
     qs = (1, 2, 4, 8, 16, 64, 128, 256, 1024, 10000)
     if len(sys.argv) > 1:
         qs = tuple(int(x) for x in sys.argv[1].split(","))
