@@ -74,8 +74,23 @@ type Index struct {
 	metric Metric
 }
 
+// Options of New beyond the defaults. NoBF16Copy drops the bf16 copy of the corpus the library keeps for
+// dim <= 512 (a third of the index's device memory): batches of 8 and more then run as tf32, smaller ones on
+// the flat fp32 scan; results are identical either way.
+type Options struct {
+	NoBF16Copy  bool
+	ReserveRows int64
+}
+
 func New(dim int, metric Metric, device int) (*Index, error) {
-	cfg := C.qg_config{device: C.int(device)}
+	return NewWithOptions(dim, metric, device, Options{})
+}
+
+func NewWithOptions(dim int, metric Metric, device int, opt Options) (*Index, error) {
+	cfg := C.qg_config{device: C.int(device), reserve_rows: C.int64_t(opt.ReserveRows)}
+	if opt.NoBF16Copy {
+		cfg.flags = C.QG_FLAG_NO_BF16_COPY
+	}
 	var h *C.qg_index
 	if err := call(func() C.int { return C.qg_index_create(&h, C.int(dim), C.int(metric), &cfg) }); err != nil {
 		return nil, err

@@ -191,21 +191,40 @@ struct Walk {
 }  // namespace qh_hnsw
 
 // qh_index internals needed here (defined in host.cpp)
-extern "C" int qh_internal_index_handle(qh_index* idx, qg_index** h, int* dim);
+extern "C" int qh_internal_index_lock(qh_index* idx, qg_index** h, int* dim, void** guard);
+extern "C" void qh_internal_index_unlock(void* guard);
+namespace {
+// shared lock of the index for the duration of a walk (host.cpp: qh_internal_index_lock)
+struct IndexReadGuard {
+  void* g = nullptr;
+  ~IndexReadGuard() { if (g) qh_internal_index_unlock(g); }
+};
+}  // namespace
 extern "C" const char* qh_internal_row_id(qh_index* idx, int64_t row);
 extern "C" int64_t qh_internal_id_row(qh_index* idx, const char* id);
 extern "C" int qh_internal_fail(int code, const char* msg);
 extern "C" qh_results* qh_internal_results_new(int nq);
 extern "C" void qh_internal_results_push(qh_results* r, int q, const char* id, float dist);
 
+// the lock-step walk; the caller holds the index's shared lock (IndexReadGuard) and passes the device handle
+static int hnsw_search_batch_held(qh_index* idx, qg_index* h, int idim, const qh_hnsw_graph* g, const float* queries,
+                                  int nq, int dim, int k, qh_results** out, int64_t* out_evals, int64_t* out_steps);
+
 extern "C" int qh_hnsw_search_batch(qh_index* idx, const qh_hnsw_graph* g, const float* queries, int nq, int dim,
                                     int k, qh_results** out, int64_t* out_evals, int64_t* out_steps) {
-  using namespace qh_hnsw;
   if (!idx || !g || !out) return qh_internal_fail(QG_ERR_INVALID, "null argument");
   *out = nullptr;
   qg_index* h = nullptr;
   int idim = 0;
-  if (int rc = qh_internal_index_handle(idx, &h, &idim)) return rc;  // also uploads write-combined Inserts
+  IndexReadGuard guard;
+  if (int rc = qh_internal_index_lock(idx, &h, &idim, &guard.g)) return rc;  // also uploads write-combined Inserts
+  return hnsw_search_batch_held(idx, h, idim, g, queries, nq, dim, k, out, out_evals, out_steps);
+}
+
+static int hnsw_search_batch_held(qh_index* idx, qg_index* h, int idim, const qh_hnsw_graph* g, const float* queries,
+                                  int nq, int dim, int k, qh_results** out, int64_t* out_evals, int64_t* out_steps) {
+  using namespace qh_hnsw;
+  *out = nullptr;
   if (nq <= 0 || !queries) return qh_internal_fail(QG_ERR_INVALID, "no queries provided");
   if (dim != idim) {
     const std::string msg = "query dimension mismatch: expected " + std::to_string(idim) + ", got " + std::to_string(dim);
@@ -415,7 +434,8 @@ extern "C" int qh_hnsw_upload(qh_index* idx, const qh_hnsw_graph* g, qh_hnsw_dev
   *out = nullptr;
   qg_index* h = nullptr;
   int idim = 0;
-  if (int rc = qh_internal_index_handle(idx, &h, &idim)) return rc;
+  IndexReadGuard guard;
+  if (int rc = qh_internal_index_lock(idx, &h, &idim, &guard.g)) return rc;
   std::unique_ptr<qh_hnsw_dev> d(new qh_hnsw_dev());
   d->owner = idx;
   d->host = *g;
@@ -453,7 +473,8 @@ extern "C" int qh_hnsw_search_device(qh_index* idx, qh_hnsw_dev* d, const float*
   if (d->owner != idx) return qh_internal_fail(QG_ERR_INVALID, "graph does not belong to this index");
   qg_index* h = nullptr;
   int idim = 0;
-  if (int rc = qh_internal_index_handle(idx, &h, &idim)) return rc;
+  IndexReadGuard guard;
+  if (int rc = qh_internal_index_lock(idx, &h, &idim, &guard.g)) return rc;
   if (nq <= 0 || !queries) return qh_internal_fail(QG_ERR_INVALID, "no queries provided");
   if (dim != idim) {
     const std::string msg = "query dimension mismatch: expected " + std::to_string(idim) + ", got " + std::to_string(dim);
@@ -484,7 +505,7 @@ extern "C" int qh_hnsw_search_device(qh_index* idx, qh_hnsw_dev* d, const float*
       std::memcpy(rq.data() + u * dim, queries + (size_t)redo[u] * dim, (size_t)dim * 4);
     qh_results* rr = nullptr;
     std::vector<int64_t> rev(redo.size());
-    if (int rc = qh_hnsw_search_batch(idx, &d->host, rq.data(), (int)redo.size(), dim, k, &rr, rev.data(), nullptr)) return rc;
+    if (int rc = hnsw_search_batch_held(idx, h, idim, &d->host, rq.data(), (int)redo.size(), dim, k, &rr, rev.data(), nullptr)) return rc;
     for (size_t u = 0; u < redo.size(); ++u) {
       const int cnt = qh_results_count(rr, (int)u);
       for (int j = 0; j < cnt; ++j) redone[u].emplace_back(qh_results_id(rr, (int)u, j), qh_results_distance(rr, (int)u, j));
@@ -571,7 +592,8 @@ extern "C" int qh_hnsw_search_negative(qh_index* idx, qh_hnsw_dev* d, const floa
   if (neg_dim == dim) {  // a dimension mismatch makes DistanceFunc fail for every candidate: all are skipped (:404-406)
     qg_index* h = nullptr;
     int idim = 0;
-    if (int rc = qh_internal_index_handle(idx, &h, &idim)) return rc;
+    IndexReadGuard guard;
+    if (int rc = qh_internal_index_lock(idx, &h, &idim, &guard.g)) return rc;
     std::vector<uint32_t> rows((size_t)n0);
     for (int j = 0; j < n0; ++j) {
       const int64_t r = qh_internal_id_row(idx, qh_results_id(initial, 0, j));

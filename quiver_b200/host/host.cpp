@@ -69,13 +69,25 @@ struct qh_index {
 
 namespace {
 
-// Upload the write-combined Inserts (caller holds idx->mu exclusively). On failure the rows stay pending.
+// Upload the write-combined Inserts (caller holds idx->mu exclusively). If the upload fails the buffered rows
+// are dropped together with their ids (they are the last pending_rows entries of idx->ids), so that the id
+// table and the device rows stay in step: the failing call reports the error, a retry of those Inserts works,
+// and later searches are not poisoned by rows that can never be flushed.
 int flush_locked(qh_index* idx) {
   if (idx->pending_rows == 0) return 0;
   int64_t first = 0;
-  if (int rc = qg_index_upload(idx->h, idx->pending.data(), idx->pending_rows, &first)) return gpu_fail(rc);
-  if (first + idx->pending_rows != (int64_t)idx->ids.size())
-    return fail(QG_ERR_CUDA, "insert buffer and device rows out of step");
+  int rc = qg_index_upload(idx->h, idx->pending.data(), idx->pending_rows, &first);
+  if (rc == 0 && first + idx->pending_rows != (int64_t)idx->ids.size()) rc = -1;
+  if (rc != 0) {
+    const int err = rc > 0 ? gpu_fail(rc) : fail(QG_ERR_CUDA, "insert buffer and device rows out of step");
+    for (int64_t i = 0; i < idx->pending_rows && !idx->ids.empty(); ++i) {
+      idx->rows.erase(idx->ids.back());
+      idx->ids.pop_back();
+    }
+    idx->pending.clear();
+    idx->pending_rows = 0;
+    return err;
+  }
   idx->pending.clear();
   idx->pending_rows = 0;
   return 0;
@@ -525,11 +537,14 @@ int qh_index_batch_search(qh_index* idx, const float* queries, int nq, int dim, 
   std::shared_lock<std::shared_mutex> lk = lock_flushed(idx, &flush_rc);
   if (flush_rc) return flush_rc;
   // SearchWithRequest order (hybrid_index.go:392-402): query dim, negative dim, k
-  if (idx->dim > 0 && dim != idx->dim)
+  // vectorDim is 0 while the index holds no vector (set at the first Insert, reset when the last one is deleted,
+  // hybrid_index.go:118-119, 282-284): an empty index takes any query and answers with no results
+  const bool dim_known = !idx->rows.empty();
+  if (dim_known && dim != idx->dim)
     return fail(QG_ERR_DIM, "query dimension mismatch: expected " + std::to_string(idx->dim) + ", got " +
                                 std::to_string(dim));
   const bool neg_given = negatives != nullptr && neg_dim > 0;
-  if (neg_given && neg_dim != idx->dim)
+  if (neg_given && dim_known && neg_dim != idx->dim)
     return fail(QG_ERR_DIM, "negative example dimension mismatch: expected " + std::to_string(idx->dim) + ", got " +
                                 std::to_string(neg_dim));
   if (k <= 0) return fail(QG_ERR_K, "k must be positive");
@@ -909,20 +924,25 @@ int qh_debug_equal_fold(const char* a, const char* b) {
 
 // ---- internals shared with hnsw_walk.cpp -------------------------------------------------------------
 extern "C" {
-int qh_internal_index_handle(qh_index* idx, qg_index** h, int* dim) {
-  {
-    std::unique_lock<std::shared_mutex> wl(idx->mu);
-    if (int rc = flush_locked(idx)) return rc;
-  }
+// The HNSW walks read device rows and the id table for as long as they run: they hold the index's shared lock
+// (taken once nothing is pending, like every other reader) through this guard, so an Insert that grows the
+// arrays or a compaction cannot free them under kernels in flight. *guard is released with
+// qh_internal_index_unlock; the two lookups below must only be called while it is held.
+int qh_internal_index_lock(qh_index* idx, qg_index** h, int* dim, void** guard) {
+  *guard = nullptr;
+  int flush_rc = 0;
+  std::shared_lock<std::shared_mutex> lk = lock_flushed(idx, &flush_rc);
+  if (flush_rc) return flush_rc;
   *h = idx->h;
   *dim = idx->dim;
+  *guard = new std::shared_lock<std::shared_mutex>(std::move(lk));
   return 0;
 }
+void qh_internal_index_unlock(void* guard) { delete static_cast<std::shared_lock<std::shared_mutex>*>(guard); }
 const char* qh_internal_row_id(qh_index* idx, int64_t row) {
   return (row >= 0 && row < (int64_t)idx->ids.size()) ? idx->ids[(size_t)row].c_str() : "";
 }
 int64_t qh_internal_id_row(qh_index* idx, const char* id) {
-  std::shared_lock<std::shared_mutex> lk(idx->mu);
   auto it = idx->rows.find(id ? id : "");
   return it == idx->rows.end() ? -1 : it->second;
 }

@@ -232,3 +232,32 @@ def test_batch_distance_exact(capi, oracle, metric):
                 want = oracle.distance(metric, queries[b], corpus[rows[b, j]])
                 assert out[b, j].view(np.uint32) == want.view(np.uint32), (metric, b, j, out[b, j], want)
     idx.close()
+
+
+@pytest.mark.parametrize("dim,metric", [(32, "l2"), (64, "dot"), (96, "l2"), (128, "l2"), (128, "cosine"), (256, "dot"),
+                                        (768, "cosine"), (1536, "l2")])
+def test_dense_flat_scan_with_threshold_exchange(capi, oracle, dim, metric):
+    """scan.cuh: scan_dense_kernel on an index WITHOUT the bf16 copy, large enough for the threshold exchange
+    between the CTAs (several tiles per warp), with tombstones, exact duplicates, every query-block size and the
+    k ranges that change the exchange rule (kp = 32 / 64 / 128: r = 1 / 2 / 4; kp >= 256: no exchange)."""
+    m = METRICS[metric]
+    rng = np.random.default_rng(dim + 31 * m)
+    n = {32: 400_000, 64: 200_000, 96: 150_000, 128: 120_000, 256: 60_000, 768: 30_000, 1536: 12_000}[dim]
+    corpus = rng.standard_normal((n, dim)).astype(np.float32)
+    corpus[n // 2:n // 2 + 40] = corpus[17]  # ties: (distance, row) order must hold across CTAs
+    queries = np.concatenate([rng.standard_normal((7, dim)).astype(np.float32), corpus[17:18]])
+    idx = capi.Index(dim, m, flags=capi.FLAG_NO_BF16_COPY)
+    idx.upload(corpus)
+    dead = rng.choice(n, n // 50, replace=False)
+    idx.tombstone(dead)
+    live = np.ones(n, dtype=np.uint8)
+    live[dead] = 0
+    for k, nq in ((10, 1), (1, 1), (50, 1), (100, 1), (300, 1), (10, 2), (10, 3), (40, 7), (10, 5), (10, 4)):
+        dist, row, cnt, _ = idx.search(queries[:nq], k)
+        assert idx.stats()["path"] == 1, idx.stats()  # batches below 8 queries: flat scan (tf32 regime from 8 on)
+        for i in {0, nq // 2, nq - 1}:
+            od, orow = oracle.exact_search(corpus, queries[i], k, m, 0, live)
+            assert cnt[i] == len(od), (k, nq, i, cnt[i])
+            assert np.array_equal(row[i, :len(orow)], orow), (dim, metric, k, nq, i, row[i], orow)
+            assert np.array_equal(dist[i, :len(od)].view(np.uint32), od.view(np.uint32))
+    idx.close()
