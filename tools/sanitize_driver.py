@@ -11,6 +11,22 @@ from quiver_b200 import capi  # noqa: E402
 
 rng = np.random.default_rng(0)
 STRING = 1 << 2
+# the dense flat scan with its threshold exchange (an index without the bf16 copy; several tiles per warp)
+for metric, d, n in ((1, 128, 60000), (0, 96, 50000), (2, 768, 12000)):
+    corpus = rng.standard_normal((n, d)).astype(np.float32)
+    idx = capi.Index(d, metric, flags=capi.FLAG_NO_BF16_COPY)
+    idx.upload(corpus)
+    q = rng.standard_normal((4, d)).astype(np.float32)
+    idx.search(q[:1], 10)
+    idx.search(q[:1], 100)
+    idx.search(q[:2], 40)
+    idx.search(q[:4], 10)
+    idx.tombstone(np.arange(0, n, 5))
+    idx.search(q[:1], 10)
+    idx.close()
+if os.environ.get("SAN_ONLY") == "dense":
+    print("sanitize driver done (dense flat scan only)")
+    sys.exit(0)
 for metric, d, n in ((1, 128, 20000), (0, 96, 12000), (1, 768, 9000)):
     corpus = rng.standard_normal((n, d)).astype(np.float32)
     idx = capi.Index(d, metric)
