@@ -1297,13 +1297,13 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
   if (tc_possible && gather != nullptr) {
     // A selective filter has a compacted row list. Three ways to serve the batch, costed in row reads:
     //  - flat gather scan: only the matching rows, but at most max_qb queries per pass and through row-sized
-    //    gathers (counted at 1.5x: 2.6-4.0 TB/s measured on 10M x 768 against 7 TB/s for a dense stream);
+    //    gathers (counted at 1.2x: 5.9 TB/s measured on 10M x 768 against 6.8 TB/s for a dense stream);
     //  - masked tensor-core scan: every row of the index once per plan.n_cols queries;
     //  - dense VIEW of the matching rows (build_filter_view: read + write once, cached in the filter) and the
     //    tensor-core scan over it.
     const int flat_qb = scan_fast_supported(dp) ? scan_fast_max_qb(dp) : 8;
     const double tc_passes = (double)((q + plan.n_cols - 1) / plan.n_cols);
-    const double flat_cost = 1.5 * (double)((q + flat_qb - 1) / flat_qb) * (double)n_pass;
+    const double flat_cost = 1.2 * (double)((q + flat_qb - 1) / flat_qb) * (double)n_pass;
     const double tc_cost = tc_passes * (double)idx->n_rows;
     const bool view_cached = a.filter->view_n >= 0 && a.filter->view_rows == idx->n_rows &&
                              a.filter->view_live_epoch == idx->live_epoch && a.filter->view_facet_epoch == idx->facet_epoch;
@@ -1474,9 +1474,11 @@ static int search_enqueue(qg_index* idx, Workspace* w, const SearchArgs& a, cuda
   }
 
   const bool fast = scan_fast_supported(dp) && mode != MODE_L1;
-  // consecutive rows (no row list) take the dense kernel; QG_SCAN_DENSE=0 keeps the round-1 fast kernel
+  // scans over the fast dimensions take the dense kernel; QG_SCAN_DENSE=0 keeps the round-1 fast kernel
   static const bool dense_on = [] { const char* e = std::getenv("QG_SCAN_DENSE"); return e == nullptr || std::atoi(e) != 0; }();
-  const bool dense = fast && gather == nullptr && dense_on;
+  // row lists (gather) take it too unless QG_SCAN_DENSE_GATHER=0 (then the round-1 fast kernel)
+  static const bool dense_gather_on = [] { const char* e = std::getenv("QG_SCAN_DENSE_GATHER"); return e == nullptr || std::atoi(e) != 0; }();
+  const bool dense = fast && dense_on && (gather == nullptr || dense_gather_on);
   int tile_rows, nw = SCAN_NW, stages = 4, max_qb;
   if (fast) {
     tile_rows = scan_fast_tile_rows(dp);

@@ -542,7 +542,7 @@ __device__ __forceinline__ float f2_sum(uint64_t a) {
   return lo + hi;
 }
 
-template <int D, int QB, int MODE>
+template <int D, int QB, int MODE, bool GATHER>
 __global__ void __launch_bounds__(dense_nw<D, QB>() * 32, 1) scan_dense_kernel(const ScanParams p) {
   constexpr int NW = dense_nw<D, QB>();
   using Gm = DenseGeom<D, NW>;
@@ -628,20 +628,43 @@ __global__ void __launch_bounds__(dense_nw<D, QB>() * 32, 1) scan_dense_kernel(c
   const uint32_t gw = blockIdx.x * NW + warp;
   uint32_t claimed = 0;
   auto claim = [&]() -> uint32_t { return (claimed++) * gws + gw; };
-  auto issue = [&](uint32_t t, int st) {
-    if (t < n_tiles && lane == 0) {
-      const long long left = n_items - (long long)t * RT;
-      const uint32_t bytes = (uint32_t)(left < RT ? left : RT) * Gm::ROW_BYTES;
-      mbar_arrive_expect_tx(&mybar[st], bytes);
-      bulk_g2s(ring + (size_t)st * TILE_BYTES, p.vec + (size_t)t * RT * D, bytes, &mybar[st]);
+  // GATHER (scans over a row list, p.gather): a tile is RT listed rows, fetched with one bulk copy per row; lane l
+  // holds the row number of the tile's row l. The numbers of a tile are loaded one iteration before the tile is
+  // issued, so that the issue does not wait for them.
+  auto load_ids = [&](uint32_t t) -> uint32_t {
+    const long long item = (long long)t * RT + lane;
+    return (GATHER && lane < RT && item < n_items) ? __ldg(p.gather + item) : 0u;
+  };
+  auto issue = [&](uint32_t t, int st, uint32_t ids) {
+    if (t >= n_tiles) return;
+    const long long left = n_items - (long long)t * RT;
+    const uint32_t rows = (uint32_t)(left < RT ? left : RT);
+    if (!GATHER) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&mybar[st], rows * Gm::ROW_BYTES);
+        bulk_g2s(ring + (size_t)st * TILE_BYTES, p.vec + (size_t)t * RT * D, rows * Gm::ROW_BYTES, &mybar[st]);
+      }
+    } else {
+      if (lane == 0) mbar_arrive_expect_tx(&mybar[st], rows * Gm::ROW_BYTES);
+      __syncwarp();
+      if (lane < rows)
+        bulk_g2s(ring + (size_t)st * TILE_BYTES + (size_t)lane * Gm::ROW_BYTES, p.vec + (size_t)ids * D, Gm::ROW_BYTES,
+                 &mybar[st]);
     }
   };
   if (trace && threadIdx.x == 0) trace[1] = scan_global_ns();
-  uint32_t tq[S - 1];  // tiles claimed and in flight, oldest first
+  uint32_t tq[S - 1];   // tiles claimed and in flight, oldest first
+  uint32_t idq[S - 1];  // GATHER: their row numbers (lane l: row l of the tile)
 #pragma unroll
   for (int s = 0; s < S - 1; ++s) {
     tq[s] = claim();
-    issue(tq[s], s);
+    idq[s] = load_ids(tq[s]);
+    issue(tq[s], s, idq[s]);
+  }
+  uint32_t t_ahead = 0, id_ahead = 0;  // GATHER: the tile to be issued at the next iteration and its row numbers
+  if (GATHER) {
+    t_ahead = claim();
+    id_ahead = load_ids(t_ahead);
   }
 
   // row this lane owns after the butterfly
@@ -691,13 +714,23 @@ __global__ void __launch_bounds__(dense_nw<D, QB>() * 32, 1) scan_dense_kernel(c
     if (t >= n_tiles) break;  // a warp's tiles come in ascending order: nothing behind this one
     // checkpoint: take part in a prune if one was requested
     if (__shfl_sync(0xffffffffu, ld_volatile_s32(&ctl->prune_flag), 0)) cta_prune_all<QB>(ps, ctl, p.nq, p.kp);
+    const uint32_t ids_cur = idq[0];
     {
 #pragma unroll
-      for (int s = 0; s + 1 < S - 1; ++s) tq[s] = tq[s + 1];
-      const uint32_t tn = claim();
+      for (int s = 0; s + 1 < S - 1; ++s) {
+        tq[s] = tq[s + 1];
+        idq[s] = idq[s + 1];
+      }
+      const uint32_t tn = GATHER ? t_ahead : claim();
+      const uint32_t idn = GATHER ? id_ahead : 0u;
       tq[S - 2] = tn;
+      idq[S - 2] = idn;
       const int st_new = stage + (S - 1) >= S ? stage - 1 : stage + (S - 1);
-      issue(tn, st_new);
+      issue(tn, st_new, idn);
+      if (GATHER) {
+        t_ahead = claim();
+        id_ahead = load_ids(t_ahead);
+      }
     }
 
     // From its tile number XCHG_FIRST_TILE on, a warp that finds the staging area free (x_busy) fetches the
@@ -773,17 +806,16 @@ __global__ void __launch_bounds__(dense_nw<D, QB>() * 32, 1) scan_dense_kernel(c
     const long long left = n_items - item0;
     // bit r of `rowbits`: row r of the tile exists and passes the mask
     uint32_t rowbits = 0xffffffffu;
-    if (p.mask != nullptr) rowbits = __ldg(p.mask + (item0 >> 5)) >> ((uint32_t)item0 & 31u);
+    if (!GATHER && p.mask != nullptr) rowbits = __ldg(p.mask + (item0 >> 5)) >> ((uint32_t)item0 & 31u);
     if (left < RT) rowbits &= (1u << (int)left) - 1u;
+    uint32_t rowid[NSUB];  // index row of this lane's row in each sub-batch
     float rinv[NSUB];
 #pragma unroll
     for (int sb = 0; sb < NSUB; ++sb) {
+      const int r = sb * RS + my_row_in_tile;
+      rowid[sb] = GATHER ? __shfl_sync(0xffffffffu, ids_cur, r) : (uint32_t)item0 + (uint32_t)r;
       rinv[sb] = 1.f;
-      if (MODE == MODE_DOT && p.inv_norm != nullptr) {
-        const int r = sb * RS + my_row_in_tile;
-        rinv[sb] = (r < left) ? __ldg(p.inv_norm + item0 + r) : 0.f;
-      }
-
+      if (MODE == MODE_DOT && p.inv_norm != nullptr) rinv[sb] = (r < left) ? __ldg(p.inv_norm + rowid[sb]) : 0.f;
     }
     // Pacing (L2 / plain dot product; the cosine scan gets the same effect from its 1/|x| load): one 4-byte
     // load per tile and lane from a per-row array of the index, which the warp must have received before it
@@ -793,7 +825,7 @@ __global__ void __launch_bounds__(dense_nw<D, QB>() * 32, 1) scan_dense_kernel(c
     // faster (1M x 128, one query: 98 -> 88.5 us). The value itself decides nothing (see its consumer below).
     float pace_v = 0.f;
     if (MODE != MODE_DOT || p.inv_norm == nullptr) {
-      if (p.pace != nullptr && my_row_in_tile < left) pace_v = __ldg(p.pace + item0 + my_row_in_tile);
+      if (p.pace != nullptr && my_row_in_tile < left) pace_v = __ldg(p.pace + rowid[0]);
     }
     float tau_r[QB];
 #pragma unroll
@@ -902,7 +934,7 @@ __global__ void __launch_bounds__(dense_nw<D, QB>() * 32, 1) scan_dense_kernel(c
         for (int sb = 0; sb < NSUB; ++sb) {
           const int r = sb * RS + my_row_in_tile;
           if (my_unique)
-            slot[r] = ((rowbits >> r) & 1u) ? make_key(score[sb][0], (uint32_t)item0 + (uint32_t)r) : KEY_NONE;
+            slot[r] = ((rowbits >> r) & 1u) ? make_key(score[sb][0], rowid[sb]) : KEY_NONE;
         }
         ++n_deferred;
         __syncwarp();
@@ -929,12 +961,11 @@ __global__ void __launch_bounds__(dense_nw<D, QB>() * 32, 1) scan_dense_kernel(c
 #pragma unroll
       for (int sb = 0; sb < NSUB; ++sb) {
         const bool live = my_unique && ((rowbits >> (sb * RS + my_row_in_tile)) & 1u);
-        const uint32_t row = (uint32_t)item0 + (uint32_t)(sb * RS + my_row_in_tile);
 #pragma unroll
         for (int qi = 0; qi < QB; ++qi) {
           if (qi < p.nq) {  // warp-uniform
             const bool pass = live && (score[sb][qi] <= tau_r[qi]);
-            const int after = warp_append(ps.ref(qi), pass, make_key(score[sb][qi], row));
+            const int after = warp_append(ps.ref(qi), pass, make_key(score[sb][qi], rowid[sb]));
             if (after >= highwater && lane == 0) st_volatile_s32(&ctl->prune_flag, 1);
           }
         }

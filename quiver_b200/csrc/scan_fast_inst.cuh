@@ -40,7 +40,10 @@ template <int D, int QB, int MODE>
 static int launch_dense_one(const ScanParams& p, int grid, cudaStream_t st) {
   const size_t smem = scan_dense_smem<D, QB>(p.kp);
   if (smem > 227 * 1024) return fail(6, "scan: candidate pools do not fit shared memory");
-  scan_dense_kernel<D, QB, MODE><<<grid, dense_nw<D, QB>() * 32, smem, st>>>(p);
+  if (p.gather != nullptr)
+    scan_dense_kernel<D, QB, MODE, true><<<grid, dense_nw<D, QB>() * 32, smem, st>>>(p);
+  else
+    scan_dense_kernel<D, QB, MODE, false><<<grid, dense_nw<D, QB>() * 32, smem, st>>>(p);
   QG_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -104,9 +107,13 @@ static int attr_qb() {
   if constexpr (QB <= scan_fast_qb_limit<D>()) {
     if (int e = attr_one<D, QB, MODE_L2>()) return e;
     if (int e = attr_one<D, QB, MODE_DOT>()) return e;
-    QG_CUDA_OK(cudaFuncSetAttribute(scan_dense_kernel<D, QB, MODE_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    QG_CUDA_OK(cudaFuncSetAttribute(scan_dense_kernel<D, QB, MODE_L2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     227 * 1024));
-    QG_CUDA_OK(cudaFuncSetAttribute(scan_dense_kernel<D, QB, MODE_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    QG_CUDA_OK(cudaFuncSetAttribute(scan_dense_kernel<D, QB, MODE_DOT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    227 * 1024));
+    QG_CUDA_OK(cudaFuncSetAttribute(scan_dense_kernel<D, QB, MODE_L2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    227 * 1024));
+    QG_CUDA_OK(cudaFuncSetAttribute(scan_dense_kernel<D, QB, MODE_DOT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     227 * 1024));
   }
   return 0;
