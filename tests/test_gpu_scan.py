@@ -261,3 +261,39 @@ def test_dense_flat_scan_with_threshold_exchange(capi, oracle, dim, metric):
             assert np.array_equal(row[i, :len(orow)], orow), (dim, metric, k, nq, i, row[i], orow)
             assert np.array_equal(dist[i, :len(od)].view(np.uint32), od.view(np.uint32))
     idx.close()
+
+
+_ROUND1_KERNEL_SCRIPT = r"""
+import numpy as np
+from quiver_b200 import capi
+rng = np.random.default_rng(11)
+STRING = 1 << 2
+for metric, d in ((1, 128), (0, 96), (2, 768)):
+    n = 60_000 if d <= 128 else 15_000
+    corpus = rng.standard_normal((n, d)).astype(np.float32)
+    queries = rng.standard_normal((5, d)).astype(np.float32)
+    idx = capi.Index(d, metric, flags=capi.FLAG_NO_BF16_COPY)
+    idx.upload(corpus)
+    cat = rng.integers(0, 8, n).astype(np.int32)
+    idx.set_column(0, np.full(n, 2, dtype=np.uint8) | np.uint8(0x80), np.zeros(n), cat, cat)
+    flt = capi.Filter(idx, [capi.qg_pred(0, 1, 0, 1)], [capi.qg_clause(7, 0, 0, 3, STRING, 0, 0.0, 0.0)])
+    for nq, k, f in ((1, 10, None), (3, 50, None), (1, 10, flt), (4, 20, flt)):
+        dist, row, cnt, _ = idx.search(queries[:nq], k, filter=f)
+        assert idx.stats()["path"] == (2 if f is not None else 1), idx.stats()
+        xd, xr, xc = idx.search_exhaustive(queries[:nq], k, filter=f)
+        assert np.array_equal(row, xr) and np.array_equal(dist.view(np.uint32), xd.view(np.uint32)), (metric, d, nq, k)
+print("ok")
+"""
+
+
+def test_round1_fast_kernel_stays_bit_identical():
+    """QG_SCAN_DENSE=0 (read once per process) routes flat scans back to scan_fast_kernel, the round-1 kernel that is
+    kept as the opt-out: dense and row-list scans must still equal the exhaustive GPU path bit for bit."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, QG_SCAN_DENSE="0", PYTHONPATH=root)
+    out = subprocess.run([sys.executable, "-c", _ROUND1_KERNEL_SCRIPT], env=env, cwd=root, capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout + out.stderr
