@@ -1037,12 +1037,24 @@ static int filter_refresh(qg_index* idx, qg_filter* f, cudaStream_t st) {
   const long long n = idx->n_rows;
   const size_t words = (size_t)((n + 31) / 32) + 1;
   DevBuf cnt;
+  // QG_FILTER_TIMING=1: stage times of a mask (re)build on stderr (development aid)
+  static const bool timing = [] { const char* e = std::getenv("QG_FILTER_TIMING"); return e && std::atoi(e) != 0; }();
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    cudaStreamSynchronize(st);
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "filter_refresh: %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
   if (f->raw_rows != n || f->raw_facet_epoch != idx->facet_epoch) {
     // columns may be (re)built by another search's host layer: excluded until this mask has been evaluated
     std::lock_guard<std::mutex> cols_lock(idx->cols_mu);
     if (int rc = prepare_columns(idx, f)) return rc;
+    lap("prepare_columns");
     if (int rc = f->raw_mask.ensure(words * 4)) return rc;
     if (int rc = cnt.ensure(8)) return rc;
+    lap("allocate raw mask + counter");
     FilterProgDev prog{(const qg_pred*)f->d_preds.p, (int)f->preds.size(), (const qg_clause*)f->d_clauses.p,
                        (const int32_t*)f->d_iset.p, (const double*)f->d_fset.p};
     int rc = launch_filter_eval((const FacetColDev*)idx->col_table.p, prog, n, (uint32_t*)f->raw_mask.p,
@@ -1057,6 +1069,7 @@ static int filter_refresh(qg_index* idx, qg_filter* f, cudaStream_t st) {
       cnt.release();
       return rc;
     }
+    lap("filter_eval_kernel + count");
     f->raw_matches = (long long)m;
     f->raw_rows = n;
     f->raw_facet_epoch = idx->facet_epoch;
@@ -1074,6 +1087,7 @@ static int filter_refresh(qg_index* idx, qg_filter* f, cudaStream_t st) {
       cudaError_t e = cudaMemcpyAsync(&m, cnt.p, 8, cudaMemcpyDeviceToHost, st);
       if (e == cudaSuccess) e = cudaStreamSynchronize(st);
       if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, cudaGetErrorString(e)); break; }
+      lap("live AND + count (+ allocation)");
       f->comb_matches = (long long)m;
       f->gather_valid = false;
       // gather list when at most a quarter of the rows pass: the scan then reads only those rows
@@ -1085,6 +1099,7 @@ static int filter_refresh(qg_index* idx, qg_filter* f, cudaStream_t st) {
         e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { rc = fail(QG_ERR_CUDA, cudaGetErrorString(e)); break; }
         f->gather_valid = true;
+        lap("row list (allocation + compaction)");
       }
       f->comb_live_epoch = idx->live_epoch;
     } while (0);
