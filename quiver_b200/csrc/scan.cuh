@@ -681,6 +681,8 @@ __global__ void __launch_bounds__(dense_nw<D, QB>() * 32, 1) scan_dense_kernel(c
   const int xr = p.kp >> 5;  // 1, 2 or 4 (the host enables the exchange for kp <= 128 only)
   const int x_total = p.xchg != nullptr ? XCHG_FETCHES * p.nq : 0;  // fetches per launch
   bool x_pending = false;                                 // this warp issued a fetch and has to consume it
+  constexpr bool XCH = QB <= XCHG_MAX_QB;                 // larger query blocks are compiled without the exchange
+  bool x_open = XCH && p.xchg != nullptr;                 // this warp still looks for a fetch to do
   // Until a threshold exists every row would be admitted, and sixteen warps appending every row of their first
   // tiles to one pool is the most expensive part of a single-query scan (the pool overflows and is sorted while
   // all CTAs of the launch are at the same tile). A warp therefore parks the keys of its first tiles in its own
@@ -737,7 +739,7 @@ __global__ void __launch_bounds__(dense_nw<D, QB>() * 32, 1) scan_dense_kernel(c
     // published scores of one query with one bulk copy and turns them into a threshold at the first later tile
     // at which the copy has landed — nothing waits for L2 or for another warp. Repeated until a fetch has seen
     // every publisher (at most XCHG_FETCHES times per query).
-    if (x_pending && __all_sync(0xffffffffu, mbar_try_wait(xbar, (uint32_t)(ld_volatile_s32(&ctl->x_count) & 1)))) {
+    if (XCH && x_pending && __all_sync(0xffffffffu, mbar_try_wait(xbar, (uint32_t)(ld_volatile_s32(&ctl->x_count) & 1)))) {
       const int xc = ld_volatile_s32(&ctl->x_count);
       const int qi = xc % p.nq;
       float best[4];
@@ -781,12 +783,13 @@ __global__ void __launch_bounds__(dense_nw<D, QB>() * 32, 1) scan_dense_kernel(c
         st_volatile_s32(&ctl->x_busy, 0);
       }
       x_pending = false;
-    } else if (!x_pending && p.xchg != nullptr && it >= XCHG_FIRST_TILE) {
-      int got = 0;
+    } else if (XCH && !x_pending && x_open && it >= XCHG_FIRST_TILE) {
+      int got = 0;  // 1 = this warp fetches now, -1 = the exchange is over: stop looking (a warp-local decision)
       if (lane == 0) {
         const int all_full = (1 << p.nq) - 1;
-        if (ld_volatile_s32(&ctl->x_count) < x_total && ld_volatile_s32(&ctl->x_full) != all_full &&
-            ld_volatile_s32(&ctl->x_busy) == 0 && atomicCAS(&ctl->x_busy, 0, 1) == 0) {
+        if (ld_volatile_s32(&ctl->x_count) >= x_total || ld_volatile_s32(&ctl->x_full) == all_full) {
+          got = -1;
+        } else if (ld_volatile_s32(&ctl->x_busy) == 0 && atomicCAS(&ctl->x_busy, 0, 1) == 0) {
           // the owner before us may have finished the job between our look and our claim
           const int xc = ld_volatile_s32(&ctl->x_count);
           if (xc < x_total && ld_volatile_s32(&ctl->x_full) != all_full) {
@@ -799,7 +802,8 @@ __global__ void __launch_bounds__(dense_nw<D, QB>() * 32, 1) scan_dense_kernel(c
         }
       }
       got = __shfl_sync(0xffffffffu, got, 0);
-      if (got) x_pending = true;
+      if (got > 0) x_pending = true;
+      if (got < 0) x_open = false;
     }
 
     const long long item0 = (long long)t * RT;
@@ -907,7 +911,7 @@ __global__ void __launch_bounds__(dense_nw<D, QB>() * 32, 1) scan_dense_kernel(c
     // Mixing in a score keeps the wait behind the arithmetic, where the load has had the whole tile to come back.
     if ((__float_as_uint(pace_v) ^ __float_as_uint(score[0][0])) == 0x7fc12345u && pace_v != pace_v)
       st_volatile_s32(&ctl->kept, 0);
-    if (p.xchg != nullptr && it == 0) {  // publish the best score of this warp's first tile, per query
+    if (XCH && p.xchg != nullptr && it == 0) {  // publish the best score of this warp's first tile, per query
 #pragma unroll
       for (int qi = 0; qi < QB; ++qi) {
         if (qi < p.nq) {
@@ -980,7 +984,7 @@ __global__ void __launch_bounds__(dense_nw<D, QB>() * 32, 1) scan_dense_kernel(c
     __syncwarp();
     flush_deferred();
   }
-  if (x_pending) {  // no copy may outlive the CTA
+  if (XCH && x_pending) {  // no copy may outlive the CTA
     mbar_wait(xbar, (uint32_t)(ld_volatile_s32(&ctl->x_count) & 1));
     x_pending = false;
   }
