@@ -697,12 +697,15 @@ __global__ void __launch_bounds__(dense_nw<D, QB>() * 32, 1) scan_dense_kernel(c
   auto flush_deferred = [&]() {
     const int n = n_deferred * RT;
     for (int base = 0; base < n; base += RT) {
-      if (__shfl_sync(0xffffffffu, ld_volatile_s32(&ctl->prune_flag), 0)) cta_prune_all<QB>(ps, ctl, p.nq, p.kp);
       const float thr = fminf(*reinterpret_cast<volatile float*>(&tau[0]), *reinterpret_cast<volatile float*>(&tau_ext[0]));
       const uint64_t key = lane < RT ? deferred[base + lane] : KEY_NONE;
       const bool pass = key != KEY_NONE && key_score(key) <= thr;
       const int after = warp_append(ps.ref(0), pass, key);
       if (after >= highwater && lane == 0) st_volatile_s32(&ctl->prune_flag, 1);
+      // a look at the flag after EVERY chunk, the last one included: the caller appends the rows of its current
+      // tile right after this returns, and a warp may add one tile's worth of keys between two looks
+      __syncwarp();
+      if (__shfl_sync(0xffffffffu, ld_volatile_s32(&ctl->prune_flag), 0)) cta_prune_all<QB>(ps, ctl, p.nq, p.kp);
     }
     n_deferred = 0;
   };
