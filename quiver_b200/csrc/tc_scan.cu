@@ -884,6 +884,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
 
     int acc = pp;  // unit u uses buffer u % n_acc; this group drains every second unit
     uint32_t acc_phase = 0;
+    const bool warp_idle = (q - lane) >= p.nq;  // warp-uniform: the warp's 32 queries are consecutive
     // one block: units are tiles and the group sees every second tile; two blocks: every tile, its block
     for (long long it = (NBLK == 2 ? 0 : pp);; it += (NBLK == 2 ? 1 : 2)) {
       const int xb = (int)(it % TS_XS);
@@ -906,6 +907,22 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
       const long long tile = tile_of(w);
       if (it == 0 && warp == 4 && lane == 0) dbg_stamp(p.dbg, 4);
       tc_fence_after();
+      if (NBLK == 1 && warp_idle) {  // (one-block kernels only: the branch costs the two-block kernel 3 %)
+        // none of this warp's 32 queries exists (a batch smaller than the query block: a single query leaves
+        // 15 of the 16 epilogue warps without one): hand the buffers straight back, read and score nothing
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&tmem_empty[acc]);
+          if (!RAW) mbar_arrive(&xs_empty[xb]);
+        }
+        acc += 2;
+        if (acc >= n_acc) {
+          acc -= n_acc;
+          acc_phase ^= 1u;
+        }
+        continue;
+      }
       const uint32_t d_addr = tmem_base + lane_base + (uint32_t)(d_off + acc * ROWS);
       // all of this warp's accumulator chunks are requested before the first one is consumed
       uint32_t araw[NCH][16];
