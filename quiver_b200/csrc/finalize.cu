@@ -613,11 +613,21 @@ __global__ void __launch_bounds__(FC_THREADS, 2) finalize_cand_kernel(const Fina
 
   // ---- exact re-rank of the selected candidates (one warp per candidate) ----
   // the rows are scattered over the corpus: the warp's later candidates are pulled towards L2 / L1 first
-  for (int c = warp + FC_WARPS; c < nsel; c += FC_WARPS) {
+  const bool lane_rerank = cp.lane_rerank != 0;
+  if (lane_rerank) {
+    // one LANE per candidate: every lane runs the reference's sequential sum for its own row (32 independent
+    // chains per warp), a few warps do all the work — a twentieth of the instructions of the warp-per-candidate
+    // form, whose single summing lane keeps 31 others waiting
+    for (int c = tid; c < nsel; c += FC_THREADS) {
+      const uint32_t rid = key_row(sel[c]);
+      ex[c] = make_key(exact_distance_lane(p.metric, p.arith, qv, p.vec + (size_t)rid * p.dp, p.d, p.dp), rid);
+    }
+  }
+  for (int c = warp + FC_WARPS; !lane_rerank && c < nsel; c += FC_WARPS) {
     const char* rowp = reinterpret_cast<const char*>(p.vec + (size_t)key_row(sel[c]) * p.dp);
     if (lane * 128 < p.dp * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + lane * 128));
   }
-  for (int c = warp; c < nsel; c += 3 * FC_WARPS) {  // three candidates of the warp per pass
+  for (int c = warp; !lane_rerank && c < nsel; c += 3 * FC_WARPS) {  // three candidates of the warp per pass
     const float* rows3[3];
     uint32_t rid[3];
     int nb = 0;
@@ -666,7 +676,13 @@ __global__ void __launch_bounds__(FC_THREADS, 2) finalize_cand_kernel(const Fina
       extra = cap - nsel;
       certified = false;
     }
-    for (int c = warp; c < extra; c += 3 * FC_WARPS) {
+    if (lane_rerank) {
+      for (int c = tid; c < extra; c += FC_THREADS) {
+        const uint32_t rid = key_row(ex[nsel + c]);
+        ex[nsel + c] = make_key(exact_distance_lane(p.metric, p.arith, qv, p.vec + (size_t)rid * p.dp, p.d, p.dp), rid);
+      }
+    }
+    for (int c = warp; !lane_rerank && c < extra; c += 3 * FC_WARPS) {
       const float* rows3[3];
       uint32_t rid[3];
       int nb = 0;
@@ -1004,7 +1020,16 @@ int launch_finalize_cand(const FinalizeCandParams& p, int nq, cudaStream_t st) {
                               (size_t)0, st, p, nq));
     return 0;
   }
-  QG_CUDA_OK(launch_chained(finalize_cand_kernel, dim3(nq), dim3(FC_THREADS), finalize_cand_smem(p.cap), st, p));
+  static const bool lane_on = [] {
+    const char* e = std::getenv("QG_FINALIZE_LANE");
+    return e == nullptr || std::atoi(e) != 0;
+  }();
+  FinalizeCandParams pl = p;
+  // Measured (1M x 128, 10 000 queries, us per 2 048 queries): L2 k=10 100 -> 181, k=100 297 -> 342 (two CTAs per
+  // SM: the latency of a lane's 128-step chain counts, not the instructions saved); cosine, whose distance is
+  // three sums, k=10 145 -> 171 but k=100 551 -> 321. So: cosine with 64 or more candidates to re-rank.
+  pl.lane_rerank = (lane_on && (p.base.dp & 3) == 0 && p.base.metric == METRIC_COSINE && p.kp >= 64) ? 1 : 0;
+  QG_CUDA_OK(launch_chained(finalize_cand_kernel, dim3(nq), dim3(FC_THREADS), finalize_cand_smem(p.cap), st, pl));
   return 0;
 }
 

@@ -40,6 +40,7 @@ struct FinalizeCandParams {
   double tc_gamma;          // bound on |tensor-core dot - exact dot| / (|q| |x|)
   double tc_norm_gamma;     // raw L2 scan: bound on the extra accumulation error / |x|^2 (the norm rides in the MMA), else 0
   unsigned long long* dbg;  // optional [16] phase time stamps of CTA 0 (development aid), else nullptr
+  int lane_rerank;          // exact re-rank with one lane per candidate (needs dp % 4 == 0) instead of one warp per candidate
   FinalizeParams base;      // vec, dp, d, queries, negatives, metric, arith, mode, cosine, k, gamma,
                             // max_norm2, outputs, row_base (partial / nb unused)
 };
