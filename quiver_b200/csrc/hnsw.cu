@@ -248,9 +248,16 @@ __device__ __forceinline__ bool search_layer(const HnswKParams& p, const float* 
 }
 
 
-constexpr int HNSW_WARPS = 16;
+constexpr int HNSW_WARPS = 16;  // the builder's kernels
+#ifndef QG_HNSW_SEARCH_WARPS
+#define QG_HNSW_SEARCH_WARPS 16
+#endif
+// walks in flight per SM. Measured at 1M x 128, efSearch 128 (10 000 queries): 16 warps 239-253 k queries/s,
+// 24 warps 255 k, 32 warps (64 registers, smaller candidate heaps) 240 k: occupancy is not what bounds the walk.
+constexpr int HNSW_SEARCH_WARPS = QG_HNSW_SEARCH_WARPS;
+constexpr int HNSW_MAX_WARPS = HNSW_WARPS > HNSW_SEARCH_WARPS ? HNSW_WARPS : HNSW_SEARCH_WARPS;
 
-__global__ void __launch_bounds__(HNSW_WARPS * 32, 1) hnsw_search_kernel(const HnswKParams p) {
+__global__ void __launch_bounds__(HNSW_SEARCH_WARPS * 32, 1) hnsw_search_kernel(const HnswKParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // per-warp slice: query | result heap (ef0 + 1) | candidate heap | pending ids / distances
@@ -263,7 +270,7 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32, 1) hnsw_search_kernel(const H
   HRes* cand = reinterpret_cast<HRes*>(base + q_bytes + res_bytes);
   uint32_t* pend_idx = reinterpret_cast<uint32_t*>(base + q_bytes + res_bytes + (size_t)p.cand_cap * 8);
   float* pend_d = reinterpret_cast<float*>(pend_idx + 32);
-  const size_t slot = (size_t)blockIdx.x * HNSW_WARPS + warp;
+  const size_t slot = (size_t)blockIdx.x * HNSW_SEARCH_WARPS + warp;
   uint32_t* vis = p.visited + slot * (size_t)p.n_words;
   uint32_t* touched = p.touched + slot * (size_t)HNSW_TOUCH_CAP;
   int n_touched = 0;
@@ -547,7 +554,7 @@ __global__ void __launch_bounds__(256) hnsw_link_kernel(const HnswBuildKParams p
 }
 
 size_t hnsw_workspace_bytes(long long n_nodes, int sm_count) {
-  const size_t slots = (size_t)sm_count * HNSW_WARPS;
+  const size_t slots = (size_t)sm_count * HNSW_MAX_WARPS;
   const size_t n_words = (size_t)((n_nodes + 31) / 32);
   return slots * n_words * 4 + slots * (size_t)HNSW_TOUCH_CAP * 4 + 256;
 }
@@ -567,7 +574,7 @@ int launch_hnsw_search(const HnswDevGraph& g, const float* vec, int dp, int d, i
   p.nq = nq;
   p.kk = kk;
   p.ef0 = ef0;
-  const size_t slots = (size_t)sm_count * HNSW_WARPS;
+  const size_t slots = (size_t)sm_count * HNSW_SEARCH_WARPS;
   p.n_words = (g.n_nodes + 31) / 32;
   p.visited = static_cast<uint32_t*>(workspace);
   p.touched = p.visited + slots * (size_t)p.n_words;
@@ -579,11 +586,11 @@ int launch_hnsw_search(const HnswDevGraph& g, const float* vec, int dp, int d, i
   // shared memory per warp: query, result heap, pending slots, and the rest of ~13.5 KB for the candidate heap
   const size_t q_bytes = ((size_t)dp * 4 + 15) & ~(size_t)15;
   const size_t res_bytes = ((size_t)(ef0 + 2) * 8 + 15) & ~(size_t)15;
-  const size_t budget = (size_t)216 * 1024 / HNSW_WARPS;
+  const size_t budget = (size_t)216 * 1024 / HNSW_SEARCH_WARPS;
   if (q_bytes + res_bytes + 256 + 64 * 8 > budget)
     return fail(QG_ERR_UNSUPPORTED, "hnsw search: dimension / efSearch too large for the kernel's shared-memory slice");
   p.cand_cap = (int)((budget - q_bytes - res_bytes - 256) / 8);
-  const size_t smem = (q_bytes + res_bytes + (size_t)p.cand_cap * 8 + 256) * HNSW_WARPS;
+  const size_t smem = (q_bytes + res_bytes + (size_t)p.cand_cap * 8 + 256) * HNSW_SEARCH_WARPS;
   static bool attr_done[64] = {};
   int dev = 0;
   QG_CUDA_OK(cudaGetDevice(&dev));
@@ -592,8 +599,8 @@ int launch_hnsw_search(const HnswDevGraph& g, const float* vec, int dp, int d, i
     attr_done[dev] = true;
   }
   QG_CUDA_OK(cudaMemsetAsync(p.next_query, 0, 4, st));
-  const int grid = (int)std::min<long long>(sm_count, (nq + HNSW_WARPS - 1) / HNSW_WARPS);
-  hnsw_search_kernel<<<grid, HNSW_WARPS * 32, smem, st>>>(p);
+  const int grid = (int)std::min<long long>(sm_count, (nq + HNSW_SEARCH_WARPS - 1) / HNSW_SEARCH_WARPS);
+  hnsw_search_kernel<<<grid, HNSW_SEARCH_WARPS * 32, smem, st>>>(p);
   QG_CUDA_OK(cudaGetLastError());
   return 0;
 }
