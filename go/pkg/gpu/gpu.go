@@ -289,6 +289,88 @@ func (x *Index) BatchDistance(q []float32, rows []uint32, out []float32) error {
 	})
 }
 
+// SearchExhaustive is ExactIndex.Search as the reference literally runs it — the exact distance of every live row,
+// a full sort, the first k (exact.go:114-129) — on the device: no thresholds and no certificate. It is what
+// UseExactSearch (search.go:12-31) maps to when a caller wants the slow path by name, and the GPU-side oracle of
+// the parity tests.
+func (x *Index) SearchExhaustive(q vectortypes.F32, k int) ([]types.BasicSearchResult, error) {
+	x.mu.RLock()
+	defer x.mu.RUnlock()
+	dist := make([]float32, k)
+	rows := make([]int64, k)
+	var cnt C.int
+	if err := call(func() C.int {
+		return C.qg_search_exhaustive(x.h, (*C.float)(unsafe.Pointer(&q[0])), 1, C.int(len(q)), C.int(k), nil,
+			(*C.float)(unsafe.Pointer(&dist[0])), (*C.int64_t)(unsafe.Pointer(&rows[0])), &cnt)
+	}); err != nil {
+		return nil, err
+	}
+	out := make([]types.BasicSearchResult, 0, int(cnt))
+	for j := 0; j < int(cnt); j++ {
+		out = append(out, types.BasicSearchResult{ID: x.ids[rows[j]], Distance: dist[j]})
+	}
+	return out, nil
+}
+
+// Graph is an HNSW graph resident on the device next to the index's rows: hnsw.Search (hnsw.go:602-713) runs as one
+// kernel launch for a whole batch of queries (a warp per query, the reference's heaps, visit order and stop rules —
+// step-identical to the host walk). Build constructs the graph on the device (batched inserts, the reference's
+// neighbour selection and prune rule); Upload takes a graph the Go side already holds (HNSW.Nodes flattened).
+type Graph struct {
+	h   *C.qg_hnsw
+	idx *Index
+}
+
+func (x *Index) BuildGraph(m, maxM0, efConstruction, maxLevel int, seed uint64) (*Graph, error) {
+	x.mu.RLock()
+	defer x.mu.RUnlock()
+	var g *C.qg_hnsw
+	if err := call(func() C.int {
+		return C.qg_hnsw_build(x.h, C.int(m), C.int(maxM0), C.int(efConstruction), C.int(maxLevel), C.uint64_t(seed), 0, &g)
+	}); err != nil {
+		return nil, err
+	}
+	return &Graph{h: g, idx: x}, nil
+}
+
+// UploadGraph: level[i] = top layer of node i, adj0 = layer-0 lists (nodes x maxM0, 0xFFFFFFFF padded), the upper
+// layers as one CSR (layout in quiver_gpu.h: qg_hnsw_upload; qg_hnsw_export writes the same arrays).
+func (x *Index) UploadGraph(m, maxM0, entryPoint, currentLevel int, level []int32, adj0 []uint32, upperOff []int64,
+	upperAdj []uint32) (*Graph, error) {
+	var g *C.qg_hnsw
+	var ua *C.uint32_t
+	if len(upperAdj) > 0 {
+		ua = (*C.uint32_t)(unsafe.Pointer(&upperAdj[0]))
+	}
+	if err := call(func() C.int {
+		return C.qg_hnsw_upload(x.h, C.int64_t(len(level)), C.int(m), C.int(maxM0), C.int(entryPoint), C.int(currentLevel),
+			(*C.int32_t)(unsafe.Pointer(&level[0])), (*C.uint32_t)(unsafe.Pointer(&adj0[0])),
+			(*C.int64_t)(unsafe.Pointer(&upperOff[0])), ua, &g)
+	}); err != nil {
+		return nil, err
+	}
+	return &Graph{h: g, idx: x}, nil
+}
+
+// Search walks the graph for every query of the batch. count[i] < k: the graph walk under-filled, the caller runs
+// the exact pass (hnsw.go:676-710 — Index.BatchSearch over those queries); count[i] < 0: the query's candidate heap
+// outgrew the kernel's shared-memory slice, repeat it with the host walk (never seen at efSearch = 128).
+func (g *Graph) Search(qs []float32, nq, k, efSearch int) (rows []uint32, dist []float32, count []int32, err error) {
+	g.idx.mu.RLock()
+	defer g.idx.mu.RUnlock()
+	rows = make([]uint32, nq*k)
+	dist = make([]float32, nq*k)
+	count = make([]int32, nq)
+	err = call(func() C.int {
+		return C.qg_hnsw_search_batch(g.idx.h, g.h, (*C.float)(unsafe.Pointer(&qs[0])), C.int(nq), C.int(g.idx.dim), C.int(k),
+			C.int(efSearch), (*C.uint32_t)(unsafe.Pointer(&rows[0])), (*C.float)(unsafe.Pointer(&dist[0])),
+			(*C.int)(unsafe.Pointer(&count[0])), nil)
+	})
+	return
+}
+
+func (g *Graph) Close() { C.qg_hnsw_destroy(g.h) }
+
 // Group drives every GPU of the box from this one process (qg_group_*: one worker thread, stream, index and
 // NCCL communicator per device inside libquivergpu). It is what DB.BatchSearch (pkg/core/db.go:707-845) hands a
 // batch to when the collection spans GPUs: row-sharded (every GPU scans its shard, one all-gather of the
