@@ -1,5 +1,4 @@
-# full GPU suite, smoke, the judged bench line, the reference arm
-timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
+# full GPU suite, smoke, the judged bench line
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 300 gpurun_out/bench_n1.err | tail -2
-timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 300 gpurun_out/bench_ref.json
