@@ -4,7 +4,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from quiver_b200 import capi
 n, d, metric, q, k, iters = [int(x) for x in sys.argv[1:7]]
-idx = capi.Index(d, metric, reserve_rows=n)
+idx = capi.Index(d, metric, reserve_rows=n, flags=int(os.environ.get("PROF_FLAGS", "0")))
 idx.upload_synthetic(1 if metric == 1 else 2, 42, 0, n)
 dq = torch.floor(torch.rand((q, d), device="cuda:0") * 218) if metric == 1 else torch.randn((q, d), device="cuda:0")
 dist = torch.empty((q, k), dtype=torch.float32, device="cuda:0")
